@@ -1,0 +1,142 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE ONLY.  Build oracle/_ref/ from the reference sources WHERE THEY LIE.
+
+Nothing under /root/reference is copied into the repository: line ranges of the reference's own
+files are spliced between our preludes/launchers in a temporary directory, compiled, and only
+the resulting shared objects are kept under oracle/_ref/ (git-ignored, travels to the GPU box).
+
+  libref_host.so  g++   src/rtpose/modelDescriptor{,Factory}.cpp (unmodified)
+                        examples/rtpose/rtpose.cpp:144-152, 549-751, 808-1076 (ColumnCompare,
+                        connectLimbs, connectLimbsCOCO)  src/caffe/util/im2col.cpp:8-56 (im2col_cpu)
+  libref_cpm.so   nvcc  src/caffe/cpm/layers/imresize_layer.cu:8-18,97-155
+                        src/caffe/cpm/layers/nms_layer.cu:13-113
+                        (sm_100a; default -fmad, as the reference Makefile:410 passes no fmad flag)
+
+Flags: the reference Makefile (:326,405,409) uses `-O3 -march=native -std=c++11`; we drop
+-march=native so that the host arithmetic is the portable SSE2 one (no machine-dependent FMA
+contraction) - stated in DESIGN.md.
+
+The reference's own build system is not run.  If /root/reference is absent (GPU box) this script
+is a no-op and the prebuilt .so files are used.
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("RTPOSE_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+
+
+def lines(path, ranges):
+    src = open(os.path.join(REF, path)).read().split("\n")
+    out = []
+    for a, b in ranges:
+        out.append("#line %d \"%s\"" % (a, path))
+        out.extend(src[a - 1:b])
+    return "\n".join(out) + "\n"
+
+
+HOST_WRAPPER = r'''
+// ---- wrappers (ours) ----
+extern "C" int ref_connect(int model, const float* heatmap, const float* peaks, int max_peaks,
+                           int netW, int netH, int dispW, int dispH,
+                           int min_cnt, float min_score, float inter_thr, int min_above,
+                           float* joints, double* subset_out, int subset_cap, int* subset_rows) {
+    NET_RESOLUTION_WIDTH = netW; NET_RESOLUTION_HEIGHT = netH;
+    DISPLAY_RESOLUTION_WIDTH = dispW; DISPLAY_RESOLUTION_HEIGHT = dispH;
+    global.connect_min_subset_cnt = min_cnt; global.connect_min_subset_score = min_score;
+    global.connect_inter_threshold = inter_thr; global.connect_inter_min_above_threshold = min_above;
+    std::unique_ptr<ModelDescriptor> md;
+    ModelDescriptorFactory::createModelDescriptor(
+        model == 0 ? ModelDescriptorFactory::Type::MPI_15 : ModelDescriptorFactory::Type::COCO_18, md);
+    std::vector<std::vector<double>> subset;
+    std::vector<std::vector<std::vector<double>>> connection;
+    int cnt = model == 0 ? connectLimbs(subset, connection, heatmap, peaks, max_peaks, joints, md.get())
+                         : connectLimbsCOCO(subset, connection, heatmap, peaks, max_peaks, joints, md.get());
+    if (subset_rows) *subset_rows = (int)subset.size();
+    if (subset_out) {
+        const int w = md->get_number_parts() + 3;
+        for (int i = 0; i < (int)subset.size() && i < subset_cap; i++)
+            for (int j = 0; j < w; j++) subset_out[i * w + j] = subset[i][j];
+    }
+    return cnt;
+}
+
+extern "C" int ref_model_descriptor(int model, int* num_parts, int* num_limbs, int* limb_seq, int* map_idx,
+                                    char* names, int names_cap) {
+    std::unique_ptr<ModelDescriptor> md;
+    try {
+        ModelDescriptorFactory::createModelDescriptor(
+            model == 0 ? ModelDescriptorFactory::Type::MPI_15 : ModelDescriptorFactory::Type::COCO_18, md);
+    } catch (...) { return -1; }
+    *num_parts = md->get_number_parts();
+    *num_limbs = md->number_limb_sequence();
+    for (int i = 0; i < 2 * *num_limbs; i++) { limb_seq[i] = md->get_limb_sequence()[i]; map_idx[i] = md->get_map_idx()[i]; }
+    std::string all;
+    const int nmaps = *num_parts + 1 + 2 * *num_limbs;
+    for (int i = 0; i < nmaps; i++) { all += md->get_part_name(i); all += "\n"; }
+    snprintf(names, names_cap, "%s", all.c_str());
+    return 0;
+}
+
+extern "C" void ref_im2col(const float* im, int channels, int height, int width, int kh, int kw,
+                           int ph, int pw, int sh, int sw, float* col) {
+    caffe::im2col_cpu<float>(im, channels, height, width, kh, kw, ph, pw, sh, sw, 1, 1, col);
+}
+'''
+
+
+def build_host(tmp):
+    tu = ('#include "%s"\n' % os.path.join(HERE, "ref_host_prelude.h")
+          + lines("examples/rtpose/rtpose.cpp", [(144, 152), (549, 751), (808, 1076)])
+          + "namespace caffe {\n" + lines("src/caffe/util/im2col.cpp", [(8, 56)]) + "}\n"
+          + HOST_WRAPPER)
+    src = os.path.join(tmp, "ref_host_tu.cpp")
+    open(src, "w").write(tu)
+    out = os.path.join(OUT, "libref_host.so")
+    cmd = ["g++", "-O3", "-std=c++11", "-fPIC", "-shared", "-w", "-I" + os.path.join(REF, "include"), src,
+           os.path.join(REF, "src/rtpose/modelDescriptor.cpp"),
+           os.path.join(REF, "src/rtpose/modelDescriptorFactory.cpp"), "-o", out]
+    subprocess.check_call(cmd)
+    return out
+
+
+def build_cpm(tmp, keep_sass=False):
+    tu = ('#include "%s"\n' % os.path.join(HERE, "ref_cpm_prelude.cuh")
+          + "namespace caffe {\n"
+          + lines("src/caffe/cpm/layers/imresize_layer.cu", [(8, 18), (97, 155)])
+          + lines("src/caffe/cpm/layers/nms_layer.cu", [(13, 113)])
+          + "}\n"
+          + '#include "%s"\n' % os.path.join(HERE, "ref_cpm_launch.cuh"))
+    src = os.path.join(tmp, "ref_cpm_tu.cu")
+    open(src, "w").write(tu)
+    out = os.path.join(OUT, "libref_cpm.so")
+    cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+           "-shared", "-w", src, "-o", out]
+    subprocess.check_call(cmd)
+    if keep_sass:
+        sass = subprocess.check_output(["cuobjdump", "-sass", out]).decode()
+        open(os.path.join(OUT, "ref_cpm.sass"), "w").write(sass)
+    return out
+
+
+def main():
+    if not os.path.isdir(REF):
+        print("build_ref: %s absent - keeping prebuilt oracle/_ref" % REF)
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="rtpose_ref_")
+    try:
+        print("built", build_host(tmp))
+        if shutil.which("nvcc"):
+            print("built", build_cpm(tmp, keep_sass="--sass" in sys.argv))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,247 @@
+"""CPU tests that PIN THE ORACLE before anything trusts it:
+
+  * graph table            == tests/golden/netspec_*.json parsed from the reference prototxts
+  * model descriptors      == the reference's own modelDescriptorFactory.cpp (oracle/_ref, when built)
+  * im2col                 == the reference's own im2col_cpu (oracle/_ref)                    bit-exact
+  * connectLimbs / COCO    == the reference's own functions (oracle/_ref) on seeded scenes    bit-exact
+  * MAX pooling            == upstream Caffe known-answer vector (test_pooling_layer.cpp:49-120)
+  * convolution            vs a naive direct loop at 1e-4 (the bar of test_convolution_layer.cpp:231-265)
+  * INTER_AREA             == committed cv2 fixtures (tests/golden/area_cv2.npz)               bit-exact
+  * stage-level goldens    == tests/golden/parse_*.npz (peaks, joints, subset, JSON)          bit-exact
+ImResize/NMS are pinned against the reference's own CUDA kernels in tests/test_gpu_reference.py.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from caffe_rtpose_b200 import synth
+from oracle import orc
+
+MODELS = [(orc.COCO_18, "coco"), (orc.MPI_15, "mpi")]
+
+
+@pytest.mark.parametrize("model,name", MODELS)
+def test_graph_matches_prototxt_fixture(model, name, golden_dir):
+    spec = json.load(open(os.path.join(golden_dir, "netspec_%s.json" % name)))
+    mine = orc.Net(model).layers()
+    assert len(mine) == len(spec["layers"]) == 183
+    for a, b in zip(mine, spec["layers"]):
+        assert a["name"] == b["name"] and a["type"] == b["type"]
+        assert a["bottom"] == b["bottom"] and [a["top"]] == b["top"]
+        if a["type"] == "Convolution":
+            assert (a["num_output"], a["kernel_size"], a["pad"], a["stride"]) == (
+                b["num_output"], b["kernel_size"], b["pad"], b["stride"])
+            assert b["weight_filler"] == {"type": "gaussian", "std": "0.01"}
+        if a["type"] == "Pooling":
+            assert (a["kernel_size"], a["stride"], a["pad"], b["pool"]) == (b["kernel_size"], b["stride"], b["pad"], "MAX")
+    nms = spec["layers"][-1]
+    assert nms["num_parts"] == orc.num_parts(model) and nms["max_peaks"] == orc.max_peaks(model)
+    assert spec["layers"][-2]["factor"] == 8.0
+    # conv table used by the weight generator == oracle's
+    assert orc.Net(model).convs() == synth.conv_table(model)
+
+
+def test_flops_match_baseline():
+    assert orc.flops(orc.COCO_18, 368, 656) == 484634285056.0
+    assert orc.flops(orc.COCO_18, 736, 992) == 1465723203584.0
+    assert orc.flops(orc.MPI_15, 368, 496) == 361694564352.0
+
+
+@pytest.mark.parametrize("model,name", MODELS)
+def test_model_descriptor_vs_reference_code(model, name):
+    R = orc.ref_host()
+    if R is None:
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    import ctypes as C
+    npart, nlimb = C.c_int(), C.c_int()
+    ls, mi = np.zeros(64, np.int32), np.zeros(64, np.int32)
+    names = C.create_string_buffer(8192)
+    assert R.ref_model_descriptor(model, C.byref(npart), C.byref(nlimb), ls, mi, names, 8192) == 0
+    assert npart.value == orc.num_parts(model)
+    assert list(ls[:2 * nlimb.value]) == orc.limb_seq(model) == synth._LIMBS[model]
+    assert list(mi[:2 * nlimb.value]) == orc.map_idx(model) == synth._MAPIDX[model]
+    ref_names = names.value.decode().split("\n")[:-1]
+    assert ref_names == [orc.lib().orc_model_map_name(model, i).decode() for i in range(orc.num_maps(model))]
+
+
+def test_im2col_vs_reference_code():
+    R = orc.ref_host()
+    if R is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(0)
+    for (c, h, w, k, pad) in [(3, 7, 9, 3, 1), (5, 11, 6, 7, 3), (4, 5, 5, 1, 0)]:
+        im = rng.standard_normal((c, h, w)).astype(np.float32)
+        col = orc.im2col(im, k, pad)
+        ref = np.empty_like(col)
+        R.ref_im2col(im, c, h, w, k, k, pad, pad, 1, 1, ref)
+        assert np.array_equal(col, ref)
+
+
+def test_maxpool_known_answer_upstream():
+    # test_pooling_layer.cpp:49-120 (kernel 2, stride 1)
+    x = np.tile(np.array([[1, 2, 5, 2, 3], [9, 4, 1, 4, 8], [1, 2, 5, 2, 3]], np.float32), (2, 2, 1, 1))
+    y = orc.maxpool(x, 2, 1, 0)
+    assert y.shape == (2, 2, 2, 4)
+    assert np.array_equal(y, np.tile(np.array([[9, 5, 5, 8], [9, 5, 5, 8]], np.float32), (2, 2, 1, 1)))
+
+
+def test_maxpool_ceil_dims():
+    # pooling_layer.cpp:90-93: ceil -> odd sizes keep the last partial window
+    x = np.arange(2 * 5 * 7, dtype=np.float32).reshape(1, 2, 5, 7)
+    y = orc.maxpool(x, 2, 2, 0)
+    assert y.shape == (1, 2, 3, 4)
+    assert y[0, 0, 2, 3] == x[0, 0, 4, 6] and y[0, 0, 0, 0] == x[0, 0, 1, 1]
+
+
+def _naive_conv(x, w, b, pad):
+    n, cin, h, ww = x.shape
+    cout, _, k, _ = w.shape
+    xp = np.zeros((n, cin, h + 2 * pad, ww + 2 * pad), np.float64)
+    xp[:, :, pad:pad + h, pad:pad + ww] = x
+    out = np.zeros((n, cout, h + 2 * pad - k + 1, ww + 2 * pad - k + 1), np.float64)
+    for o in range(cout):
+        for y in range(out.shape[2]):
+            for xx in range(out.shape[3]):
+                out[:, o, y, xx] = (xp[:, :, y:y + k, xx:xx + k] * w[o]).sum((1, 2, 3)) + b[o]
+    return out
+
+
+@pytest.mark.parametrize("k,pad", [(3, 1), (1, 0), (7, 3)])
+def test_conv_vs_naive_loop(k, pad):
+    # upstream bar: 1e-4 vs caffe_conv (test_convolution_layer.cpp:231-265, 443-468), Gaussian-filled 2x3x6x4
+    rng = np.random.default_rng(k)
+    x = rng.standard_normal((2, 3, 6, 4)).astype(np.float32)
+    w = rng.standard_normal((4, 3, k, k)).astype(np.float32)
+    b = rng.standard_normal(4).astype(np.float32)
+    assert np.abs(orc.conv2d(x, w, b, pad) - _naive_conv(x, w, b, pad)).max() < 1e-4
+
+
+def test_relu():
+    x = np.array([-1.5, 0.0, 2.0, -0.0], np.float32)
+    orc.lib().orc_relu(x, x.size)
+    assert np.array_equal(x, np.array([0, 0, 2, 0], np.float32))
+
+
+def test_inter_area_vs_cv2_fixture(golden_dir):
+    d = np.load(os.path.join(golden_dir, "area_cv2.npz"))
+    n = len([k for k in d.files if k.startswith("src")])
+    assert n >= 6
+    for i in range(n):
+        dst = d["dst%d" % i]
+        assert np.array_equal(orc.resize_area(d["src%d" % i], dst.shape[0], dst.shape[1]), dst)
+
+
+def test_inter_area_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    img = synth.make_frame(3, 180, 320)
+    for dh, dw in [(92, 164), (80, 140), (90, 160), (60, 160)]:
+        assert np.array_equal(orc.resize_area(img, dh, dw), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA))
+
+
+def test_scale_targets():
+    # 656x368 @ {1, .85, .70} -> 656x368, 560x320, 464x272
+    assert [orc.scale_target(656, 368, 1.0, 0.15, i) for i in range(3)] == [(656, 368), (560, 320), (464, 272)]
+    assert [synth.scale_geometry(656, 368, 1.0, 0.15, i)[:2] for i in range(3)] == [(656, 368), (560, 320), (464, 272)]
+
+
+def test_preprocess_pad_and_normalise():
+    img = synth.make_frame(1, 90, 160)
+    out = orc.preprocess(img, 48, 96, 2, 1.0, 0.3)
+    assert out.shape == (2, 3, 48, 96)
+    r0 = orc.resize_area(img, 48, 96)
+    assert np.array_equal(out[0], (r0.transpose(2, 0, 1).astype(np.float32) / np.float32(256) - np.float32(0.5)))
+    tw, th = orc.scale_target(96, 48, 1.0, 0.3, 1)
+    assert (tw, th) == (80, 48) or (tw, th) == (80, 34 + 14)  # 16*ceil(67.2/16)=80, 16*ceil(33.6/16)=48
+    padw = (96 - tw) // 2
+    assert np.all(out[1][:, :, :padw] == 0) and np.all(out[1][:, :, padw + tw:] == 0)
+
+
+@pytest.mark.parametrize("name", ["coco", "coco_s3", "mpi"])
+def test_stage_goldens(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, "parse_%s.npz" % name))
+    model, net_w, net_h, disp_w, disp_h, S, _ = [int(v) for v in g["meta"]]
+    full = orc.imresize(g["maps"], net_h, net_w, float(g["start_scale"]), float(g["scale_gap"]))
+    peaks = orc.nms(full, orc.num_parts(model), orc.max_peaks(model), float(g["nms_threshold"]))
+    assert np.array_equal(peaks, g["peaks"])
+    cnt, joints, subset = orc.connect(model, full, peaks, disp_w, disp_h, want_subset=True)
+    assert cnt == len(g["joints"]) and cnt >= 3
+    assert np.array_equal(joints, g["joints"]) and np.array_equal(subset, g["subset"])
+    assert orc.json_text(joints, orc.num_parts(model)) == str(g["json"])
+
+
+@pytest.mark.parametrize("model,net_w,net_h,n", [(orc.COCO_18, 328, 184, 8), (orc.MPI_15, 248, 184, 5), (orc.COCO_18, 656, 368, 22)])
+def test_connect_vs_reference_code(model, net_w, net_h, n):
+    if orc.ref_host() is None:
+        pytest.skip("oracle/_ref not built")
+    for seed in range(3):
+        people = synth.make_people(model, n, net_w, net_h, seed=seed, drop_prob=0.2)
+        maps = synth.make_maps(model, people, net_w, net_h, seed=seed)
+        full = orc.imresize(maps, net_h, net_w, 1.0, 0.3)
+        thr, p = orc.default_params(model)
+        peaks = orc.nms(full, orc.num_parts(model), orc.max_peaks(model), thr)
+        assert peaks[:, 0, 0].max() <= orc.max_peaks(model)
+        cnt, joints, subset = orc.connect(model, full, peaks, 2 * net_w, 2 * net_h, want_subset=True)
+        p0 = orc.ConnectParams(p.min_subset_cnt, p.min_subset_score, p.inter_threshold, p.inter_min_above, 0)
+        c2, j2, s2 = orc.ref_connect(model, full, peaks, 2 * net_w, 2 * net_h, p0)
+        assert cnt == c2 and cnt >= n // 2
+        assert np.array_equal(joints, j2) and np.array_equal(subset, s2)
+
+
+def test_connect_special_cases_vs_reference_code():
+    """nA==0 / nB==0 singleton rows, duplicate check (COCO only), nothing at all."""
+    if orc.ref_host() is None:
+        pytest.skip("oracle/_ref not built")
+    for model, net_w, net_h in [(orc.COCO_18, 328, 184), (orc.MPI_15, 248, 184)]:
+        P, mp = orc.num_parts(model), orc.max_peaks(model)
+        thr, p = orc.default_params(model)
+        p0 = orc.ConnectParams(p.min_subset_cnt, p.min_subset_score, p.inter_threshold, p.inter_min_above, 0)
+        people = synth.make_people(model, 5, net_w, net_h, seed=5, drop_prob=0.0)
+        for drop in ([2, 3, 4], [1], list(range(P)), [0, 14, 15, 16, 17][:3]):
+            ppl = [{k: v for k, v in q.items() if k not in drop} for q in people]
+            maps = synth.make_maps(model, ppl, net_w, net_h, seed=1)
+            full = orc.imresize(maps, net_h, net_w, 1.0, 0.3)
+            peaks = orc.nms(full, P, mp, thr)
+            a = orc.connect(model, full, peaks, net_w, net_h, want_subset=True)
+            b = orc.ref_connect(model, full, peaks, net_w, net_h, p0)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_nms_quirks():
+    """strict >, border exclusion, score>0 filter, width-for-height window bound (nms_layer.cu:79)."""
+    H, W = 20, 40
+    m = np.zeros((2, H, W), np.float32)
+    m[0, 5, 5] = 1.0
+    m[0, 5, 6] = 1.0            # tie with neighbour -> neither is a peak (strict >)
+    m[0, 10, 10] = 0.9
+    m[0, 9, 10] = -5.0          # negative neighbour ignored in the centroid (score > 0)
+    m[0, 10, 11] = 0.3
+    m[0, 0, 20] = 2.0           # border row: never a peak
+    m[0, H - 2, 30] = 0.8       # bottom interior row: window rows H..H+1 alias channel 1 rows 0..1
+    m[1, 0, 30] = 0.4
+    pk = orc.nms(m, 1, 8, 0.05)
+    assert pk[0, 0, 0] == 2
+    x, y, s = pk[0, 1]
+    assert s == np.float32(0.9) and y == 10 and abs(x - (10 * 0.9 + 11 * 0.3) / 1.2) < 1e-6
+    x, y, s = pk[0, 2]
+    assert s == np.float32(0.8) and abs(y - ((H - 2) * 0.8 + H * 0.4) / 1.2) < 1e-5  # aliased row pulled y down
+
+
+def test_nms_count_unclamped_and_first_max_peaks_kept():
+    H, W = 16, 64
+    m = np.zeros((2, H, W), np.float32)
+    for i in range(10):
+        m[0, 3 + (i % 2) * 6, 4 + 5 * i] = 0.5 + 0.01 * i
+    pk = orc.nms(m, 1, 4, 0.05)
+    assert pk[0, 0, 0] == 10                     # total, not clamped (nms_layer.cu:110)
+    assert [int(round(v)) for v in pk[0, 1:, 1]] == [3, 3, 3, 3]  # raster order: the y=3 row first
+
+
+def test_json_format():
+    j = np.zeros((1, 18, 3), np.float32)
+    j[0, 0] = (618.56, 289.597, 0.950805)
+    t = orc.json_text(j, 18, 0.5)
+    assert t.startswith('{\n"version":0.1,\n"bodies":[\n{\n"joints":[1237.12,579.194,0.950805,0,0,0,')
+    assert t.endswith("]\n}]\n}\n")
+    assert orc.json_text(np.zeros((0, 18, 3), np.float32), 18) == '{\n"version":0.1,\n"bodies":[\n]\n}\n'
