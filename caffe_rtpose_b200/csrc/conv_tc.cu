@@ -1,0 +1,390 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (B200), hand-written PTX.
+//
+// Replaces cudnnConvolutionForward + cudnnAddTensor + ReLU (src/caffe/layers/cudnn_conv_layer.cu:11-46,
+// cudnn_relu_layer.cu:19) and the Concat copies (concat_layer.cu:40-43) for every 3x3 / 7x7 / 1x1
+// convolution of the deploy graph.  Arithmetic contract = Caffe's conv (base_conv_layer.cpp:257-279):
+// out = W * im2col(in) + bias, zero padding, stride 1.
+//
+// Mapping to the hardware
+//   * GEMM view: D[m][co] = sum_{tap} sum_{c} A[m + shift(tap)][c] * Wt[co][tap*C + c], M = flat padded
+//     pixels (common.h), so the A tile of one (tap, 64-channel block) is ONE 2-D TMA box {64 ch x 128 rows}
+//     at a shifted row coordinate; zero padding = TMA out-of-bounds fill + never-written gap rows.
+//   * TMA (cp.async.bulk.tensor.3d, SWIZZLE_128B) stages A and B tiles into shared memory, completion on
+//     mbarriers; a STAGES-deep ring overlaps loads with MMAs.
+//   * One elected thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32), M=128, N=BN,
+//     K=16 per instruction, accumulator in TMEM (BN columns x 128 lanes, fp32).
+//   * Split precision: activations and weights are stored as P bf16 "planes" whose sum is the fp32 value
+//     (hi / mid / lo).  For P planes the kernel issues the P(P+1)/2 cross products (i + j < P) into the same
+//     TMEM accumulator: P=1 plain bf16, P=2 ~2^-16 relative, P=3 ~fp32.  The accumulation itself is fp32.
+//   * Epilogue warps read TMEM with tcgen05.ld (32 lanes x 16 columns), add bias, ReLU, re-split into
+//     planes and store NHWC bf16 (channel-slice stores implement Concat), or - for the last stage - store
+//     the planar fp32 concat_stage7 blob directly (coalesced along x).
+//   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+//     (each owns the TMEM lane quadrant warp_id % 4).
+#include <cuda.h>
+
+#include <string>
+
+#include "common.h"
+#include "conv_tc.h"
+
+namespace pe {
+
+struct TcArgs {
+    const float* bias;
+    __nv_bfloat16* out; int out_pitch, out_coff; long long out_plane;
+    float* planar; int planar_C, planar_coff;
+    int cout, relu;
+    int ksize, pad, kblocks_per_tap, cin_k;   // cin_k = channels per tap in the weight K ordering
+    int W, H, Wp, Hs;
+    long long M;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4
+//   (8 rows x 128 B = 1024 B -> 64) | [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor kind::f16 (InstrDescriptor): c_format F32 (bit 4), a/b format BF16 (bits 7,10),
+// K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;          // bf16 elements per K block = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+
+template <int BN, int PLANES, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    constexpr int A_BYTES = TC_BM * 128;
+    constexpr int B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+    constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
+    constexpr uint32_t IDESC = umma_idesc(TC_BM, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024 B
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m0 = (long long)blockIdx.x * TC_BM;
+    const int n0 = blockIdx.y * BN;
+    const int taps = a.ksize * a.ksize;
+    const int num_k = taps * a.kblocks_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        for (int it = 0; it < num_k; it++) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            const int tap = it / a.kblocks_per_tap, kb = it % a.kblocks_per_tap;
+            const int r = tap / a.ksize, q = tap % a.ksize;
+            const int row0 = (int)(m0 + (long long)(r - a.pad) * a.Wp + (q - a.pad));
+            uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+#pragma unroll
+            for (int p = 0; p < PLANES; p++) tma_load_3d(st + p * A_BYTES, &tmA, &full_bar[s], kb * TC_BK, row0, p);
+#pragma unroll
+            for (int p = 0; p < PLANES; p++)
+                tma_load_3d(st + PLANES * A_BYTES + p * B_BYTES, &tmB, &full_bar[s], tap * a.cin_k + kb * TC_BK, n0, p);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        for (int it = 0; it < num_k; it++) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+            const uint32_t sb = sa + PLANES * A_BYTES;
+            bool first = (it == 0);
+#pragma unroll
+            for (int pa = 0; pa < PLANES; pa++)
+#pragma unroll
+                for (int pb = 0; pb < PLANES - pa; pb++) {
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++) {
+                        const uint64_t da = umma_desc(sa + pa * A_BYTES + k * 32);
+                        const uint64_t db = umma_desc(sb + pb * B_BYTES + k * 32);
+                        umma_bf16(tmem_base, da, db, IDESC, first ? 0u : 1u);
+                        first = false;
+                    }
+                }
+            umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs have read it
+        }
+        umma_commit(&tmem_full_bar);      // accumulator complete
+    } else if (warp >= 2) {
+        // ===== epilogue =====
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const int quad = warp & 3;
+        const long long m = m0 + quad * 32 + lane;
+        const int per_img = a.Hs * a.Wp;
+        bool valid = m < a.M;
+        int n = 0, y = 0, x = 0;
+        if (valid) {
+            n = (int)(m / per_img);
+            const int rem = (int)(m % per_img);
+            y = rem / a.Wp; x = rem % a.Wp;
+            valid = (x < a.W) && (y < a.H);
+        }
+        const int cout8 = (a.cout + 7) & ~7;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            __syncwarp();
+            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);   // warp-collective
+            if (valid) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int co = n0 + c0 + j;
+                    float t = __uint_as_float(r[j]) + (co < a.cout ? __ldg(a.bias + co) : 0.f);
+                    if (a.relu) t = fmaxf(t, 0.f);
+                    v[j] = t;
+                }
+                if (a.planar) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int co = n0 + c0 + j;
+                        if (co < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + co) * a.H + y) * a.W + x] = v[j];
+                    }
+                } else {
+                    uint32_t pk[PLANES][8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        float r0 = v[j], r1 = v[j + 1];
+#pragma unroll
+                        for (int p = 0; p < PLANES; p++) {
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(r0), h1 = __float2bfloat16_rn(r1);
+                            pk[p][j / 2] = pack_bf16(h0, h1);
+                            r0 = __fsub_rn(r0, __bfloat162float(h0));
+                            r1 = __fsub_rn(r1, __bfloat162float(h1));
+                        }
+                    }
+                    __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + n0 + c0;
+#pragma unroll
+                    for (int p = 0; p < PLANES; p++) {
+                        uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
+                        if (n0 + c0 < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+                        if (n0 + c0 + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int tc_cout_pad(int cout) {
+    if (cout >= 128) return (cout + 127) / 128 * 128;
+    if (cout > 48) return 64;
+    if (cout > 32) return 48;
+    if (cout > 16) return 32;
+    return 16;
+}
+static int tc_bn(int cout_pad) { return cout_pad >= 128 ? 128 : cout_pad; }
+
+static int stage_bytes(int bn, int planes) { return planes * (TC_BM * 128 + bn * 128); }
+static int pick_stages(int bn, int planes) {
+    const int s = (200 * 1024) / stage_bytes(bn, planes);
+    return s >= 6 ? 6 : (s >= 4 ? 4 : (s >= 3 ? 3 : 2));
+}
+
+template <int BN, int PLANES, int STAGES>
+static int launch_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
+    auto kern = conv_tc_kernel<BN, PLANES, STAGES>;
+    static bool attr_set = false;
+    const int smem = STAGES * stage_bytes(BN, PLANES) + 1024;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    const CUtensorMap* maps = (const CUtensorMap*)l.maps;
+    kern<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], a);
+    return 1;
+}
+
+template <int BN>
+static int launch_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
+    switch (l.d.planes) {
+        case 1: return launch_inst<BN, 1, (200 * 1024) / (1 * (TC_BM * 128 + BN * 128)) >= 6 ? 6 : 4>(l, a, grid, st);
+        case 2: return launch_inst<BN, 2, (200 * 1024) / (2 * (TC_BM * 128 + BN * 128)) >= 4 ? 4 : 3>(l, a, grid, st);
+        default: return launch_inst<BN, 3, (200 * 1024) / (3 * (TC_BM * 128 + BN * 128)) >= 3 ? 3 : 2>(l, a, grid, st);
+    }
+}
+
+int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return -1; }
+    if (d.in_cused % TC_BK) { err = "input channels not a multiple of 64"; return -1; }
+    out.d = d;
+    out.bn = tc_bn(d.cout_pad);
+    CUtensorMap* maps = nullptr;
+    if (posix_memalign((void**)&maps, 64, 2 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
+    const int taps = d.ksize * d.ksize;
+    const cuuint64_t K = (cuuint64_t)taps * d.in_cused;
+    {   // A: [planes][M][pitch] bf16, box {64, 128, 1}
+        cuuint64_t dims[3] = {(cuuint64_t)d.in_cused, (cuuint64_t)d.geo.M, (cuuint64_t)d.planes};
+        cuuint64_t strides[2] = {(cuuint64_t)d.in_pitch * 2, (cuuint64_t)d.in_plane * 2};
+        cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&maps[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d.in, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r); free(maps); return -1; }
+    }
+    {   // B: [planes][cout_pad][K] bf16, box {64, BN, 1}
+        cuuint64_t dims[3] = {K, (cuuint64_t)d.cout_pad, (cuuint64_t)d.planes};
+        cuuint64_t strides[2] = {K * 2, K * 2 * (cuuint64_t)d.cout_pad};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)out.bn, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&maps[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d.w, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r); free(maps); return -1; }
+    }
+    out.maps = maps;
+    out.stages = pick_stages(out.bn, d.planes);
+    out.smem_bytes = out.stages * stage_bytes(out.bn, d.planes) + 1024;
+    return 0;
+}
+
+void tc_layer_destroy(TcLayer& l) {
+    if (l.maps) free(l.maps);
+    l.maps = nullptr;
+}
+
+int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
+    const TcLayerDesc& d = l.d;
+    TcArgs a;
+    a.bias = d.bias;
+    a.out = (__nv_bfloat16*)d.out; a.out_pitch = d.out_pitch; a.out_coff = d.out_coff; a.out_plane = d.out_plane;
+    a.planar = d.planar; a.planar_C = d.planar_C; a.planar_coff = d.planar_coff;
+    a.cout = d.cout; a.relu = d.relu;
+    a.ksize = d.ksize; a.pad = d.pad; a.kblocks_per_tap = d.in_cused / TC_BK; a.cin_k = d.in_cused;
+    a.W = d.geo.W; a.H = d.geo.H; a.Wp = d.geo.Wp; a.Hs = d.geo.Hs;
+    a.M = (long long)nimg * d.geo.Hs * d.geo.Wp;
+    dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), (unsigned)(d.cout_pad / l.bn));
+    switch (l.bn) {
+        case 128: return launch_bn<128>(l, a, grid, st);
+        case 64: return launch_bn<64>(l, a, grid, st);
+        case 48: return launch_bn<48>(l, a, grid, st);
+        case 32: return launch_bn<32>(l, a, grid, st);
+        default: return launch_bn<16>(l, a, grid, st);
+    }
+}
+
+}  // namespace pe

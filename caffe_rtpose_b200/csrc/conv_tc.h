@@ -1,0 +1,29 @@
+// tcgen05 implicit-GEMM convolution (host interface).  See conv_tc.cu.
+#pragma once
+#include <string>
+
+#include "common.h"
+
+namespace pe {
+
+struct TcLayerDesc {
+    const void* in; int in_pitch, in_cused; long long in_plane;   // bf16 planes [P][M][pitch]
+    const void* w;                                                // bf16 planes [P][cout_pad][K]
+    const float* bias;
+    int cout, cout_pad, ksize, pad, relu, planes;
+    Geo geo;                                                      // geo.N = max images
+    void* out; int out_pitch, out_coff; long long out_plane;      // bf16 planes, or
+    float* planar; int planar_C, planar_coff;                     // final fp32 maps (N, planar_C, H, W)
+};
+struct TcLayer {
+    void* maps = nullptr;   // host copy of the two CUtensorMap (A, B), 64-byte aligned
+    TcLayerDesc d;
+    int bn = 0, stages = 0, smem_bytes = 0;
+};
+
+int tc_cout_pad(int cout);   // N-tile granularity used for a layer with `cout` outputs
+int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err);
+void tc_layer_destroy(TcLayer& l);
+int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st);   // returns kernels launched
+
+}  // namespace pe

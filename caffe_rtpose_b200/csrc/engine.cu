@@ -1,0 +1,696 @@
+// libposeengine.so - C ABI implementation (include/poseengine.h).  Host orchestration of one GPU worker:
+// what warmup()/processFrame() do around caffe::Net in examples/rtpose/rtpose.cpp:173-237, 1079-1203,
+// re-designed for B200: a fixed execution plan (plan.cpp) over flat padded NHWC activations, one stream,
+// asynchronous forwards, KB-sized results returned through pinned memory.  No CPU fallback anywhere.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+#include "conv_tc.h"
+
+using namespace pe;
+
+static thread_local std::string g_create_error;
+
+struct HostWeights { std::vector<float> w, b; bool set = false; };
+
+struct pe_engine {
+    pe_config cfg;
+    NetPlan plan;
+    const ModelTables* mt = nullptr;
+    Geo geo[4];
+    int planes = 0;         // 0: fp32 SIMT, else bf16 planes
+    int elem = 4;
+    std::vector<void*> acts;        // device
+    std::vector<long long> act_plane;  // elements per plane
+    std::vector<HostWeights> hw;    // per conv
+    bool committed = false;
+    // packed weights (one device buffer): per conv offsets (bytes)
+    void* d_packed = nullptr; size_t packed_bytes = 0;
+    std::vector<size_t> w_off, b_off;
+    std::vector<int> cout_pad, cin_pad;
+    std::vector<TcLayer> tc;        // tcgen05 per-conv launch state
+    // io
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[16];
+    uint8_t* d_frames = nullptr; uint8_t* d_resized = nullptr;
+    uint8_t* h_frames = nullptr;    // pinned staging
+    float* d_planar = nullptr; float* h_planar = nullptr;
+    std::vector<void*> d_tabs;
+    PreArgs pre;
+    float* d_maps = nullptr; float* h_maps = nullptr;
+    PostDev post;
+    float* h_joints = nullptr; int* h_num_people = nullptr; float* h_peaks = nullptr;
+    AxisTap *d_xtab = nullptr, *d_ytab = nullptr;
+    float start_scale_f, scale_gap_f;
+    int last_n = 0;
+    long long launches = 0;
+    std::string err;
+    double flops_per_scale = 0;
+};
+
+static int fail(pe_engine* e, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(e, call) do { cudaError_t err_ = (call); if (err_ != cudaSuccess) \
+    return fail(e, PE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err_), __FILE__, __LINE__); } while (0)
+
+extern "C" const char* pe_last_error(const pe_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+// ---------------------------------------------------------------------------------------------
+// model descriptor tables
+// ---------------------------------------------------------------------------------------------
+extern "C" int pe_model_num_parts(int model) { return model_tables(model).num_parts; }
+extern "C" int pe_model_num_limbs(int model) { return model_tables(model).num_limbs; }
+extern "C" const int* pe_model_limb_sequence(int model) { return model_tables(model).limb_seq; }
+extern "C" const int* pe_model_map_idx(int model) { return model_tables(model).map_idx; }
+extern "C" const char* pe_model_part_name(int model, int idx) { return model_part_name(model, idx); }
+
+// ---------------------------------------------------------------------------------------------
+// INTER_AREA decimation tables (OpenCV imgproc/resize.cpp computeResizeAreaTab), built on the host
+// in double precision exactly as cv::resize does, then used by area_resize_kernel.
+// ---------------------------------------------------------------------------------------------
+static void area_table(int ssize, int dsize, double scale, std::vector<int>& ofs, std::vector<int>& si,
+                       std::vector<float>& alpha) {
+    ofs.assign(1, 0); si.clear(); alpha.clear();
+    for (int dx = 0; dx < dsize; dx++) {
+        const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+        const double cell = std::min(scale, ssize - fsx1);
+        int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+        sx2 = std::min(sx2, ssize - 1);
+        sx1 = std::min(sx1, sx2);
+        if (sx1 - fsx1 > 1e-3) { si.push_back(sx1 - 1); alpha.push_back((float)((sx1 - fsx1) / cell)); }
+        for (int sx = sx1; sx < sx2; sx++) { si.push_back(sx); alpha.push_back((float)(1.0 / cell)); }
+        if (fsx2 - sx2 > 1e-3) { si.push_back(sx2); alpha.push_back((float)(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)); }
+        ofs.push_back((int)si.size());
+    }
+}
+
+template <typename T>
+static int upload(pe_engine* e, const std::vector<T>& v, const T** out) {
+    void* d = nullptr;
+    CK(e, cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    CK(e, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    e->d_tabs.push_back(d);
+    *out = (const T*)d;
+    return PE_OK;
+}
+
+static int build_pre_tables(pe_engine* e) {
+    const pe_config& c = e->cfg;
+    PreArgs& a = e->pre;
+    memset(&a, 0, sizeof a);
+    a.S = c.num_scales; a.disp_w = c.disp_w; a.disp_h = c.disp_h; a.net_w = c.net_w; a.net_h = c.net_h;
+    for (int i = 0; i < c.num_scales; i++) {
+        // rtpose.cpp:509-511: float scale = START_SCALE - i*SCALE_GAP; target = 16*ceil(NET*scale/16)
+        const float scale = (float)(c.start_scale - i * c.scale_gap);
+        const int tw = (int)(16 * ceil(c.net_w * scale / 16)), th = (int)(16 * ceil(c.net_h * scale / 16));
+        if (tw > c.net_w || th > c.net_h || tw <= 0 || th <= 0)
+            return fail(e, PE_ERR_INVALID, "scale %d gives target %dx%d outside net %dx%d (CHECK_LE rtpose.cpp:513-514)", i, tw,
+                        th, c.net_w, c.net_h);
+        AreaTab& t = a.tab[i];
+        t.tw = tw; t.th = th; t.padw = (c.net_w - tw) / 2; t.padh = (c.net_h - th) / 2;
+        const double inv_x = (double)tw / c.disp_w, inv_y = (double)th / c.disp_h;
+        const double sx = 1. / inv_x, sy = 1. / inv_y;
+        if (!(tw == c.disp_w && th == c.disp_h) && (sx < 1 || sy < 1))
+            return fail(e, PE_ERR_INVALID, "INTER_AREA upscaling (display %dx%d -> %dx%d) is not supported", c.disp_w, c.disp_h, tw, th);
+        const int ix = (int)lrint(sx), iy = (int)lrint(sy);
+        t.fast = fabs(sx - ix) < 2.220446049250313e-16 && fabs(sy - iy) < 2.220446049250313e-16;
+        t.iscale_x = ix; t.iscale_y = iy;
+        std::vector<int> ofs, si; std::vector<float> al;
+        area_table(c.disp_w, tw, sx, ofs, si, al);
+        if (upload(e, ofs, &t.x_ofs) || upload(e, si, &t.x_si) || upload(e, al, &t.x_alpha)) return PE_ERR_CUDA;
+        area_table(c.disp_h, th, sy, ofs, si, al);
+        if (upload(e, ofs, &t.y_ofs) || upload(e, si, &t.y_si) || upload(e, al, &t.y_alpha)) return PE_ERR_CUDA;
+    }
+    return PE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------------------------
+static int pooled(int v) { return (int)ceilf((float)(v - 2) / 2) + 1; }  // pooling_layer.cpp:90-93, k=2 s=2 pad=0
+
+static void set_post_params(pe_engine* e) {
+    PostParams& p = e->post.p;
+    const pe_config& c = e->cfg;
+    p.model = c.model; p.num_parts = e->mt->num_parts; p.num_limbs = e->mt->num_limbs; p.num_maps = e->mt->num_maps;
+    p.max_peaks = e->mt->max_peaks;
+    p.net_w = c.net_w; p.net_h = c.net_h; p.w8 = e->geo[3].W; p.h8 = e->geo[3].H; p.disp_w = c.disp_w; p.disp_h = c.disp_h;
+    p.num_scales = c.num_scales;
+}
+
+extern "C" int pe_create(const pe_config* cfg, pe_engine** out) {
+    if (!cfg || !out) return fail(nullptr, PE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->model != PE_MODEL_MPI_15 && cfg->model != PE_MODEL_COCO_18) return fail(nullptr, PE_ERR_INVALID, "unknown model %d", cfg->model);
+    if (cfg->net_w <= 0 || cfg->net_h <= 0 || cfg->net_w % 8 || cfg->net_h % 8)
+        return fail(nullptr, PE_ERR_INVALID, "net resolution %dx%d must be positive multiples of 8", cfg->net_w, cfg->net_h);
+    if (cfg->num_scales < 1 || cfg->num_scales > PE_MAX_SCALES) return fail(nullptr, PE_ERR_INVALID, "num_scales %d out of [1,%d]", cfg->num_scales, PE_MAX_SCALES);
+    if (cfg->max_batch < 1 || cfg->max_batch > 64) return fail(nullptr, PE_ERR_INVALID, "max_batch %d out of [1,64]", cfg->max_batch);
+    if (cfg->disp_w <= 0 || cfg->disp_h <= 0) return fail(nullptr, PE_ERR_INVALID, "bad display resolution");
+    if (cfg->precision < 0 || cfg->precision > 3) return fail(nullptr, PE_ERR_INVALID, "unknown precision %d", cfg->precision);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, PE_ERR_CUDA, "no CUDA device visible: the pose engine has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, PE_ERR_INVALID, "device %d out of range (%d visible)", cfg->device, ndev);
+
+    pe_engine* e = new pe_engine();
+    e->cfg = *cfg;
+    e->mt = &model_tables(cfg->model);
+    e->planes = cfg->precision;  // 0 fp32, else number of bf16 planes
+    e->elem = e->planes == 0 ? 4 : 2;
+    e->start_scale_f = (float)cfg->start_scale;  // ImResizeLayer::SetStartScale(float)
+    e->scale_gap_f = (float)cfg->scale_gap;
+    auto bail = [&](int rc) { g_create_error = e->err; pe_destroy(e); return rc; };
+#define CKC(call) do { cudaError_t err_ = (call); if (err_ != cudaSuccess) { \
+    fail(e, PE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err_), __FILE__, __LINE__); return bail(PE_ERR_CUDA); } } while (0)
+    CKC(cudaSetDevice(cfg->device));
+    if (e->planes) {
+        cudaDeviceProp prop;
+        CKC(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major != 10) { fail(e, PE_ERR_INVALID, "tcgen05 precision modes need sm_100 (found sm_%d%d)", prop.major, prop.minor); return bail(PE_ERR_INVALID); }
+    }
+    CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; i++) CKC(cudaEventCreate(&e->ev[i]));
+
+    const int N = cfg->max_batch * cfg->num_scales;
+    int w = cfg->net_w, h = cfg->net_h;
+    for (int l = 0; l < 4; l++) {
+        e->geo[l] = make_geo(w, h, l == 3 ? 3 : 1, N);
+        w = pooled(w); h = pooled(h);
+    }
+    if (e->geo[3].W * 8 != cfg->net_w || e->geo[3].H * 8 != cfg->net_h) { fail(e, PE_ERR_INVALID, "net size not divisible by 8 after pooling"); return bail(PE_ERR_INVALID); }
+    e->plan = build_plan(cfg->model, e->planes ? 64 : 32, e->planes ? 64 : 16);
+    e->hw.resize(e->plan.convs.size());
+    // FLOPs: 2*Cout*Cin*k^2*Hout*Wout per conv and image
+    e->flops_per_scale = 0;
+    for (auto& c : e->plan.convs) {
+        const Geo& g = e->geo[c.level];
+        c.flops_per_image = 2.0 * c.cout * c.cin * c.k * c.k * g.H * g.W;
+        e->flops_per_scale += c.flops_per_image;
+    }
+    // activations
+    e->acts.assign(e->plan.acts.size(), nullptr);
+    e->act_plane.assign(e->plan.acts.size(), 0);
+    for (size_t i = 0; i < e->plan.acts.size(); i++) {
+        const ActSpec& a = e->plan.acts[i];
+        const Geo& g = e->geo[a.level];
+        e->act_plane[i] = g.M * a.C;
+        const size_t bytes = (size_t)e->act_plane[i] * e->elem * (e->planes ? e->planes : 1);
+        CKC(cudaMalloc(&e->acts[i], bytes));
+        CKC(cudaMemsetAsync(e->acts[i], 0, bytes, e->stream));
+    }
+    // io buffers
+    const size_t frame_bytes = (size_t)cfg->disp_w * cfg->disp_h * 3;
+    CKC(cudaMalloc(&e->d_frames, frame_bytes * cfg->max_batch));
+    CKC(cudaMallocHost(&e->h_frames, frame_bytes * cfg->max_batch));
+    CKC(cudaMalloc(&e->d_resized, (size_t)N * cfg->net_w * cfg->net_h * 3));
+    const size_t planar_n = (size_t)N * 3 * cfg->net_w * cfg->net_h;
+    CKC(cudaMalloc(&e->d_planar, planar_n * sizeof(float)));
+    CKC(cudaMallocHost(&e->h_planar, planar_n * sizeof(float)));
+    const size_t maps_n = (size_t)N * e->mt->num_maps * e->geo[3].W * e->geo[3].H;
+    CKC(cudaMalloc(&e->d_maps, maps_n * sizeof(float)));
+    CKC(cudaMemsetAsync(e->d_maps, 0, maps_n * sizeof(float), e->stream));
+    CKC(cudaMallocHost(&e->h_maps, maps_n * sizeof(float)));
+    if (build_pre_tables(e)) return bail(PE_ERR_INVALID);
+    e->pre.frames = e->d_frames; e->pre.resized = e->d_resized;
+    e->pre.out = e->acts[e->plan.input_act]; e->pre.kp = e->plan.kp_input;
+    e->pre.out_plane = e->act_plane[e->plan.input_act]; e->pre.planes = e->planes;
+    e->pre.Wp = e->geo[0].Wp; e->pre.Hs = e->geo[0].Hs;
+
+    // post-processing state
+    set_post_params(e);
+    PostDev& pd = e->post;
+    {
+        PostParams& p = pd.p;
+        p.start_scale = e->start_scale_f; p.scale_gap = e->scale_gap_f;
+        // rtpose.cpp:212-226
+        p.min_subset_cnt = 3; p.min_subset_score = 0.4f;
+        if (cfg->model == PE_MODEL_MPI_15) { p.nms_threshold = 0.2f; p.inter_threshold = 0.01f; p.inter_min_above = 8; }
+        else { p.nms_threshold = 0.05f; p.inter_threshold = 0.050f; p.inter_min_above = 9; }
+    }
+    for (int i = 0; i < 2 * e->mt->num_limbs; i++) { pd.md.limb_seq[i] = e->mt->limb_seq[i]; pd.md.map_idx[i] = e->mt->map_idx[i]; }
+    const int B = cfg->max_batch, P = e->mt->num_parts, MP = e->mt->max_peaks, NL = e->mt->num_limbs;
+    pd.maps = e->d_maps;
+    CKC(cudaMalloc(&e->d_xtab, sizeof(AxisTap) * cfg->num_scales * cfg->net_w));
+    CKC(cudaMalloc(&e->d_ytab, sizeof(AxisTap) * cfg->num_scales * cfg->net_h));
+    pd.xtab = e->d_xtab; pd.ytab = e->d_ytab;
+    const int wpr = (cfg->net_w + 31) / 32;
+    CKC(cudaMalloc(&pd.flags, sizeof(unsigned) * (size_t)B * P * cfg->net_h * wpr));
+    CKC(cudaMalloc(&pd.peaks, sizeof(float) * (size_t)B * P * (MP + 1) * 3));
+    CKC(cudaMalloc(&pd.cands, sizeof(Cand) * (size_t)B * NL * MP * MP));
+    CKC(cudaMalloc(&pd.cand_count, sizeof(int) * (size_t)B * NL));
+    CKC(cudaMalloc(&pd.conns, sizeof(Conn) * (size_t)B * NL * MP));
+    CKC(cudaMalloc(&pd.conn_count, sizeof(int) * (size_t)B * NL));
+    CKC(cudaMemset(pd.conn_count, 0, sizeof(int) * (size_t)B * NL));
+    CKC(cudaMalloc(&pd.subset, sizeof(double) * (size_t)B * PE_MAX_SUBSET_ROWS * (P + 3)));
+    CKC(cudaMalloc(&pd.subset_rows, sizeof(int) * B));
+    CKC(cudaMalloc(&pd.joints, sizeof(float) * (size_t)B * PE_MAX_PEOPLE * P * 3));
+    CKC(cudaMalloc(&pd.num_people, sizeof(int) * B));
+    CKC(cudaMallocHost(&e->h_joints, sizeof(float) * (size_t)B * PE_MAX_PEOPLE * P * 3));
+    CKC(cudaMallocHost(&e->h_num_people, sizeof(int) * B));
+    CKC(cudaMallocHost(&e->h_peaks, sizeof(float) * (size_t)B * P * (MP + 1) * 3));
+    launch_axis_tables(e->d_xtab, e->d_ytab, pd.p, e->stream);
+    e->launches += 2;
+    CKC(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return PE_OK;
+}
+
+extern "C" void pe_destroy(pe_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void* p : e->acts) if (p) cudaFree(p);
+    for (void* p : e->d_tabs) cudaFree(p);
+    for (auto& t : e->tc) tc_layer_destroy(t);
+    cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_resized); cudaFree(e->d_planar); cudaFree(e->d_maps);
+    cudaFreeHost(e->h_frames); cudaFreeHost(e->h_planar); cudaFreeHost(e->h_maps);
+    cudaFree(e->d_xtab); cudaFree(e->d_ytab);
+    PostDev& pd = e->post;
+    cudaFree(pd.flags); cudaFree(pd.peaks); cudaFree(pd.cands); cudaFree(pd.cand_count); cudaFree(pd.conns);
+    cudaFree(pd.conn_count); cudaFree(pd.subset); cudaFree(pd.subset_rows); cudaFree(pd.joints); cudaFree(pd.num_people);
+    cudaFreeHost(e->h_joints); cudaFreeHost(e->h_num_people); cudaFreeHost(e->h_peaks);
+    for (int i = 0; i < 16; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+extern "C" int pe_num_conv_layers(const pe_engine* e) { return e ? (int)e->plan.convs.size() : 0; }
+extern "C" int pe_conv_layer_info(const pe_engine* e, int idx, char* name64, int* cout, int* cin, int* ksize) {
+    if (!e || idx < 0 || idx >= (int)e->plan.convs.size()) return PE_ERR_INVALID;
+    const ConvSpec& c = e->plan.convs[idx];
+    if (name64) snprintf(name64, 64, "%s", c.name.c_str());
+    if (cout) *cout = c.cout;
+    if (cin) *cin = c.cin;
+    if (ksize) *ksize = c.k;
+    return PE_OK;
+}
+extern "C" int pe_set_conv_weights(pe_engine* e, const char* layer_name, const float* w, size_t nw, const float* b, size_t nb) {
+    if (!e || !layer_name || !w || !b) return fail(e, PE_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < e->plan.convs.size(); i++) {
+        const ConvSpec& c = e->plan.convs[i];
+        if (c.name != layer_name) continue;
+        // shape mismatch is fatal in the reference (net.cpp:770-786)
+        if (nw != (size_t)c.cout * c.cin * c.k * c.k || nb != (size_t)c.cout)
+            return fail(e, PE_ERR_INVALID, "layer %s: expected %d x %d x %d x %d weights and %d biases", layer_name, c.cout, c.cin, c.k, c.k, c.cout);
+        e->hw[i].w.assign(w, w + nw);
+        e->hw[i].b.assign(b, b + nb);
+        e->hw[i].set = true;
+        e->committed = false;
+        return PE_OK;
+    }
+    return PE_OK;  // unknown source layers are ignored (net.cpp:757-763)
+}
+extern "C" int pe_load_weights_file(pe_engine* e, const char* path) {
+    if (!e || !path) return fail(e, PE_ERR_INVALID, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(e, PE_ERR_IO, "cannot open %s", path);
+    char magic[4]; uint32_t hdr[2];
+    if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "RTPW", 4) || fread(hdr, 4, 2, f) != 2 || hdr[0] != 1) {
+        fclose(f); return fail(e, PE_ERR_IO, "%s: not an RTPW v1 weight file", path);
+    }
+    for (uint32_t i = 0; i < hdr[1]; i++) {
+        char name[64]; uint32_t dims[3];
+        if (fread(name, 1, 64, f) != 64 || fread(dims, 4, 3, f) != 3) { fclose(f); return fail(e, PE_ERR_IO, "%s: truncated", path); }
+        name[63] = 0;
+        const size_t nw = (size_t)dims[0] * dims[1] * dims[2] * dims[2];
+        std::vector<float> w(nw), b(dims[0]);
+        if (fread(w.data(), 4, nw, f) != nw || fread(b.data(), 4, dims[0], f) != dims[0]) { fclose(f); return fail(e, PE_ERR_IO, "%s: truncated", path); }
+        const int rc = pe_set_conv_weights(e, name, w.data(), nw, b.data(), b.size());
+        if (rc) { fclose(f); return rc; }
+    }
+    fclose(f);
+    return PE_OK;
+}
+
+static inline void split_bf16(float x, int planes, uint16_t* out) {
+    float r = x;
+    for (int p = 0; p < planes; p++) {
+        uint32_t u; memcpy(&u, &r, 4);
+        uint16_t h;
+        if ((u & 0x7f800000u) == 0x7f800000u) h = (uint16_t)(u >> 16);
+        else { const uint32_t lsb = (u >> 16) & 1u; h = (uint16_t)((u + 0x7fffu + lsb) >> 16); }  // RNE
+        out[p] = h;
+        const uint32_t hu = (uint32_t)h << 16; float hf; memcpy(&hf, &hu, 4);
+        r = r - hf;
+    }
+}
+
+extern "C" int pe_commit_weights(pe_engine* e) {
+    if (!e) return PE_ERR_INVALID;
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t nc = e->plan.convs.size();
+    for (size_t i = 0; i < nc; i++)
+        if (!e->hw[i].set) return fail(e, PE_ERR_STATE, "weights of layer %s were never set", e->plan.convs[i].name.c_str());
+    e->w_off.assign(nc, 0); e->b_off.assign(nc, 0); e->cout_pad.assign(nc, 0); e->cin_pad.assign(nc, 0);
+    size_t total = 0;
+    auto align256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    for (size_t i = 0; i < nc; i++) {
+        const ConvSpec& c = e->plan.convs[i];
+        e->cin_pad[i] = c.in_cused;
+        e->cout_pad[i] = e->planes ? tc_cout_pad(c.cout) : (c.cout + 63) / 64 * 64;
+        const size_t K = (size_t)(c.im2col_input ? 1 : c.k * c.k) * e->cin_pad[i];
+        e->w_off[i] = total;
+        total = align256(total + K * e->cout_pad[i] * e->elem * (e->planes ? e->planes : 1));
+        e->b_off[i] = total;
+        total = align256(total + (size_t)e->cout_pad[i] * 4);
+    }
+    std::vector<uint8_t> host(total, 0);
+    for (size_t i = 0; i < nc; i++) {
+        const ConvSpec& c = e->plan.convs[i];
+        const HostWeights& hw = e->hw[i];
+        const int taps = c.im2col_input ? 1 : c.k * c.k, cp = e->cin_pad[i], cop = e->cout_pad[i];
+        const size_t K = (size_t)taps * cp;
+        auto src = [&](int co, int kk) -> float {  // engine K index -> Caffe weight (co, ci, r, s)
+            if (c.im2col_input) {
+                if (kk >= 27) return 0.f;
+                const int tap = kk / 3, ci = kk % 3;
+                return hw.w[((size_t)co * 3 + ci) * 9 + tap];
+            }
+            const int tap = kk / cp, ec = kk % cp;
+            const int ci = ec < (int)c.cin_map.size() ? c.cin_map[ec] : -1;
+            if (ci < 0) return 0.f;
+            return hw.w[((size_t)co * c.cin + ci) * c.k * c.k + tap];
+        };
+        if (e->planes == 0) {  // fp32 [K][cout_pad]
+            float* W = (float*)(host.data() + e->w_off[i]);
+            for (size_t kk = 0; kk < K; kk++)
+                for (int co = 0; co < c.cout; co++) W[kk * cop + co] = src(co, (int)kk);
+        } else {               // bf16 planes [P][cout_pad][K]  (K-major rows: the tcgen05 B operand)
+            uint16_t* W = (uint16_t*)(host.data() + e->w_off[i]);
+            const size_t plane = (size_t)cop * K;
+            for (int co = 0; co < c.cout; co++)
+                for (size_t kk = 0; kk < K; kk++) {
+                    uint16_t h[3];
+                    split_bf16(src(co, (int)kk), e->planes, h);
+                    for (int p = 0; p < e->planes; p++) W[p * plane + (size_t)co * K + kk] = h[p];
+                }
+        }
+        float* B = (float*)(host.data() + e->b_off[i]);
+        for (int co = 0; co < c.cout; co++) B[co] = hw.b[co];
+    }
+    if (e->d_packed) { cudaFree(e->d_packed); e->d_packed = nullptr; }
+    CK(e, cudaMalloc(&e->d_packed, total));
+    CK(e, cudaMemcpy(e->d_packed, host.data(), total, cudaMemcpyHostToDevice));
+    e->packed_bytes = total;
+    if (e->planes) {
+        for (auto& t : e->tc) tc_layer_destroy(t);
+        e->tc.assign(nc, TcLayer());
+        for (size_t i = 0; i < nc; i++) {
+            const ConvSpec& c = e->plan.convs[i];
+            const Geo& g = e->geo[c.level];
+            TcLayerDesc d;
+            d.in = e->acts[c.in_act]; d.in_pitch = e->plan.acts[c.in_act].C; d.in_cused = c.in_cused; d.in_plane = e->act_plane[c.in_act];
+            d.w = (char*)e->d_packed + e->w_off[i]; d.bias = (const float*)((char*)e->d_packed + e->b_off[i]);
+            d.cout = c.cout; d.cout_pad = e->cout_pad[i]; d.ksize = c.im2col_input ? 1 : c.k; d.pad = c.im2col_input ? 0 : c.pad;
+            d.relu = c.relu; d.planes = e->planes; d.geo = g;
+            if (c.out_act >= 0) {
+                d.out = e->acts[c.out_act]; d.out_pitch = e->plan.acts[c.out_act].C; d.out_coff = c.out_coff; d.out_plane = e->act_plane[c.out_act];
+                d.planar = nullptr; d.planar_C = 0; d.planar_coff = 0;
+            } else {
+                d.out = nullptr; d.out_pitch = 0; d.out_coff = 0; d.out_plane = 0;
+                d.planar = e->d_maps; d.planar_C = e->mt->num_maps; d.planar_coff = c.planar_coff;
+            }
+            std::string err;
+            if (tc_layer_create(d, e->tc[i], err)) return fail(e, PE_ERR_CUDA, "layer %s: %s", c.name.c_str(), err.c_str());
+        }
+    }
+    e->committed = true;
+    return PE_OK;
+}
+extern "C" size_t pe_packed_weights_bytes(const pe_engine* e) { return e ? e->packed_bytes : 0; }
+extern "C" void* pe_packed_weights_device_ptr(pe_engine* e) { return e ? e->d_packed : nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+// layer accessors
+// ---------------------------------------------------------------------------------------------
+extern "C" int pe_nms_get_max_peaks(const pe_engine* e) { return e ? e->mt->max_peaks : 0; }
+extern "C" int pe_nms_get_num_parts(const pe_engine* e) { return e ? e->mt->num_parts : 0; }
+extern "C" float pe_nms_get_threshold(const pe_engine* e) { return e ? e->post.p.nms_threshold : 0.f; }
+extern "C" int pe_nms_set_threshold(pe_engine* e, float t) { if (!e) return PE_ERR_INVALID; e->post.p.nms_threshold = t; return PE_OK; }
+static int rebuild_axis(pe_engine* e) {
+    CK(e, cudaSetDevice(e->cfg.device));
+    e->post.p.start_scale = e->start_scale_f; e->post.p.scale_gap = e->scale_gap_f;
+    launch_axis_tables(e->d_xtab, e->d_ytab, e->post.p, e->stream);
+    e->launches += 2;
+    return PE_OK;
+}
+extern "C" int pe_resize_set_start_scale(pe_engine* e, float s) { if (!e) return PE_ERR_INVALID; e->start_scale_f = s; return rebuild_axis(e); }
+extern "C" int pe_resize_set_scale_gap(pe_engine* e, float g) { if (!e) return PE_ERR_INVALID; e->scale_gap_f = g; return rebuild_axis(e); }
+extern "C" float pe_resize_get_start_scale(const pe_engine* e) { return e ? e->start_scale_f : 0.f; }
+extern "C" float pe_resize_get_scale_gap(const pe_engine* e) { return e ? e->scale_gap_f : 0.f; }
+extern "C" int pe_set_connect_params(pe_engine* e, int min_cnt, float min_score, float inter_thr, int min_above) {
+    if (!e) return PE_ERR_INVALID;
+    PostParams& p = e->post.p;
+    p.min_subset_cnt = min_cnt; p.min_subset_score = min_score; p.inter_threshold = inter_thr; p.inter_min_above = min_above;
+    return PE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+static int run_op(pe_engine* e, const OpRef& op, int nimg) {
+    if (op.type == 0) {
+        const ConvSpec& c = e->plan.convs[op.idx];
+        const Geo& g = e->geo[c.level];
+        const long long M = (long long)nimg * g.Hs * g.Wp;
+        if (e->planes) {
+            e->launches += tc_layer_launch(e->tc[op.idx], nimg, e->stream);
+            return PE_OK;
+        }
+        ConvArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = e->acts[c.in_act]; a.in_pitch = e->plan.acts[c.in_act].C;
+        a.w = (char*)e->d_packed + e->w_off[op.idx]; a.bias = (const float*)((char*)e->d_packed + e->b_off[op.idx]);
+        if (c.out_act >= 0) { a.out = e->acts[c.out_act]; a.out_pitch = e->plan.acts[c.out_act].C; a.out_coff = c.out_coff; }
+        else { a.planar = e->d_maps; a.planar_C = e->mt->num_maps; a.planar_coff = c.planar_coff; }
+        a.cin_pad = e->cin_pad[op.idx]; a.cout = c.cout; a.cout_pad = e->cout_pad[op.idx];
+        a.ksize = c.im2col_input ? 1 : c.k; a.pad = c.im2col_input ? 0 : c.pad; a.relu = c.relu;
+        a.W = g.W; a.H = g.H; a.Wp = g.Wp; a.Hs = g.Hs; a.N = nimg; a.M = M;
+        e->launches += launch_conv_simt(a, e->stream);
+    } else if (op.type == 1) {
+        const PoolSpec& p = e->plan.pools[op.idx];
+        const Geo& gi = e->geo[p.level_in]; const Geo& go = e->geo[p.level_in + 1];
+        PoolArgs a;
+        a.in = e->acts[p.in_act]; a.out = e->acts[p.out_act]; a.C = e->plan.acts[p.in_act].C;
+        a.in_plane = e->act_plane[p.in_act]; a.out_plane = e->act_plane[p.out_act]; a.planes = e->planes;
+        a.Wi = gi.W; a.Hi = gi.H; a.Wpi = gi.Wp; a.Hsi = gi.Hs; a.Wo = go.W; a.Ho = go.H; a.Wpo = go.Wp; a.Hso = go.Hs; a.N = nimg;
+        e->launches += launch_pool(a, e->stream);
+    } else {
+        const CopySpec& c = e->plan.copies[op.idx];
+        const Geo& g = e->geo[3];
+        CopyArgs a;
+        a.src = e->acts[c.src_act]; a.dst = e->acts[c.dst_act]; a.pitch = e->plan.acts[c.src_act].C; a.channels = c.channels;
+        a.elem_bytes = e->elem; a.M = (long long)nimg * g.Hs * g.Wp; a.plane = e->act_plane[c.src_act]; a.planes = e->planes;
+        e->launches += launch_copy_channels(a, e->stream);
+    }
+    return PE_OK;
+}
+
+static int run_post_and_return(pe_engine* e, int n) {
+    e->post.maps = e->d_maps;
+    e->launches += launch_post(e->post, n, e->stream);
+    const int P = e->mt->num_parts, MP = e->mt->max_peaks;
+    CK(e, cudaMemcpyAsync(e->h_joints, e->post.joints, sizeof(float) * (size_t)n * PE_MAX_PEOPLE * P * 3, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(e->h_num_people, e->post.num_people, sizeof(int) * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(e->h_peaks, e->post.peaks, sizeof(float) * (size_t)n * P * (MP + 1) * 3, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaGetLastError());
+    e->last_n = n;
+    return PE_OK;
+}
+
+static int run_net(pe_engine* e, int n) {
+    if (!e->committed) return fail(e, PE_ERR_STATE, "pe_commit_weights has not been called");
+    const int nimg = n * e->cfg.num_scales;
+    for (const OpRef& op : e->plan.order) { const int rc = run_op(e, op, nimg); if (rc) return rc; }
+    return run_post_and_return(e, n);
+}
+
+static int check_n(pe_engine* e, int n) {
+    if (!e) return PE_ERR_INVALID;
+    if (n < 1 || n > e->cfg.max_batch) return fail(e, PE_ERR_INVALID, "n=%d outside [1, max_batch=%d]", n, e->cfg.max_batch);
+    return PE_OK;
+}
+
+extern "C" int pe_forward_frames_device(pe_engine* e, const void* d_frames, int n) {
+    int rc = check_n(e, n); if (rc) return rc;
+    CK(e, cudaSetDevice(e->cfg.device));
+    PreArgs a = e->pre;
+    a.frames = (const uint8_t*)d_frames; a.nframes = n;
+    e->launches += launch_preprocess(a, e->stream);
+    return run_net(e, n);
+}
+extern "C" int pe_forward_frames(pe_engine* e, const uint8_t* const* frames, int n) {
+    int rc = check_n(e, n); if (rc) return rc;
+    if (!frames) return fail(e, PE_ERR_INVALID, "null frames");
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t fb = (size_t)e->cfg.disp_w * e->cfg.disp_h * 3;
+    CK(e, cudaStreamSynchronize(e->stream));  // the pinned staging buffer is reused
+    for (int i = 0; i < n; i++) memcpy(e->h_frames + i * fb, frames[i], fb);
+    CK(e, cudaMemcpyAsync(e->d_frames, e->h_frames, fb * n, cudaMemcpyHostToDevice, e->stream));
+    return pe_forward_frames_device(e, e->d_frames, n);
+}
+extern "C" int pe_forward_net_input(pe_engine* e, const float* net_input, int n) {
+    int rc = check_n(e, n); if (rc) return rc;
+    if (!net_input) return fail(e, PE_ERR_INVALID, "null input");
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t cnt = (size_t)n * e->cfg.num_scales * 3 * e->cfg.net_w * e->cfg.net_h;
+    CK(e, cudaStreamSynchronize(e->stream));
+    memcpy(e->h_planar, net_input, cnt * sizeof(float));
+    CK(e, cudaMemcpyAsync(e->d_planar, e->h_planar, cnt * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    PreArgs a = e->pre;
+    a.nframes = n;
+    e->launches += launch_input_from_planar(e->d_planar, a, n * e->cfg.num_scales, e->stream);
+    return run_net(e, n);
+}
+extern "C" int pe_forward_maps(pe_engine* e, const float* maps8, int n) {
+    int rc = check_n(e, n); if (rc) return rc;
+    if (!maps8) return fail(e, PE_ERR_INVALID, "null maps");
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t cnt = (size_t)n * e->cfg.num_scales * e->mt->num_maps * e->geo[3].W * e->geo[3].H;
+    CK(e, cudaStreamSynchronize(e->stream));
+    memcpy(e->h_maps, maps8, cnt * sizeof(float));
+    CK(e, cudaMemcpyAsync(e->d_maps, e->h_maps, cnt * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    return run_post_and_return(e, n);
+}
+
+extern "C" int pe_sync(pe_engine* e) {
+    if (!e) return PE_ERR_INVALID;
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return PE_OK;
+}
+extern "C" int pe_fetch(pe_engine* e, int idx, float* joints, int* num_people, float* peaks) {
+    if (!e) return PE_ERR_INVALID;
+    if (idx < 0 || idx >= e->last_n) return fail(e, PE_ERR_INVALID, "frame index %d outside the last forward (n=%d)", idx, e->last_n);
+    int rc = pe_sync(e); if (rc) return rc;
+    const int P = e->mt->num_parts, MP = e->mt->max_peaks;
+    if (num_people) *num_people = e->h_num_people[idx];
+    if (joints) memcpy(joints, e->h_joints + (size_t)idx * PE_MAX_PEOPLE * P * 3, sizeof(float) * PE_MAX_PEOPLE * P * 3);
+    if (peaks) memcpy(peaks, e->h_peaks + (size_t)idx * P * (MP + 1) * 3, sizeof(float) * P * (MP + 1) * 3);
+    return PE_OK;
+}
+extern "C" int pe_fetch_maps(pe_engine* e, float* maps8, int n) {
+    int rc = check_n(e, n); if (rc) return rc;
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t cnt = (size_t)n * e->cfg.num_scales * e->mt->num_maps * e->geo[3].W * e->geo[3].H;
+    CK(e, cudaMemcpyAsync(e->h_maps, e->d_maps, cnt * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    memcpy(maps8, e->h_maps, cnt * sizeof(float));
+    return PE_OK;
+}
+extern "C" int pe_fetch_blob(pe_engine* e, const char* blob_name, float* out, size_t cap, int* c, int* h, int* w) {
+    if (!e || !blob_name) return PE_ERR_INVALID;
+    CK(e, cudaSetDevice(e->cfg.device));
+    const int nimg = std::max(e->last_n, 1) * e->cfg.num_scales;
+    for (const BlobRef& b : e->plan.blobs) {
+        if (b.name != blob_name) continue;
+        Geo g = e->geo[e->plan.acts[b.act].level];
+        g.N = nimg;
+        const size_t cnt = (size_t)nimg * b.c * g.H * g.W;
+        if (c) *c = b.c;
+        if (h) *h = g.H;
+        if (w) *w = g.W;
+        if (!out) return PE_OK;
+        if (cnt > cap) return fail(e, PE_ERR_INVALID, "blob %s needs %zu floats", blob_name, cnt);
+        float* d = nullptr;
+        CK(e, cudaMalloc(&d, cnt * sizeof(float)));
+        e->launches += launch_act_to_nchw(e->acts[b.act], e->plan.acts[b.act].C, b.coff, b.c, e->act_plane[b.act], e->planes, g, d, e->stream);
+        CK(e, cudaMemcpyAsync(out, d, cnt * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        cudaFree(d);
+        return PE_OK;
+    }
+    return fail(e, PE_ERR_INVALID, "unknown blob %s", blob_name);
+}
+
+// ---------------------------------------------------------------------------------------------
+// JSON (rtpose.cpp:1383-1416): ostream default formatting == %g
+// ---------------------------------------------------------------------------------------------
+extern "C" int pe_write_json(const float* joints, int num_people, int num_parts, double frame_scale, char* buf, int cap) {
+    std::string s;
+    char t[64];
+    const double scale = 1.0 / frame_scale;
+    s += "{\n\"version\":0.1,\n\"bodies\":[\n";
+    for (int ip = 0; ip < num_people; ip++) {
+        s += "{\n\"joints\":[";
+        for (int ij = 0; ij < num_parts; ij++) {
+            const float* j = joints + ((size_t)ip * num_parts + ij) * 3;
+            snprintf(t, sizeof t, "%g,%g,%g", scale * j[0], scale * j[1], (double)j[2]);
+            s += t;
+            if (ij < num_parts - 1) s += ",";
+        }
+        s += "]\n}";
+        if (ip < num_people - 1) s += ",\n";
+    }
+    s += "]\n}\n";
+    if (buf && (int)s.size() < cap) memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+// ---------------------------------------------------------------------------------------------
+// measurement support
+// ---------------------------------------------------------------------------------------------
+extern "C" int pe_event_record(pe_engine* e, int slot) {
+    if (!e || slot < 0 || slot >= 16) return PE_ERR_INVALID;
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaEventRecord(e->ev[slot], e->stream));
+    return PE_OK;
+}
+extern "C" int pe_event_elapsed_ms(pe_engine* e, int a, int b, float* ms) {
+    if (!e || a < 0 || a >= 16 || b < 0 || b >= 16 || !ms) return PE_ERR_INVALID;
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaEventSynchronize(e->ev[b]));
+    CK(e, cudaEventElapsedTime(ms, e->ev[a], e->ev[b]));
+    return PE_OK;
+}
+extern "C" int pe_profile_layers(pe_engine* e, int n, float* ms, char* names, double* flops, int cap) {
+    int rc = check_n(e, n); if (rc) return rc;
+    if (!e->committed) return fail(e, PE_ERR_STATE, "pe_commit_weights has not been called");
+    CK(e, cudaSetDevice(e->cfg.device));
+    const int nimg = n * e->cfg.num_scales;
+    const int nops = (int)e->plan.order.size();
+    std::vector<cudaEvent_t> evs(nops + 1);
+    for (auto& v : evs) CK(e, cudaEventCreate(&v));
+    CK(e, cudaEventRecord(evs[0], e->stream));
+    for (int i = 0; i < nops; i++) {
+        rc = run_op(e, e->plan.order[i], nimg);
+        if (rc) return rc;
+        CK(e, cudaEventRecord(evs[i + 1], e->stream));
+    }
+    CK(e, cudaStreamSynchronize(e->stream));
+    int written = 0;
+    for (int i = 0; i < nops && written < cap; i++) {
+        const OpRef& op = e->plan.order[i];
+        float t = 0.f;
+        CK(e, cudaEventElapsedTime(&t, evs[i], evs[i + 1]));
+        ms[written] = t;
+        const char* nm = op.type == 0 ? e->plan.convs[op.idx].name.c_str() : op.type == 1 ? e->plan.pools[op.idx].name.c_str() : "copy_F";
+        if (names) snprintf(names + 64 * written, 64, "%s", nm);
+        if (flops) flops[written] = op.type == 0 ? e->plan.convs[op.idx].flops_per_image * nimg : 0.0;
+        written++;
+    }
+    for (auto& v : evs) cudaEventDestroy(v);
+    return written;
+}
+extern "C" long long pe_launch_count(const pe_engine* e) { return e ? e->launches : 0; }
+extern "C" double pe_conv_flops_per_scale(const pe_engine* e) { return e ? e->flops_per_scale : 0.0; }

@@ -1,0 +1,65 @@
+// Device-side structs and host launchers of the engine's kernels (internal).
+#pragma once
+#include "common.h"
+
+namespace pe {
+
+struct AxisTap { int i0, i1, i2, i3; float d; };
+struct Cand { float conn; int p; };
+struct Conn { int a, b; float score; };
+struct ModelDev { int limb_seq[40]; int map_idx[40]; };
+
+struct PostDev {
+    PostParams p;
+    ModelDev md;
+    const float* maps;        // [frames][S][C][h8][w8]
+    const AxisTap* xtab;      // [S][net_w]
+    const AxisTap* ytab;      // [S][net_h]
+    unsigned* flags;          // [frames][parts][net_h][ceil(net_w/32)]
+    float* peaks;             // [frames][parts][max_peaks+1][3]
+    Cand* cands;              // [frames][limbs][max_peaks^2]
+    int* cand_count;          // [frames][limbs]
+    Conn* conns;              // [frames][limbs][max_peaks]
+    int* conn_count;          // [frames][limbs]
+    double* subset;           // [frames][PE_MAX_SUBSET_ROWS][parts+3]
+    int* subset_rows;         // [frames]
+    float* joints;            // [frames][PE_MAX_PEOPLE][parts][3]
+    int* num_people;          // [frames]
+};
+
+void launch_axis_tables(AxisTap* xtab, AxisTap* ytab, const PostParams& p, cudaStream_t st);
+int launch_post(const PostDev& pd, int nframes, cudaStream_t st);
+
+// ---- preprocessing (pre.cu)
+struct AreaTab {           // OpenCV INTER_AREA decimation tables for one scale, device pointers
+    const int* x_ofs; const int* x_si; const float* x_alpha;   // per dst x: [x_ofs[dx], x_ofs[dx+1]) entries
+    const int* y_ofs; const int* y_si; const float* y_alpha;
+    int tw, th, padw, padh, fast, iscale_x, iscale_y;
+};
+struct PreArgs {
+    const uint8_t* frames;    // [nframes][disp_h][disp_w][3] BGR
+    uint8_t* resized;         // [nframes][S][net_h][net_w][3] scratch (only th x tw used)
+    AreaTab tab[PE_MAX_SCALES];
+    int nframes, S, disp_w, disp_h, net_w, net_h;
+    // im2col'ed network input, flat padded level-0 geometry
+    void* out; int kp; long long out_plane; int planes;   // planes == 0: fp32, else bf16 planes
+    int Wp, Hs;
+};
+int launch_preprocess(const PreArgs& a, cudaStream_t st);
+// planar fp32 net input [N][3][H][W] -> im2col'ed input
+int launch_input_from_planar(const float* planar, const PreArgs& a, int nimages, cudaStream_t st);
+
+// ---- convolution / pooling (conv_simt.cu, conv_tc.cu, pool.cu)
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+struct PoolArgs {
+    const void* in; void* out; int C; long long in_plane, out_plane; int planes;  // planes==0: fp32
+    int Wi, Hi, Wpi, Hsi, Wo, Ho, Wpo, Hso, N;
+};
+int launch_pool(const PoolArgs& a, cudaStream_t st);
+struct CopyArgs { const void* src; void* dst; int pitch, channels, elem_bytes; long long M, plane; int planes; };
+int launch_copy_channels(const CopyArgs& a, cudaStream_t st);
+// activation (flat padded, fp32 or bf16 planes) -> NCHW fp32 (debug / pe_fetch_blob)
+int launch_act_to_nchw(const void* act, int pitch, int coff, int c, long long plane, int planes, const Geo& g,
+                       float* out, cudaStream_t st);
+
+}  // namespace pe

@@ -1,0 +1,126 @@
+// 2x2 stride-2 MAX pooling (ceil dims), channel-slice copy and layout conversion on the flat padded layout.
+//
+// Pooling semantics: src/caffe/layers/pooling_layer.cpp:90-93 (ceil), :128-187 (max over the window clipped
+// to the image).  Activations are either fp32 [M][C] or bf16 "planes" whose SUM is the value (split
+// precision for the tcgen05 conv, see conv_tc.cu); the max is taken on the reconstructed value and the
+// winner's planes are copied, which keeps the split exact.
+#include "common.h"
+#include "kernels.h"
+
+namespace pe {
+
+__global__ void __launch_bounds__(256) pool_f32_kernel(PoolArgs a) {
+    const int cv = a.C / 4;  // float4 groups
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rows_out = (long long)a.N * a.Hso * a.Wpo;
+    if (idx >= rows_out * cv) return;
+    const int g = (int)(idx % cv);
+    const long long mo = idx / cv;
+    const int n = (int)(mo / ((long long)a.Hso * a.Wpo));
+    const int rem = (int)(mo % ((long long)a.Hso * a.Wpo));
+    const int yo = rem / a.Wpo, xo = rem % a.Wpo;
+    if (xo >= a.Wo || yo >= a.Ho) return;
+    float4 best = make_float4(-3.402823466e+38F, -3.402823466e+38F, -3.402823466e+38F, -3.402823466e+38F);
+    for (int dy = 0; dy < 2; dy++)
+        for (int dx = 0; dx < 2; dx++) {
+            const int yi = 2 * yo + dy, xi = 2 * xo + dx;
+            if (yi < a.Hi && xi < a.Wi) {
+                const long long mi = ((long long)n * a.Hsi + yi) * a.Wpi + xi;
+                const float4 v = *((const float4*)((const float*)a.in + mi * a.C) + g);
+                best.x = v.x > best.x ? v.x : best.x; best.y = v.y > best.y ? v.y : best.y;
+                best.z = v.z > best.z ? v.z : best.z; best.w = v.w > best.w ? v.w : best.w;
+            }
+        }
+    *((float4*)((float*)a.out + mo * a.C) + g) = best;
+}
+
+__global__ void __launch_bounds__(256) pool_bf16_kernel(PoolArgs a) {
+    const int cv = a.C / 2;  // bf16x2 groups
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rows_out = (long long)a.N * a.Hso * a.Wpo;
+    if (idx >= rows_out * cv) return;
+    const int g = (int)(idx % cv);
+    const long long mo = idx / cv;
+    const int n = (int)(mo / ((long long)a.Hso * a.Wpo));
+    const int rem = (int)(mo % ((long long)a.Hso * a.Wpo));
+    const int yo = rem / a.Wpo, xo = rem % a.Wpo;
+    if (xo >= a.Wo || yo >= a.Ho) return;
+    float bx = -3.402823466e+38F, by = -3.402823466e+38F;
+    __nv_bfloat162 px[3], py[3];
+    for (int p = 0; p < 3; p++) { px[p] = __float2bfloat162_rn(0.f); py[p] = px[p]; }
+    for (int dy = 0; dy < 2; dy++)
+        for (int dx = 0; dx < 2; dx++) {
+            const int yi = 2 * yo + dy, xi = 2 * xo + dx;
+            if (yi < a.Hi && xi < a.Wi) {
+                const long long mi = ((long long)n * a.Hsi + yi) * a.Wpi + xi;
+                __nv_bfloat162 v[3];
+                float sx = 0.f, sy = 0.f;
+                for (int p = 0; p < a.planes; p++) {
+                    v[p] = *((const __nv_bfloat162*)((const __nv_bfloat16*)a.in + p * a.in_plane + mi * a.C) + g);
+                    sx += __low2float(v[p]); sy += __high2float(v[p]);
+                }
+                if (sx > bx) { bx = sx; for (int p = 0; p < a.planes; p++) px[p] = v[p]; }
+                if (sy > by) { by = sy; for (int p = 0; p < a.planes; p++) py[p] = v[p]; }
+            }
+        }
+    for (int p = 0; p < a.planes; p++) {
+        __nv_bfloat162 o = __halves2bfloat162(__low2bfloat16(px[p]), __high2bfloat16(py[p]));
+        *((__nv_bfloat162*)((__nv_bfloat16*)a.out + p * a.out_plane + mo * a.C) + g) = o;
+    }
+}
+
+int launch_pool(const PoolArgs& a, cudaStream_t st) {
+    const long long rows_out = (long long)a.N * a.Hso * a.Wpo;
+    if (a.planes == 0) {
+        const long long total = rows_out * (a.C / 4);
+        pool_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    } else {
+        const long long total = rows_out * (a.C / 2);
+        pool_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    }
+    return 1;
+}
+
+// copy the first `channels` channels of every row (all planes); 16-byte chunks
+__global__ void __launch_bounds__(256) copy_channels_kernel(CopyArgs a) {
+    const int chunks = a.channels * a.elem_bytes / 16;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int np = a.planes == 0 ? 1 : a.planes;
+    if (idx >= a.M * chunks * np) return;
+    const int ch = (int)(idx % chunks);
+    const long long r = idx / chunks;
+    const long long row = r % a.M;
+    const int p = (int)(r / a.M);
+    const size_t off = ((size_t)p * a.plane + (size_t)row * a.pitch) * a.elem_bytes + (size_t)ch * 16;
+    *(uint4*)((char*)a.dst + off) = *(const uint4*)((const char*)a.src + off);
+}
+int launch_copy_channels(const CopyArgs& a, cudaStream_t st) {
+    const int chunks = a.channels * a.elem_bytes / 16;
+    const long long total = a.M * chunks * (a.planes == 0 ? 1 : a.planes);
+    copy_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    return 1;
+}
+
+__global__ void __launch_bounds__(256) act_to_nchw_kernel(const void* act, int pitch, int coff, int c, long long plane,
+                                                          int planes, Geo g, float* out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)g.N * c * g.H * g.W;
+    if (idx >= total) return;
+    const int x = (int)(idx % g.W);
+    const int y = (int)((idx / g.W) % g.H);
+    const int ch = (int)((idx / ((long long)g.W * g.H)) % c);
+    const int n = (int)(idx / ((long long)g.W * g.H * c));
+    const long long m = ((long long)n * g.Hs + y) * g.Wp + x;
+    float v = 0.f;
+    if (planes == 0) v = ((const float*)act)[m * pitch + coff + ch];
+    else for (int p = 0; p < planes; p++) v += __bfloat162float(((const __nv_bfloat16*)act)[p * plane + m * pitch + coff + ch]);
+    out[idx] = v;
+}
+int launch_act_to_nchw(const void* act, int pitch, int coff, int c, long long plane, int planes, const Geo& g,
+                       float* out, cudaStream_t st) {
+    const long long total = (long long)g.N * c * g.H * g.W;
+    act_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(act, pitch, coff, c, plane, planes, g, out);
+    return 1;
+}
+
+}  // namespace pe

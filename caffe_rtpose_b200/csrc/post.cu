@@ -1,0 +1,492 @@
+// Post-processing on the GPU: multi-scale ImResize/average fused with the NMS peak finder, PAF line
+// integral, greedy bipartite limb assignment and person assembly.
+//
+// What it replaces:
+//   ImResizeLayer::Forward_gpu + imresize_cubic_kernel   src/caffe/cpm/layers/imresize_layer.cu:98-193
+//   NmsLayer::Forward_gpu (register/scan/write)          src/caffe/cpm/layers/nms_layer.cu:14-184
+//   connectLimbs / connectLimbsCOCO (host C++)           examples/rtpose/rtpose.cpp:549-751, 808-1076
+//
+// B200-first design: the reference materialises a 55 MB full-resolution tensor (57x368x656 fp32), copies
+// it to the host and walks it on one CPU thread.  Here the full-resolution value of any (channel,y,x) is a
+// pure function of the 0.86 MB stride-8 maps (L2 resident), so it is evaluated ON THE FLY wherever the
+// algorithm looks at it: the NMS tiles, the 7x7 centroid windows and the 10 PAF samples per candidate
+// pair.  Nothing full-resolution is ever written; the only outputs are the 14 KB peaks blob and the joints.
+//
+// Arithmetic: every float/double operation below is written with explicit round-to-nearest intrinsics in
+// the order (and with the FMA contractions) that nvcc emits for the reference kernels, and that the host
+// compiler emits for connectLimbs*, so results are bit-identical to the oracle (tests/test_gpu_post.py).
+#include "common.h"
+#include "kernels.h"
+
+namespace pe {
+
+// ------------------------------------------------------------------------------------------------
+// cubic_interpolation (imresize_layer.cu:8-18) with nvcc's contraction pattern (see oracle.cpp)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic_ref(float v0, float v1, float v2, float v3, float d) {
+    const float h = __fmul_rn(0.5f, v0);
+    const float a = __fmaf_rn(v3, 0.5f, __fmaf_rn(v2, -1.5f, __fmaf_rn(v1, 1.5f, -h)));
+    const float t1 = __fmul_rn(__fmul_rn(__fmul_rn(a, d), d), d);
+    const double b = __fma_rn((double)v3, -0.5, __fma_rn((double)v2, 2.0, (double)__fmaf_rn(v1, -2.5f, v0)));
+    const double dd = (double)d;
+    double acc = __fma_rn(dd, __dmul_rn(dd, b), (double)t1);
+    const float t3 = __fmul_rn(d, __fmaf_rn(v2, 0.5f, -h));
+    acc = __dadd_rn(acc, (double)t3);
+    acc = __dadd_rn(acc, (double)v1);
+    return __double2float_rn(acc);
+}
+
+// Per-scale, per-output-coordinate source taps of imresize_cubic_kernel (imresize_layer.cu:110-140).
+// Built once per (net size, scales) by axis_table_kernel with the kernel's own arithmetic.
+__global__ void axis_table_kernel(AxisTap* tab, int t, int ori, int num_scales, float start_scale, float scale_gap) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (x >= t || n >= num_scales) return;
+    const float f = __fmaf_rn((float)n, scale_gap, __fsub_rn(1.0f, start_scale));
+    const int pad = (int)floorf(__fmul_rn((float)(ori / 2), f));
+    const int o = ori - 2 * pad;
+    const float q = __fdiv_rn((float)t, (float)o);
+    const float offset = __fmaf_rn(q, 0.5f, -0.5f);
+    const float on_ori = __fmul_rn(__fsub_rn((float)x, offset), __fdiv_rn((float)o, (float)t));
+    int n1 = __double2int_rz(__dadd_rn((double)on_ori, 1e-5));
+    n1 = n1 < 0 ? 0 : n1;
+    AxisTap a;
+    a.i0 = ((n1 - 1 < 0) ? n1 : (n1 - 1)) + pad;
+    const int n2 = (n1 + 1 >= o) ? (o - 1) : (n1 + 1);
+    a.i3 = ((n2 + 1 >= o) ? (o - 1) : (n2 + 1)) + pad;
+    a.d = __fsub_rn(on_ori, (float)n1);
+    a.i1 = n1 + pad;
+    a.i2 = n2 + pad;
+    tab[(size_t)n * t + x] = a;
+}
+
+struct FullRes {
+    const float* maps;     // this frame: [S][C][h8][w8]
+    const AxisTap* xt;     // [S][net_w]
+    const AxisTap* yt;     // [S][net_h]
+    int S, C, h8, w8, net_w, net_h;
+    float inv_div;         // (float)S
+};
+
+// resized_map[c][y][x] of the reference, evaluated from the stride-8 maps
+__device__ __forceinline__ float fullres_at(const FullRes& fr, int c, int y, int x) {
+    float sum = 0.f;
+    const size_t plane = (size_t)fr.h8 * fr.w8;
+    for (int n = 0; n < fr.S; n++) {
+        const AxisTap ax = fr.xt[n * fr.net_w + x];
+        const AxisTap ay = fr.yt[n * fr.net_h + y];
+        const float* s = fr.maps + ((size_t)n * fr.C + c) * plane;
+        const float* r0 = s + (size_t)ay.i0 * fr.w8;
+        const float* r1 = s + (size_t)ay.i1 * fr.w8;
+        const float* r2 = s + (size_t)ay.i2 * fr.w8;
+        const float* r3 = s + (size_t)ay.i3 * fr.w8;
+        const float t0 = cubic_ref(__ldg(r0 + ax.i0), __ldg(r0 + ax.i1), __ldg(r0 + ax.i2), __ldg(r0 + ax.i3), ax.d);
+        const float t1 = cubic_ref(__ldg(r1 + ax.i0), __ldg(r1 + ax.i1), __ldg(r1 + ax.i2), __ldg(r1 + ax.i3), ax.d);
+        const float t2 = cubic_ref(__ldg(r2 + ax.i0), __ldg(r2 + ax.i1), __ldg(r2 + ax.i2), __ldg(r2 + ax.i3), ax.d);
+        const float t3 = cubic_ref(__ldg(r3 + ax.i0), __ldg(r3 + ax.i1), __ldg(r3 + ax.i2), __ldg(r3 + ax.i3), ax.d);
+        sum = __fadd_rn(sum, cubic_ref(t0, t1, t2, t3, ay.d));
+    }
+    return __fdiv_rn(sum, fr.inv_div);
+}
+
+__device__ __forceinline__ FullRes make_fullres(const PostDev& pd, int frame) {
+    FullRes fr;
+    fr.S = pd.p.num_scales; fr.C = pd.p.num_maps; fr.h8 = pd.p.h8; fr.w8 = pd.p.w8;
+    fr.net_w = pd.p.net_w; fr.net_h = pd.p.net_h;
+    fr.maps = pd.maps + (size_t)frame * fr.S * fr.C * fr.h8 * fr.w8;
+    fr.xt = pd.xtab; fr.yt = pd.ytab;
+    fr.inv_div = (float)fr.S;
+    return fr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1: resize + nms_register_kernel (nms_layer.cu:14-46) fused.
+// One CTA = one 32x8 full-resolution tile of one (frame, part); values incl. the 1-pixel halo are
+// produced in shared memory, the strict 8-neighbour test runs from there, and each warp row becomes
+// one 32-bit word of the peak bitmask (warp ballot) - raster order is preserved by construction.
+// ------------------------------------------------------------------------------------------------
+#define NMS_TX 32
+#define NMS_TY 8
+__global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
+    __shared__ float tile[NMS_TY + 2][NMS_TX + 2];
+    const int part = blockIdx.z % pd.p.num_parts, frame = blockIdx.z / pd.p.num_parts;
+    const FullRes fr = make_fullres(pd, frame);
+    const int W = pd.p.net_w, H = pd.p.net_h;
+    const int x0 = blockIdx.x * NMS_TX - 1, y0 = blockIdx.y * NMS_TY - 1;
+    for (int i = threadIdx.x; i < (NMS_TY + 2) * (NMS_TX + 2); i += 256) {
+        const int ty = i / (NMS_TX + 2), tx = i % (NMS_TX + 2);
+        const int x = x0 + tx, y = y0 + ty;
+        float v = 0.f;
+        if (x >= 0 && x < W && y >= 0 && y < H) v = fullres_at(fr, part, y, x);
+        tile[ty][tx] = v;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x = blockIdx.x * NMS_TX + lx, y = blockIdx.y * NMS_TY + ly;
+    bool peak = false;
+    if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {
+        const float v = tile[ly + 1][lx + 1];
+        if (v > pd.p.nms_threshold) {
+            peak = v > tile[ly][lx + 1] && v > tile[ly + 2][lx + 1] && v > tile[ly + 1][lx] && v > tile[ly + 1][lx + 2] &&
+                   v > tile[ly][lx] && v > tile[ly + 2][lx] && v > tile[ly + 2][lx + 2] && v > tile[ly][lx + 2];
+        }
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, peak);
+    if (lx == 0 && y < H) {
+        const int words_per_row = (W + 31) / 32;
+        pd.flags[((size_t)(frame * pd.p.num_parts + part) * H + y) * words_per_row + blockIdx.x] = word;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 2: thrust::exclusive_scan + writeResultKernel (nms_layer.cu:176, 49-113) fused.
+// One CTA per (frame, part): block-wide popcount scan of the bitmask words gives every peak its raster
+// rank; the first max_peaks get the 7x7 score-weighted centroid (window values re-evaluated on the fly,
+// including the reference's width-for-height bound that aliases into the next channel's first rows).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nms_write_kernel(PostDev pd) {
+    __shared__ int s_scan[256];
+    __shared__ int s_pos[128];       // flat y*W+x of the first max_peaks peaks
+    __shared__ float s_win[4][49];
+    __shared__ int s_total;
+    const int part = blockIdx.x, frame = blockIdx.y;
+    const int W = pd.p.net_w, H = pd.p.net_h, MP = pd.p.max_peaks;
+    const int words_per_row = (W + 31) / 32;
+    const int nwords = H * words_per_row;
+    const unsigned* flags = pd.flags + (size_t)(frame * pd.p.num_parts + part) * nwords;
+    const int per = (nwords + 255) / 256;
+    const int w0 = threadIdx.x * per, w1 = min(w0 + per, nwords);
+    int cnt = 0;
+    for (int w = w0; w < w1; w++) cnt += __popc(flags[w]);
+    s_scan[threadIdx.x] = cnt;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 256 counts
+    for (int off = 1; off < 256; off <<= 1) {
+        int v = 0;
+        if ((int)threadIdx.x >= off) v = s_scan[threadIdx.x - off];
+        __syncthreads();
+        s_scan[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int rank = s_scan[threadIdx.x] - cnt;  // exclusive
+    if (threadIdx.x == 255) s_total = s_scan[255];
+    for (int w = w0; w < w1 && rank < MP; w++) {
+        unsigned bits = flags[w];
+        const int y = w / words_per_row, xb = (w % words_per_row) * 32;
+        while (bits && rank < MP) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            s_pos[rank++] = y * W + xb + b;
+        }
+    }
+    __syncthreads();
+    const int total = s_total;
+    const int n = min(total, MP);
+    float* out = pd.peaks + (size_t)(frame * pd.p.num_parts + part) * (MP + 1) * 3;
+    if (threadIdx.x == 0) out[0] = (float)total;  // total, not clamped (nms_layer.cu:110)
+    const FullRes fr = make_fullres(pd, frame);
+    const int g = threadIdx.x >> 6, l = threadIdx.x & 63;
+    for (int base = 0; base < n; base += 4) {
+        const int k = base + g;
+        if (k < n && l < 49) {
+            const int px = s_pos[k] % W, py = s_pos[k] / W;
+            const int dy = l / 7 - 3, dx = l % 7 - 3;
+            const int yy = py + dy, xx = px + dx;
+            float v = 0.f;
+            if (yy > 0 && yy < W && xx > 0 && xx < W) {       // sic: W for both (nms_layer.cu:79,81)
+                // rows >= H alias the following channel's first rows: src_pointer[(y+dy)*width + x+dx]
+                const int cc = part + yy / H, ry = yy % H;
+                v = (cc < pd.p.num_maps) ? fullres_at(fr, cc, ry, xx) : 0.f;
+            }
+            s_win[g][l] = v;
+        }
+        __syncthreads();
+        if (k < n && l == 0) {
+            const int px = s_pos[k] % W, py = s_pos[k] / W;
+            float x_acc = 0.f, y_acc = 0.f, score_acc = 0.f;
+            for (int dy = -3; dy < 4; dy++) {
+                if ((py + dy) > 0 && (py + dy) < W) {
+                    for (int dx = -3; dx < 4; dx++) {
+                        if ((px + dx) > 0 && (px + dx) < W) {
+                            const float score = s_win[g][(dy + 3) * 7 + dx + 3];
+                            if (score > 0) {
+                                x_acc = __fmaf_rn((float)(px + dx), score, x_acc);
+                                y_acc = __fmaf_rn((float)(py + dy), score, y_acc);
+                                score_acc = __fadd_rn(score_acc, score);
+                            }
+                        }
+                    }
+                }
+            }
+            float* o = out + (k + 1) * 3;
+            o[0] = __fdiv_rn(x_acc, score_acc);
+            o[1] = __fdiv_rn(y_acc, score_acc);
+            o[2] = s_win[g][24];  // the peak's own value
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 3: PAF line integral (rtpose.cpp:900-949 / 611-647).  One thread per candidate pair (i,j);
+// grid = (pair chunks, limb, frame).  Candidates that pass go to a per-limb list keyed by their
+// position p = (i-1)*nB + (j-1) in the reference's nested loop (used as the tie-break of the sort).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) paf_score_kernel(PostDev pd) {
+    const int limb = blockIdx.y, frame = blockIdx.z;
+    const ModelDev& md = pd.md;
+    const int MP = pd.p.max_peaks, poff = 3 * (MP + 1);
+    const int pa = md.limb_seq[2 * limb], pb = md.limb_seq[2 * limb + 1];
+    const float* peaks = pd.peaks + (size_t)frame * pd.p.num_parts * poff;
+    const float* candA = peaks + pa * poff;
+    const float* candB = peaks + pb * poff;
+    const int nA = min((int)candA[0], MP), nB = min((int)candB[0], MP);
+    const int npairs = nA * nB;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const int i = p / nB + 1, j = p % nB + 1;
+    const bool coco = pd.p.model != PE_MODEL_MPI_15;
+    const float s_x = candA[i * 3], s_y = candA[i * 3 + 1];
+    const float d_x = __fsub_rn(candB[j * 3], candA[i * 3]);
+    const float d_y = __fsub_rn(candB[j * 3 + 1], candA[i * 3 + 1]);
+    float norm_vec;
+    if (coco) {
+        norm_vec = __fsqrt_rn(__fadd_rn(__fmul_rn(d_x, d_x), __fmul_rn(d_y, d_y)));
+    } else {  // pow(d_x,2) + pow(d_y,2) in double (rtpose.cpp:618)
+        const double dx2 = __dmul_rn((double)d_x, (double)d_x), dy2 = __dmul_rn((double)d_y, (double)d_y);
+        norm_vec = __double2float_rn(__dsqrt_rn(__dadd_rn(dx2, dy2)));
+    }
+    if ((double)norm_vec < 1e-6) return;
+    const float vec_x = __fdiv_rn(d_x, norm_vec), vec_y = __fdiv_rn(d_y, norm_vec);
+    const FullRes fr = make_fullres(pd, frame);
+    const int W = pd.p.net_w, H = pd.p.net_h;
+    const int cx = md.map_idx[2 * limb], cy = md.map_idx[2 * limb + 1];
+    float sum = 0.f;
+    int count = 0;
+    for (int lm = 0; lm < 10; lm++) {
+        int my = (int)roundf(__fadd_rn(s_y, __fdiv_rn(__fmul_rn((float)lm, d_y), 10.0f)));
+        int mx = (int)roundf(__fadd_rn(s_x, __fdiv_rn(__fmul_rn((float)lm, d_x), 10.0f)));
+        // COCO clamps the upper bounds (rtpose.cpp:920-927); MPI does not (:629-633) and would read
+        // past the channel - the engine clamps both (identical whenever the reference is in bounds).
+        mx = min(max(mx, 0), W - 1);
+        my = min(max(my, 0), H - 1);
+        const float score = __fadd_rn(__fmul_rn(vec_x, fullres_at(fr, cx, my, mx)), __fmul_rn(vec_y, fullres_at(fr, cy, my, mx)));
+        if (score > pd.p.inter_threshold) { sum = __fadd_rn(sum, score); count++; }
+    }
+    if (count > pd.p.inter_min_above) {
+        const int lf = frame * pd.p.num_limbs + limb;
+        const int slot = atomicAdd(&pd.cand_count[lf], 1);
+        Cand c;
+        c.conn = __fdiv_rn(sum, (float)count);
+        c.p = p;
+        pd.cands[(size_t)lf * MP * MP + slot] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 4: sort candidates by connection score (descending; ColumnCompare rtpose.cpp:144-152, ties
+// broken by loop position - std::sort leaves them unspecified) + greedy one-to-one selection
+// (rtpose.cpp:953-980).  One CTA per (limb, frame); bitonic sort on 64-bit keys in shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned order_key(float f) {  // monotone float -> uint
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(512) limb_greedy_kernel(PostDev pd) {
+    extern __shared__ unsigned long long s_keys[];
+    __shared__ unsigned char occA[128], occB[128];
+    const int limb = blockIdx.x, frame = blockIdx.y;
+    const int MP = pd.p.max_peaks, poff = 3 * (MP + 1);
+    const int lf = frame * pd.p.num_limbs + limb;
+    const int ncand = pd.cand_count[lf];
+    const Cand* cands = pd.cands + (size_t)lf * MP * MP;
+    int n2 = 1;
+    while (n2 < ncand) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (i < ncand) k = ((unsigned long long)(~order_key(cands[i].conn)) << 32) | (unsigned)cands[i].p;
+        s_keys[i] = k;
+    }
+    if (threadIdx.x < 128) { occA[threadIdx.x] = 0; occB[threadIdx.x] = 0; }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s_keys[i], b = s_keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        const ModelDev& md = pd.md;
+        const int pa = md.limb_seq[2 * limb], pb = md.limb_seq[2 * limb + 1];
+        const float* peaks = pd.peaks + (size_t)frame * pd.p.num_parts * poff;
+        const int nA = min((int)peaks[pa * poff], MP), nB = min((int)peaks[pb * poff], MP);
+        const int num = min(nA, nB);
+        Conn* out = pd.conns + (size_t)lf * MP;
+        int cnt = 0;
+        for (int row = 0; row < ncand && cnt < num; row++) {
+            const unsigned long long key = s_keys[row];
+            const int p = (int)(key & 0xffffffffu);
+            const int i = p / nB + 1, j = p % nB + 1;
+            if (!occA[i - 1] && !occB[j - 1]) {
+                const unsigned ok = ~(unsigned)(key >> 32);
+                const unsigned u = (ok & 0x80000000u) ? (ok & 0x7fffffffu) : ~ok;
+                Conn c;
+                c.a = pa * poff + i * 3 + 2;
+                c.b = pb * poff + j * 3 + 2;
+                c.score = __uint_as_float(u);
+                out[cnt++] = c;
+                occA[i - 1] = 1; occB[j - 1] = 1;
+            }
+        }
+        pd.conn_count[lf] = cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 5: person assembly + joint output (rtpose.cpp:847-895, 984-1073).  Inherently sequential over
+// limbs and connections; the scan over existing rows is parallel.  One CTA per frame.  Row layout as in
+// the reference: num_parts index slots (flat index of the peak's score in the peaks blob, 0 = empty),
+// then [num_parts+1] = score (double), [num_parts+2] = count.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) assemble_kernel(PostDev pd) {
+    __shared__ int s_rows;
+    const int frame = blockIdx.x;
+    const ModelDev& md = pd.md;
+    const int P = pd.p.num_parts, MP = pd.p.max_peaks, poff = 3 * (MP + 1);
+    const int S_CNT = P + 2, S_SCORE = P + 1, S_SIZE = P + 3;
+    const bool coco = pd.p.model != PE_MODEL_MPI_15;
+    const float* peaks = pd.peaks + (size_t)frame * P * poff;
+    double* subset = pd.subset + (size_t)frame * PE_MAX_SUBSET_ROWS * S_SIZE;
+    if (threadIdx.x == 0) s_rows = 0;
+    __syncthreads();
+
+    auto append = [&](int slot_a, double va, int slot_b, double vb, double cnt, double score) {
+        // called by thread 0 only
+        const int r = s_rows;
+        if (r < PE_MAX_SUBSET_ROWS) {
+            double* row = subset + (size_t)r * S_SIZE;
+            for (int q = 0; q < S_SIZE; q++) row[q] = 0.0;
+            row[slot_a] = va;
+            if (slot_b >= 0) row[slot_b] = vb;
+            row[S_CNT] = cnt;
+            row[S_SCORE] = score;
+            s_rows = r + 1;
+        }
+    };
+
+    for (int k = 0; k < pd.p.num_limbs; k++) {
+        const int pa = md.limb_seq[2 * k], pb = md.limb_seq[2 * k + 1];
+        const int nA = min((int)peaks[pa * poff], MP), nB = min((int)peaks[pb * poff], MP);
+        if (nA == 0 && nB == 0) continue;
+        if (nA == 0 || nB == 0) {
+            const int part = nA == 0 ? pb : pa, n = nA == 0 ? nB : nA;
+            for (int i = 1; i <= n; i++) {
+                const int off = part * poff + i * 3 + 2;
+                int found = 0;
+                if (coco) {  // duplicate check exists only in connectLimbsCOCO (rtpose.cpp:852-860)
+                    const int rows = s_rows;
+                    for (int j = threadIdx.x; j < rows; j += blockDim.x)
+                        if (subset[(size_t)j * S_SIZE + part] == (double)off) found = 1;
+                }
+                found = __syncthreads_or(found);
+                if (!found && threadIdx.x == 0) append(part, (double)off, -1, 0.0, 1.0, (double)peaks[off]);
+                __syncthreads();
+            }
+            continue;
+        }
+        const int lf = frame * pd.p.num_limbs + k;
+        const int nc = pd.conn_count[lf];
+        const Conn* conns = pd.conns + (size_t)lf * MP;
+        if (k == 0) {
+            if (threadIdx.x == 0)
+                for (int i = 0; i < nc; i++) {
+                    const Conn c = conns[i];
+                    const double sc = __dadd_rn((double)__fadd_rn(peaks[c.a], peaks[c.b]), (double)c.score);
+                    append(pa, (double)c.a, pb, (double)c.b, 2.0, sc);
+                }
+            __syncthreads();
+            continue;
+        }
+        for (int i = 0; i < nc; i++) {
+            const Conn c = conns[i];
+            const int rows = s_rows;
+            int found = 0;
+            for (int j = threadIdx.x; j < rows; j += blockDim.x) {
+                double* row = subset + (size_t)j * S_SIZE;
+                if (row[pa] == (double)c.a) {
+                    row[pb] = (double)c.b;
+                    found = 1;
+                    row[S_CNT] = row[S_CNT] + 1.0;
+                    row[S_SCORE] = __dadd_rn(__dadd_rn(row[S_SCORE], (double)peaks[c.b]), (double)c.score);
+                }
+            }
+            found = __syncthreads_or(found);
+            if (!found && threadIdx.x == 0) {
+                const double sc = __dadd_rn((double)__fadd_rn(peaks[c.a], peaks[c.b]), (double)c.score);
+                append(pa, (double)c.a, pb, (double)c.b, 2.0, sc);
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int rows = s_rows;
+        float* joints = pd.joints + (size_t)frame * PE_MAX_PEOPLE * P * 3;
+        int cnt = 0;
+        for (int i = 0; i < rows; i++) {
+            const double* row = subset + (size_t)i * S_SIZE;
+            if (row[S_CNT] >= (double)pd.p.min_subset_cnt &&
+                __ddiv_rn(row[S_SCORE], row[S_CNT]) > (double)pd.p.min_subset_score) {
+                for (int j = 0; j < P; j++) {
+                    const int idx = (int)row[j];
+                    float* o = joints + (size_t)cnt * P * 3 + j * 3;
+                    if (idx) {
+                        o[2] = peaks[idx];
+                        o[1] = __fdiv_rn(__fmul_rn(peaks[idx - 1], (float)pd.p.disp_h), (float)pd.p.net_h);
+                        o[0] = __fdiv_rn(__fmul_rn(peaks[idx - 2], (float)pd.p.disp_w), (float)pd.p.net_w);
+                    } else {
+                        o[0] = o[1] = o[2] = 0.f;
+                    }
+                }
+                cnt++;
+                if (cnt == PE_MAX_PEOPLE) break;
+            }
+        }
+        pd.num_people[frame] = cnt;
+        pd.subset_rows[frame] = rows;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+void launch_axis_tables(AxisTap* xtab, AxisTap* ytab, const PostParams& p, cudaStream_t st) {
+    axis_table_kernel<<<dim3((p.net_w + 127) / 128, p.num_scales), 128, 0, st>>>(xtab, p.net_w, p.w8, p.num_scales,
+                                                                                   p.start_scale, p.scale_gap);
+    axis_table_kernel<<<dim3((p.net_h + 127) / 128, p.num_scales), 128, 0, st>>>(ytab, p.net_h, p.h8, p.num_scales,
+                                                                                   p.start_scale, p.scale_gap);
+}
+
+int launch_post(const PostDev& pd, int nframes, cudaStream_t st) {
+    const PostParams& p = pd.p;
+    const int MP = p.max_peaks;
+    cudaMemsetAsync(pd.peaks, 0, sizeof(float) * (size_t)nframes * p.num_parts * (MP + 1) * 3, st);
+    cudaMemsetAsync(pd.cand_count, 0, sizeof(int) * (size_t)nframes * p.num_limbs, st);
+    dim3 g1((p.net_w + NMS_TX - 1) / NMS_TX, (p.net_h + NMS_TY - 1) / NMS_TY, nframes * p.num_parts);
+    nms_flags_kernel<<<g1, 256, 0, st>>>(pd);
+    nms_write_kernel<<<dim3(p.num_parts, nframes), 256, 0, st>>>(pd);
+    paf_score_kernel<<<dim3((MP * MP + 127) / 128, p.num_limbs, nframes), 128, 0, st>>>(pd);
+    int n2 = 1;
+    while (n2 < MP * MP) n2 <<= 1;
+    limb_greedy_kernel<<<dim3(p.num_limbs, nframes), 512, sizeof(unsigned long long) * n2, st>>>(pd);
+    assemble_kernel<<<nframes, 128, 0, st>>>(pd);
+    return 5;  // kernels launched
+}
+
+}  // namespace pe

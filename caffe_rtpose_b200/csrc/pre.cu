@@ -1,0 +1,142 @@
+// Frame -> network input on the GPU.
+//
+// Replaces the single-threaded host loop of getFrameFromCam (examples/rtpose/rtpose.cpp:508-518):
+//   per scale i: cv::resize(display_img, (tw,th), INTER_AREA)  ->  process_and_pad_image(..., normalize=1)
+//   (rtpose.cpp:239-269: centre pad with zeros, v/256 - 0.5, planar BGR), followed by a 2.9 MB/scale H2D copy.
+// Here the uint8 display image is uploaded once (2.76 MB) and two kernels produce the conv stack's input:
+//   1. area_resize_kernel  - OpenCV's INTER_AREA arithmetic (resizeArea_<uchar,float,float> /
+//      resizeAreaFast_), bit-exact: float accumulation in table order, no FMA, round-half-even saturate;
+//   2. input_im2col_kernel - pad + normalise + gather the 3x3x3 patch of every pixel, so that conv1_1
+//      becomes a K=27 GEMM on the same implicit-GEMM kernel as every other layer.
+#include "common.h"
+#include "kernels.h"
+
+namespace pe {
+
+__global__ void __launch_bounds__(256) area_resize_kernel(PreArgs a) {
+    const int s = blockIdx.y, f = blockIdx.z;
+    const AreaTab t = a.tab[s];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= t.tw * t.th) return;
+    const int dx = idx % t.tw, dy = idx / t.tw;
+    const uint8_t* src = a.frames + (size_t)f * a.disp_h * a.disp_w * 3;
+    uint8_t* dst = a.resized + ((size_t)(f * a.S + s) * a.net_h * a.net_w + (size_t)dy * t.tw + dx) * 3;
+    if (t.tw == a.disp_w && t.th == a.disp_h) {  // cv::resize with equal sizes copies
+        const uint8_t* p = src + ((size_t)dy * a.disp_w + dx) * 3;
+        dst[0] = p[0]; dst[1] = p[1]; dst[2] = p[2];
+        return;
+    }
+    if (t.fast) {  // integer ratios: resizeAreaFast_ (2x2 uses the (sum+2)>>2 SIMD specialisation)
+        int s0 = 0, s1 = 0, s2 = 0;
+        for (int yy = 0; yy < t.iscale_y; yy++)
+            for (int xx = 0; xx < t.iscale_x; xx++) {
+                const uint8_t* p = src + ((size_t)(dy * t.iscale_y + yy) * a.disp_w + dx * t.iscale_x + xx) * 3;
+                s0 += p[0]; s1 += p[1]; s2 += p[2];
+            }
+        if (t.iscale_x == 2 && t.iscale_y == 2) {
+            dst[0] = (uint8_t)((s0 + 2) >> 2); dst[1] = (uint8_t)((s1 + 2) >> 2); dst[2] = (uint8_t)((s2 + 2) >> 2);
+        } else {
+            const float sc = __fdiv_rn(1.f, (float)(t.iscale_x * t.iscale_y));
+            dst[0] = (uint8_t)min(max(__float2int_rn(__fmul_rn((float)s0, sc)), 0), 255);
+            dst[1] = (uint8_t)min(max(__float2int_rn(__fmul_rn((float)s1, sc)), 0), 255);
+            dst[2] = (uint8_t)min(max(__float2int_rn(__fmul_rn((float)s2, sc)), 0), 255);
+        }
+        return;
+    }
+    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
+    const int k0 = t.x_ofs[dx], k1 = t.x_ofs[dx + 1];
+    const int j0 = t.y_ofs[dy], j1 = t.y_ofs[dy + 1];
+    for (int j = j0; j < j1; j++) {
+        const uint8_t* row = src + (size_t)t.y_si[j] * a.disp_w * 3;
+        const float beta = t.y_alpha[j];
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        for (int k = k0; k < k1; k++) {
+            const uint8_t* p = row + (size_t)t.x_si[k] * 3;
+            const float alpha = t.x_alpha[k];
+            b0 = __fadd_rn(b0, __fmul_rn((float)p[0], alpha));
+            b1 = __fadd_rn(b1, __fmul_rn((float)p[1], alpha));
+            b2 = __fadd_rn(b2, __fmul_rn((float)p[2], alpha));
+        }
+        sum0 = __fadd_rn(sum0, __fmul_rn(beta, b0));
+        sum1 = __fadd_rn(sum1, __fmul_rn(beta, b1));
+        sum2 = __fadd_rn(sum2, __fmul_rn(beta, b2));
+    }
+    dst[0] = (uint8_t)min(max(__float2int_rn(sum0), 0), 255);
+    dst[1] = (uint8_t)min(max(__float2int_rn(sum1), 0), 255);
+    dst[2] = (uint8_t)min(max(__float2int_rn(sum2), 0), 255);
+}
+
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+    h = __float2bfloat16_rn(x);
+    const float r = __fsub_rn(x, __bfloat162float(h));
+    m = __float2bfloat16_rn(r);
+    l = __float2bfloat16_rn(__fsub_rn(r, __bfloat162float(m)));
+}
+
+// SRC = 0: uint8 resized images (pad + normalise here);  SRC = 1: planar fp32 net input (already padded/normalised)
+template <int SRC>
+__global__ void __launch_bounds__(128) input_im2col_kernel(PreArgs a, const float* planar, int nimages) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_img = (long long)a.Hs * a.Wp;
+    if (m >= per_img * nimages) return;
+    const int n = (int)(m / per_img);
+    const int rem = (int)(m % per_img);
+    const int y = rem / a.Wp, x = rem % a.Wp;
+    if (x >= a.net_w || y >= a.net_h) return;  // gap rows stay zero
+    float v[27];
+    const int s = n % a.S;
+    const AreaTab t = a.tab[SRC == 0 ? s : 0];
+    const uint8_t* img = a.resized + (size_t)n * a.net_h * a.net_w * 3;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int yy = y + r - 1, xx = x + q - 1;
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (yy >= 0 && yy < a.net_h && xx >= 0 && xx < a.net_w) {
+                if (SRC == 0) {
+                    const int oy = yy - t.padh, ox = xx - t.padw;
+                    if (oy >= 0 && oy < t.th && ox >= 0 && ox < t.tw) {
+                        const uint8_t* p = img + ((size_t)oy * t.tw + ox) * 3;
+                        c0 = __fsub_rn(__fdiv_rn((float)p[0], 256.0f), 0.5f);
+                        c1 = __fsub_rn(__fdiv_rn((float)p[1], 256.0f), 0.5f);
+                        c2 = __fsub_rn(__fdiv_rn((float)p[2], 256.0f), 0.5f);
+                    }
+                } else {
+                    const size_t pl = (size_t)a.net_h * a.net_w;
+                    const float* p = planar + (size_t)n * 3 * pl + (size_t)yy * a.net_w + xx;
+                    c0 = p[0]; c1 = p[pl]; c2 = p[2 * pl];
+                }
+            }
+            v[(r * 3 + q) * 3 + 0] = c0; v[(r * 3 + q) * 3 + 1] = c1; v[(r * 3 + q) * 3 + 2] = c2;
+        }
+    if (a.planes == 0) {
+        float* o = (float*)a.out + (size_t)m * a.kp;
+        for (int k = 0; k < a.kp; k++) o[k] = k < 27 ? v[k] : 0.f;
+    } else {
+        __nv_bfloat16* o0 = (__nv_bfloat16*)a.out + (size_t)m * a.kp;
+        for (int k = 0; k < a.kp; k++) {
+            __nv_bfloat16 h, mm, l;
+            split3(k < 27 ? v[k] : 0.f, h, mm, l);
+            o0[k] = h;
+            if (a.planes > 1) o0[a.out_plane + k] = mm;
+            if (a.planes > 2) o0[2 * a.out_plane + k] = l;
+        }
+    }
+}
+
+int launch_preprocess(const PreArgs& a, cudaStream_t st) {
+    dim3 g((a.net_w * a.net_h + 255) / 256, a.S, a.nframes);
+    area_resize_kernel<<<g, 256, 0, st>>>(a);
+    const long long rows = (long long)a.Hs * a.Wp * a.nframes * a.S;
+    input_im2col_kernel<0><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(a, nullptr, a.nframes * a.S);
+    return 2;
+}
+
+int launch_input_from_planar(const float* planar, const PreArgs& a, int nimages, cudaStream_t st) {
+    const long long rows = (long long)a.Hs * a.Wp * nimages;
+    input_im2col_kernel<1><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(a, planar, nimages);
+    return 1;
+}
+
+}  // namespace pe

@@ -1,0 +1,366 @@
+"""Host-side mirror of the reference's per-GPU interface over the C ABI (include/poseengine.h).
+
+The reference's worker holds a `caffe::Net`, a `caffe::NmsLayer*`, a `caffe::ImResizeLayer*` and a
+`ModelDescriptor` (examples/rtpose/rtpose.cpp:133-142, 173-237) and calls, per frame,
+`nms_layer->SetThreshold(...)`, `ForwardFrom(0)`, `connectLimbs*` (rtpose.cpp:1145-1166).  `PoseEngine`
+keeps those names and argument meanings (`nms_layer.SetThreshold`, `resize_layer.SetStartScale`,
+`model_descriptor.get_limb_sequence()` ...) and routes everything to libposeengine.so, the hand-written
+sm_100a implementation.  There is no CPU or PyTorch fallback: if the shared library is missing or no
+B200 is visible the constructor raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libposeengine.so")
+
+MPI_15, COCO_18 = 0, 1
+PREC_FP32_SIMT, PREC_BF16X1, PREC_BF16X2, PREC_BF16X3 = 0, 1, 2, 3
+MAX_PEOPLE = 96
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("model", C.c_int), ("net_w", C.c_int), ("net_h", C.c_int), ("disp_w", C.c_int),
+                ("disp_h", C.c_int), ("num_scales", C.c_int), ("start_scale", C.c_double), ("scale_gap", C.c_double),
+                ("max_batch", C.c_int), ("precision", C.c_int)]
+
+
+class PoseEngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/poseengine.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "pe_create", "pe_destroy", "pe_last_error", "pe_num_conv_layers", "pe_conv_layer_info", "pe_set_conv_weights",
+    "pe_load_weights_file", "pe_commit_weights", "pe_nms_get_max_peaks", "pe_nms_get_num_parts", "pe_nms_get_threshold",
+    "pe_nms_set_threshold", "pe_resize_set_start_scale", "pe_resize_set_scale_gap", "pe_resize_get_start_scale",
+    "pe_resize_get_scale_gap", "pe_set_connect_params", "pe_forward_frames", "pe_forward_frames_device",
+    "pe_forward_net_input", "pe_forward_maps", "pe_fetch", "pe_fetch_maps", "pe_fetch_blob", "pe_sync", "pe_write_json",
+    "pe_model_num_parts", "pe_model_num_limbs", "pe_model_limb_sequence", "pe_model_map_idx", "pe_model_part_name",
+    "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
+    "pe_packed_weights_bytes", "pe_packed_weights_device_ptr",
+]
+
+
+def lib():
+    """Load libposeengine.so.  Fails loudly: the engine has no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PoseEngineError("%s is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(or `make -C caffe_rtpose_b200`); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.pe_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+    L.pe_destroy.argtypes = [C.c_void_p]
+    L.pe_last_error.restype = C.c_char_p
+    L.pe_last_error.argtypes = [C.c_void_p]
+    L.pe_num_conv_layers.argtypes = [C.c_void_p]
+    L.pe_conv_layer_info.argtypes = [C.c_void_p, C.c_int, C.c_char_p] + [C.POINTER(C.c_int)] * 3
+    L.pe_set_conv_weights.argtypes = [C.c_void_p, C.c_char_p, _f32p, C.c_size_t, _f32p, C.c_size_t]
+    L.pe_load_weights_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.pe_commit_weights.argtypes = [C.c_void_p]
+    for f in ("pe_nms_get_max_peaks", "pe_nms_get_num_parts"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    for f in ("pe_nms_get_threshold", "pe_resize_get_start_scale", "pe_resize_get_scale_gap"):
+        getattr(L, f).argtypes = [C.c_void_p]
+        getattr(L, f).restype = C.c_float
+    for f in ("pe_nms_set_threshold", "pe_resize_set_start_scale", "pe_resize_set_scale_gap"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_float]
+    L.pe_set_connect_params.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int]
+    L.pe_forward_frames.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
+    L.pe_forward_frames_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.pe_forward_net_input.argtypes = [C.c_void_p, _f32p, C.c_int]
+    L.pe_forward_maps.argtypes = [C.c_void_p, _f32p, C.c_int]
+    L.pe_fetch.argtypes = [C.c_void_p, C.c_int, _f32p, C.POINTER(C.c_int), C.c_void_p]
+    L.pe_fetch_maps.argtypes = [C.c_void_p, _f32p, C.c_int]
+    L.pe_fetch_blob.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t] + [C.POINTER(C.c_int)] * 3
+    L.pe_sync.argtypes = [C.c_void_p]
+    L.pe_write_json.argtypes = [_f32p, C.c_int, C.c_int, C.c_double, C.c_char_p, C.c_int]
+    for f in ("pe_model_num_parts", "pe_model_num_limbs"):
+        getattr(L, f).argtypes = [C.c_int]
+    for f in ("pe_model_limb_sequence", "pe_model_map_idx"):
+        getattr(L, f).argtypes = [C.c_int]
+        getattr(L, f).restype = C.POINTER(C.c_int)
+    L.pe_model_part_name.argtypes = [C.c_int, C.c_int]
+    L.pe_model_part_name.restype = C.c_char_p
+    L.pe_event_record.argtypes = [C.c_void_p, C.c_int]
+    L.pe_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.pe_profile_layers.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_char_p, C.c_void_p, C.c_int]
+    L.pe_launch_count.argtypes = [C.c_void_p]
+    L.pe_launch_count.restype = C.c_longlong
+    L.pe_conv_flops_per_scale.argtypes = [C.c_void_p]
+    L.pe_conv_flops_per_scale.restype = C.c_double
+    L.pe_packed_weights_bytes.argtypes = [C.c_void_p]
+    L.pe_packed_weights_bytes.restype = C.c_size_t
+    L.pe_packed_weights_device_ptr.argtypes = [C.c_void_p]
+    L.pe_packed_weights_device_ptr.restype = C.c_void_p
+    _lib = L
+    return L
+
+
+class ModelDescriptor:
+    """include/rtpose/modelDescriptor.h API: get_number_parts, number_limb_sequence, get_limb_sequence,
+    get_map_idx, get_part_name."""
+
+    def __init__(self, model):
+        L = lib()
+        self.model = model
+        self._np = L.pe_model_num_parts(model)
+        self._nl = L.pe_model_num_limbs(model)
+        ls, mi = L.pe_model_limb_sequence(model), L.pe_model_map_idx(model)
+        self._limb = [ls[i] for i in range(2 * self._nl)]
+        self._map = [mi[i] for i in range(2 * self._nl)]
+
+    def get_number_parts(self):
+        return self._np
+
+    def number_limb_sequence(self):
+        return self._nl
+
+    def get_limb_sequence(self):
+        return self._limb
+
+    def get_map_idx(self):
+        return self._map
+
+    def get_part_name(self, idx):
+        if not 0 <= idx < self._np + 1 + 2 * self._nl:
+            raise IndexError(idx)  # std::map::at throws in the reference
+        return lib().pe_model_part_name(self.model, idx).decode()
+
+
+class ModelDescriptorFactory:
+    """include/rtpose/modelDescriptorFactory.h: Type::{MPI_15, COCO_18}, createModelDescriptor."""
+
+    class Type:
+        MPI_15, COCO_18 = MPI_15, COCO_18
+
+    @staticmethod
+    def createModelDescriptor(type_):
+        if type_ not in (MPI_15, COCO_18):
+            raise RuntimeError("Undefined ModelDescriptor selected.")  # modelDescriptorFactory.cpp:57-60
+        return ModelDescriptor(type_)
+
+
+class NmsLayer:
+    """caffe::NmsLayer<float> accessors (nms_layer.hpp:21-27)."""
+
+    def __init__(self, eng):
+        self._e = eng
+
+    def type(self):
+        return "Nms"
+
+    def GetMaxPeaks(self):
+        return lib().pe_nms_get_max_peaks(self._e._h)
+
+    def GetNumParts(self):
+        return lib().pe_nms_get_num_parts(self._e._h)
+
+    def GetThreshold(self):
+        return lib().pe_nms_get_threshold(self._e._h)
+
+    def SetThreshold(self, t):
+        self._e._ck(lib().pe_nms_set_threshold(self._e._h, float(t)))
+
+
+class ImResizeLayer:
+    """caffe::ImResizeLayer<float> accessors (imresize_layer.hpp:20-29)."""
+
+    def __init__(self, eng):
+        self._e = eng
+
+    def type(self):
+        return "ImResize"
+
+    def SetStartScale(self, s):
+        self._e._ck(lib().pe_resize_set_start_scale(self._e._h, float(s)))
+
+    def SetScaleGap(self, g):
+        self._e._ck(lib().pe_resize_set_scale_gap(self._e._h, float(g)))
+
+    def GetStartScale(self):
+        return lib().pe_resize_get_start_scale(self._e._h)
+
+    def GetScaleGap(self):
+        return lib().pe_resize_get_scale_gap(self._e._h)
+
+
+class PoseEngine:
+    """One GPU worker (the reference's NetCopy + warmup(), rtpose.cpp:133-142, 173-237)."""
+
+    def __init__(self, model=COCO_18, net_w=656, net_h=368, disp_w=1280, disp_h=720, num_scales=1, start_scale=1.0,
+                 scale_gap=0.3, device=0, max_batch=1, precision=PREC_BF16X2):
+        L = lib()
+        cfg = _Config(device, model, net_w, net_h, disp_w, disp_h, num_scales, start_scale, scale_gap, max_batch, precision)
+        h = C.c_void_p()
+        rc = L.pe_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise PoseEngineError("pe_create failed (%d): %s" % (rc, L.pe_last_error(None).decode()))
+        self._h = h
+        self.cfg = cfg
+        self.model = model
+        self.num_parts = L.pe_nms_get_num_parts(h)
+        self.max_peaks = L.pe_nms_get_max_peaks(h)
+        self.num_maps = self.num_parts + 1 + 2 * L.pe_model_num_limbs(model)
+        self.nms_layer = NmsLayer(self)
+        self.resize_layer = ImResizeLayer(self)
+        self.model_descriptor = ModelDescriptorFactory.createModelDescriptor(model)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PoseEngineError("poseengine error %d: %s" % (rc, lib().pe_last_error(self._h).decode()))
+
+    # ---- weights (Net::CopyTrainedLayersFrom) -------------------------------------------------
+    def conv_layers(self):
+        L = lib()
+        out = []
+        name = C.create_string_buffer(64)
+        a, b, k = C.c_int(), C.c_int(), C.c_int()
+        for i in range(L.pe_num_conv_layers(self._h)):
+            self._ck(L.pe_conv_layer_info(self._h, i, name, C.byref(a), C.byref(b), C.byref(k)))
+            out.append((name.value.decode(), a.value, b.value, k.value))
+        return out
+
+    def set_weights(self, weights, commit=True):
+        for name, (w, b) in weights.items():
+            w = np.ascontiguousarray(w, np.float32)
+            b = np.ascontiguousarray(b, np.float32)
+            self._ck(lib().pe_set_conv_weights(self._h, name.encode(), w, w.size, b, b.size))
+        if commit:
+            self.commit_weights()
+
+    def load_weights_file(self, path, commit=True):
+        self._ck(lib().pe_load_weights_file(self._h, path.encode()))
+        if commit:
+            self.commit_weights()
+
+    def commit_weights(self):
+        self._ck(lib().pe_commit_weights(self._h))
+
+    def set_connect_params(self, min_subset_cnt, min_subset_score, inter_threshold, inter_min_above):
+        self._ck(lib().pe_set_connect_params(self._h, min_subset_cnt, min_subset_score, inter_threshold, inter_min_above))
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward_frames(self, frames):
+        """frames: list of uint8 BGR HWC display images (host)."""
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        for f in frames:
+            assert f.shape == (self.cfg.disp_h, self.cfg.disp_w, 3), f.shape
+        ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+        self._keep = frames
+        self._ck(lib().pe_forward_frames(self._h, ptrs, len(frames)))
+
+    def forward_frames_device(self, dev_ptr, n):
+        self._ck(lib().pe_forward_frames_device(self._h, C.c_void_p(dev_ptr), n))
+
+    def forward_net_input(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        n = x.shape[0] // self.cfg.num_scales
+        assert x.shape == (n * self.cfg.num_scales, 3, self.cfg.net_h, self.cfg.net_w), x.shape
+        self._ck(lib().pe_forward_net_input(self._h, x, n))
+
+    def forward_maps(self, maps8):
+        maps8 = np.ascontiguousarray(maps8, np.float32)
+        n = maps8.shape[0] // self.cfg.num_scales
+        assert maps8.shape == (n * self.cfg.num_scales, self.num_maps, self.cfg.net_h // 8, self.cfg.net_w // 8), maps8.shape
+        self._ck(lib().pe_forward_maps(self._h, maps8, n))
+
+    def sync(self):
+        self._ck(lib().pe_sync(self._h))
+
+    def fetch(self, idx=0):
+        joints = np.zeros((MAX_PEOPLE, self.num_parts, 3), np.float32)
+        peaks = np.zeros((self.num_parts, self.max_peaks + 1, 3), np.float32)
+        n = C.c_int()
+        self._ck(lib().pe_fetch(self._h, idx, joints, C.byref(n), peaks.ctypes.data_as(C.c_void_p)))
+        return n.value, joints[:n.value].copy(), peaks
+
+    def fetch_maps(self, n=1):
+        out = np.zeros((n * self.cfg.num_scales, self.num_maps, self.cfg.net_h // 8, self.cfg.net_w // 8), np.float32)
+        self._ck(lib().pe_fetch_maps(self._h, out, n))
+        return out
+
+    def fetch_blob(self, name):
+        c, h, w = C.c_int(), C.c_int(), C.c_int()
+        self._ck(lib().pe_fetch_blob(self._h, name.encode(), None, 0, C.byref(c), C.byref(h), C.byref(w)))
+        # number of images of the last forward is not exported; over-allocate for max_batch
+        n = self.cfg.max_batch * self.cfg.num_scales
+        out = np.zeros((n, c.value, h.value, w.value), np.float32)
+        self._ck(lib().pe_fetch_blob(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), out.size, C.byref(c),
+                                     C.byref(h), C.byref(w)))
+        return out
+
+    def json(self, joints, frame_scale=1.0):
+        return write_json(joints, self.num_parts, frame_scale)
+
+    # ---- measurement --------------------------------------------------------------------------
+    def event_record(self, slot):
+        self._ck(lib().pe_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._ck(lib().pe_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+    def profile_layers(self, n=1):
+        cap = 256
+        ms = np.zeros(cap, np.float32)
+        names = C.create_string_buffer(64 * cap)
+        flops = np.zeros(cap, np.float64)
+        k = lib().pe_profile_layers(self._h, n, ms, names, flops.ctypes.data_as(C.c_void_p), cap)
+        if k < 0:
+            self._ck(-k)
+        raw = names.raw
+        return [(raw[64 * i:64 * (i + 1)].split(b"\0")[0].decode(), float(ms[i]), float(flops[i])) for i in range(k)]
+
+    def launch_count(self):
+        return lib().pe_launch_count(self._h)
+
+    def conv_flops_per_scale(self):
+        return lib().pe_conv_flops_per_scale(self._h)
+
+    def packed_weights(self):
+        return lib().pe_packed_weights_device_ptr(self._h), lib().pe_packed_weights_bytes(self._h)
+
+
+def write_json(joints, num_parts, frame_scale=1.0):
+    """displayFrame's JSON writer (rtpose.cpp:1383-1416)."""
+    joints = np.ascontiguousarray(joints, np.float32).reshape(-1, num_parts, 3)
+    cap = 64 + joints.shape[0] * (num_parts * 48 + 32)
+    buf = C.create_string_buffer(cap)
+    src = joints if joints.size else np.zeros(1, np.float32)
+    n = lib().pe_write_json(src, joints.shape[0], num_parts, frame_scale, buf, cap)
+    assert n < cap
+    return buf.value.decode()
+
+
+def write_weights_file(path, weights, table):
+    """Flat RTPW v1 file (see pe_load_weights_file)."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(b"RTPW" + struct.pack("<II", 1, len(table)))
+        for name, co, ci, k in table:
+            w, b = weights[name]
+            f.write(name.encode().ljust(64, b"\0") + struct.pack("<III", co, ci, k))
+            f.write(np.ascontiguousarray(w, np.float32).tobytes())
+            f.write(np.ascontiguousarray(b, np.float32).tobytes())

@@ -1,0 +1,138 @@
+/* poseengine.h - C ABI of libposeengine.so, the B200-native drop-in for the hot path of
+ * examples/rtpose (CMU-Perceptual-Computing-Lab/caffe_rtpose).
+ *
+ * Every entry point below replaces a call that examples/rtpose/rtpose.cpp makes into Caffe / its own
+ * host code for the per-frame path; the reference site is cited on each.
+ * Plain C: opaque handle, plain pointers and sizes, int return codes (0 = PE_OK), no exceptions,
+ * no torch / CUDA types.  One handle per GPU worker thread (as the reference keeps one caffe::Net per
+ * thread, rtpose.cpp:183); calls on one handle must not be concurrent.
+ *
+ * There is NO CPU fallback: every call needs the CUDA device named at pe_create.
+ */
+#ifndef POSEENGINE_H
+#define POSEENGINE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PE_OK 0
+#define PE_ERR_INVALID 1   /* bad argument / unsupported configuration */
+#define PE_ERR_CUDA 2      /* CUDA runtime / driver failure (message in pe_last_error) */
+#define PE_ERR_STATE 3     /* call out of order (e.g. forward before weights) */
+#define PE_ERR_IO 4        /* file could not be read / parsed */
+
+#define PE_MODEL_MPI_15 0  /* ModelDescriptorFactory::Type::MPI_15  (modelDescriptorFactory.h:16-19) */
+#define PE_MODEL_COCO_18 1 /* ModelDescriptorFactory::Type::COCO_18 */
+
+/* arithmetic of the convolution stack */
+#define PE_PREC_FP32_SIMT 0 /* fp32 FFMA implicit GEMM (CUDA cores) - the exact-fp32 debugging reference */
+#define PE_PREC_BF16X1 1    /* tcgen05 bf16 x bf16 -> fp32 (fast, NOT parity grade) */
+#define PE_PREC_BF16X2 2    /* tcgen05, activations/weights split in 2 bf16 planes, 3 MMAs (~2^-16) */
+#define PE_PREC_BF16X3 3    /* tcgen05, 3 planes, 6 MMAs (~fp32) */
+
+#define PE_MAX_PEOPLE 96   /* RENDER_MAX_PEOPLE, renderFunctions.h:6 / rtpose.cpp:88 */
+
+typedef struct pe_engine pe_engine;
+
+typedef struct pe_config {
+    int device;          /* CUDA ordinal; Caffe::SetDevice(device_id)                 rtpose.cpp:178 */
+    int model;           /* PE_MODEL_*; the reference infers it from nms num_parts    rtpose.cpp:212-229 */
+    int net_w, net_h;    /* --net_resolution (multiples of 8)                          rtpose.cpp:64,1693 */
+    int disp_w, disp_h;  /* --resolution: joints are reported in display pixels        rtpose.cpp:63,1058-1062 */
+    int num_scales;      /* --num_scales == blob dim 0 of one forward                  rtpose.cpp:71,188 */
+    double start_scale;  /* --start_scale                                              rtpose.cpp:69 */
+    double scale_gap;    /* --scale_gap                                                rtpose.cpp:70 */
+    int max_batch;       /* frames per forward on this GPU (1 = the reference's behaviour) */
+    int precision;       /* PE_PREC_* */
+} pe_config;
+
+/* new caffe::Net(proto, TEST) + Reshape + warmup()                          rtpose.cpp:173-237 */
+int pe_create(const pe_config* cfg, pe_engine** out);
+void pe_destroy(pe_engine* e);
+/* last error text of this handle (or of the failed pe_create when e == NULL) */
+const char* pe_last_error(const pe_engine* e);
+
+/* ---- weights: Net::CopyTrainedLayersFrom                                   rtpose.cpp:184, net.cpp:750-803
+ * Layers are matched by name; w is (Cout, Cin, kh, kw) row-major fp32, b is (Cout)  (base_conv_layer.cpp:135-142). */
+int pe_num_conv_layers(const pe_engine* e);
+int pe_conv_layer_info(const pe_engine* e, int idx, char* name64, int* cout, int* cin, int* ksize);
+int pe_set_conv_weights(pe_engine* e, const char* layer_name, const float* w, size_t nw, const float* b, size_t nb);
+/* flat file: "RTPW" u32 version=1 u32 nlayers { char name[64]; u32 cout,cin,k; f32 w[]; f32 b[] } */
+int pe_load_weights_file(pe_engine* e, const char* path);
+/* pack + upload; must be called once after the weights are set and before any forward */
+int pe_commit_weights(pe_engine* e);
+
+/* ---- caffe::NmsLayer<float> accessors                                      nms_layer.hpp:24-27, rtpose.cpp:195,207,1145 */
+int pe_nms_get_max_peaks(const pe_engine* e);
+int pe_nms_get_num_parts(const pe_engine* e);
+float pe_nms_get_threshold(const pe_engine* e);
+int pe_nms_set_threshold(pe_engine* e, float threshold);
+/* ---- caffe::ImResizeLayer<float> accessors                                 imresize_layer.hpp:24-29, rtpose.cpp:201-202 */
+int pe_resize_set_start_scale(pe_engine* e, float start_scale);
+int pe_resize_set_scale_gap(pe_engine* e, float scale_gap);
+float pe_resize_get_start_scale(const pe_engine* e);
+float pe_resize_get_scale_gap(const pe_engine* e);
+/* ---- global.connect_* thresholds                                           rtpose.cpp:106-111, 212-226 */
+int pe_set_connect_params(pe_engine* e, int min_subset_cnt, float min_subset_score, float inter_threshold,
+                          int inter_min_above_threshold);
+
+/* ---- per-frame hot loop (processFrame, rtpose.cpp:1099-1203).  All forwards are asynchronous on the
+ * engine's stream; pe_fetch* synchronises.  n <= max_batch frames per call.
+ *
+ * pe_forward_frames: HOST display images, uint8 BGR HWC disp_h x disp_w (what getFrameFromCam holds after
+ * warpAffine, rtpose.cpp:484).  Does H2D + the scale loop / INTER_AREA / pad / normalise of rtpose.cpp:508-518
+ * on the GPU + net + resize + NMS + connectLimbs*. */
+int pe_forward_frames(pe_engine* e, const uint8_t* const* frames, int n);
+/* same, frames already resident in device memory (n consecutive disp_h*disp_w*3 images) */
+int pe_forward_frames_device(pe_engine* e, const void* d_frames, int n);
+/* HOST net input as the reference uploads it: n x num_scales x 3 x net_h x net_w fp32 planar
+ * (frame.data, rtpose.cpp:1131-1133) */
+int pe_forward_net_input(pe_engine* e, const float* net_input, int n);
+/* test hook at the concat_stage7 boundary: HOST stride-8 maps n x num_scales x C x net_h/8 x net_w/8;
+ * runs resize + NMS + connectLimbs* only (SURVEY.md section 8d "map injection") */
+int pe_forward_maps(pe_engine* e, const float* maps8, int n);
+
+/* results of frame `idx` of the last forward.  joints: PE_MAX_PEOPLE x num_parts x 3 (x,y in display pixels,
+ * score) as connectLimbs* fills it (rtpose.cpp:1051-1073); peaks (optional): the NMS top blob
+ * num_parts x (max_peaks+1) x 3 (nms_layer.cpp:17-29), count in [part][0][0]. */
+int pe_fetch(pe_engine* e, int idx, float* joints, int* num_people, float* peaks);
+/* stride-8 net output of the last forward, n x num_scales x C x net_h/8 x net_w/8 (blob "concat_stage7") */
+int pe_fetch_maps(pe_engine* e, float* maps8, int n);
+/* debugging / layer-wise parity: NCHW fp32 copy of an intermediate blob by its prototxt top name */
+int pe_fetch_blob(pe_engine* e, const char* blob_name, float* out, size_t cap, int* c, int* h, int* w);
+/* block until the engine's stream is idle */
+int pe_sync(pe_engine* e);
+
+/* JSON writer of displayFrame (rtpose.cpp:1383-1416).  Returns the text length (writes if < cap). */
+int pe_write_json(const float* joints, int num_people, int num_parts, double frame_scale, char* buf, int cap);
+
+/* ---- model descriptor tables (modelDescriptorFactory.cpp:6-28,30-55) */
+int pe_model_num_parts(int model);
+int pe_model_num_limbs(int model);
+const int* pe_model_limb_sequence(int model);
+const int* pe_model_map_idx(int model);
+const char* pe_model_part_name(int model, int idx);
+
+/* ---- measurement support (bench.py) */
+/* device time, CUDA events on the engine stream: slot in [0,16) */
+int pe_event_record(pe_engine* e, int slot);
+int pe_event_elapsed_ms(pe_engine* e, int slot_a, int slot_b, float* ms);
+/* one instrumented forward of the last-submitted batch: per conv-layer device ms (events between launches).
+ * names: 64 bytes per layer.  Returns the number of ops written (<= cap). */
+int pe_profile_layers(pe_engine* e, int n, float* ms, char* names, double* flops, int cap);
+/* kernels launched by this handle since creation (for the bench's gpu_launches claim) */
+long long pe_launch_count(const pe_engine* e);
+/* algorithmic conv FLOPs of one frame-scale at the configured net size */
+double pe_conv_flops_per_scale(const pe_engine* e);
+/* one-time weight replica broadcast for --num_gpu N frame sharding (rank 0's packed weights -> all):
+ * exports / imports the packed device buffer so that the host layer (NCCL via torch.distributed or
+ * ncclBroadcast in rtpose.bin) can move it.  Returns size in bytes. */
+size_t pe_packed_weights_bytes(const pe_engine* e);
+void* pe_packed_weights_device_ptr(pe_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
