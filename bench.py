@@ -1,0 +1,326 @@
+#!/usr/bin/env python3
+"""bench.py - frames/sec of the rtpose hot path at 656x368 COCO-18 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            one rank per GPU (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle) on the host cores
+
+Workload (config.workload = "C2"): COCO model, net 656x368, 1 scale, synthetic 1280x720 uint8 BGR stream
+(64 distinct frames, 177 MB > L2), random-init "W-he" weights, B frames per forward.
+A step = one forward of B frames per GPU through the whole path: INTER_AREA/pad/normalise, the 92-conv
+stack, fused resize+NMS, PAF integral + greedy assignment + assembly, results to pinned host memory.
+
+  value     frames/s, all GPUs, frames already resident in HBM (pe_forward_frames_device)
+  e2e       frames/s through the public C-ABI call with HOST (pinned) frames: H2D of every frame and D2H of
+            joints/peaks inside the timed region, two handles per GPU so copies overlap compute
+  roofline  conv stack (tcgen05 kernel, all its launches of one step): algorithmic FLOPs / device time
+            from CUDA events on the engine stream, vs the measured bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle (Caffe CPU arithmetic, im2col + OpenBLAS sgemm, all host cores) on one full frame
+Frames are sharded one-per-GPU; the only collective is the init broadcast of the packed weights (NCCL).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NET_W, NET_H, DISP_W, DISP_H = 656, 368, 1280, 720
+N_FRAMES = 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="frames per forward per GPU")
+    ap.add_argument("--precision", type=int, default=2, help="0 fp32 SIMT, 1 bf16, 2 bf16x2 (parity mode), 3 bf16x3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks_info():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured"
+    return 1400.0, 6650.0, "fallback"  # B200_PROFILING.md fallback (sustained), "of fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_full_frame(model, weights, frame):
+    """The oracle (reference CPU path restated) on ONE full frame with every host core; ~10-30 s of CPU work."""
+    from oracle import orc
+    net = orc.Net(model)
+    net.set_weights(weights)
+    band = frame[:96]
+    net.process_frame(np.ascontiguousarray(band), 48, NET_W)  # warm-up on a band (BLAS threads, page faults)
+    t = time.time()
+    cnt, joints, peaks, _ = net.process_frame(frame, NET_H, NET_W)
+    dt = time.time() - t
+    return {"value": 1.0 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 full 1280x720 frame (net 656x368, 1 scale, whole path incl. resize/NMS/connect), %.1f s, after a "
+                      "656x48 band warm-up; im2col + OpenBLAS sgemm, %d threads" % (dt, os.cpu_count())}, (cnt, joints, peaks)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path = the oracle port (the reference
+    cannot be built here: no glog/gflags/boost/OpenCV-C++/protoc; its Forward_cpu for Nms/ImResize are
+    different algorithms - SURVEY.md section 0).  One step = one 656x48 BAND of a frame (13% of a frame) through
+    the whole path; frames/s is scaled by the band fraction.  Rank 0 only."""
+    if rank != 0:
+        return
+    from caffe_rtpose_b200 import synth
+    from oracle import orc
+    model = orc.COCO_18
+    W = synth.make_weights(model, "he")
+    net = orc.Net(model)
+    net.set_weights(W)
+    band_h = 48
+    disp_band = 96
+    frames = [np.ascontiguousarray(synth.make_frame(i)[:disp_band]) for i in range(4)]
+    frac = band_h / float(NET_H)
+    for i in range(args.warmup):
+        net.process_frame(frames[i % 4], band_h, NET_W)
+    t0 = time.time()
+    for i in range(args.steps):
+        net.process_frame(frames[i % 4], band_h, NET_W)
+    dt = time.time() - t0
+    fps = args.steps * frac / dt
+    line = {"metric": "frames/sec at 656x368 COCO-18", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "C2: COCO 656x368, 1 scale, synthetic 720p stream, W-he random-init weights",
+                       "step": "one 656x48 band (13.04% of a frame) through the whole CPU path; value scaled to full frames"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d steps x one 656x48 band of a 1280x720 frame, scaled by 48/368" % args.steps},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    from caffe_rtpose_b200 import engine, synth
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    model = engine.COCO_18
+    B = args.batch
+
+    # ---- engines: two handles per GPU (as the reference runs one Net per worker thread) so that the H2D of
+    # one batch overlaps the compute of the other in the end-to-end loop
+    engs = [engine.PoseEngine(model, NET_W, NET_H, DISP_W, DISP_H, device=local_rank, max_batch=B, precision=args.precision)
+            for _ in range(2)]
+    table = synth.conv_table(model)
+    if rank == 0:
+        W = synth.make_weights(model, "he")
+    else:  # layout only; the values arrive by broadcast
+        W = {name: (np.zeros((co, ci, k, k), np.float32), np.zeros(co, np.float32)) for name, co, ci, k in table}
+    for e in engs:
+        e.set_weights(W)
+    if world > 1:
+        # the ONE collective of the path: rank 0's packed weight replica -> every GPU over NVLink (NCCL)
+        class _Dev:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+        for e in engs:
+            ptr, nbytes = e.packed_weights()
+            t = torch.as_tensor(_Dev(ptr, nbytes), device="cuda")
+            dist.broadcast(t, src=0)
+        torch.cuda.synchronize()
+
+    # ---- frames: 64 distinct synthetic 720p frames, sharded round-robin over ranks; pinned host + device copies
+    frame_bytes = DISP_H * DISP_W * 3
+    host = torch.empty((N_FRAMES, DISP_H, DISP_W, 3), dtype=torch.uint8, pin_memory=True)
+    hnp = host.numpy()
+    for i in range(N_FRAMES):
+        hnp[i] = synth.make_frame(rank * N_FRAMES + i)
+    dev = host.cuda(non_blocking=False)
+    nb = N_FRAMES // B
+
+    def batch_dev(i):
+        return dev.data_ptr() + (i % nb) * B * frame_bytes
+
+    def batch_host(i):
+        j = (i % nb) * B
+        return [hnp[j + k] for k in range(B)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumreduce(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    e0 = engs[0]
+    # ---- (1) device-resident throughput
+    for i in range(args.warmup):
+        e0.forward_frames_device(batch_dev(i), B)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = sum(e.launch_count() for e in engs)
+    e0.event_record(0)
+    for i in range(args.steps):
+        e0.forward_frames_device(batch_dev(args.warmup + i), B)
+    e0.event_record(1)
+    barrier()
+    ms_dev = maxreduce(e0.event_elapsed_ms(0, 1))
+    launches = sumreduce(sum(e.launch_count() for e in engs) - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_dev * 1e-3)
+
+    # ---- (2) end to end through the public call: host frames in, joints out, every step
+    for i in range(2):
+        engs[i].forward_frames(batch_host(i))
+    for e in engs:
+        e.fetch(0)
+    barrier()
+    t0 = time.perf_counter()
+    got = 0
+    for i in range(args.steps):
+        e = engs[i % 2]
+        if i >= 2:
+            for k in range(B):
+                n, joints, _ = e.fetch(k)   # results of step i-2 (sync on that handle's stream only)
+            got += 1
+        e.forward_frames(batch_host(i))
+    for j in range(min(2, args.steps)):
+        e = engs[(args.steps - 1 - j) % 2]
+        for k in range(B):
+            e.fetch(k)
+        got += 1
+    torch.cuda.synchronize()
+    dt_e2e = maxreduce(time.perf_counter() - t0)
+    assert got == args.steps
+    e2e = world * B * args.steps / dt_e2e
+    P, MP = e0.num_parts, e0.max_peaks
+    d2h = B * (engine.MAX_PEOPLE * P * 3 * 4 + 4 + P * (MP + 1) * 3 * 4)
+
+    if rank == 0:
+        # ---- (3) roofline of the dominant kernel (conv stack), instrumented pass with events between launches
+        e0.forward_frames_device(batch_dev(0), B)
+        e0.sync()
+        prof = e0.profile_layers(B)
+        conv = [(n, ms, fl) for (n, ms, fl) in prof if fl > 0]
+        conv_ms = sum(ms for _, ms, _ in conv)
+        conv_flops = sum(fl for _, _, fl in conv)
+        other_ms = sum(ms for _, ms, fl in prof if fl == 0)
+        peak, _, how = peaks_info()
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+        step_ms = ms_dev / args.steps
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": "%s (bf16 dense, sustained)" % how,
+                    "kernel": "pe::conv_tc_kernel<BN,PLANES,STAGES> (tcgen05/TMEM/TMA), %d launches per step" % len(conv),
+                    "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "avg_launch_us": 1e3 * conv_ms / len(conv),
+                    "share_of_step": conv_ms / step_ms, "other_layer_ms_per_step": other_ms,
+                    "note": "algorithmic FLOPs (2*Cout*Cin*k^2*H*W); precision mode %d issues %d tensor-core MMAs per "
+                            "algorithmic MAC" % (args.precision, {0: 0, 1: 1, 2: 3, 3: 6}[args.precision])}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu, (ocnt, ojoints, opeaks) = cpu_baseline_full_frame(model, W, hnp[0])
+            e1 = engs[1]
+            e1.forward_frames([hnp[0]])
+            cnt, joints, peaks = e1.fetch(0)
+            cpu["parity_note"] = "frame 0: people engine/oracle %d/%d, peaks found %d/%d" % (
+                cnt, ocnt, int(peaks[:, 0, 0].sum()), int(opeaks[:, 0, 0].sum()))
+        line = {"metric": "frames/sec at 656x368 COCO-18", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": {0: "f32", 1: "bf16", 2: "bf16x2 (split, fp32 accumulate)", 3: "bf16x3 (split, fp32 accumulate)"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": "C2: COCO 656x368, 1 scale, synthetic 720p stream, W-he random-init weights",
+                           "frames_per_step_per_gpu": B, "precision_mode": args.precision, "sharding": "frames round-robin, one rank per GPU",
+                           "l2": "64 distinct frames (177 MB) cycled > 126 MB L2; activations of one step >> L2",
+                           "collective": "init broadcast of packed weights only (NCCL)" if world > 1 else "none"},
+                "clocks": clocks,
+                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": d2h,
+                        "how": "pe_forward_frames (pinned host frames) + pe_fetch every step, two handles per GPU, wall clock max over ranks"},
+                "gpu_launches": int(launches),
+                "roofline": roofline}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    for e in engs:
+        e.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

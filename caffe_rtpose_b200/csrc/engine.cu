@@ -544,9 +544,22 @@ extern "C" int pe_forward_frames(pe_engine* e, const uint8_t* const* frames, int
     if (!frames) return fail(e, PE_ERR_INVALID, "null frames");
     CK(e, cudaSetDevice(e->cfg.device));
     const size_t fb = (size_t)e->cfg.disp_w * e->cfg.disp_h * 3;
-    CK(e, cudaStreamSynchronize(e->stream));  // the pinned staging buffer is reused
-    for (int i = 0; i < n; i++) memcpy(e->h_frames + i * fb, frames[i], fb);
-    CK(e, cudaMemcpyAsync(e->d_frames, e->h_frames, fb * n, cudaMemcpyHostToDevice, e->stream));
+    // Page-locked caller buffers are DMA'd directly (fully asynchronous); pageable ones go through the
+    // engine's pinned staging buffer, which forces a stream sync because that buffer is reused.
+    bool pinned = true;
+    for (int i = 0; i < n && pinned; i++) {
+        cudaPointerAttributes at;
+        if (!frames[i]) return fail(e, PE_ERR_INVALID, "null frame %d", i);
+        if (cudaPointerGetAttributes(&at, frames[i]) != cudaSuccess || at.type != cudaMemoryTypeHost) { pinned = false; cudaGetLastError(); }
+    }
+    if (pinned) {
+        for (int i = 0; i < n; i++)
+            CK(e, cudaMemcpyAsync(e->d_frames + i * fb, frames[i], fb, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        CK(e, cudaStreamSynchronize(e->stream));
+        for (int i = 0; i < n; i++) memcpy(e->h_frames + i * fb, frames[i], fb);
+        CK(e, cudaMemcpyAsync(e->d_frames, e->h_frames, fb * n, cudaMemcpyHostToDevice, e->stream));
+    }
     return pe_forward_frames_device(e, e->d_frames, n);
 }
 extern "C" int pe_forward_net_input(pe_engine* e, const float* net_input, int n) {

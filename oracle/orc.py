@@ -48,10 +48,18 @@ def find_blas():
     import site
     roots = site.getsitepackages() + [os.path.dirname(os.path.dirname(np.__file__))]
     for r in roots:
-        for pat in ("opencv_python_headless.libs/libopenblas*.so*", "scipy.libs/libscipy_openblas-*.so",
-                    "scipy.libs/libscipy_openblas*.so"):
+        # scipy's OpenBLAS (LP64, exports scipy_cblas_sgemm) is self-contained; the one bundled with
+        # opencv needs its sibling libgfortran/libquadmath preloaded.
+        for pat in ("scipy.libs/libscipy_openblas-*.so", "opencv_python_headless.libs/libopenblas*.so*"):
             hits = sorted(glob.glob(os.path.join(r, pat)))
             if hits:
+                if "opencv" in pat:
+                    for dep in ("libquadmath*", "libgfortran*"):
+                        for d in sorted(glob.glob(os.path.join(os.path.dirname(hits[0]), dep))):
+                            try:
+                                C.CDLL(d, mode=C.RTLD_GLOBAL)
+                            except OSError:
+                                pass
                 return hits[0]
     return None
 
@@ -101,6 +109,7 @@ def lib():
     blas = find_blas()
     if blas:
         L.orc_load_blas(blas.encode())
+    L.orc_set_threads(os.cpu_count() or 1)
     _lib = L
     return L
 

@@ -1,0 +1,73 @@
+"""CPU tests of the drop-in boundary: libposeengine.so loads, exports every symbol include/poseengine.h
+declares, fails loudly without a GPU (no CPU fallback), and its host-only entry points (JSON writer, model
+descriptor tables) match the oracle and the reference's own modelDescriptorFactory.cpp."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from caffe_rtpose_b200 import engine, synth
+from oracle import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "poseengine.h")).read()
+    declared = sorted(set(re.findall(r"\b(pe_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 35
+    L = C.CDLL(engine.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), "missing export %s" % name
+    assert sorted(engine.ABI_SYMBOLS) == declared
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(engine.PoseEngineError, match="no CPU fallback"):
+        engine.PoseEngine()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "caffe_rtpose_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("(see oracle.cpp)", "").replace("the oracle", "").replace("to the oracle", ""), f
+
+
+@pytest.mark.parametrize("model", [engine.MPI_15, engine.COCO_18])
+def test_model_descriptor_api(model):
+    md = engine.ModelDescriptorFactory.createModelDescriptor(model)
+    assert md.get_number_parts() == orc.num_parts(model)
+    assert md.number_limb_sequence() == len(orc.limb_seq(model)) // 2
+    assert md.get_limb_sequence() == orc.limb_seq(model)
+    assert md.get_map_idx() == orc.map_idx(model)
+    n = md.get_number_parts() + 1 + 2 * md.number_limb_sequence()
+    assert [md.get_part_name(i) for i in range(n)] == [orc.lib().orc_model_map_name(model, i).decode() for i in range(n)]
+    with pytest.raises(IndexError):
+        md.get_part_name(n)
+    with pytest.raises(RuntimeError):
+        engine.ModelDescriptorFactory.createModelDescriptor(7)
+
+
+def test_json_writer_matches_oracle():
+    rng = np.random.default_rng(0)
+    j = (rng.uniform(0, 1300, (3, 18, 3))).astype(np.float32)
+    j[1, 4] = 0
+    for scale in (1.0, 0.5, 1.7777):
+        assert engine.write_json(j, 18, scale) == orc.json_text(j, 18, scale)
+    assert engine.write_json(np.zeros((0, 15, 3), np.float32), 15) == orc.json_text(np.zeros((0, 15, 3), np.float32), 15)
+
+
+def test_weight_file_roundtrip(tmp_path):
+    w = synth.make_weights(engine.MPI_15, "caffe")
+    p = str(tmp_path / "w.rtpw")
+    engine.write_weights_file(p, w, synth.conv_table(engine.MPI_15))
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"RTPW" and len(raw) > 4 * 51000000

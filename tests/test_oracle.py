@@ -171,7 +171,7 @@ def test_stage_goldens(name, golden_dir):
     assert orc.json_text(joints, orc.num_parts(model)) == str(g["json"])
 
 
-@pytest.mark.parametrize("model,net_w,net_h,n", [(orc.COCO_18, 328, 184, 8), (orc.MPI_15, 248, 184, 5), (orc.COCO_18, 656, 368, 22)])
+@pytest.mark.parametrize("model,net_w,net_h,n", [(orc.COCO_18, 320, 176, 8), (orc.MPI_15, 240, 176, 5), (orc.COCO_18, 656, 368, 22)])
 def test_connect_vs_reference_code(model, net_w, net_h, n):
     if orc.ref_host() is None:
         pytest.skip("oracle/_ref not built")
@@ -193,7 +193,7 @@ def test_connect_special_cases_vs_reference_code():
     """nA==0 / nB==0 singleton rows, duplicate check (COCO only), nothing at all."""
     if orc.ref_host() is None:
         pytest.skip("oracle/_ref not built")
-    for model, net_w, net_h in [(orc.COCO_18, 328, 184), (orc.MPI_15, 248, 184)]:
+    for model, net_w, net_h in [(orc.COCO_18, 320, 176), (orc.MPI_15, 240, 176)]:
         P, mp = orc.num_parts(model), orc.max_peaks(model)
         thr, p = orc.default_params(model)
         p0 = orc.ConnectParams(p.min_subset_cnt, p.min_subset_score, p.inter_threshold, p.inter_min_above, 0)

@@ -56,9 +56,9 @@ def gen_parse(model, name, net_w, net_h, disp_w, disp_h, n_people, num_scales, s
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_area()
-    gen_parse(orc.COCO_18, "coco", 328, 184, 640, 360, 6, 1, 11)
-    gen_parse(orc.COCO_18, "coco_s3", 328, 184, 640, 360, 5, 3, 12)
-    gen_parse(orc.MPI_15, "mpi", 248, 184, 320, 240, 4, 1, 13)
+    gen_parse(orc.COCO_18, "coco", 320, 176, 640, 352, 6, 1, 11)
+    gen_parse(orc.COCO_18, "coco_s3", 320, 176, 640, 352, 5, 3, 12)
+    gen_parse(orc.MPI_15, "mpi", 240, 176, 480, 352, 4, 1, 13)
 
 
 if __name__ == "__main__":
