@@ -22,6 +22,7 @@
 //   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
 //     (each owns the TMEM lane quadrant warp_id % 4).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -38,6 +39,7 @@ struct TcArgs {
     int ksize, pad, kblocks_per_tap, cin_k;   // cin_k = channels per tap in the weight K ordering
     int W, H, Wp, Hs;
     long long M;
+    int base_off_mode;   // window kernel: 1 = set the descriptor base_offset field for row-shifted A operands
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -107,6 +109,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
+}
+// Same, for an operand whose first row is NOT on a 1024-byte swizzle-atom boundary (row-shifted view of a
+// larger tile): base_offset field [49,52) = (start address >> 7) & 7 (PTX ISA, tcgen05 matrix descriptor).
+__device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, uint32_t base_off) {
+    return umma_desc(saddr) | ((uint64_t)(base_off & 7u) << 49);
 }
 // instruction descriptor kind::f16 (InstrDescriptor): c_format F32 (bit 4), a/b format BF16 (bits 7,10),
 // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
@@ -272,6 +279,191 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Window variant (default): the A tiles of the k taps of one filter row are 1-row shifts of each other in the
+// flat padded layout, so ONE TMA box of 128+k-1 (rounded to 136) rows per (filter row, channel block) feeds
+// all k taps through row-shifted UMMA descriptors.  A traffic from L2 drops k-fold (7x for the 7x7 layers that
+// are 68 % of the FLOPs); A windows and per-tap B tiles run in two independent mbarrier rings.
+// Split precision P=2 uses N-concatenation: MMA1 = A_hi x [B_hi;B_lo] (N = 2*BN, TMEM columns [0,BN) = hi*hi,
+// [BN,2BN) = hi*lo) and MMA2 = A_lo x B_hi accumulated into [BN,2BN): 2 instructions instead of 3 per K=16
+// step, A_hi read once, and the large hi*hi chain sits alone in its accumulator (the tensor core's fp32
+// accumulation truncates, so a shorter chain per accumulator is also more accurate).  The epilogue adds the
+// two accumulators in fp32.
+// ------------------------------------------------------------------------------------------------
+constexpr int TCW_ROWS = 136;                 // 128 + 7 - 1 rounded up to a multiple of 8
+constexpr int TCW_A_BYTES = TCW_ROWS * 128;   // 17408 = 17 * 1024
+
+template <int BN, int PLANES, int NA, int NB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    static_assert(PLANES == 1 || PLANES == 2, "window kernel supports 1 or 2 planes");
+    constexpr int B_BYTES = BN * 128;
+    constexpr int A_SLOT = PLANES * TCW_A_BYTES;
+    constexpr int B_SLOT = PLANES * B_BYTES;
+    constexpr int ACC_COLS = PLANES * BN;
+    constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : 256));
+    constexpr uint32_t IDESC1 = umma_idesc(TC_BM, PLANES * BN);   // A_hi x [B_hi;B_lo]
+    constexpr uint32_t IDESC2 = umma_idesc(TC_BM, BN);            // A_lo x B_hi
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + NA * A_SLOT;
+    __shared__ __align__(8) uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m0 = (long long)blockIdx.x * TC_BM;
+    const int n0 = blockIdx.y * BN;
+    const int ks = a.ksize;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer: windows and per-tap weight tiles in consumption order =====
+        int aw = 0, bt = 0;
+        for (int kb = 0; kb < a.kblocks_per_tap; kb++)
+            for (int r = 0; r < ks; r++) {
+                {
+                    const int s = aw % NA;
+                    mbar_wait(&a_empty[s], ((uint32_t)(aw / NA) & 1u) ^ 1u);
+                    mbar_expect_tx(&a_full[s], A_SLOT);
+                    const int row0 = (int)(m0 + (long long)(r - a.pad) * a.Wp - a.pad);
+#pragma unroll
+                    for (int p = 0; p < PLANES; p++)
+                        tma_load_3d(smem_a + s * A_SLOT + p * TCW_A_BYTES, &tmA, &a_full[s], kb * TC_BK, row0, p);
+                    aw++;
+                }
+                for (int q = 0; q < ks; q++) {
+                    const int s = bt % NB;
+                    mbar_wait(&b_empty[s], ((uint32_t)(bt / NB) & 1u) ^ 1u);
+                    mbar_expect_tx(&b_full[s], B_SLOT);
+                    const int tap = r * ks + q;
+#pragma unroll
+                    for (int p = 0; p < PLANES; p++)
+                        tma_load_3d(smem_b + s * B_SLOT + p * B_BYTES, &tmB, &b_full[s], tap * a.cin_k + kb * TC_BK, n0, p);
+                    bt++;
+                }
+            }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        int aw = 0, bt = 0;
+        bool first = true;
+        for (int kb = 0; kb < a.kblocks_per_tap; kb++)
+            for (int r = 0; r < ks; r++) {
+                const int sa_slot = aw % NA;
+                mbar_wait(&a_full[sa_slot], (uint32_t)(aw / NA) & 1u);
+                const uint32_t sa = smem_u32(smem_a + sa_slot * A_SLOT);
+                for (int q = 0; q < ks; q++) {
+                    const int sb_slot = bt % NB;
+                    mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem_b + sb_slot * B_SLOT);
+                    const uint32_t boff = a.base_off_mode ? (uint32_t)q : 0u;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++) {
+                        const uint64_t db = umma_desc(sb + k * 32);   // rows [0, PLANES*BN): B_hi then B_lo
+                        const uint64_t da0 = umma_desc_off(sa + q * 128 + k * 32, boff);
+                        umma_bf16(tmem_base, da0, db, IDESC1, first ? 0u : 1u);
+                        if (PLANES == 2) {
+                            const uint64_t da1 = umma_desc_off(sa + TCW_A_BYTES + q * 128 + k * 32, boff);
+                            umma_bf16(tmem_base + BN, da1, db, IDESC2, 1u);   // += A_lo x B_hi into the hi*lo columns
+                        }
+                        first = false;
+                    }
+                    umma_commit(&b_empty[sb_slot]);
+                    bt++;
+                }
+                umma_commit(&a_empty[sa_slot]);
+                aw++;
+            }
+        umma_commit(&tmem_full_bar);
+    } else if (warp >= 2) {
+        // ===== epilogue =====
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const int quad = warp & 3;
+        const long long m = m0 + quad * 32 + lane;
+        const int per_img = a.Hs * a.Wp;
+        bool valid = m < a.M;
+        int n = 0, y = 0, x = 0;
+        if (valid) {
+            n = (int)(m / per_img);
+            const int rem = (int)(m % per_img);
+            y = rem / a.Wp; x = rem % a.Wp;
+            valid = (x < a.W) && (y < a.H);
+        }
+        const int cout8 = (a.cout + 7) & ~7;
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16], r2[16];
+            __syncwarp();
+            tmem_ld16(trow + (uint32_t)c0, r);
+            if (PLANES == 2) tmem_ld16(trow + (uint32_t)(BN + c0), r2);
+            if (valid) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int co = n0 + c0 + j;
+                    float t = __uint_as_float(r[j]);
+                    if (PLANES == 2) t += __uint_as_float(r2[j]);
+                    t += (co < a.cout ? __ldg(a.bias + co) : 0.f);
+                    if (a.relu) t = fmaxf(t, 0.f);
+                    v[j] = t;
+                }
+                if (a.planar) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int co = n0 + c0 + j;
+                        if (co < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + co) * a.H + y) * a.W + x] = v[j];
+                    }
+                } else {
+                    uint32_t pk[PLANES][8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        float r0 = v[j], r1 = v[j + 1];
+#pragma unroll
+                        for (int p = 0; p < PLANES; p++) {
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(r0), h1 = __float2bfloat16_rn(r1);
+                            pk[p][j / 2] = pack_bf16(h0, h1);
+                            r0 = __fsub_rn(r0, __bfloat162float(h0));
+                            r1 = __fsub_rn(r1, __bfloat162float(h1));
+                        }
+                    }
+                    __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + n0 + c0;
+#pragma unroll
+                    for (int p = 0; p < PLANES; p++) {
+                        uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
+                        if (n0 + c0 < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+                        if (n0 + c0 + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -326,6 +518,30 @@ static int launch_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t 
     }
 }
 
+template <int BN, int PLANES, int NA, int NB>
+static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
+    auto kern = conv_tcw_kernel<BN, PLANES, NA, NB>;
+    static bool attr_set = false;
+    const int smem = NA * PLANES * TCW_A_BYTES + NB * PLANES * BN * 128 + 1024;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    const CUtensorMap* maps = (const CUtensorMap*)l.maps;
+    kern<<<grid, TC_THREADS, smem, st>>>(maps[2], maps[1], a);
+    return 1;
+}
+template <int BN>
+static int launch_win_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
+    if (l.d.planes == 1) return launch_win_inst<BN, 1, 3, (BN >= 128 ? 8 : 10)>(l, a, grid, st);
+    return launch_win_inst<BN, 2, 2, (BN >= 128 ? 4 : 6)>(l, a, grid, st);
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return -1; }
@@ -333,7 +549,7 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
     out.d = d;
     out.bn = tc_bn(d.cout_pad);
     CUtensorMap* maps = nullptr;
-    if (posix_memalign((void**)&maps, 64, 2 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
+    if (posix_memalign((void**)&maps, 64, 3 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
     const int taps = d.ksize * d.ksize;
     const cuuint64_t K = (cuuint64_t)taps * d.in_cused;
     {   // A: [planes][M][pitch] bf16, box {64, 128, 1}
@@ -345,6 +561,16 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r); free(maps); return -1; }
+    }
+    {   // A window: same tensor, box {64, 136, 1} (128 + k - 1 rows serve the k taps of one filter row)
+        cuuint64_t dims[3] = {(cuuint64_t)d.in_cused, (cuuint64_t)d.geo.M, (cuuint64_t)d.planes};
+        cuuint64_t strides[2] = {(cuuint64_t)d.in_pitch * 2, (cuuint64_t)d.in_plane * 2};
+        cuuint32_t box[3] = {TC_BK, TCW_ROWS, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&maps[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d.in, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(A window) failed: " + std::to_string((int)r); free(maps); return -1; }
     }
     {   // B: [planes][cout_pad][K] bf16, box {64, BN, 1}
         cuuint64_t dims[3] = {K, (cuuint64_t)d.cout_pad, (cuuint64_t)d.planes};
@@ -378,6 +604,18 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
     a.W = d.geo.W; a.H = d.geo.H; a.Wp = d.geo.Wp; a.Hs = d.geo.Hs;
     a.M = (long long)nimg * d.geo.Hs * d.geo.Wp;
     dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), (unsigned)(d.cout_pad / l.bn));
+    static const int variant = env_int("PE_TC_VARIANT", 1);     // 1: window kernel, 0: one TMA tile per tap
+    static const int baseoff = env_int("PE_TC_BASEOFF", 1);
+    a.base_off_mode = baseoff;
+    if (variant == 1 && d.planes <= 2) {
+        switch (l.bn) {
+            case 128: return launch_win_bn<128>(l, a, grid, st);
+            case 64: return launch_win_bn<64>(l, a, grid, st);
+            case 48: return launch_win_bn<48>(l, a, grid, st);
+            case 32: return launch_win_bn<32>(l, a, grid, st);
+            default: return launch_win_bn<16>(l, a, grid, st);
+        }
+    }
     switch (l.bn) {
         case 128: return launch_bn<128>(l, a, grid, st);
         case 64: return launch_bn<64>(l, a, grid, st);

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) pool_f32_kernel(PoolArgs a) {
 }
 
 __global__ void __launch_bounds__(256) pool_bf16_kernel(PoolArgs a) {
-    const int cv = a.C / 2;  // bf16x2 groups
+    const int cv = a.C / 8;  // 8 channels (16 bytes) per thread and plane
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rows_out = (long long)a.N * a.Hso * a.Wpo;
     if (idx >= rows_out * cv) return;
@@ -45,27 +45,39 @@ __global__ void __launch_bounds__(256) pool_bf16_kernel(PoolArgs a) {
     const int rem = (int)(mo % ((long long)a.Hso * a.Wpo));
     const int yo = rem / a.Wpo, xo = rem % a.Wpo;
     if (xo >= a.Wo || yo >= a.Ho) return;
-    float bx = -3.402823466e+38F, by = -3.402823466e+38F;
-    __nv_bfloat162 px[3], py[3];
-    for (int p = 0; p < 3; p++) { px[p] = __float2bfloat162_rn(0.f); py[p] = px[p]; }
+    float best[8];
+    uint16_t sel[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { best[j] = -3.402823466e+38F; sel[0][j] = sel[1][j] = sel[2][j] = 0; }
     for (int dy = 0; dy < 2; dy++)
         for (int dx = 0; dx < 2; dx++) {
             const int yi = 2 * yo + dy, xi = 2 * xo + dx;
             if (yi < a.Hi && xi < a.Wi) {
                 const long long mi = ((long long)n * a.Hsi + yi) * a.Wpi + xi;
-                __nv_bfloat162 v[3];
-                float sx = 0.f, sy = 0.f;
+                uint4 v[3];
+                float sum[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) sum[j] = 0.f;
                 for (int p = 0; p < a.planes; p++) {
-                    v[p] = *((const __nv_bfloat162*)((const __nv_bfloat16*)a.in + p * a.in_plane + mi * a.C) + g);
-                    sx += __low2float(v[p]); sy += __high2float(v[p]);
+                    v[p] = *((const uint4*)((const __nv_bfloat16*)a.in + (size_t)p * a.in_plane + mi * a.C) + g);
+                    const uint16_t* h = (const uint16_t*)&v[p];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) sum[j] += __uint_as_float((uint32_t)h[j] << 16);
                 }
-                if (sx > bx) { bx = sx; for (int p = 0; p < a.planes; p++) px[p] = v[p]; }
-                if (sy > by) { by = sy; for (int p = 0; p < a.planes; p++) py[p] = v[p]; }
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (sum[j] > best[j]) {
+                        best[j] = sum[j];
+                        for (int p = 0; p < a.planes; p++) sel[p][j] = ((const uint16_t*)&v[p])[j];
+                    }
             }
         }
     for (int p = 0; p < a.planes; p++) {
-        __nv_bfloat162 o = __halves2bfloat162(__low2bfloat16(px[p]), __high2bfloat16(py[p]));
-        *((__nv_bfloat162*)((__nv_bfloat16*)a.out + p * a.out_plane + mo * a.C) + g) = o;
+        uint4 o;
+        uint16_t* oh = (uint16_t*)&o;
+#pragma unroll
+        for (int j = 0; j < 8; j++) oh[j] = sel[p][j];
+        *((uint4*)((__nv_bfloat16*)a.out + (size_t)p * a.out_plane + mo * a.C) + g) = o;
     }
 }
 
@@ -75,7 +87,7 @@ int launch_pool(const PoolArgs& a, cudaStream_t st) {
         const long long total = rows_out * (a.C / 4);
         pool_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
     } else {
-        const long long total = rows_out * (a.C / 2);
+        const long long total = rows_out * (a.C / 8);
         pool_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
     }
     return 1;

@@ -107,18 +107,71 @@ __device__ __forceinline__ FullRes make_fullres(const PostDev& pd, int frame) {
 // ------------------------------------------------------------------------------------------------
 #define NMS_TX 32
 #define NMS_TY 8
+#define NMS_HROWS 8
 __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
     __shared__ float tile[NMS_TY + 2][NMS_TX + 2];
+    __shared__ float hrow[NMS_HROWS][NMS_TX + 2];
     const int part = blockIdx.z % pd.p.num_parts, frame = blockIdx.z / pd.p.num_parts;
     const FullRes fr = make_fullres(pd, frame);
     const int W = pd.p.net_w, H = pd.p.net_h;
     const int x0 = blockIdx.x * NMS_TX - 1, y0 = blockIdx.y * NMS_TY - 1;
-    for (int i = threadIdx.x; i < (NMS_TY + 2) * (NMS_TX + 2); i += 256) {
-        const int ty = i / (NMS_TX + 2), tx = i % (NMS_TX + 2);
-        const int x = x0 + tx, y = y0 + ty;
-        float v = 0.f;
-        if (x >= 0 && x < W && y >= 0 && y < H) v = fullres_at(fr, part, y, x);
-        tile[ty][tx] = v;
+    const int ylo = max(y0, 0), yhi = min(y0 + NMS_TY + 1, H - 1);
+    // Separable evaluation: the horizontal cubic of a (source row, x) pair does not depend on the output row,
+    // so it is computed once per tile (<= NMS_HROWS source rows) instead of 4x per output pixel.  Same
+    // operations on the same operands as fullres_at -> bit-identical values.
+    constexpr int NOUT = (NMS_TY + 2) * (NMS_TX + 2);
+    float acc[2] = {0.f, 0.f};
+    bool separable = true;
+    for (int n = 0; n < fr.S; n++) {
+        const int rlo = fr.yt[n * H + ylo].i0, rhi = fr.yt[n * H + yhi].i3;
+        if (rhi - rlo + 1 > NMS_HROWS) separable = false;
+    }
+    if (separable) {
+        const size_t plane = (size_t)fr.h8 * fr.w8;
+        for (int n = 0; n < fr.S; n++) {
+            const int rlo = fr.yt[n * H + ylo].i0, rhi = fr.yt[n * H + yhi].i3;
+            const int nrows = rhi - rlo + 1;
+            const float* s = fr.maps + ((size_t)n * fr.C + part) * plane;
+            __syncthreads();
+            for (int it = threadIdx.x; it < nrows * (NMS_TX + 2); it += 256) {
+                const int r = it / (NMS_TX + 2), tx = it % (NMS_TX + 2);
+                const int x = x0 + tx;
+                float v = 0.f;
+                if (x >= 0 && x < W) {
+                    const AxisTap ax = fr.xt[n * W + x];
+                    const float* row = s + (size_t)(rlo + r) * fr.w8;
+                    v = cubic_ref(__ldg(row + ax.i0), __ldg(row + ax.i1), __ldg(row + ax.i2), __ldg(row + ax.i3), ax.d);
+                }
+                hrow[r][tx] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int i = threadIdx.x + q * 256;
+                if (i < NOUT) {
+                    const int ty = i / (NMS_TX + 2), tx = i % (NMS_TX + 2);
+                    const int x = x0 + tx, y = y0 + ty;
+                    if (x >= 0 && x < W && y >= 0 && y < H) {
+                        const AxisTap ay = fr.yt[n * H + y];
+                        acc[q] = __fadd_rn(acc[q], cubic_ref(hrow[ay.i0 - rlo][tx], hrow[ay.i1 - rlo][tx], hrow[ay.i2 - rlo][tx],
+                                                             hrow[ay.i3 - rlo][tx], ay.d));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int i = threadIdx.x + q * 256;
+            if (i < NOUT) tile[i / (NMS_TX + 2)][i % (NMS_TX + 2)] = __fdiv_rn(acc[q], fr.inv_div);
+        }
+    } else {
+        for (int i = threadIdx.x; i < NOUT; i += 256) {
+            const int ty = i / (NMS_TX + 2), tx = i % (NMS_TX + 2);
+            const int x = x0 + tx, y = y0 + ty;
+            float v = 0.f;
+            if (x >= 0 && x < W && y >= 0 && y < H) v = fullres_at(fr, part, y, x);
+            tile[ty][tx] = v;
+        }
     }
     __syncthreads();
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
@@ -354,8 +407,10 @@ __global__ void __launch_bounds__(512) limb_greedy_kernel(PostDev pd) {
 // the reference: num_parts index slots (flat index of the peak's score in the peaks blob, 0 = empty),
 // then [num_parts+1] = score (double), [num_parts+2] = count.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) assemble_kernel(PostDev pd) {
+__global__ void __launch_bounds__(256) assemble_kernel(PostDev pd) {
     __shared__ int s_rows;
+    __shared__ int s_conn_of_slot[130];   // peak slot of part A (1..max_peaks) -> connection index of this limb
+    __shared__ int s_found[130];
     const int frame = blockIdx.x;
     const ModelDev& md = pd.md;
     const int P = pd.p.num_parts, MP = pd.p.max_peaks, poff = 3 * (MP + 1);
@@ -379,25 +434,37 @@ __global__ void __launch_bounds__(128) assemble_kernel(PostDev pd) {
             s_rows = r + 1;
         }
     };
-
+    // The reference walks connections (and, in the nA==0/nB==0 branches, peaks) one at a time over all rows.
+    // Within one limb every connection has a distinct part-A peak and rows created during the limb carry that
+    // limb's own A peaks, so the per-connection row scans are independent: one parallel pass over the rows
+    // (row -> its connection through s_conn_of_slot) followed by the in-order appends gives the same rows in the
+    // same order.
     for (int k = 0; k < pd.p.num_limbs; k++) {
         const int pa = md.limb_seq[2 * k], pb = md.limb_seq[2 * k + 1];
         const int nA = min((int)peaks[pa * poff], MP), nB = min((int)peaks[pb * poff], MP);
         if (nA == 0 && nB == 0) continue;
+        const int rows = s_rows;
         if (nA == 0 || nB == 0) {
             const int part = nA == 0 ? pb : pa, n = nA == 0 ? nB : nA;
-            for (int i = 1; i <= n; i++) {
-                const int off = part * poff + i * 3 + 2;
-                int found = 0;
-                if (coco) {  // duplicate check exists only in connectLimbsCOCO (rtpose.cpp:852-860)
-                    const int rows = s_rows;
-                    for (int j = threadIdx.x; j < rows; j += blockDim.x)
-                        if (subset[(size_t)j * S_SIZE + part] == (double)off) found = 1;
+            for (int i = threadIdx.x; i <= n; i += blockDim.x) s_found[i] = 0;
+            __syncthreads();
+            if (coco) {  // duplicate check exists only in connectLimbsCOCO (rtpose.cpp:852-860)
+                for (int j = threadIdx.x; j < rows; j += blockDim.x) {
+                    const double v = subset[(size_t)j * S_SIZE + part];
+                    if (v != 0.0) {
+                        const int slot = ((int)v - part * poff - 2) / 3;
+                        if (slot >= 1 && slot <= n && (double)(part * poff + slot * 3 + 2) == v) s_found[slot] = 1;
+                    }
                 }
-                found = __syncthreads_or(found);
-                if (!found && threadIdx.x == 0) append(part, (double)off, -1, 0.0, 1.0, (double)peaks[off]);
-                __syncthreads();
             }
+            __syncthreads();
+            if (threadIdx.x == 0)
+                for (int i = 1; i <= n; i++)
+                    if (!s_found[i]) {
+                        const int off = part * poff + i * 3 + 2;
+                        append(part, (double)off, -1, 0.0, 1.0, (double)peaks[off]);
+                    }
+            __syncthreads();
             continue;
         }
         const int lf = frame * pd.p.num_limbs + k;
@@ -413,26 +480,37 @@ __global__ void __launch_bounds__(128) assemble_kernel(PostDev pd) {
             __syncthreads();
             continue;
         }
-        for (int i = 0; i < nc; i++) {
-            const Conn c = conns[i];
-            const int rows = s_rows;
-            int found = 0;
-            for (int j = threadIdx.x; j < rows; j += blockDim.x) {
-                double* row = subset + (size_t)j * S_SIZE;
-                if (row[pa] == (double)c.a) {
-                    row[pb] = (double)c.b;
-                    found = 1;
-                    row[S_CNT] = row[S_CNT] + 1.0;
-                    row[S_SCORE] = __dadd_rn(__dadd_rn(row[S_SCORE], (double)peaks[c.b]), (double)c.score);
+        if (nc == 0) continue;
+        for (int i = threadIdx.x; i <= MP; i += blockDim.x) { s_conn_of_slot[i] = -1; s_found[i] = 0; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) s_conn_of_slot[(conns[i].a - pa * poff - 2) / 3] = i;
+        __syncthreads();
+        for (int j = threadIdx.x; j < rows; j += blockDim.x) {
+            double* row = subset + (size_t)j * S_SIZE;
+            const double v = row[pa];
+            if (v != 0.0) {
+                const int slot = ((int)v - pa * poff - 2) / 3;
+                if (slot >= 1 && slot <= MP) {
+                    const int ci = s_conn_of_slot[slot];
+                    if (ci >= 0 && (double)conns[ci].a == v) {
+                        const Conn c = conns[ci];
+                        row[pb] = (double)c.b;
+                        row[S_CNT] = row[S_CNT] + 1.0;
+                        row[S_SCORE] = __dadd_rn(__dadd_rn(row[S_SCORE], (double)peaks[c.b]), (double)c.score);
+                        s_found[ci] = 1;
+                    }
                 }
             }
-            found = __syncthreads_or(found);
-            if (!found && threadIdx.x == 0) {
-                const double sc = __dadd_rn((double)__fadd_rn(peaks[c.a], peaks[c.b]), (double)c.score);
-                append(pa, (double)c.a, pb, (double)c.b, 2.0, sc);
-            }
-            __syncthreads();
         }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int i = 0; i < nc; i++)
+                if (!s_found[i]) {
+                    const Conn c = conns[i];
+                    const double sc = __dadd_rn((double)__fadd_rn(peaks[c.a], peaks[c.b]), (double)c.score);
+                    append(pa, (double)c.a, pb, (double)c.b, 2.0, sc);
+                }
+        __syncthreads();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -485,7 +563,7 @@ int launch_post(const PostDev& pd, int nframes, cudaStream_t st) {
     int n2 = 1;
     while (n2 < MP * MP) n2 <<= 1;
     limb_greedy_kernel<<<dim3(p.num_limbs, nframes), 512, sizeof(unsigned long long) * n2, st>>>(pd);
-    assemble_kernel<<<nframes, 128, 0, st>>>(pd);
+    assemble_kernel<<<nframes, 256, 0, st>>>(pd);
     return 5;  // kernels launched
 }
 

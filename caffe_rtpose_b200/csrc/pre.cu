@@ -74,68 +74,75 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16&
 }
 
 // SRC = 0: uint8 resized images (pad + normalise here);  SRC = 1: planar fp32 net input (already padded/normalised)
+// One thread = 8 consecutive patch channels of one pixel (k = 8*part .. 8*part+7, k = (r*3+s)*3 + c), so a row of
+// the im2col'ed input is written with coalesced 16/32-byte vector stores.
 template <int SRC>
-__global__ void __launch_bounds__(128) input_im2col_kernel(PreArgs a, const float* planar, int nimages) {
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) input_im2col_kernel(PreArgs a, const float* planar, int nimages) {
+    const int parts = a.kp / 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_img = (long long)a.Hs * a.Wp;
-    if (m >= per_img * nimages) return;
+    if (idx >= per_img * nimages * parts) return;
+    const int part = (int)(idx % parts);
+    const long long m = idx / parts;
     const int n = (int)(m / per_img);
     const int rem = (int)(m % per_img);
     const int y = rem / a.Wp, x = rem % a.Wp;
     if (x >= a.net_w || y >= a.net_h) return;  // gap rows stay zero
-    float v[27];
     const int s = n % a.S;
-    const AreaTab t = a.tab[SRC == 0 ? s : 0];
+    const AreaTab& t = a.tab[SRC == 0 ? s : 0];
     const uint8_t* img = a.resized + (size_t)n * a.net_h * a.net_w * 3;
+    float v[8];
 #pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const int yy = y + r - 1, xx = x + q - 1;
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    for (int j = 0; j < 8; j++) {
+        const int k = part * 8 + j;
+        float val = 0.f;
+        if (k < 27) {
+            const int tap = k / 3, c = k % 3;
+            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
             if (yy >= 0 && yy < a.net_h && xx >= 0 && xx < a.net_w) {
                 if (SRC == 0) {
                     const int oy = yy - t.padh, ox = xx - t.padw;
-                    if (oy >= 0 && oy < t.th && ox >= 0 && ox < t.tw) {
-                        const uint8_t* p = img + ((size_t)oy * t.tw + ox) * 3;
-                        c0 = __fsub_rn(__fdiv_rn((float)p[0], 256.0f), 0.5f);
-                        c1 = __fsub_rn(__fdiv_rn((float)p[1], 256.0f), 0.5f);
-                        c2 = __fsub_rn(__fdiv_rn((float)p[2], 256.0f), 0.5f);
-                    }
+                    if (oy >= 0 && oy < t.th && ox >= 0 && ox < t.tw)
+                        val = __fsub_rn(__fdiv_rn((float)img[((size_t)oy * t.tw + ox) * 3 + c], 256.0f), 0.5f);
                 } else {
-                    const size_t pl = (size_t)a.net_h * a.net_w;
-                    const float* p = planar + (size_t)n * 3 * pl + (size_t)yy * a.net_w + xx;
-                    c0 = p[0]; c1 = p[pl]; c2 = p[2 * pl];
+                    val = planar[((size_t)n * 3 + c) * a.net_h * a.net_w + (size_t)yy * a.net_w + xx];
                 }
             }
-            v[(r * 3 + q) * 3 + 0] = c0; v[(r * 3 + q) * 3 + 1] = c1; v[(r * 3 + q) * 3 + 2] = c2;
         }
+        v[j] = val;
+    }
     if (a.planes == 0) {
-        float* o = (float*)a.out + (size_t)m * a.kp;
-        for (int k = 0; k < a.kp; k++) o[k] = k < 27 ? v[k] : 0.f;
+        float4* o = (float4*)((float*)a.out + (size_t)m * a.kp + part * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else {
-        __nv_bfloat16* o0 = (__nv_bfloat16*)a.out + (size_t)m * a.kp;
-        for (int k = 0; k < a.kp; k++) {
-            __nv_bfloat16 h, mm, l;
-            split3(k < 27 ? v[k] : 0.f, h, mm, l);
-            o0[k] = h;
-            if (a.planes > 1) o0[a.out_plane + k] = mm;
-            if (a.planes > 2) o0[2 * a.out_plane + k] = l;
+        uint32_t pk[3][4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            __nv_bfloat16 h0, m0, l0, h1, m1, l1;
+            split3(v[j], h0, m0, l0);
+            split3(v[j + 1], h1, m1, l1);
+            pk[0][j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            pk[1][j / 2] = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
+            pk[2][j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
         }
+        __nv_bfloat16* o0 = (__nv_bfloat16*)a.out + (size_t)m * a.kp + part * 8;
+        for (int p = 0; p < a.planes; p++)
+            *(uint4*)(o0 + (size_t)p * a.out_plane) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
     }
 }
 
 int launch_preprocess(const PreArgs& a, cudaStream_t st) {
     dim3 g((a.net_w * a.net_h + 255) / 256, a.S, a.nframes);
     area_resize_kernel<<<g, 256, 0, st>>>(a);
-    const long long rows = (long long)a.Hs * a.Wp * a.nframes * a.S;
-    input_im2col_kernel<0><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(a, nullptr, a.nframes * a.S);
+    const long long work = (long long)a.Hs * a.Wp * a.nframes * a.S * (a.kp / 8);
+    input_im2col_kernel<0><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(a, nullptr, a.nframes * a.S);
     return 2;
 }
 
 int launch_input_from_planar(const float* planar, const PreArgs& a, int nimages, cudaStream_t st) {
-    const long long rows = (long long)a.Hs * a.Wp * nimages;
-    input_im2col_kernel<1><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(a, planar, nimages);
+    const long long work = (long long)a.Hs * a.Wp * nimages * (a.kp / 8);
+    input_im2col_kernel<1><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(a, planar, nimages);
     return 1;
 }
 

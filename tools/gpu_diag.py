@@ -13,9 +13,8 @@ sys.path.insert(0, ROOT)
 from caffe_rtpose_b200 import engine, synth  # noqa: E402
 from oracle import orc  # noqa: E402
 
-BLOBS = ["image", "conv1_1", "conv1_2", "pool1_stage1", "conv2_2", "pool2_stage1", "conv3_4", "pool3_stage1", "conv4_2",
-         "conv4_4_CPM", "conv5_3_CPM_L1", "conv5_4_CPM_L2", "conv5_5_CPM_L1", "conv5_5_CPM_L2", "Mconv1_stage2_L1",
-         "Mconv5_stage2_L2", "Mconv7_stage2_L1", "Mconv7_stage3_L2", "Mconv6_stage6_L1"]
+BLOBS = ["image", "conv1_1", "conv1_2", "pool1_stage1", "conv2_2", "conv3_4", "conv4_2",
+         "conv4_4_CPM", "conv5_3_CPM_L1", "conv5_4_CPM_L2", "Mconv1_stage2_L1", "Mconv5_stage2_L2", "Mconv6_stage6_L1"]
 
 
 def rel(a, b):
@@ -122,10 +121,9 @@ if __name__ == "__main__":
         post_diag()
     if what in ("simt", "all"):
         conv_diag([engine.PREC_FP32_SIMT])
+    precs = [int(v) for v in os.environ.get("DIAG_PRECS", "1,2").split(",")]
     if what in ("tc", "all"):
-        conv_diag([engine.PREC_BF16X1, engine.PREC_BF16X2, engine.PREC_BF16X3])
+        conv_diag(precs)
     if what in ("time", "all"):
-        timing(engine.PREC_FP32_SIMT)
-        for p in (1, 2, 3):
-            timing(p)
-        timing(2, batch=4)
+        for p in precs:
+            timing(p, batch=int(os.environ.get("DIAG_BATCH", "8")))
