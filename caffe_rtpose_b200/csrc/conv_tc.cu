@@ -39,7 +39,7 @@ struct TcArgs {
     int ksize, pad, kblocks_per_tap, cin_k;   // cin_k = channels per tap in the weight K ordering
     int W, H, Wp, Hs;
     long long M;
-    int base_off_mode;   // window kernel: 1 = set the descriptor base_offset field for row-shifted A operands
+    int n_tiles_n; long long total_tiles;   // persistent window kernel: tile = (m_tile, n_tile), n fastest
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -292,6 +292,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 constexpr int TCW_ROWS = 136;                 // 128 + 7 - 1 rounded up to a multiple of 8
 constexpr int TCW_A_BYTES = TCW_ROWS * 128;   // 17408 = 17 * 1024
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// PERSISTENT: grid = min(#tiles, #SMs); every role loops over tiles t = blockIdx.x, +gridDim.x, ...  The TMA and
+// MMA rings run straight through tile boundaries, and the TMEM accumulator is double-buffered (2 x P*BN
+// columns) so the epilogue of tile i overlaps the main loop of tile i+1 - this removes the per-tile
+// prologue/epilogue latency that dominated the short-K layers (conv1_x, conv2_x).
 template <int BN, int PLANES, int NA, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -300,7 +308,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int A_SLOT = PLANES * TCW_A_BYTES;
     constexpr int B_SLOT = PLANES * B_BYTES;
     constexpr int ACC_COLS = PLANES * BN;
-    constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : 256));
+    constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
     constexpr uint32_t IDESC1 = umma_idesc(TC_BM, PLANES * BN);   // A_hi x [B_hi;B_lo]
     constexpr uint32_t IDESC2 = umma_idesc(TC_BM, BN);            // A_lo x B_hi
 
@@ -309,18 +317,18 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + NA * A_SLOT;
     __shared__ __align__(8) uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long m0 = (long long)blockIdx.x * TC_BM;
-    const int n0 = blockIdx.y * BN;
     const int ks = a.ksize;
+    const int n_tiles_n = a.n_tiles_n;
+    const long long total_tiles = a.total_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        mbar_init(&tmem_full_bar, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -334,127 +342,145 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         // ===== TMA producer: windows and per-tap weight tiles in consumption order =====
         int aw = 0, bt = 0;
-        for (int kb = 0; kb < a.kblocks_per_tap; kb++)
-            for (int r = 0; r < ks; r++) {
-                {
-                    const int s = aw % NA;
-                    mbar_wait(&a_empty[s], ((uint32_t)(aw / NA) & 1u) ^ 1u);
-                    mbar_expect_tx(&a_full[s], A_SLOT);
-                    const int row0 = (int)(m0 + (long long)(r - a.pad) * a.Wp - a.pad);
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const long long m0 = (t / n_tiles_n) * TC_BM;
+            const int n0 = (int)(t % n_tiles_n) * BN;
+            for (int kb = 0; kb < a.kblocks_per_tap; kb++)
+                for (int r = 0; r < ks; r++) {
+                    {
+                        const int s = aw % NA;
+                        mbar_wait(&a_empty[s], ((uint32_t)(aw / NA) & 1u) ^ 1u);
+                        mbar_expect_tx(&a_full[s], A_SLOT);
+                        const int row0 = (int)(m0 + (long long)(r - a.pad) * a.Wp - a.pad);
 #pragma unroll
-                    for (int p = 0; p < PLANES; p++)
-                        tma_load_3d(smem_a + s * A_SLOT + p * TCW_A_BYTES, &tmA, &a_full[s], kb * TC_BK, row0, p);
-                    aw++;
-                }
-                for (int q = 0; q < ks; q++) {
-                    const int s = bt % NB;
-                    mbar_wait(&b_empty[s], ((uint32_t)(bt / NB) & 1u) ^ 1u);
-                    mbar_expect_tx(&b_full[s], B_SLOT);
-                    const int tap = r * ks + q;
+                        for (int p = 0; p < PLANES; p++)
+                            tma_load_3d(smem_a + s * A_SLOT + p * TCW_A_BYTES, &tmA, &a_full[s], kb * TC_BK, row0, p);
+                        aw++;
+                    }
+                    for (int q = 0; q < ks; q++) {
+                        const int s = bt % NB;
+                        mbar_wait(&b_empty[s], ((uint32_t)(bt / NB) & 1u) ^ 1u);
+                        mbar_expect_tx(&b_full[s], B_SLOT);
+                        const int tap = r * ks + q;
 #pragma unroll
-                    for (int p = 0; p < PLANES; p++)
-                        tma_load_3d(smem_b + s * B_SLOT + p * B_BYTES, &tmB, &b_full[s], tap * a.cin_k + kb * TC_BK, n0, p);
-                    bt++;
+                        for (int p = 0; p < PLANES; p++)
+                            tma_load_3d(smem_b + s * B_SLOT + p * B_BYTES, &tmB, &b_full[s], tap * a.cin_k + kb * TC_BK, n0, p);
+                        bt++;
+                    }
                 }
-            }
+        }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
-        int aw = 0, bt = 0;
-        bool first = true;
-        for (int kb = 0; kb < a.kblocks_per_tap; kb++)
-            for (int r = 0; r < ks; r++) {
-                const int sa_slot = aw % NA;
-                mbar_wait(&a_full[sa_slot], (uint32_t)(aw / NA) & 1u);
-                const uint32_t sa = smem_u32(smem_a + sa_slot * A_SLOT);
-                for (int q = 0; q < ks; q++) {
-                    const int sb_slot = bt % NB;
-                    mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
-                    tc_fence_after();
-                    const uint32_t sb = smem_u32(smem_b + sb_slot * B_SLOT);
-                    const uint32_t boff = a.base_off_mode ? (uint32_t)q : 0u;
+        int aw = 0, bt = 0, ti = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ti++) {
+            const int as = ti & 1;
+            mbar_wait(&tmem_empty[as], ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)(as * ACC_COLS);
+            bool first = true;
+            for (int kb = 0; kb < a.kblocks_per_tap; kb++)
+                for (int r = 0; r < ks; r++) {
+                    const int sa_slot = aw % NA;
+                    mbar_wait(&a_full[sa_slot], (uint32_t)(aw / NA) & 1u);
+                    const uint32_t sa = smem_u32(smem_a + sa_slot * A_SLOT);
+                    for (int q = 0; q < ks; q++) {
+                        const int sb_slot = bt % NB;
+                        mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(smem_b + sb_slot * B_SLOT);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++) {
-                        const uint64_t db = umma_desc(sb + k * 32);   // rows [0, PLANES*BN): B_hi then B_lo
-                        const uint64_t da0 = umma_desc_off(sa + q * 128 + k * 32, boff);
-                        umma_bf16(tmem_base, da0, db, IDESC1, first ? 0u : 1u);
-                        if (PLANES == 2) {
-                            const uint64_t da1 = umma_desc_off(sa + TCW_A_BYTES + q * 128 + k * 32, boff);
-                            umma_bf16(tmem_base + BN, da1, db, IDESC2, 1u);   // += A_lo x B_hi into the hi*lo columns
+                        for (int k = 0; k < TC_BK / 16; k++) {
+                            // row-shifted view of the window: start address + q rows; the swizzle phase follows the
+                            // absolute smem address (verified on B200: base_offset must stay 0)
+                            const uint64_t db = umma_desc(sb + k * 32);   // rows [0, PLANES*BN): B_hi then B_lo
+                            const uint64_t da0 = umma_desc(sa + q * 128 + k * 32);
+                            umma_bf16(acc, da0, db, IDESC1, first ? 0u : 1u);
+                            if (PLANES == 2) {
+                                const uint64_t da1 = umma_desc(sa + TCW_A_BYTES + q * 128 + k * 32);
+                                umma_bf16(acc + BN, da1, db, IDESC2, 1u);   // += A_lo x B_hi into the hi*lo columns
+                            }
+                            first = false;
                         }
-                        first = false;
+                        umma_commit(&b_empty[sb_slot]);
+                        bt++;
                     }
-                    umma_commit(&b_empty[sb_slot]);
-                    bt++;
+                    umma_commit(&a_empty[sa_slot]);
+                    aw++;
                 }
-                umma_commit(&a_empty[sa_slot]);
-                aw++;
-            }
-        umma_commit(&tmem_full_bar);
+            umma_commit(&tmem_full[as]);
+        }
     } else if (warp >= 2) {
         // ===== epilogue =====
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
         const int quad = warp & 3;
-        const long long m = m0 + quad * 32 + lane;
         const int per_img = a.Hs * a.Wp;
-        bool valid = m < a.M;
-        int n = 0, y = 0, x = 0;
-        if (valid) {
-            n = (int)(m / per_img);
-            const int rem = (int)(m % per_img);
-            y = rem / a.Wp; x = rem % a.Wp;
-            valid = (x < a.W) && (y < a.H);
-        }
         const int cout8 = (a.cout + 7) & ~7;
-        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t r[16], r2[16];
-            __syncwarp();
-            tmem_ld16(trow + (uint32_t)c0, r);
-            if (PLANES == 2) tmem_ld16(trow + (uint32_t)(BN + c0), r2);
+        int ti = 0;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ti++) {
+            const long long m0 = (t / n_tiles_n) * TC_BM;
+            const int n0 = (int)(t % n_tiles_n) * BN;
+            const int as = ti & 1;
+            mbar_wait(&tmem_full[as], (uint32_t)(ti >> 1) & 1u);
+            tc_fence_after();
+            const long long m = m0 + quad * 32 + lane;
+            bool valid = m < a.M;
+            int n = 0, y = 0, x = 0;
             if (valid) {
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int co = n0 + c0 + j;
-                    float t = __uint_as_float(r[j]);
-                    if (PLANES == 2) t += __uint_as_float(r2[j]);
-                    t += (co < a.cout ? __ldg(a.bias + co) : 0.f);
-                    if (a.relu) t = fmaxf(t, 0.f);
-                    v[j] = t;
-                }
-                if (a.planar) {
+                n = (int)(m / per_img);
+                const int rem = (int)(m % per_img);
+                y = rem / a.Wp; x = rem % a.Wp;
+                valid = (x < a.W) && (y < a.H);
+            }
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[16], r2[16];
+                __syncwarp();
+                tmem_ld16(trow + (uint32_t)c0, r);
+                if (PLANES == 2) tmem_ld16(trow + (uint32_t)(BN + c0), r2);
+                if (valid) {
+                    float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const int co = n0 + c0 + j;
-                        if (co < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + co) * a.H + y) * a.W + x] = v[j];
+                        float tv = __uint_as_float(r[j]);
+                        if (PLANES == 2) tv += __uint_as_float(r2[j]);
+                        tv += (co < a.cout ? __ldg(a.bias + co) : 0.f);
+                        if (a.relu) tv = fmaxf(tv, 0.f);
+                        v[j] = tv;
                     }
-                } else {
-                    uint32_t pk[PLANES][8];
+                    if (a.planar) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        float r0 = v[j], r1 = v[j + 1];
+                        for (int j = 0; j < 16; j++) {
+                            const int co = n0 + c0 + j;
+                            if (co < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + co) * a.H + y) * a.W + x] = v[j];
+                        }
+                    } else {
+                        uint32_t pk[PLANES][8];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            float r0 = v[j], r1 = v[j + 1];
+#pragma unroll
+                            for (int p = 0; p < PLANES; p++) {
+                                const __nv_bfloat16 h0 = __float2bfloat16_rn(r0), h1 = __float2bfloat16_rn(r1);
+                                pk[p][j / 2] = pack_bf16(h0, h1);
+                                r0 = __fsub_rn(r0, __bfloat162float(h0));
+                                r1 = __fsub_rn(r1, __bfloat162float(h1));
+                            }
+                        }
+                        __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + n0 + c0;
 #pragma unroll
                         for (int p = 0; p < PLANES; p++) {
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(r0), h1 = __float2bfloat16_rn(r1);
-                            pk[p][j / 2] = pack_bf16(h0, h1);
-                            r0 = __fsub_rn(r0, __bfloat162float(h0));
-                            r1 = __fsub_rn(r1, __bfloat162float(h1));
+                            uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
+                            if (n0 + c0 < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+                            if (n0 + c0 + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
                         }
-                    }
-                    __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + n0 + c0;
-#pragma unroll
-                    for (int p = 0; p < PLANES; p++) {
-                        uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
-                        if (n0 + c0 < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
-                        if (n0 + c0 + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
                     }
                 }
             }
+            __syncwarp();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);   // 4 epilogue warps -> accumulator free for tile ti+2
         }
-        __syncwarp();
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
@@ -605,9 +631,12 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
     a.M = (long long)nimg * d.geo.Hs * d.geo.Wp;
     dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), (unsigned)(d.cout_pad / l.bn));
     static const int variant = env_int("PE_TC_VARIANT", 1);     // 1: window kernel, 0: one TMA tile per tap
-    static const int baseoff = env_int("PE_TC_BASEOFF", 1);
-    a.base_off_mode = baseoff;
     if (variant == 1 && d.planes <= 2) {
+        static int nsm = 0;
+        if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+        a.n_tiles_n = (int)grid.y;
+        a.total_tiles = (long long)grid.x * grid.y;
+        grid = dim3((unsigned)(a.total_tiles < nsm ? a.total_tiles : nsm), 1, 1);
         switch (l.bn) {
             case 128: return launch_win_bn<128>(l, a, grid, st);
             case 64: return launch_win_bn<64>(l, a, grid, st);
