@@ -98,6 +98,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4
 //   (8 rows x 128 B = 1024 B -> 64) | [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
@@ -131,6 +140,7 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // bf16 elements per K block = one 128-byte swizzle row
 constexpr int TC_THREADS = 192;
+constexpr int TCW_THREADS = 320;      // window kernel: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
 
 template <int BN, int PLANES, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -301,7 +311,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // columns) so the epilogue of tile i overlaps the main loop of tile i+1 - this removes the per-tile
 // prologue/epilogue latency that dominated the short-K layers (conv1_x, conv2_x).
 template <int BN, int PLANES, int NA, int NB>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCW_THREADS, 1)
 conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     static_assert(PLANES == 1 || PLANES == 2, "window kernel supports 1 or 2 planes");
     constexpr int B_BYTES = BN * 128;
@@ -319,16 +329,18 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ __align__(8) uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB];
     __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_bias[512];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ks = a.ksize;
+    for (int i = threadIdx.x; i < 512; i += TCW_THREADS) s_bias[i] = (i < a.cout) ? a.bias[i] : 0.f;
     const int n_tiles_n = a.n_tiles_n;
     const long long total_tiles = a.total_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -352,9 +364,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         mbar_wait(&a_empty[s], ((uint32_t)(aw / NA) & 1u) ^ 1u);
                         mbar_expect_tx(&a_full[s], A_SLOT);
                         const int row0 = (int)(m0 + (long long)(r - a.pad) * a.Wp - a.pad);
-#pragma unroll
-                        for (int p = 0; p < PLANES; p++)
-                            tma_load_3d(smem_a + s * A_SLOT + p * TCW_A_BYTES, &tmA, &a_full[s], kb * TC_BK, row0, p);
+                        tma_load_3d(smem_a + s * A_SLOT, &tmA, &a_full[s], kb * TC_BK, row0, 0);   // box {64, 136, PLANES}
                         aw++;
                     }
                     for (int q = 0; q < ks; q++) {
@@ -362,9 +372,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         mbar_wait(&b_empty[s], ((uint32_t)(bt / NB) & 1u) ^ 1u);
                         mbar_expect_tx(&b_full[s], B_SLOT);
                         const int tap = r * ks + q;
-#pragma unroll
-                        for (int p = 0; p < PLANES; p++)
-                            tma_load_3d(smem_b + s * B_SLOT + p * B_BYTES, &tmB, &b_full[s], tap * a.cin_k + kb * TC_BK, n0, p);
+                        tma_load_3d(smem_b + s * B_SLOT, &tmB, &b_full[s], tap * a.cin_k + kb * TC_BK, n0, 0);   // box {64, BN, PLANES}
                         bt++;
                     }
                 }
@@ -410,8 +418,13 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             umma_commit(&tmem_full[as]);
         }
     } else if (warp >= 2) {
-        // ===== epilogue =====
+        // ===== epilogue: 8 warps; warp w owns TMEM lanes 32*(w%4).. and the column half (w-2)/4 =====
+        constexpr bool SPLIT = (BN / 2) % 16 == 0;            // BN = 128, 64, 32: two warps share a lane quadrant
+        constexpr int HALF = SPLIT ? BN / 2 : BN;             // columns per warp
+        constexpr int NCHUNK = HALF / 16;
         const int quad = warp & 3;
+        const int half = SPLIT ? (warp - 2) / 4 : 0;
+        const bool active_half = SPLIT || (warp - 2) / 4 == 0;
         const int per_img = a.Hs * a.Wp;
         const int cout8 = (a.cout + 7) & ~7;
         int ti = 0;
@@ -430,56 +443,67 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 y = rem / a.Wp; x = rem % a.Wp;
                 valid = (x < a.W) && (y < a.H);
             }
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[16], r2[16];
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS + half * HALF);
+            if (active_half) {
+                uint32_t r[2][16], r2[2][16];
                 __syncwarp();
-                tmem_ld16(trow + (uint32_t)c0, r);
-                if (PLANES == 2) tmem_ld16(trow + (uint32_t)(BN + c0), r2);
-                if (valid) {
-                    float v[16];
+                tmem_ld16_nowait(trow, r[0]);
+                if (PLANES == 2) tmem_ld16_nowait(trow + BN, r2[0]);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int co = n0 + c0 + j;
-                        float tv = __uint_as_float(r[j]);
-                        if (PLANES == 2) tv += __uint_as_float(r2[j]);
-                        tv += (co < a.cout ? __ldg(a.bias + co) : 0.f);
-                        if (a.relu) tv = fmaxf(tv, 0.f);
-                        v[j] = tv;
+                for (int c = 0; c < NCHUNK; c++) {
+                    const int cur = c & 1;
+                    if (c + 1 < NCHUNK) {   // prefetch the next 16 columns while this chunk is converted and stored
+                        __syncwarp();
+                        tmem_ld16_nowait(trow + (uint32_t)((c + 1) * 16), r[cur ^ 1]);
+                        if (PLANES == 2) tmem_ld16_nowait(trow + (uint32_t)(BN + (c + 1) * 16), r2[cur ^ 1]);
                     }
-                    if (a.planar) {
+                    const int cb = n0 + half * HALF + c * 16;   // first output channel of this chunk
+                    if (valid) {
+                        float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
-                            const int co = n0 + c0 + j;
-                            if (co < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + co) * a.H + y) * a.W + x] = v[j];
+                            float tv = __uint_as_float(r[cur][j]);
+                            if (PLANES == 2) tv += __uint_as_float(r2[cur][j]);
+                            tv += s_bias[cb + j];
+                            if (a.relu) tv = fmaxf(tv, 0.f);
+                            v[j] = tv;
                         }
-                    } else {
-                        uint32_t pk[PLANES][8];
+                        if (a.planar) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            float r0 = v[j], r1 = v[j + 1];
+                            for (int j = 0; j < 16; j++)
+                                if (cb + j < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + cb + j) * a.H + y) * a.W + x] = v[j];
+                        } else {
+                            uint32_t pk[PLANES][8];
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                float r0 = v[j], r1 = v[j + 1];
+#pragma unroll
+                                for (int p = 0; p < PLANES; p++) {
+                                    const __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);   // one packed conversion
+                                    const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+                                    pk[p][j / 2] = hu;
+                                    if (p + 1 < PLANES) {
+                                        r0 = __fsub_rn(r0, __uint_as_float(hu << 16));
+                                        r1 = __fsub_rn(r1, __uint_as_float(hu & 0xffff0000u));
+                                    }
+                                }
+                            }
+                            __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + cb;
 #pragma unroll
                             for (int p = 0; p < PLANES; p++) {
-                                const __nv_bfloat16 h0 = __float2bfloat16_rn(r0), h1 = __float2bfloat16_rn(r1);
-                                pk[p][j / 2] = pack_bf16(h0, h1);
-                                r0 = __fsub_rn(r0, __bfloat162float(h0));
-                                r1 = __fsub_rn(r1, __bfloat162float(h1));
+                                uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
+                                if (cb < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+                                if (cb + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
                             }
                         }
-                        __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + n0 + c0;
-#pragma unroll
-                        for (int p = 0; p < PLANES; p++) {
-                            uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
-                            if (n0 + c0 < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
-                            if (n0 + c0 + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
-                        }
                     }
+                    if (c + 1 < NCHUNK) tmem_ld_wait();
                 }
             }
             __syncwarp();
             tc_fence_before();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);   // 4 epilogue warps -> accumulator free for tile ti+2
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);   // 8 epilogue warps -> accumulator free for tile ti+2
         }
     }
     __syncthreads();
@@ -554,7 +578,7 @@ static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStr
         attr_set = true;
     }
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
-    kern<<<grid, TC_THREADS, smem, st>>>(maps[2], maps[1], a);
+    kern<<<grid, TCW_THREADS, smem, st>>>(maps[2], maps[3], a);
     return 1;
 }
 template <int BN>
@@ -575,7 +599,7 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
     out.d = d;
     out.bn = tc_bn(d.cout_pad);
     CUtensorMap* maps = nullptr;
-    if (posix_memalign((void**)&maps, 64, 3 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
+    if (posix_memalign((void**)&maps, 64, 4 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
     const int taps = d.ksize * d.ksize;
     const cuuint64_t K = (cuuint64_t)taps * d.in_cused;
     {   // A: [planes][M][pitch] bf16, box {64, 128, 1}
@@ -591,7 +615,7 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
     {   // A window: same tensor, box {64, 136, 1} (128 + k - 1 rows serve the k taps of one filter row)
         cuuint64_t dims[3] = {(cuuint64_t)d.in_cused, (cuuint64_t)d.geo.M, (cuuint64_t)d.planes};
         cuuint64_t strides[2] = {(cuuint64_t)d.in_pitch * 2, (cuuint64_t)d.in_plane * 2};
-        cuuint32_t box[3] = {TC_BK, TCW_ROWS, 1};
+        cuuint32_t box[3] = {TC_BK, TCW_ROWS, (cuuint32_t)(d.planes <= 2 ? d.planes : 1)};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = enc(&maps[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d.in, dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -607,6 +631,16 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r); free(maps); return -1; }
+    }
+    {   // B for the window kernel: box {64, BN, planes} -> one TMA op brings [B_hi ; B_lo]
+        cuuint64_t dims[3] = {K, (cuuint64_t)d.cout_pad, (cuuint64_t)d.planes};
+        cuuint64_t strides[2] = {K * 2, K * 2 * (cuuint64_t)d.cout_pad};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)out.bn, (cuuint32_t)(d.planes <= 2 ? d.planes : 1)};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&maps[3], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d.w, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(B window) failed: " + std::to_string((int)r); free(maps); return -1; }
     }
     out.maps = maps;
     out.stages = pick_stages(out.bn, d.planes);

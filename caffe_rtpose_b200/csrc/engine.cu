@@ -52,6 +52,7 @@ struct pe_engine {
     AxisTap *d_xtab = nullptr, *d_ytab = nullptr;
     float start_scale_f, scale_gap_f;
     int last_n = 0;
+    bool input_lo_dirty = false;   // the planar-input path wrote non-zero lo planes / channels >= 32 of the input buffer
     long long launches = 0;
     std::string err;
     double flops_per_scale = 0;
@@ -536,6 +537,11 @@ extern "C" int pe_forward_frames_device(pe_engine* e, const void* d_frames, int 
     CK(e, cudaSetDevice(e->cfg.device));
     PreArgs a = e->pre;
     a.frames = (const uint8_t*)d_frames; a.nframes = n;
+    if (e->input_lo_dirty) {   // the uint8 path only writes the hi plane; drop what the planar path left behind
+        const size_t bytes = (size_t)e->act_plane[e->plan.input_act] * e->elem * (e->planes ? e->planes : 1);
+        CK(e, cudaMemsetAsync(e->acts[e->plan.input_act], 0, bytes, e->stream));
+        e->input_lo_dirty = false;
+    }
     e->launches += launch_preprocess(a, e->stream);
     return run_net(e, n);
 }
@@ -573,6 +579,7 @@ extern "C" int pe_forward_net_input(pe_engine* e, const float* net_input, int n)
     PreArgs a = e->pre;
     a.nframes = n;
     e->launches += launch_input_from_planar(e->d_planar, a, n * e->cfg.num_scales, e->stream);
+    e->input_lo_dirty = e->planes > 0;
     return run_net(e, n);
 }
 extern "C" int pe_forward_maps(pe_engine* e, const float* maps8, int n) {

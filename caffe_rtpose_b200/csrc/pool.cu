@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) pool_f32_kernel(PoolArgs a) {
     *((float4*)((float*)a.out + mo * a.C) + g) = best;
 }
 
+template <int PLANES>
 __global__ void __launch_bounds__(256) pool_bf16_kernel(PoolArgs a) {
     const int cv = a.C / 8;  // 8 channels (16 bytes) per thread and plane
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,40 +46,42 @@ __global__ void __launch_bounds__(256) pool_bf16_kernel(PoolArgs a) {
     const int rem = (int)(mo % ((long long)a.Hso * a.Wpo));
     const int yo = rem / a.Wpo, xo = rem % a.Wpo;
     if (xo >= a.Wo || yo >= a.Ho) return;
-    float best[8];
-    uint16_t sel[3][8];
+    // issue all window loads first (4 positions x PLANES x 16 B in flight per thread), then reduce
+    uint4 v[4][PLANES];
+    bool ok[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { best[j] = -3.402823466e+38F; sel[0][j] = sel[1][j] = sel[2][j] = 0; }
-    for (int dy = 0; dy < 2; dy++)
-        for (int dx = 0; dx < 2; dx++) {
-            const int yi = 2 * yo + dy, xi = 2 * xo + dx;
-            if (yi < a.Hi && xi < a.Wi) {
-                const long long mi = ((long long)n * a.Hsi + yi) * a.Wpi + xi;
-                uint4 v[3];
-                float sum[8];
+    for (int w = 0; w < 4; w++) {
+        const int yi = 2 * yo + (w >> 1), xi = 2 * xo + (w & 1);
+        ok[w] = yi < a.Hi && xi < a.Wi;
+        const long long mi = ((long long)n * a.Hsi + (ok[w] ? yi : 2 * yo)) * a.Wpi + (ok[w] ? xi : 2 * xo);
 #pragma unroll
-                for (int j = 0; j < 8; j++) sum[j] = 0.f;
-                for (int p = 0; p < a.planes; p++) {
-                    v[p] = *((const uint4*)((const __nv_bfloat16*)a.in + (size_t)p * a.in_plane + mi * a.C) + g);
-                    const uint16_t* h = (const uint16_t*)&v[p];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) sum[j] += __uint_as_float((uint32_t)h[j] << 16);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (sum[j] > best[j]) {
-                        best[j] = sum[j];
-                        for (int p = 0; p < a.planes; p++) sel[p][j] = ((const uint16_t*)&v[p])[j];
-                    }
-            }
-        }
-    for (int p = 0; p < a.planes; p++) {
-        uint4 o;
-        uint16_t* oh = (uint16_t*)&o;
-#pragma unroll
-        for (int j = 0; j < 8; j++) oh[j] = sel[p][j];
-        *((uint4*)((__nv_bfloat16*)a.out + (size_t)p * a.out_plane + mo * a.C) + g) = o;
+        for (int p = 0; p < PLANES; p++)
+            v[w][p] = __ldg((const uint4*)((const __nv_bfloat16*)a.in + (size_t)p * a.in_plane + mi * a.C) + g);
     }
+    uint4 o[PLANES];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        float best = -3.402823466e+38F;
+        int bw = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            float sum = 0.f;
+#pragma unroll
+            for (int p = 0; p < PLANES; p++) sum += __uint_as_float((uint32_t)((const uint16_t*)&v[w][p])[j] << 16);
+            if (ok[w] && sum > best) { best = sum; bw = w; }
+        }
+#pragma unroll
+        for (int p = 0; p < PLANES; p++) {
+            uint16_t h = ((const uint16_t*)&v[0][p])[j];
+            if (bw == 1) h = ((const uint16_t*)&v[1][p])[j];
+            if (bw == 2) h = ((const uint16_t*)&v[2][p])[j];
+            if (bw == 3) h = ((const uint16_t*)&v[3][p])[j];
+            ((uint16_t*)&o[p])[j] = h;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < PLANES; p++)
+        *((uint4*)((__nv_bfloat16*)a.out + (size_t)p * a.out_plane + mo * a.C) + g) = o[p];
 }
 
 int launch_pool(const PoolArgs& a, cudaStream_t st) {
@@ -88,7 +91,9 @@ int launch_pool(const PoolArgs& a, cudaStream_t st) {
         pool_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
     } else {
         const long long total = rows_out * (a.C / 8);
-        pool_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+        if (a.planes == 1) pool_bf16_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+        else if (a.planes == 2) pool_bf16_kernel<2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+        else pool_bf16_kernel<3><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
     }
     return 1;
 }

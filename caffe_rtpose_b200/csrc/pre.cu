@@ -78,7 +78,10 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16&
 // the im2col'ed input is written with coalesced 16/32-byte vector stores.
 template <int SRC>
 __global__ void __launch_bounds__(256) input_im2col_kernel(PreArgs a, const float* planar, int nimages) {
-    const int parts = a.kp / 8;
+    // uint8 pixels normalised by /256-0.5 are exact in bf16 (8 significant bits), so the SRC=0 path fills only the
+    // hi plane and only the 32 channels that can be non-zero (27 used); everything else stays zero from init
+    // (the engine clears the other planes when it switches from the planar-input path, see engine.cu).
+    const int parts = (SRC == 0 && a.planes > 0) ? 4 : a.kp / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_img = (long long)a.Hs * a.Wp;
     if (idx >= per_img * nimages * parts) return;
@@ -127,7 +130,8 @@ __global__ void __launch_bounds__(256) input_im2col_kernel(PreArgs a, const floa
             pk[2][j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
         }
         __nv_bfloat16* o0 = (__nv_bfloat16*)a.out + (size_t)m * a.kp + part * 8;
-        for (int p = 0; p < a.planes; p++)
+        const int np = SRC == 0 ? 1 : a.planes;
+        for (int p = 0; p < np; p++)
             *(uint4*)(o0 + (size_t)p * a.out_plane) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
     }
 }
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(256) input_im2col_kernel(PreArgs a, const floa
 int launch_preprocess(const PreArgs& a, cudaStream_t st) {
     dim3 g((a.net_w * a.net_h + 255) / 256, a.S, a.nframes);
     area_resize_kernel<<<g, 256, 0, st>>>(a);
-    const long long work = (long long)a.Hs * a.Wp * a.nframes * a.S * (a.kp / 8);
+    const long long work = (long long)a.Hs * a.Wp * a.nframes * a.S * (a.planes > 0 ? 4 : a.kp / 8);
     input_im2col_kernel<0><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(a, nullptr, a.nframes * a.S);
     return 2;
 }
