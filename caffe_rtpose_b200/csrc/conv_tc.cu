@@ -310,13 +310,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // MMA rings run straight through tile boundaries, and the TMEM accumulator is double-buffered (2 x P*BN
 // columns) so the epilogue of tile i overlaps the main loop of tile i+1 - this removes the per-tile
 // prologue/epilogue latency that dominated the short-K layers (conv1_x, conv2_x).
-template <int BN, int PLANES, int NA, int NB>
+template <int BN, int PLANES, int NA, int NB, int ROWB>
 __global__ void __launch_bounds__(TCW_THREADS, 1)
 conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     static_assert(PLANES == 1 || PLANES == 2, "window kernel supports 1 or 2 planes");
     constexpr int B_BYTES = BN * 128;
     constexpr int A_SLOT = PLANES * TCW_A_BYTES;
-    constexpr int B_SLOT = PLANES * B_BYTES;
+    constexpr int B_TAP = PLANES * B_BYTES;                 // one tap: [B_hi ; B_lo]
+    constexpr int B_SLOT = (ROWB ? 3 : 1) * B_TAP;          // ROWB: all taps of a filter row (ksize <= 3) share a slot
     constexpr int ACC_COLS = PLANES * BN;
     constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
     constexpr uint32_t IDESC1 = umma_idesc(TC_BM, PLANES * BN);   // A_hi x [B_hi;B_lo]
@@ -367,13 +368,22 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         tma_load_3d(smem_a + s * A_SLOT, &tmA, &a_full[s], kb * TC_BK, row0, 0);   // box {64, 136, PLANES}
                         aw++;
                     }
-                    for (int q = 0; q < ks; q++) {
+                    if (ROWB) {   // short-K / narrow-N layers: one barrier round trip per filter row instead of per tap
                         const int s = bt % NB;
                         mbar_wait(&b_empty[s], ((uint32_t)(bt / NB) & 1u) ^ 1u);
-                        mbar_expect_tx(&b_full[s], B_SLOT);
-                        const int tap = r * ks + q;
-                        tma_load_3d(smem_b + s * B_SLOT, &tmB, &b_full[s], tap * a.cin_k + kb * TC_BK, n0, 0);   // box {64, BN, PLANES}
+                        mbar_expect_tx(&b_full[s], ks * B_TAP);
+                        for (int q = 0; q < ks; q++)
+                            tma_load_3d(smem_b + s * B_SLOT + q * B_TAP, &tmB, &b_full[s], (r * ks + q) * a.cin_k + kb * TC_BK, n0, 0);
                         bt++;
+                    } else {
+                        for (int q = 0; q < ks; q++) {
+                            const int s = bt % NB;
+                            mbar_wait(&b_empty[s], ((uint32_t)(bt / NB) & 1u) ^ 1u);
+                            mbar_expect_tx(&b_full[s], B_TAP);
+                            const int tap = r * ks + q;
+                            tma_load_3d(smem_b + s * B_SLOT, &tmB, &b_full[s], tap * a.cin_k + kb * TC_BK, n0, 0);   // box {64, BN, PLANES}
+                            bt++;
+                        }
                     }
                 }
         }
@@ -391,26 +401,41 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int sa_slot = aw % NA;
                     mbar_wait(&a_full[sa_slot], (uint32_t)(aw / NA) & 1u);
                     const uint32_t sa = smem_u32(smem_a + sa_slot * A_SLOT);
-                    for (int q = 0; q < ks; q++) {
+                    // descriptors are built once per operand; K steps and row shifts only move the 14-bit start address
+                    const uint64_t dA0 = umma_desc(sa), dA1 = umma_desc(sa + TCW_A_BYTES);
+                    if (ROWB) {
                         const int sb_slot = bt % NB;
                         mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
                         tc_fence_after();
-                        const uint32_t sb = smem_u32(smem_b + sb_slot * B_SLOT);
+                        const uint64_t dB = umma_desc(smem_u32(smem_b + sb_slot * B_SLOT));
+                        for (int q = 0; q < ks; q++) {
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 16; k++) {
-                            // row-shifted view of the window: start address + q rows; the swizzle phase follows the
-                            // absolute smem address (verified on B200: base_offset must stay 0)
-                            const uint64_t db = umma_desc(sb + k * 32);   // rows [0, PLANES*BN): B_hi then B_lo
-                            const uint64_t da0 = umma_desc(sa + q * 128 + k * 32);
-                            umma_bf16(acc, da0, db, IDESC1, first ? 0u : 1u);
-                            if (PLANES == 2) {
-                                const uint64_t da1 = umma_desc(sa + TCW_A_BYTES + q * 128 + k * 32);
-                                umma_bf16(acc + BN, da1, db, IDESC2, 1u);   // += A_lo x B_hi into the hi*lo columns
+                            for (int k = 0; k < TC_BK / 16; k++) {
+                                const uint64_t db = dB + (uint64_t)(q * (B_TAP >> 4) + k * 2);
+                                umma_bf16(acc, dA0 + (uint64_t)(q * 8 + k * 2), db, IDESC1, first ? 0u : 1u);
+                                if (PLANES == 2) umma_bf16(acc + BN, dA1 + (uint64_t)(q * 8 + k * 2), db, IDESC2, 1u);
+                                first = false;
                             }
-                            first = false;
                         }
                         umma_commit(&b_empty[sb_slot]);
                         bt++;
+                    } else {
+                        for (int q = 0; q < ks; q++) {
+                            const int sb_slot = bt % NB;
+                            mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
+                            tc_fence_after();
+                            const uint64_t dB = umma_desc(smem_u32(smem_b + sb_slot * B_SLOT));
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; k++) {
+                                // row-shifted view of the window: start address + q rows (q*128 B = q*8 units); the swizzle
+                                // phase follows the absolute smem address (verified on B200: base_offset must stay 0)
+                                umma_bf16(acc, dA0 + (uint64_t)(q * 8 + k * 2), dB + (uint64_t)(k * 2), IDESC1, first ? 0u : 1u);
+                                if (PLANES == 2) umma_bf16(acc + BN, dA1 + (uint64_t)(q * 8 + k * 2), dB + (uint64_t)(k * 2), IDESC2, 1u);
+                                first = false;
+                            }
+                            umma_commit(&b_empty[sb_slot]);
+                            bt++;
+                        }
                     }
                     umma_commit(&a_empty[sa_slot]);
                     aw++;
@@ -568,11 +593,11 @@ static int launch_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t 
     }
 }
 
-template <int BN, int PLANES, int NA, int NB>
+template <int BN, int PLANES, int NA, int NB, int ROWB>
 static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
-    auto kern = conv_tcw_kernel<BN, PLANES, NA, NB>;
+    auto kern = conv_tcw_kernel<BN, PLANES, NA, NB, ROWB>;
     static bool attr_set = false;
-    const int smem = NA * PLANES * TCW_A_BYTES + NB * PLANES * BN * 128 + 1024;
+    const int smem = NA * PLANES * TCW_A_BYTES + NB * (ROWB ? 3 : 1) * PLANES * BN * 128 + 1024;
     if (!attr_set) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_set = true;
@@ -583,8 +608,12 @@ static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStr
 }
 template <int BN>
 static int launch_win_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
-    if (l.d.planes == 1) return launch_win_inst<BN, 1, 3, (BN >= 128 ? 8 : 10)>(l, a, grid, st);
-    return launch_win_inst<BN, 2, 2, (BN >= 128 ? 4 : 6)>(l, a, grid, st);
+    if (BN <= 64 && l.d.ksize <= 3) {   // narrow-N layers (conv1_x, the 1x1 heads): filter-row B slots
+        if (l.d.planes == 1) return launch_win_inst<(BN <= 64 ? BN : 64), 1, 3, 4, 1>(l, a, grid, st);
+        return launch_win_inst<(BN <= 64 ? BN : 64), 2, 2, 3, 1>(l, a, grid, st);
+    }
+    if (l.d.planes == 1) return launch_win_inst<BN, 1, 3, (BN >= 128 ? 8 : 10), 0>(l, a, grid, st);
+    return launch_win_inst<BN, 2, 2, (BN >= 128 ? 4 : 6), 0>(l, a, grid, st);
 }
 
 static int env_int(const char* name, int dflt) {
