@@ -44,7 +44,9 @@ ABI_SYMBOLS = [
     "pe_forward_net_input", "pe_forward_maps", "pe_fetch", "pe_fetch_maps", "pe_fetch_blob", "pe_sync", "pe_write_json",
     "pe_model_num_parts", "pe_model_num_limbs", "pe_model_limb_sequence", "pe_model_map_idx", "pe_model_part_name",
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
-    "pe_packed_weights_bytes", "pe_packed_weights_device_ptr",
+    "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
+    "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
+    "pe_caffemodel_last_error",
 ]
 
 
@@ -66,6 +68,14 @@ def lib():
     L.pe_set_conv_weights.argtypes = [C.c_void_p, C.c_char_p, _f32p, C.c_size_t, _f32p, C.c_size_t]
     L.pe_load_weights_file.argtypes = [C.c_void_p, C.c_char_p]
     L.pe_commit_weights.argtypes = [C.c_void_p]
+    L.pe_load_caffemodel.argtypes = [C.c_void_p, C.c_char_p]
+    L.pe_caffemodel_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.pe_caffemodel_close.argtypes = [C.c_void_p]
+    L.pe_caffemodel_num_layers.argtypes = [C.c_void_p]
+    L.pe_caffemodel_layer.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+    L.pe_caffemodel_blob.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+    L.pe_caffemodel_last_error.restype = C.c_char_p
     for f in ("pe_nms_get_max_peaks", "pe_nms_get_num_parts"):
         getattr(L, f).argtypes = [C.c_void_p]
     for f in ("pe_nms_get_threshold", "pe_resize_get_start_scale", "pe_resize_get_scale_gap"):
@@ -257,6 +267,15 @@ class PoseEngine:
     def commit_weights(self):
         self._ck(lib().pe_commit_weights(self._h))
 
+    def load_caffemodel(self, path, commit=True):
+        """Net::CopyTrainedLayersFrom(trained_filename) for a binary .caffemodel (rtpose.cpp:184)."""
+        rc = lib().pe_load_caffemodel(self._h, path.encode())
+        if rc != 0:
+            raise PoseEngineError("pe_load_caffemodel failed (%d): %s / %s" % (
+                rc, lib().pe_caffemodel_last_error().decode(), lib().pe_last_error(self._h).decode()))
+        if commit:
+            self.commit_weights()
+
     def set_connect_params(self, min_subset_cnt, min_subset_score, inter_threshold, inter_min_above):
         self._ck(lib().pe_set_connect_params(self._h, min_subset_cnt, min_subset_score, inter_threshold, inter_min_above))
 
@@ -364,3 +383,72 @@ def write_weights_file(path, weights, table):
             f.write(name.encode().ljust(64, b"\0") + struct.pack("<III", co, ci, k))
             f.write(np.ascontiguousarray(w, np.float32).tobytes())
             f.write(np.ascontiguousarray(b, np.float32).tobytes())
+
+
+def read_caffemodel(path):
+    """Host-only: list of (name, type, [(ndarray, shape), ...]) from a binary .caffemodel (no GPU needed)."""
+    L = lib()
+    h = C.c_void_p()
+    rc = L.pe_caffemodel_open(path.encode(), C.byref(h))
+    if rc != 0:
+        raise PoseEngineError("pe_caffemodel_open failed (%d): %s" % (rc, L.pe_caffemodel_last_error().decode()))
+    out = []
+    try:
+        name, typ = C.create_string_buffer(64), C.create_string_buffer(32)
+        nb = C.c_int()
+        for i in range(L.pe_caffemodel_num_layers(h)):
+            L.pe_caffemodel_layer(h, i, name, typ, C.byref(nb))
+            blobs = []
+            for j in range(nb.value):
+                p = C.POINTER(C.c_float)()
+                cnt, nd = C.c_size_t(), C.c_int()
+                dims = (C.c_longlong * 8)()
+                L.pe_caffemodel_blob(h, i, j, C.byref(p), C.byref(cnt), C.byref(nd), dims)
+                arr = np.ctypeslib.as_array(p, shape=(cnt.value,)).copy() if cnt.value else np.zeros(0, np.float32)
+                blobs.append((arr, tuple(dims[k] for k in range(nd.value))))
+            out.append((name.value.decode(), typ.value.decode(), blobs))
+    finally:
+        L.pe_caffemodel_close(h)
+    return out
+
+
+def _pb_varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _pb_len(field, payload):
+    return _pb_varint((field << 3) | 2) + _pb_varint(len(payload)) + payload
+
+
+def write_caffemodel(path, weights, table, legacy_v1=False, legacy_dims=False):
+    """Serialise weights as a binary caffe NetParameter (`layer`=100, or V1 `layers`=2), BlobProto.data packed,
+    shape as BlobShape or legacy num/channels/height/width - the wire format of pose_iter_*.caffemodel."""
+    net = _pb_len(1, b"synthetic_rtpose")
+    for name, co, ci, k in table:
+        w, b = weights[name]
+        blobs = b""
+        for arr, shape in ((w, (co, ci, k, k)), (b, (co,))):
+            data = _pb_len(5, np.ascontiguousarray(arr, "<f4").tobytes())
+            if legacy_dims:
+                s4 = (1,) * (4 - len(shape)) + tuple(shape)
+                dims = b"".join(_pb_varint((f << 3) | 0) + _pb_varint(v) for f, v in zip((1, 2, 3, 4), s4))
+            else:
+                dims = _pb_len(7, _pb_len(1, b"".join(_pb_varint(v) for v in shape)))
+            blobs += _pb_len(6 if legacy_v1 else 7, dims + data)
+        if legacy_v1:
+            layer = _pb_len(4, name.encode()) + _pb_varint((5 << 3) | 0) + _pb_varint(4) + blobs   # type CONVOLUTION = 4
+            net += _pb_len(2, layer)
+        else:
+            layer = _pb_len(1, name.encode()) + _pb_len(2, b"Convolution") + blobs
+            net += _pb_len(100, layer)
+            net += _pb_len(100, _pb_len(1, ("relu_" + name).encode()) + _pb_len(2, b"ReLU"))   # blob-less layer, ignored
+    with open(path, "wb") as f:
+        f.write(net)

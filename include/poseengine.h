@@ -61,6 +61,19 @@ int pe_conv_layer_info(const pe_engine* e, int idx, char* name64, int* cout, int
 int pe_set_conv_weights(pe_engine* e, const char* layer_name, const float* w, size_t nw, const float* b, size_t nb);
 /* flat file: "RTPW" u32 version=1 u32 nlayers { char name[64]; u32 cout,cin,k; f32 w[]; f32 b[] } */
 int pe_load_weights_file(pe_engine* e, const char* path);
+/* .caffemodel (binary NetParameter, caffe.proto:92-95 `layer`=100 / legacy `layers`=2): the file rtpose.bin
+ * passes to CopyTrainedLayersFrom (rtpose.cpp:59,184).  Matching by layer name, unknown layers ignored,
+ * blob-count / shape mismatch is an error (net.cpp:750-786). */
+int pe_load_caffemodel(pe_engine* e, const char* path);
+/* host-only iteration over a .caffemodel (no GPU needed) */
+typedef struct pe_caffemodel pe_caffemodel;
+int pe_caffemodel_open(const char* path, pe_caffemodel** out);
+void pe_caffemodel_close(pe_caffemodel* m);
+int pe_caffemodel_num_layers(const pe_caffemodel* m);
+int pe_caffemodel_layer(const pe_caffemodel* m, int idx, char* name64, char* type32, int* num_blobs);
+int pe_caffemodel_blob(const pe_caffemodel* m, int layer, int blob, const float** data, size_t* count, int* ndim,
+                       long long* dims8);
+const char* pe_caffemodel_last_error(void);
 /* pack + upload; must be called once after the weights are set and before any forward */
 int pe_commit_weights(pe_engine* e);
 

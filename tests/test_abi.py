@@ -71,3 +71,27 @@ def test_weight_file_roundtrip(tmp_path):
     engine.write_weights_file(p, w, synth.conv_table(engine.MPI_15))
     raw = open(p, "rb").read()
     assert raw[:4] == b"RTPW" and len(raw) > 4 * 51000000
+
+
+@pytest.mark.parametrize("v1,legacy_dims", [(False, False), (True, True), (False, True)])
+def test_caffemodel_wire_reader(tmp_path, v1, legacy_dims):
+    """pe_caffemodel_*: binary NetParameter walker (caffe.proto:10-22, 92-95, 311-329, 1272-1276), host only."""
+    table = [("conv1_1", 4, 3, 3), ("Mconv7_stage6_L2", 5, 7, 1)]
+    rng = np.random.default_rng(1)
+    w = {n: (rng.standard_normal((co, ci, k, k)).astype(np.float32), rng.standard_normal(co).astype(np.float32))
+         for n, co, ci, k in table}
+    p = str(tmp_path / "m.caffemodel")
+    engine.write_caffemodel(p, w, table, legacy_v1=v1, legacy_dims=legacy_dims)
+    layers = [l for l in engine.read_caffemodel(p) if l[2]]
+    assert [l[0] for l in layers] == [t[0] for t in table]
+    for (name, typ, blobs), (n, co, ci, k) in zip(layers, table):
+        assert typ == ("V1:4" if v1 else "Convolution")
+        assert np.array_equal(blobs[0][0], w[n][0].ravel()) and np.array_equal(blobs[1][0], w[n][1])
+        assert blobs[0][1] == (co, ci, k, k)
+        assert blobs[1][1] == ((1, 1, 1, co) if legacy_dims else (co,))
+    with pytest.raises(engine.PoseEngineError):
+        engine.read_caffemodel(str(tmp_path / "missing.caffemodel"))
+    bad = tmp_path / "bad.caffemodel"
+    bad.write_bytes(b"\x92\x06\xff\xff\xff\xff\x0f garbage")
+    with pytest.raises(engine.PoseEngineError):
+        engine.read_caffemodel(str(bad))

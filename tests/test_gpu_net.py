@@ -141,3 +141,25 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(engine.PoseEngineError, match="expected"):
         eng.set_weights({"conv1_1": (np.zeros((64, 3, 5, 5), np.float32), np.zeros(64, np.float32))}, commit=False)
     eng.close()
+
+
+def test_load_caffemodel_equals_set_weights(small, tmp_path):
+    """Net::CopyTrainedLayersFrom path: a .caffemodel written in the reference's wire format loads to the same net."""
+    s = small
+    p = str(tmp_path / "he.caffemodel")
+    engine.write_caffemodel(p, s["W"], synth.conv_table(s["model"]))
+    eng = engine.PoseEngine(s["model"], s["net_w"], s["net_h"], 320, 192, precision=engine.PREC_BF16X2)
+    eng.load_caffemodel(p)
+    eng.forward_frames(s["frames"][:1])
+    maps = eng.fetch_maps(1)
+    eng.set_weights(s["W"])
+    eng.forward_frames(s["frames"][:1])
+    assert np.array_equal(maps, eng.fetch_maps(1))
+    # shape mismatch is fatal in the reference (net.cpp:770-786) and an error here
+    bad = dict(s["W"])
+    bad["conv1_2"] = (np.zeros((64, 64, 1, 1), np.float32), np.zeros(64, np.float32))
+    tbl = [(n, co, ci, (1 if n == "conv1_2" else k)) for n, co, ci, k in synth.conv_table(s["model"])]
+    engine.write_caffemodel(p, bad, tbl)
+    with pytest.raises(engine.PoseEngineError):
+        eng.load_caffemodel(p)
+    eng.close()
