@@ -24,6 +24,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include <string>
 
 #include "common.h"
@@ -119,11 +121,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Same, for an operand whose first row is NOT on a 1024-byte swizzle-atom boundary (row-shifted view of a
-// larger tile): base_offset field [49,52) = (start address >> 7) & 7 (PTX ISA, tcgen05 matrix descriptor).
-__device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, uint32_t base_off) {
-    return umma_desc(saddr) | ((uint64_t)(base_off & 7u) << 49);
-}
+// A row-shifted view of a larger tile (start address not on a 1024-byte swizzle-atom boundary) uses the same
+// descriptor with the shifted start address: on B200 the swizzle phase follows the absolute shared-memory address
+// bits, and the base_offset field [49,52) must stay 0 (measured: setting it to (addr>>7)&7 gives wrong results).
 // instruction descriptor kind::f16 (InstrDescriptor): c_format F32 (bit 4), a/b format BF16 (bits 7,10),
 // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
@@ -573,11 +573,13 @@ static int pick_stages(int bn, int planes) {
 template <int BN, int PLANES, int STAGES>
 static int launch_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
     auto kern = conv_tc_kernel<BN, PLANES, STAGES>;
-    static bool attr_set = false;
     const int smem = STAGES * stage_bytes(BN, PLANES) + 1024;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_done{0};   // bit d: attribute set on device d (it is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_done.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
+        attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
     kern<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], a);
@@ -596,11 +598,13 @@ static int launch_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t 
 template <int BN, int PLANES, int NA, int NB, int ROWB>
 static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
     auto kern = conv_tcw_kernel<BN, PLANES, NA, NB, ROWB>;
-    static bool attr_set = false;
     const int smem = NA * PLANES * TCW_A_BYTES + NB * (ROWB ? 3 : 1) * PLANES * BN * 128 + 1024;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_done{0};   // bit d: attribute set on device d (it is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_done.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
+        attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
     kern<<<grid, TCW_THREADS, smem, st>>>(maps[2], maps[3], a);

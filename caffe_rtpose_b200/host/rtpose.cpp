@@ -1,0 +1,437 @@
+// rtpose.bin - host pipeline over libposeengine.so with the reference's command line
+// (examples/rtpose/rtpose.cpp:50-72 flags; :1459-1549 thread topology: one producer, --num_gpu workers each
+// owning one engine handle, one re-orderer, one writer).  Host code is plain C++17 (the reference's gflags / glog /
+// boost / OpenCV are not available here and are not needed for this path); all math is behind the C ABI.
+//
+// Supported sources: --image_dir with .bmp (24-bit) and .ppm (P6) files, or --synthetic N procedural frames.
+// .jpg/.png/--video/--camera need an image/video codec and are rejected with an explicit message.  Display,
+// keyboard handling and --write_frames (rendering) are not part of this path.
+#include <dirent.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "caffe/cpm/layers/imresize_layer.hpp"
+#include "caffe/cpm/layers/nms_layer.hpp"
+#include "poseengine.h"
+#include "rtpose/modelDescriptorFactory.h"
+
+// ---------------------------------------------------------------------------------------------- flags
+struct Flag { std::string value, help; bool is_bool; };
+static std::map<std::string, Flag> g_flags;
+static void define(const char* name, const char* dflt, const char* help, bool is_bool = false) { g_flags[name] = {dflt, help, is_bool}; }
+static std::string F(const char* n) { return g_flags.at(n).value; }
+static int Fi(const char* n) { return atoi(F(n).c_str()); }
+static double Fd(const char* n) { return atof(F(n).c_str()); }
+static bool Fb(const char* n) { const std::string v = F(n); return v == "true" || v == "1"; }
+
+static void define_flags() {
+    // names, defaults and help strings of rtpose.cpp:50-72
+    define("fullscreen", "false", "Run in fullscreen mode (press f during runtime to toggle)", true);
+    define("part_to_show", "0", "Part to show from the start.");
+    define("write_frames", "", "Write frames with format prefix%06d.jpg");
+    define("no_frame_drops", "false", "Dont drop frames.", true);
+    define("write_json", "", "Write joint data with json format as prefix%06d.json");
+    define("camera", "0", "The camera index for VideoCapture.");
+    define("video", "", "Use a video file instead of the camera.");
+    define("image_dir", "", "Process a directory of images.");
+    define("start_frame", "0", "Skip to frame # of video");
+    define("caffemodel", "model/coco/pose_iter_440000.caffemodel", "Caffe model.");
+    define("caffeproto", "model/coco/pose_deploy_linevec.prototxt", "Caffe deploy prototxt.");
+    define("resolution", "1280x720", "The image resolution (display).");
+    define("net_resolution", "656x368", "Multiples of 16.");
+    define("camera_resolution", "1280x720", "Size of the camera frames to ask for.");
+    define("start_device", "0", "GPU device start number.");
+    define("num_gpu", "1", "The number of GPU devices to use.");
+    define("start_scale", "1", "Initial scale. Must cv::Match net_resolution");
+    define("scale_gap", "0.3", "Scale gap between scales. No effect unless num_scales>1");
+    define("num_scales", "1", "Number of scales to average");
+    define("no_display", "false", "Do not open a display window.", true);
+    define("no_text", "false", "Do not write text on output images.", true);
+    define("logtostderr", "false", "glog compatibility: log to stderr", true);
+    // extensions of this implementation (not in the reference)
+    define("synthetic", "0", "[extension] process N procedurally generated frames instead of a camera/video/image_dir");
+    define("random_init", "", "[extension] 'he' or 'caffe': random weights instead of --caffemodel (no checkpoint offline)");
+    define("model", "", "[extension] COCO or MPI when --caffeproto is not readable");
+    define("precision", "2", "[extension] conv arithmetic: 0 fp32 SIMT, 1 bf16, 2 split-bf16 parity mode");
+    define("batch", "1", "[extension] frames per forward per GPU (1 = the reference's behaviour)");
+}
+
+static int parse_flags(int argc, char** argv) {
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "--help" || a == "-help") {
+            for (auto& kv : g_flags) printf("  --%s (%s) default: \"%s\"\n", kv.first.c_str(), kv.second.help.c_str(), kv.second.value.c_str());
+            exit(0);
+        }
+        if (a.rfind("--", 0) != 0 && a.rfind("-", 0) == 0) a = "-" + a;   // gflags accepts -flag too
+        if (a.rfind("--", 0) != 0) { fprintf(stderr, "ERROR: unexpected argument '%s'\n", argv[i]); return 1; }
+        a = a.substr(2);
+        std::string name = a, value;
+        bool has_value = false;
+        const size_t eq = a.find('=');
+        if (eq != std::string::npos) { name = a.substr(0, eq); value = a.substr(eq + 1); has_value = true; }
+        if (!g_flags.count(name) && name.rfind("no", 0) == 0 && g_flags.count(name.substr(2)) && g_flags[name.substr(2)].is_bool) {
+            g_flags[name.substr(2)].value = "false";   // gflags --noflag
+            continue;
+        }
+        if (!g_flags.count(name)) { fprintf(stderr, "ERROR: unknown command line flag '%s'\n", name.c_str()); return 1; }
+        Flag& f = g_flags[name];
+        if (f.is_bool && !has_value) { f.value = "true"; continue; }
+        if (!has_value) {
+            if (i + 1 >= argc) { fprintf(stderr, "ERROR: flag '--%s' is missing its argument\n", name.c_str()); return 1; }
+            value = argv[++i];
+        }
+        f.value = value;
+    }
+    return 0;
+}
+
+#define LOG_INFO(...) do { fprintf(stderr, "I rtpose] " __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
+#define LOG_ERROR(...) do { fprintf(stderr, "E rtpose] " __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
+
+// ---------------------------------------------------------------------------------------------- frames
+struct Frame {
+    int index = 0, video_frame_number = 0;
+    double scale = 1.0;                      // display / original (rtpose.cpp:474-480); identity here
+    std::vector<uint8_t> bgr;                // display image, HWC BGR
+    std::string stem;                        // for <stem>.json with --image_dir
+    int num_people = 0;
+    std::vector<float> joints;
+    double t_commit = 0, t_done = 0;
+};
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static bool read_ppm(const std::string& path, int& w, int& h, std::vector<uint8_t>& bgr) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char magic[3] = {0};
+    int maxv = 0;
+    if (fscanf(f, "%2s", magic) != 1 || strcmp(magic, "P6")) { fclose(f); return false; }
+    int vals[3], got = 0;
+    while (got < 3) {
+        int c = fgetc(f);
+        if (c == '#') { while (c != '\n' && c != EOF) c = fgetc(f); continue; }
+        if (c == EOF) { fclose(f); return false; }
+        if (c >= '0' && c <= '9') { ungetc(c, f); if (fscanf(f, "%d", &vals[got]) != 1) { fclose(f); return false; } got++; }
+    }
+    w = vals[0]; h = vals[1]; maxv = vals[2];
+    fgetc(f);
+    if (maxv != 255 || w <= 0 || h <= 0) { fclose(f); return false; }
+    std::vector<uint8_t> rgb((size_t)w * h * 3);
+    const bool ok = fread(rgb.data(), 1, rgb.size(), f) == rgb.size();
+    fclose(f);
+    if (!ok) return false;
+    bgr.resize(rgb.size());
+    for (size_t i = 0; i < rgb.size(); i += 3) { bgr[i] = rgb[i + 2]; bgr[i + 1] = rgb[i + 1]; bgr[i + 2] = rgb[i]; }
+    return true;
+}
+
+static bool read_bmp(const std::string& path, int& w, int& h, std::vector<uint8_t>& bgr) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint8_t hd[54];
+    if (fread(hd, 1, 54, f) != 54 || hd[0] != 'B' || hd[1] != 'M') { fclose(f); return false; }
+    const uint32_t off = hd[10] | (hd[11] << 8) | (hd[12] << 16) | ((uint32_t)hd[13] << 24);
+    const int32_t bw = (int32_t)(hd[18] | (hd[19] << 8) | (hd[20] << 16) | ((uint32_t)hd[21] << 24));
+    const int32_t bh = (int32_t)(hd[22] | (hd[23] << 8) | (hd[24] << 16) | ((uint32_t)hd[25] << 24));
+    const int bpp = hd[28] | (hd[29] << 8), comp = hd[30];
+    if (bpp != 24 || comp != 0 || bw <= 0 || bh == 0) { fclose(f); return false; }
+    w = bw; h = bh < 0 ? -bh : bh;
+    const size_t stride = ((size_t)w * 3 + 3) & ~(size_t)3;
+    std::vector<uint8_t> row(stride);
+    bgr.resize((size_t)w * h * 3);
+    fseek(f, off, SEEK_SET);
+    for (int y = 0; y < h; y++) {
+        if (fread(row.data(), 1, stride, f) != stride) { fclose(f); return false; }
+        const int dy = bh < 0 ? y : h - 1 - y;   // bottom-up unless the height is negative
+        memcpy(&bgr[(size_t)dy * w * 3], row.data(), (size_t)w * 3);
+    }
+    fclose(f);
+    return true;
+}
+
+static void synthetic_frame(int idx, int w, int h, std::vector<uint8_t>& bgr) {
+    bgr.resize((size_t)w * h * 3);
+    uint32_t s = 0x9E3779B9u * (uint32_t)(idx + 1);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            for (int c = 0; c < 3; c++) {
+                s = s * 1664525u + 1013904223u;
+                const int low = 128 + (int)(100.0 * sin((x + 31 * c) / 41.0) * cos((y + 17 * idx) / 57.0));
+                bgr[((size_t)y * w + x) * 3 + c] = (uint8_t)std::min(255, std::max(0, (low + (int)(s >> 24)) / 2));
+            }
+}
+
+// ---------------------------------------------------------------------------------------------- queue
+template <typename T>
+class BlockingQueue {   // the subset of caffe::BlockingQueue the demo uses (push / try_pop / pop / size), std-only
+public:
+    void push(T v) { { std::lock_guard<std::mutex> l(m_); q_.push(std::move(v)); } cv_.notify_one(); }
+    bool try_pop(T* out) { std::lock_guard<std::mutex> l(m_); if (q_.empty()) return false; *out = std::move(q_.front()); q_.pop(); return true; }
+    bool pop(T* out, const std::atomic<bool>& quit) {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return !q_.empty() || quit.load(); });
+        if (q_.empty()) return false;
+        *out = std::move(q_.front()); q_.pop(); return true;
+    }
+    size_t size() { std::lock_guard<std::mutex> l(m_); return q_.size(); }
+    void wake() { cv_.notify_all(); }
+private:
+    std::mutex m_; std::condition_variable cv_; std::queue<T> q_;
+};
+
+struct Global {
+    BlockingQueue<Frame> input_queue, output_queue;
+    std::priority_queue<int, std::vector<int>, std::greater<int>> dropped_index;
+    std::mutex mutex;
+    std::atomic<bool> producer_done{false}, quit{false};
+    std::atomic<int> produced{0}, finished{0};
+    int disp_w = 0, disp_h = 0, net_w = 0, net_h = 0, model = PE_MODEL_COCO_18, num_parts = 18;
+    std::vector<std::string> image_list;
+} global;
+
+// ---------------------------------------------------------------------------------------------- weights
+static int model_from_prototxt(const std::string& path) {   // the reference infers the model from nms num_parts (:212-229)
+    std::ifstream f(path);
+    if (!f) return -1;
+    std::string tok;
+    while (f >> tok)
+        if (tok == "num_parts:") { int v = 0; f >> v; return v == 15 ? PE_MODEL_MPI_15 : (v == 18 ? PE_MODEL_COCO_18 : -2); }
+    return -2;
+}
+
+static void random_weights(pe_engine* e, const std::string& kind) {
+    uint64_t s = 1234;
+    auto uni = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return ((s >> 11) + 0.5) / 9007199254740992.0; };
+    char name[64];
+    int co, ci, k;
+    for (int i = 0; i < pe_num_conv_layers(e); i++) {
+        pe_conv_layer_info(e, i, name, &co, &ci, &k);
+        const double stdv = kind == "caffe" ? 0.01 : sqrt(2.0 / (ci * k * k));
+        std::vector<float> w((size_t)co * ci * k * k), b(co, 0.f);
+        for (size_t j = 0; j + 1 < w.size(); j += 2) {   // Box-Muller
+            const double r = sqrt(-2.0 * log(uni())), t = 6.283185307179586 * uni();
+            w[j] = (float)(stdv * r * cos(t)); w[j + 1] = (float)(stdv * r * sin(t));
+        }
+        pe_set_conv_weights(e, name, w.data(), w.size(), b.data(), b.size());
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- threads
+static void producer() {
+    const int n_syn = Fi("synthetic");
+    const int total = n_syn > 0 ? n_syn : (int)global.image_list.size();
+    for (int i = Fi("start_frame"); i < total && !global.quit; i++) {
+        Frame fr;
+        fr.index = global.produced; fr.video_frame_number = i;
+        int w = global.disp_w, h = global.disp_h;
+        if (n_syn > 0) {
+            synthetic_frame(i, w, h, fr.bgr);
+        } else {
+            const std::string& p = global.image_list[i];
+            const bool ok = p.size() > 4 && p.substr(p.size() - 4) == ".ppm" ? read_ppm(p, w, h, fr.bgr) : read_bmp(p, w, h, fr.bgr);
+            if (!ok) { LOG_ERROR("cannot decode %s (only 24-bit .bmp and P6 .ppm are supported without an image codec)", p.c_str()); continue; }
+            if (w != global.disp_w || h != global.disp_h) {
+                LOG_ERROR("%s is %dx%d but --resolution is %dx%d: the warpAffine rescale of rtpose.cpp:474-487 is not part of "
+                          "this path; pass --resolution -1x-1 or matching images", p.c_str(), w, h, global.disp_w, global.disp_h);
+                continue;
+            }
+            const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
+            fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
+        }
+        fr.t_commit = now_s();
+        while (global.input_queue.size() > 64 && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        global.input_queue.push(std::move(fr));
+        global.produced++;
+    }
+    global.producer_done = true;
+    global.input_queue.wake();
+}
+
+static void worker(int tid) {
+    const int device = Fi("start_device") + tid, batch = std::max(1, Fi("batch"));
+    pe_config c;
+    memset(&c, 0, sizeof c);
+    c.device = device; c.model = global.model; c.net_w = global.net_w; c.net_h = global.net_h;
+    c.disp_w = global.disp_w; c.disp_h = global.disp_h; c.num_scales = Fi("num_scales");
+    c.start_scale = Fd("start_scale"); c.scale_gap = Fd("scale_gap"); c.max_batch = batch; c.precision = Fi("precision");
+    pe_engine* e = nullptr;
+    struct Done { ~Done() { global.finished++; global.output_queue.wake(); } } done_guard;   // every exit path counts
+    if (pe_create(&c, &e)) { LOG_ERROR("GPU %d: %s", device, pe_last_error(nullptr)); global.quit = true; global.input_queue.wake(); return; }
+    LOG_INFO("GPU %d: copying to person net", device);
+    int rc = 0;
+    if (!F("random_init").empty()) random_weights(e, F("random_init"));
+    else rc = pe_load_caffemodel(e, F("caffemodel").c_str());
+    if (rc || pe_commit_weights(e)) {
+        LOG_ERROR("GPU %d: cannot load %s: %s %s", device, F("caffemodel").c_str(), pe_caffemodel_last_error(), pe_last_error(e));
+        global.quit = true; global.input_queue.wake(); pe_destroy(e); return;
+    }
+    caffe::NmsLayer<float> nms_layer(e);
+    caffe::ImResizeLayer<float> resize_layer(e);
+    resize_layer.SetStartScale((float)Fd("start_scale"));
+    resize_layer.SetScaleGap((float)Fd("scale_gap"));
+    LOG_INFO("GPU %d is ready (model %s, max_peaks %d)", device, nms_layer.GetNumParts() == 15 ? "MPI" : "COCO", nms_layer.GetMaxPeaks());
+    const int P = nms_layer.GetNumParts();
+    std::vector<float> joints((size_t)PE_MAX_PEOPLE * P * 3);
+    while (!global.quit) {
+        std::vector<Frame> frames;
+        Frame fr;
+        while ((int)frames.size() < batch && global.input_queue.try_pop(&fr)) {
+            // drop frames that waited more than 0.1 s unless --no_frame_drops (rtpose.cpp:1107-1124); file and
+            // synthetic sources never drop (the reference's image_dir runs are meant to process every image)
+            const bool live = false;
+            if (live && !Fb("no_frame_drops") && now_s() - fr.t_commit > 0.1) {
+                std::lock_guard<std::mutex> l(global.mutex);
+                global.dropped_index.push(fr.index);
+                continue;
+            }
+            frames.push_back(std::move(fr));
+        }
+        if (frames.empty()) {
+            if (global.producer_done && global.input_queue.size() == 0) break;
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+            continue;
+        }
+        std::vector<const uint8_t*> ptrs;
+        for (auto& f : frames) ptrs.push_back(f.bgr.data());
+        if (pe_forward_frames(e, ptrs.data(), (int)ptrs.size())) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break; }
+        for (size_t i = 0; i < frames.size(); i++) {
+            int cnt = 0;
+            if (pe_fetch(e, (int)i, joints.data(), &cnt, nullptr)) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break; }
+            frames[i].num_people = cnt;
+            frames[i].joints.assign(joints.begin(), joints.begin() + (size_t)cnt * P * 3);
+            frames[i].t_done = now_s();
+            global.output_queue.push(std::move(frames[i]));
+        }
+    }
+    pe_destroy(e);
+}
+
+// re-order by frame index (buffer_and_order, rtpose.cpp:1214-1273) and write JSON (displayFrame, :1383-1416)
+static void orderer_and_writer(int num_workers) {
+    auto cmp = [](const Frame& a, const Frame& b) { return a.index > b.index; };
+    std::priority_queue<Frame, std::vector<Frame>, decltype(cmp)> heap(cmp);
+    int next = 0, written = 0;
+    const double t0 = now_s();
+    double last = t0;
+    const std::string out = F("write_json");
+    auto emit = [&](const Frame& fr) {
+        if (!out.empty()) {
+            char fname[1024];
+            if (F("image_dir").empty()) snprintf(fname, sizeof fname, "%s/frame%06d.json", out.c_str(), fr.video_frame_number);
+            else snprintf(fname, sizeof fname, "%s/%s.json", out.c_str(), fr.stem.c_str());
+            const int need = pe_write_json(fr.joints.data(), fr.num_people, global.num_parts, fr.scale, nullptr, 0);
+            std::vector<char> buf((size_t)need + 1);
+            pe_write_json(fr.joints.data(), fr.num_people, global.num_parts, fr.scale, buf.data(), need + 1);
+            FILE* f = fopen(fname, "wb");
+            if (f) { fwrite(buf.data(), 1, (size_t)need, f); fclose(f); }
+        }
+        written++;
+        if (written % 30 == 0) {   // the reference prints FPS every 30 frames (:1421-1441)
+            const double t = now_s();
+            LOG_INFO("frame %d  people %d  FPS %.1f  latency %.1f ms", fr.index, fr.num_people, 30.0 / (t - last), 1e3 * (fr.t_done - fr.t_commit));
+            last = t;
+        }
+    };
+    while (true) {
+        Frame fr;
+        const bool got = global.output_queue.try_pop(&fr);
+        if (got) heap.push(std::move(fr));
+        while (true) {
+            {
+                std::lock_guard<std::mutex> l(global.mutex);
+                while (!global.dropped_index.empty() && global.dropped_index.top() == next) { global.dropped_index.pop(); next++; }
+            }
+            if (!heap.empty() && heap.top().index == next) { emit(heap.top()); heap.pop(); next++; }
+            else break;
+        }
+        if (!got) {
+            if (global.finished == num_workers && global.output_queue.size() == 0) {
+                while (!heap.empty()) { emit(heap.top()); heap.pop(); }   // flush (frames lost to an error leave gaps)
+                break;
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+    }
+    const double dt = now_s() - t0;
+    LOG_INFO("Done, exiting. # frames: %d  (%.1f frames/s overall)", written, written / std::max(dt, 1e-9));
+}
+
+static bool ensure_dir(const std::string& d) {
+    struct stat st;
+    if (stat(d.c_str(), &st) == 0) return S_ISDIR(st.st_mode);
+    return mkdir(d.c_str(), 0755) == 0;
+}
+
+int main(int argc, char** argv) {
+    define_flags();
+    if (parse_flags(argc, argv)) return 1;
+    if (!F("video").empty() || (F("image_dir").empty() && Fi("synthetic") <= 0)) {
+        LOG_ERROR("camera/video capture needs a video codec that this build does not have; use --image_dir (.bmp/.ppm) or --synthetic N");
+        return 1;
+    }
+    if (!F("write_frames").empty()) LOG_ERROR("--write_frames needs the renderer + a JPEG encoder (SURVEY.md 8f rank 2); ignoring");
+    if (sscanf(F("resolution").c_str(), "%dx%d", &global.disp_w, &global.disp_h) != 2) { LOG_ERROR("Error, resolution format (%s) invalid, should be e.g., 960x540", F("resolution").c_str()); return 1; }
+    if (sscanf(F("net_resolution").c_str(), "%dx%d", &global.net_w, &global.net_h) != 2) { LOG_ERROR("Error, net resolution format (%s) invalid, should be e.g., 656x368 (multiples of 16)", F("net_resolution").c_str()); return 1; }
+    if (!F("image_dir").empty()) {   // readImageDirIfFlagEnabled (rtpose.cpp:1732-1755): sorted list of image files
+        DIR* d = opendir(F("image_dir").c_str());
+        if (!d) { LOG_ERROR("Folder %s does not exist.", F("image_dir").c_str()); return -1; }
+        while (dirent* ent = readdir(d)) {
+            const std::string n = ent->d_name;
+            const size_t dot = n.find_last_of('.');
+            const std::string ext = dot == std::string::npos ? "" : n.substr(dot);
+            if (ext == ".bmp" || ext == ".ppm") global.image_list.push_back(F("image_dir") + "/" + n);
+            else if (ext == ".jpg" || ext == ".png") LOG_ERROR("skipping %s: no JPEG/PNG codec in this build", n.c_str());
+        }
+        closedir(d);
+        std::sort(global.image_list.begin(), global.image_list.end());
+        if (global.disp_w == -1 && !global.image_list.empty()) {   // --resolution -1x-1: take it from the first image (:1683-1686)
+            std::vector<uint8_t> tmp;
+            const std::string& p = global.image_list[0];
+            if (!(p.substr(p.size() - 4) == ".ppm" ? read_ppm(p, global.disp_w, global.disp_h, tmp) : read_bmp(p, global.disp_w, global.disp_h, tmp))) return 1;
+            LOG_INFO("Setting display resolution from first image: %dx%d", global.disp_w, global.disp_h);
+        }
+    }
+    if (global.disp_w <= 0 || global.disp_h <= 0) { LOG_ERROR("Invalid resolution without video/images: %dx%d", global.disp_w, global.disp_h); return 1; }
+    LOG_INFO("Display resolution: %dx%d", global.disp_w, global.disp_h);
+    LOG_INFO("Net resolution: %dx%d", global.net_w, global.net_h);
+    if (!F("write_json").empty() && !ensure_dir(F("write_json"))) { LOG_ERROR("Could not write to or create directory %s", F("write_json").c_str()); return 1; }
+
+    int model = model_from_prototxt(F("caffeproto"));
+    if (model < 0 && !F("model").empty()) model = F("model") == "MPI" ? PE_MODEL_MPI_15 : PE_MODEL_COCO_18;
+    if (model == -1) { LOG_ERROR("cannot read --caffeproto %s (pass --model COCO|MPI to run without it)", F("caffeproto").c_str()); return 1; }
+    if (model == -2) { LOG_ERROR("Unknown number of parts! Couldn't set model"); return 1; }
+    global.model = model;
+    {
+        std::unique_ptr<ModelDescriptor> md;
+        ModelDescriptorFactory::createModelDescriptor(model == PE_MODEL_MPI_15 ? ModelDescriptorFactory::Type::MPI_15 : ModelDescriptorFactory::Type::COCO_18, md);
+        global.num_parts = md->get_number_parts();
+        LOG_INFO("Selecting %s model: %d parts, %d limbs.", model == PE_MODEL_MPI_15 ? "MPI" : "COCO", global.num_parts, md->number_limb_sequence());
+    }
+    const int num_gpu = std::max(1, Fi("num_gpu"));
+    std::vector<std::thread> workers;
+    for (int i = 0; i < num_gpu; i++) workers.emplace_back(worker, i);
+    std::thread prod(producer);
+    std::thread ord(orderer_and_writer, num_gpu);
+    prod.join();
+    for (auto& t : workers) t.join();
+    ord.join();
+    return global.quit ? 1 : 0;
+}

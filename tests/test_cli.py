@@ -1,0 +1,90 @@
+"""rtpose.bin (caffe_rtpose_b200/host/rtpose.cpp): the reference's command line (examples/rtpose/rtpose.cpp:50-72)
+over the C ABI.  CPU part: flag surface and error behaviour; GPU part: JSON files identical to the Python path."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from caffe_rtpose_b200 import engine, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "caffe_rtpose_b200", "rtpose.bin")
+
+REFERENCE_FLAGS = {  # name -> default (rtpose.cpp:50-72)
+    "fullscreen": "false", "part_to_show": "0", "write_frames": "", "no_frame_drops": "false", "write_json": "", "camera": "0",
+    "video": "", "image_dir": "", "start_frame": "0", "caffemodel": "model/coco/pose_iter_440000.caffemodel",
+    "caffeproto": "model/coco/pose_deploy_linevec.prototxt", "resolution": "1280x720", "net_resolution": "656x368",
+    "camera_resolution": "1280x720", "start_device": "0", "num_gpu": "1", "start_scale": "1", "scale_gap": "0.3",
+    "num_scales": "1", "no_display": "false", "no_text": "false"}
+
+
+def run(args, timeout=120):
+    return subprocess.run([BIN] + args, capture_output=True, text=True, timeout=timeout)
+
+
+def test_flag_surface_matches_reference():
+    r = run(["--help"])
+    assert r.returncode == 0
+    for name, dflt in REFERENCE_FLAGS.items():
+        assert '--%s (' % name in r.stdout and 'default: "%s"' % dflt in r.stdout, name
+
+
+def test_flag_errors():
+    assert run(["--bogus", "1"]).returncode == 1
+    r = run([])  # no camera/video support without a codec: explicit message, not a hang
+    assert r.returncode == 1 and "codec" in r.stderr
+    r = run(["--synthetic", "2", "--resolution", "abc", "--model", "COCO"])
+    assert r.returncode == 1 and "resolution format" in r.stderr
+
+
+def write_bmp(path, bgr):
+    h, w, _ = bgr.shape
+    stride = (w * 3 + 3) & ~3
+    rows = b"".join(bgr[y].tobytes() + b"\0" * (stride - w * 3) for y in range(h - 1, -1, -1))
+    with open(path, "wb") as f:
+        f.write(b"BM" + struct.pack("<IHHI", 54 + len(rows), 0, 0, 54))
+        f.write(struct.pack("<IiiHHIIiiII", 40, w, h, 1, 24, 0, len(rows), 2835, 2835, 0, 0))
+        f.write(rows)
+
+
+def write_ppm(path, bgr):
+    h, w, _ = bgr.shape
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        f.write(np.ascontiguousarray(bgr[:, :, ::-1]).tobytes())
+
+
+@pytest.mark.gpu
+def test_cli_json_equals_python_path(tmp_path):
+    model, net_w, net_h, disp_w, disp_h = engine.COCO_18, 160, 96, 320, 192
+    W = synth.make_weights(model, "he")
+    cm = str(tmp_path / "pose.caffemodel")
+    engine.write_caffemodel(cm, W, synth.conv_table(model))
+    proto = tmp_path / "deploy.prototxt"
+    proto.write_text('layer { name: "nms" type: "Nms" nms_param { threshold: 0.05 max_peaks: 64 num_parts: 18 } }\n')
+    img_dir = tmp_path / "frames"
+    img_dir.mkdir()
+    frames = [synth.make_frame(20 + i, disp_h, disp_w) for i in range(5)]
+    for i, f in enumerate(frames):
+        (write_bmp if i % 2 == 0 else write_ppm)(str(img_dir / ("img%03d.%s" % (i, "bmp" if i % 2 == 0 else "ppm"))), f)
+    out = tmp_path / "json"
+    r = run(["--image_dir", str(img_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "%dx%d" % (disp_w, disp_h),
+             "--net_resolution", "%dx%d" % (net_w, net_h), "--write_json", str(out), "--no_display", "--num_gpu", "1"], timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
+    eng.set_weights(W)
+    for i, f in enumerate(frames):
+        eng.forward_frames([f])
+        cnt, joints, _ = eng.fetch(0)
+        got = (out / ("img%03d.json" % i)).read_text()
+        assert got == eng.json(joints, 1.0)
+    eng.close()
+    # --resolution -1x-1 takes the size from the first image (rtpose.cpp:1683-1686); missing model file is an error
+    r = run(["--image_dir", str(img_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "-1x-1",
+             "--net_resolution", "%dx%d" % (net_w, net_h), "--no_display"], timeout=300)
+    assert r.returncode == 0 and "from first image: 320x192" in r.stderr
+    r = run(["--image_dir", str(img_dir), "--caffemodel", str(tmp_path / "none.caffemodel"), "--caffeproto", str(proto),
+             "--resolution", "320x192", "--net_resolution", "160x96"], timeout=300)
+    assert r.returncode == 1 and "cannot load" in r.stderr
