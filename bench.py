@@ -303,8 +303,15 @@ def main():
         peak, _, how = peaks_info()
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
         step_ms = ms_dev / args.steps
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
+        if os.path.exists(tp):   # dram__bytes_read+write per launch from the committed ncu capture of this same workload
+            tj = json.load(open(tp))
+            if tj.get("batch") == B and tj.get("precision") == args.precision:
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "%s (bf16 dense, sustained)" % how,
+                    "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, avg over the 92 launches of a step)",
+                    "traffic_source": traffic_src, "peak_source": "%s (bf16 dense, sustained)" % how,
                     "kernel": "pe::conv_tcw_kernel<BN,PLANES,NA,NB,ROWB> (persistent tcgen05/TMEM/TMA implicit GEMM), %d launches per step" % len(conv),
                     "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "avg_launch_us": 1e3 * conv_ms / len(conv),
                     "share_of_step": conv_ms / step_ms, "other_layer_ms_per_step": other_ms,
