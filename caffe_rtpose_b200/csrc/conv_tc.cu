@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include <string>
@@ -596,7 +597,7 @@ static int launch_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t 
 }
 
 template <int BN, int PLANES, int NA, int NB, int ROWB>
-static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
+static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
     auto kern = conv_tcw_kernel<BN, PLANES, NA, NB, ROWB>;
     const int smem = NA * PLANES * TCW_A_BYTES + NB * (ROWB ? 3 : 1) * PLANES * BN * 128 + 1024;
     static std::atomic<unsigned long long> attr_done{0};   // bit d: attribute set on device d (it is per device)
@@ -607,17 +608,17 @@ static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStr
         attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
-    kern<<<grid, TCW_THREADS, smem, st>>>(maps[2], maps[3], a);
+    kern<<<grid, TCW_THREADS, smem, st>>>(maps[2], maps[bmap], a);
     return 1;
 }
 template <int BN>
-static int launch_win_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st) {
+static int launch_win_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
     if (BN <= 64 && l.d.ksize <= 3) {   // narrow-N layers (conv1_x, the 1x1 heads): filter-row B slots
-        if (l.d.planes == 1) return launch_win_inst<(BN <= 64 ? BN : 64), 1, 3, 4, 1>(l, a, grid, st);
-        return launch_win_inst<(BN <= 64 ? BN : 64), 2, 2, 3, 1>(l, a, grid, st);
+        if (l.d.planes == 1) return launch_win_inst<(BN <= 64 ? BN : 64), 1, 3, 4, 1>(l, a, grid, st, bmap);
+        return launch_win_inst<(BN <= 64 ? BN : 64), 2, 2, 3, 1>(l, a, grid, st, bmap);
     }
-    if (l.d.planes == 1) return launch_win_inst<BN, 1, 3, (BN >= 128 ? 8 : 10), 0>(l, a, grid, st);
-    return launch_win_inst<BN, 2, 2, (BN >= 128 ? 4 : 6), 0>(l, a, grid, st);
+    if (l.d.planes == 1) return launch_win_inst<BN, 1, 3, (BN >= 128 ? 8 : 10), 0>(l, a, grid, st, bmap);
+    return launch_win_inst<BN, 2, 2, (BN >= 128 ? 4 : 6), 0>(l, a, grid, st, bmap);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -632,7 +633,7 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
     out.d = d;
     out.bn = tc_bn(d.cout_pad);
     CUtensorMap* maps = nullptr;
-    if (posix_memalign((void**)&maps, 64, 4 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
+    if (posix_memalign((void**)&maps, 64, 6 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
     const int taps = d.ksize * d.ksize;
     const cuuint64_t K = (cuuint64_t)taps * d.in_cused;
     {   // A: [planes][M][pitch] bf16, box {64, 128, 1}
@@ -675,6 +676,17 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(B window) failed: " + std::to_string((int)r); free(maps); return -1; }
     }
+    // narrower N tiles (64, 32) of the same weight matrix for small problems (one frame per forward): more CTAs
+    for (int v = 0; v < 2 && out.bn == 128; v++) {
+        cuuint64_t dims[3] = {K, (cuuint64_t)d.cout_pad, (cuuint64_t)d.planes};
+        cuuint64_t strides[2] = {K * 2, K * 2 * (cuuint64_t)d.cout_pad};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)(v == 0 ? 64 : 32), (cuuint32_t)(d.planes <= 2 ? d.planes : 1)};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&maps[4 + v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d.w, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(B narrow) failed: " + std::to_string((int)r); free(maps); return -1; }
+    }
     out.maps = maps;
     out.stages = pick_stages(out.bn, d.planes);
     out.smem_bytes = out.stages * stage_bytes(out.bn, d.planes) + 1024;
@@ -701,15 +713,28 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
     if (variant == 1 && d.planes <= 2) {
         static int nsm = 0;
         if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-        a.n_tiles_n = (int)grid.y;
-        a.total_tiles = (long long)grid.x * grid.y;
+        // Tile width: 128 output channels per CTA is the efficient shape, but a single frame at the 46x82 level has
+        // only 33 row tiles for 148 SMs.  Pick the width that maximises (CTAs that can run at once) x (relative
+        // efficiency of that MMA shape: the A operand is re-read per N tile, so narrow tiles are smem-bound).
+        int bn = l.bn, bmap = 3;
+        if (l.bn == 128) {
+            static const int narrow = env_int("PE_TC_NARROW", 1);
+            const long long mt = grid.x;
+            const double s128 = (double)std::min<long long>(mt * (d.cout_pad / 128), nsm) * 1.00;
+            const double s64 = (double)std::min<long long>(mt * (d.cout_pad / 64), nsm) * 0.80;
+            const double s32 = (double)std::min<long long>(mt * (d.cout_pad / 32), nsm) * 0.55;
+            if (narrow && s64 > s128 && s64 >= s32) { bn = 64; bmap = 4; }
+            else if (narrow && s32 > s128 && s32 > s64) { bn = 32; bmap = 5; }
+        }
+        a.n_tiles_n = d.cout_pad / bn;
+        a.total_tiles = (long long)grid.x * a.n_tiles_n;
         grid = dim3((unsigned)(a.total_tiles < nsm ? a.total_tiles : nsm), 1, 1);
-        switch (l.bn) {
-            case 128: return launch_win_bn<128>(l, a, grid, st);
-            case 64: return launch_win_bn<64>(l, a, grid, st);
-            case 48: return launch_win_bn<48>(l, a, grid, st);
-            case 32: return launch_win_bn<32>(l, a, grid, st);
-            default: return launch_win_bn<16>(l, a, grid, st);
+        switch (bn) {
+            case 128: return launch_win_bn<128>(l, a, grid, st, bmap);
+            case 64: return launch_win_bn<64>(l, a, grid, st, bmap);
+            case 48: return launch_win_bn<48>(l, a, grid, st, bmap);
+            case 32: return launch_win_bn<32>(l, a, grid, st, bmap);
+            default: return launch_win_bn<16>(l, a, grid, st, bmap);
         }
     }
     switch (l.bn) {
