@@ -106,7 +106,7 @@ __device__ __forceinline__ FullRes make_fullres(const PostDev& pd, int frame) {
 // one 32-bit word of the peak bitmask (warp ballot) - raster order is preserved by construction.
 // ------------------------------------------------------------------------------------------------
 #define NMS_TX 32
-#define NMS_TY 8
+#define NMS_TY 16
 #define NMS_HROWS 8
 __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
     __shared__ float tile[NMS_TY + 2][NMS_TX + 2];
@@ -120,7 +120,10 @@ __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
     // so it is computed once per tile (<= NMS_HROWS source rows) instead of 4x per output pixel.  Same
     // operations on the same operands as fullres_at -> bit-identical values.
     constexpr int NOUT = (NMS_TY + 2) * (NMS_TX + 2);
-    float acc[2] = {0.f, 0.f};
+    constexpr int NQ = (NOUT + 255) / 256;
+    float acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) acc[q] = 0.f;
     bool separable = true;
     for (int n = 0; n < fr.S; n++) {
         const int rlo = fr.yt[n * H + ylo].i0, rhi = fr.yt[n * H + yhi].i3;
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
             }
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
+            for (int q = 0; q < NQ; q++) {
                 const int i = threadIdx.x + q * 256;
                 if (i < NOUT) {
                     const int ty = i / (NMS_TX + 2), tx = i % (NMS_TX + 2);
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
             }
         }
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
+        for (int q = 0; q < NQ; q++) {
             const int i = threadIdx.x + q * 256;
             if (i < NOUT) tile[i / (NMS_TX + 2)][i % (NMS_TX + 2)] = __fdiv_rn(acc[q], fr.inv_div);
         }
@@ -174,20 +177,24 @@ __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
         }
     }
     __syncthreads();
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int x = blockIdx.x * NMS_TX + lx, y = blockIdx.y * NMS_TY + ly;
-    bool peak = false;
-    if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {
-        const float v = tile[ly + 1][lx + 1];
-        if (v > pd.p.nms_threshold) {
-            peak = v > tile[ly][lx + 1] && v > tile[ly + 2][lx + 1] && v > tile[ly + 1][lx] && v > tile[ly + 1][lx + 2] &&
-                   v > tile[ly][lx] && v > tile[ly + 2][lx] && v > tile[ly + 2][lx + 2] && v > tile[ly][lx + 2];
+    const int lx = threadIdx.x & 31;
+#pragma unroll
+    for (int pass = 0; pass < NMS_TY / 8; pass++) {
+        const int ly = (threadIdx.x >> 5) + pass * 8;
+        const int x = blockIdx.x * NMS_TX + lx, y = blockIdx.y * NMS_TY + ly;
+        bool peak = false;
+        if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {
+            const float v = tile[ly + 1][lx + 1];
+            if (v > pd.p.nms_threshold) {
+                peak = v > tile[ly][lx + 1] && v > tile[ly + 2][lx + 1] && v > tile[ly + 1][lx] && v > tile[ly + 1][lx + 2] &&
+                       v > tile[ly][lx] && v > tile[ly + 2][lx] && v > tile[ly + 2][lx + 2] && v > tile[ly][lx + 2];
+            }
         }
-    }
-    const unsigned word = __ballot_sync(0xffffffffu, peak);
-    if (lx == 0 && y < H) {
-        const int words_per_row = (W + 31) / 32;
-        pd.flags[((size_t)(frame * pd.p.num_parts + part) * H + y) * words_per_row + blockIdx.x] = word;
+        const unsigned word = __ballot_sync(0xffffffffu, peak);
+        if (lx == 0 && y < H) {
+            const int words_per_row = (W + 31) / 32;
+            pd.flags[((size_t)(frame * pd.p.num_parts + part) * H + y) * words_per_row + blockIdx.x] = word;
+        }
     }
 }
 

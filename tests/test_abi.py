@@ -95,3 +95,68 @@ def test_caffemodel_wire_reader(tmp_path, v1, legacy_dims):
     bad.write_bytes(b"\x92\x06\xff\xff\xff\xff\x0f garbage")
     with pytest.raises(engine.PoseEngineError):
         engine.read_caffemodel(str(bad))
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/poseengine.h must be consumable from C (the ABI a cgo/JNI/ctypes/C++ caller binds) and every call
+    used by the reference-side stub of INTEGRATION.md must link against libposeengine.so."""
+    import subprocess
+    src = tmp_path / "abi_check.c"
+    src.write_text(r"""
+#include "poseengine.h"
+#include <stdio.h>
+int main(void) {
+    pe_config c = {0};
+    pe_engine* e = 0;
+    c.model = PE_MODEL_COCO_18; c.net_w = 656; c.net_h = 368; c.disp_w = 1280; c.disp_h = 720;
+    c.num_scales = 1; c.start_scale = 1.0; c.scale_gap = 0.3; c.max_batch = 1; c.precision = PE_PREC_BF16X2;
+    int rc = pe_create(&c, &e);
+    printf("%d|%s|%d|%d\n", rc, pe_last_error(0), pe_model_num_parts(PE_MODEL_MPI_15), pe_model_limb_sequence(PE_MODEL_COCO_18)[3]);
+    float j[3] = {1.5f, 2.5f, 0.5f};
+    char buf[256];
+    pe_write_json(j, 0, 18, 1.0, buf, 256);
+    printf("%s", buf);
+    if (e) pe_destroy(e);
+    return 0;
+}
+""")
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(engine.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lposeengine", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout
+    first = out.split("\n")[0].split("|")
+    assert first[2] == "15" and first[3] == "5"
+    import torch
+    if not torch.cuda.is_available():
+        assert first[0] == "2" and "no CPU fallback" in first[1]
+    assert '"bodies":[' in out
+
+
+def test_cpp_header_shims_compile(tmp_path):
+    """include/rtpose/*.h and include/caffe/cpm/layers/*.hpp: the reference's class names and methods over the ABI."""
+    import subprocess
+    src = tmp_path / "shim_check.cpp"
+    src.write_text(r"""
+#include "rtpose/modelDescriptorFactory.h"
+#include "caffe/cpm/layers/nms_layer.hpp"
+#include "caffe/cpm/layers/imresize_layer.hpp"
+#include <cstdio>
+int main() {
+    std::unique_ptr<ModelDescriptor> md;
+    ModelDescriptorFactory::createModelDescriptor(ModelDescriptorFactory::Type::COCO_18, md);
+    printf("%d %d %s %s\n", md->get_number_parts(), md->number_limb_sequence(), md->get_part_name(19).c_str(),
+           md->get_part_name(md->get_map_idx()[0]).c_str());
+    try { md->get_part_name(99); } catch (const std::out_of_range&) { printf("oor\n"); }
+    try { ModelDescriptor bad({{0, "a"}, {1, "b"}}, {0, 1}, {2}); } catch (const std::runtime_error&) { printf("rte\n"); }
+    caffe::NmsLayer<float>* nms = nullptr; caffe::ImResizeLayer<float>* rs = nullptr; (void)nms; (void)rs;
+    return 0;
+}
+""")
+    exe = tmp_path / "shim_check"
+    libdir = os.path.dirname(engine.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                           "-lposeengine", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout.split("\n")
+    assert out[0] == "18 19 %s %s" % (orc.lib().orc_model_map_name(orc.COCO_18, 19).decode(), orc.lib().orc_model_map_name(orc.COCO_18, 31).decode())
+    assert out[1] == "oor" and out[2] == "rte"
