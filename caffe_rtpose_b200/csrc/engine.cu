@@ -40,7 +40,7 @@ struct pe_engine {
     std::vector<TcLayer> tc;        // tcgen05 per-conv launch state
     // io
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[16];
+    cudaEvent_t ev[16] = {};
     uint8_t* d_frames = nullptr; uint8_t* d_resized = nullptr;
     uint8_t* h_frames = nullptr;    // pinned staging
     float* d_planar = nullptr; float* h_planar = nullptr;
@@ -171,6 +171,8 @@ extern "C" int pe_create(const pe_config* cfg, pe_engine** out) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, PE_ERR_INVALID, "device %d out of range (%d visible)", cfg->device, ndev);
 
     pe_engine* e = new pe_engine();
+    memset(&e->post, 0, sizeof e->post);   // PODs: every pointer must be null for pe_destroy on an early failure
+    memset(&e->pre, 0, sizeof e->pre);
     e->cfg = *cfg;
     e->mt = &model_tables(cfg->model);
     e->planes = cfg->precision;  // 0 fp32, else number of bf16 planes
