@@ -52,11 +52,19 @@ struct pe_engine {
     AxisTap *d_xtab = nullptr, *d_ytab = nullptr;
     float start_scale_f, scale_gap_f;
     int last_n = 0;
-    bool input_lo_dirty = false;   // the planar-input path wrote non-zero lo planes / channels >= 32 of the input buffer
+    bool input_lo_dirty = false;
+    // CUDA graphs of the steady-state forward (92 conv + pool/copy + 5 parse kernels + result copies), one per batch
+    // size; the first forward of a size runs eagerly, the second is captured, later ones replay.  Invalidated by
+    // any setter whose value is baked into kernel arguments.
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; int seen = 0; };
+    std::map<int, GraphEntry> graphs;
+    bool use_graphs = true;   // the planar-input path wrote non-zero lo planes / channels >= 32 of the input buffer
     long long launches = 0;
     std::string err;
     double flops_per_scale = 0;
 };
+
+static void drop_graphs(pe_engine* e);
 
 static int fail(pe_engine* e, int code, const char* fmt, ...) {
     char buf[1024];
@@ -176,6 +184,7 @@ extern "C" int pe_create(const pe_config* cfg, pe_engine** out) {
     e->cfg = *cfg;
     e->mt = &model_tables(cfg->model);
     e->planes = cfg->precision;  // 0 fp32, else number of bf16 planes
+    if (const char* g = getenv("PE_GRAPH")) e->use_graphs = atoi(g) != 0;
     e->elem = e->planes == 0 ? 4 : 2;
     e->start_scale_f = (float)cfg->start_scale;  // ImResizeLayer::SetStartScale(float)
     e->scale_gap_f = (float)cfg->scale_gap;
@@ -279,6 +288,7 @@ extern "C" void pe_destroy(pe_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    drop_graphs(e);
     for (void* p : e->acts) if (p) cudaFree(p);
     for (void* p : e->d_tabs) cudaFree(p);
     for (auto& t : e->tc) tc_layer_destroy(t);
@@ -437,6 +447,7 @@ extern "C" int pe_commit_weights(pe_engine* e) {
             if (tc_layer_create(d, e->tc[i], err)) return fail(e, PE_ERR_CUDA, "layer %s: %s", c.name.c_str(), err.c_str());
         }
     }
+    drop_graphs(e);
     e->committed = true;
     return PE_OK;
 }
@@ -446,13 +457,24 @@ extern "C" void* pe_packed_weights_device_ptr(pe_engine* e) { return e ? e->d_pa
 // ---------------------------------------------------------------------------------------------
 // layer accessors
 // ---------------------------------------------------------------------------------------------
+static void drop_graphs(pe_engine* e) {
+    for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
+}
+
 extern "C" int pe_nms_get_max_peaks(const pe_engine* e) { return e ? e->mt->max_peaks : 0; }
 extern "C" int pe_nms_get_num_parts(const pe_engine* e) { return e ? e->mt->num_parts : 0; }
 extern "C" float pe_nms_get_threshold(const pe_engine* e) { return e ? e->post.p.nms_threshold : 0.f; }
-extern "C" int pe_nms_set_threshold(pe_engine* e, float t) { if (!e) return PE_ERR_INVALID; e->post.p.nms_threshold = t; return PE_OK; }
+extern "C" int pe_nms_set_threshold(pe_engine* e, float t) {
+    if (!e) return PE_ERR_INVALID;
+    if (e->post.p.nms_threshold != t) drop_graphs(e);
+    e->post.p.nms_threshold = t;
+    return PE_OK;
+}
 static int rebuild_axis(pe_engine* e) {
     CK(e, cudaSetDevice(e->cfg.device));
     e->post.p.start_scale = e->start_scale_f; e->post.p.scale_gap = e->scale_gap_f;
+    drop_graphs(e);
     launch_axis_tables(e->d_xtab, e->d_ytab, e->post.p, e->stream);
     e->launches += 2;
     return PE_OK;
@@ -464,6 +486,7 @@ extern "C" float pe_resize_get_scale_gap(const pe_engine* e) { return e ? e->sca
 extern "C" int pe_set_connect_params(pe_engine* e, int min_cnt, float min_score, float inter_thr, int min_above) {
     if (!e) return PE_ERR_INVALID;
     PostParams& p = e->post.p;
+    drop_graphs(e);
     p.min_subset_cnt = min_cnt; p.min_subset_score = min_score; p.inter_threshold = inter_thr; p.inter_min_above = min_above;
     return PE_OK;
 }
@@ -521,11 +544,50 @@ static int run_post_and_return(pe_engine* e, int n) {
     return PE_OK;
 }
 
-static int run_net(pe_engine* e, int n) {
-    if (!e->committed) return fail(e, PE_ERR_STATE, "pe_commit_weights has not been called");
+static int run_net_eager(pe_engine* e, int n) {
     const int nimg = n * e->cfg.num_scales;
     for (const OpRef& op : e->plan.order) { const int rc = run_op(e, op, nimg); if (rc) return rc; }
     return run_post_and_return(e, n);
+}
+
+static int run_net(pe_engine* e, int n) {
+    if (!e->committed) return fail(e, PE_ERR_STATE, "pe_commit_weights has not been called");
+    if (!e->use_graphs) return run_net_eager(e, n);
+    pe_engine::GraphEntry& g = e->graphs[n];
+    if (g.exec) {
+        CK(e, cudaGraphLaunch(g.exec, e->stream));
+        e->launches += g.launches;
+        e->last_n = n;
+        return PE_OK;
+    }
+    if (g.seen++ == 0) return run_net_eager(e, n);   // first use of this batch size: eager (sets kernel attributes)
+    // second use: capture the same sequence into a graph and launch it
+    const long long before = e->launches;
+    if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        e->use_graphs = false;
+        return run_net_eager(e, n);
+    }
+    const int rc = run_net_eager(e, n);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        e->launches = before;
+        e->use_graphs = false;
+        if (rc) return rc;
+        return run_net_eager(e, n);
+    }
+    g.launches = e->launches - before;
+    e->launches = before;
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; e->use_graphs = false; return run_net_eager(e, n); }
+    CK(e, cudaGraphLaunch(g.exec, e->stream));
+    e->launches += g.launches;
+    e->last_n = n;
+    return PE_OK;
 }
 
 static int check_n(pe_engine* e, int n) {
