@@ -269,7 +269,7 @@ def main():
     # two worker handles (two streams) alternate, like two of the reference's per-GPU worker threads would: the
     # small-grid parse kernels of one batch overlap the conv stack of the next.  Timed with torch CUDA events on
     # the null stream bracketing both engine streams (device-wide sync on both sides).
-    for i in range(max(args.warmup, 2)):
+    for i in range(max(args.warmup, 4)):   # >= 2 forwards per handle: the 2nd captures its CUDA graph
         engs[i % 2].forward_frames_device(batch_dev(i), B)
     barrier()
     launches0 = sum(e.launch_count() for e in engs)

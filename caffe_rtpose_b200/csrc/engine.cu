@@ -707,6 +707,13 @@ extern "C" int pe_fetch_blob(pe_engine* e, const char* blob_name, float* out, si
     return fail(e, PE_ERR_INVALID, "unknown blob %s", blob_name);
 }
 
+extern "C" void* pe_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void pe_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 // ---------------------------------------------------------------------------------------------
 // JSON (rtpose.cpp:1383-1416): ostream default formatting == %g
 // ---------------------------------------------------------------------------------------------

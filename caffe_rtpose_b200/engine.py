@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
-    "pe_caffemodel_last_error",
+    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free",
 ]
 
 
@@ -92,6 +92,9 @@ def lib():
     L.pe_fetch_maps.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.pe_fetch_blob.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t] + [C.POINTER(C.c_int)] * 3
     L.pe_sync.argtypes = [C.c_void_p]
+    L.pe_host_alloc.argtypes = [C.c_size_t]
+    L.pe_host_alloc.restype = C.c_void_p
+    L.pe_host_free.argtypes = [C.c_void_p]
     L.pe_write_json.argtypes = [_f32p, C.c_int, C.c_int, C.c_double, C.c_char_p, C.c_int]
     for f in ("pe_model_num_parts", "pe_model_num_limbs"):
         getattr(L, f).argtypes = [C.c_int]

@@ -109,7 +109,8 @@ static int parse_flags(int argc, char** argv) {
 struct Frame {
     int index = 0, video_frame_number = 0;
     double scale = 1.0;                      // display / original (rtpose.cpp:474-480); identity here
-    std::vector<uint8_t> bgr;                // display image, HWC BGR
+    std::vector<uint8_t> bgr;                // display image, HWC BGR (decode buffer)
+    std::shared_ptr<uint8_t> pinned;         // same image in page-locked memory (pe_host_alloc) for direct async DMA
     std::string stem;                        // for <stem>.json with --image_dir
     int num_people = 0;
     std::vector<float> joints;
@@ -256,6 +257,11 @@ static void producer() {
             const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
             fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
         }
+        if (void* ph = pe_host_alloc(fr.bgr.size())) {   // falls back to the staged copy inside pe_forward_frames if it fails
+            memcpy(ph, fr.bgr.data(), fr.bgr.size());
+            fr.pinned = std::shared_ptr<uint8_t>((uint8_t*)ph, [](uint8_t* q) { pe_host_free(q); });
+            std::vector<uint8_t>().swap(fr.bgr);
+        }
         fr.t_commit = now_s();
         while (global.input_queue.size() > 64 && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
         global.input_queue.push(std::move(fr));
@@ -310,7 +316,7 @@ static void worker(int tid) {
             continue;
         }
         std::vector<const uint8_t*> ptrs;
-        for (auto& f : frames) ptrs.push_back(f.bgr.data());
+        for (auto& f : frames) ptrs.push_back(f.pinned ? f.pinned.get() : f.bgr.data());
         if (pe_forward_frames(e, ptrs.data(), (int)ptrs.size())) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break; }
         for (size_t i = 0; i < frames.size(); i++) {
             int cnt = 0;

@@ -118,6 +118,11 @@ int pe_fetch_blob(pe_engine* e, const char* blob_name, float* out, size_t cap, i
 /* block until the engine's stream is idle */
 int pe_sync(pe_engine* e);
 
+/* page-locked host buffers for frames (the reference `new`s pageable frame buffers, rtpose.cpp:347-354, and pays a
+ * staged copy per frame); frames allocated here are DMA'd directly and asynchronously by pe_forward_frames. */
+void* pe_host_alloc(size_t bytes);
+void pe_host_free(void* p);
+
 /* JSON writer of displayFrame (rtpose.cpp:1383-1416).  Returns the text length (writes if < cap). */
 int pe_write_json(const float* joints, int num_people, int num_parts, double frame_scale, char* buf, int cap);
 
