@@ -348,8 +348,13 @@ def main():
             e1 = engs[1]
             e1.forward_frames([hnp[0]])
             cnt, joints, peaks = e1.fetch(0)
-            cpu["parity_note"] = "frame 0: people engine/oracle %d/%d, peaks found %d/%d" % (
+            note = "frame 0: people engine/oracle %d/%d, peaks found %d/%d" % (
                 cnt, ocnt, int(peaks[:, 0, 0].sum()), int(opeaks[:, 0, 0].sum()))
+            if cnt == ocnt and cnt > 0:
+                same_assign = bool(np.array_equal(joints[:, :, 2] > 0, ojoints[:, :, 2] > 0))
+                dj = float(np.abs(joints[:, :, :2] - ojoints[:, :, :2]).max()) if same_assign else float("nan")
+                note += "; identical part->person assignment: %s; max |joint xy - oracle| = %.2e display px" % (same_assign, dj)
+            cpu["parity_note"] = note
         line = {"metric": "frames/sec at 656x368 COCO-18", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {0: "f32", 1: "bf16", 2: "bf16x2 (split, fp32 accumulate)", 3: "bf16x3 (split, fp32 accumulate)"}[args.precision],

@@ -163,3 +163,23 @@ def test_load_caffemodel_equals_set_weights(small, tmp_path):
     with pytest.raises(engine.PoseEngineError):
         eng.load_caffemodel(p)
     eng.close()
+
+
+@pytest.mark.parametrize("prec", [engine.PREC_FP32_SIMT, engine.PREC_BF16X2])
+def test_joint_coordinates_within_1e3_px(small, prec):
+    """north_star bar: joint coordinates within 1e-3 px and identical person/limb assignment.  He-init noise at the
+    default thresholds yields a dozen spurious "people"; wherever the assignment pattern agrees (it does unless a peak
+    sits on a decision boundary) the coordinates must agree to 1e-3 net px."""
+    s = small
+    eng = engine.PoseEngine(s["model"], s["net_w"], s["net_h"], 320, 192, precision=prec)
+    eng.set_weights(s["W"])
+    eng.forward_frames(s["frames"][:1])
+    cnt, joints, peaks = eng.fetch(0)
+    ocnt, oj, opk, _ = s["onet"].process_frame(s["frames"][0], s["net_h"], s["net_w"])
+    eng.close()
+    assert ocnt >= 5
+    assert cnt == ocnt
+    assert np.array_equal(joints[:, :, 2] > 0, oj[:, :, 2] > 0)          # identical part -> person assignment
+    scale = 320.0 / s["net_w"]                                            # joints are reported in display pixels
+    assert np.abs(joints[:, :, :2] - oj[:, :, :2]).max() / scale < 1e-3
+    assert np.abs(joints[:, :, 2] - oj[:, :, 2]).max() < 20 * TOL[prec]
