@@ -123,7 +123,8 @@ if __name__ == "__main__":
         conv_diag([engine.PREC_FP32_SIMT])
     precs = [int(v) for v in os.environ.get("DIAG_PRECS", "1,2").split(",")]
     if what in ("tc", "all"):
-        conv_diag(precs)
+        nw, nh = [int(v) for v in os.environ.get("DIAG_NET", "160x96").split("x")]
+        conv_diag(precs, nw, nh)
     if what in ("time", "all"):
         for p in precs:
             timing(p, batch=int(os.environ.get("DIAG_BATCH", "8")))
