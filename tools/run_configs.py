@@ -16,7 +16,7 @@ CONFIGS = [
     ("C2", engine.COCO_18, 656, 368, 1280, 720, 1, 1.0, 0.3, 9),
     ("C2-batch1", engine.COCO_18, 656, 368, 1280, 720, 1, 1.0, 0.3, 1),
     ("C3", engine.COCO_18, 656, 368, 1280, 720, 3, 1.0, 0.15, 3),
-    ("C5-per-GPU", engine.COCO_18, 992, 736, 1280, 720, 4, 1.0, 0.15, 1),
+    ("C5-per-GPU", engine.COCO_18, 992, 736, 1920, 1080, 4, 1.0, 0.15, 1),
 ]
 
 
