@@ -52,6 +52,10 @@ struct pe_engine {
     AxisTap *d_xtab = nullptr, *d_ytab = nullptr;
     float start_scale_f, scale_gap_f;
     int last_n = 0;
+    // raw camera frames (any size) -> display image: warpAffine tables for the last (orig_w, orig_h)
+    uint8_t* d_raw = nullptr; size_t raw_cap = 0; uint8_t* h_raw = nullptr; size_t h_raw_cap = 0;
+    int warp_w = 0, warp_h = 0; double warp_scale = 1.0;
+    int *d_wa = nullptr, *d_wb = nullptr, *d_wx0 = nullptr, *d_wy0 = nullptr; short* d_wtab = nullptr;
     bool input_lo_dirty = false;
     // CUDA graphs of the steady-state forward (92 conv + pool/copy + 5 parse kernels + result copies), one per batch
     // size; the first forward of a size runs eagerly, the second is captured, later ones replay.  Invalidated by
@@ -295,6 +299,7 @@ extern "C" void pe_destroy(pe_engine* e) {
     for (void* p : e->acts) if (p) cudaFree(p);
     for (void* p : e->d_tabs) cudaFree(p);
     for (auto& t : e->tc) tc_layer_destroy(t);
+    cudaFree(e->d_raw); cudaFreeHost(e->h_raw); cudaFree(e->d_wa); cudaFree(e->d_wb); cudaFree(e->d_wx0); cudaFree(e->d_wy0); cudaFree(e->d_wtab);
     cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_resized); cudaFree(e->d_planar); cudaFree(e->d_maps);
     cudaFreeHost(e->h_frames); cudaFreeHost(e->h_planar); cudaFreeHost(e->h_maps);
     cudaFree(e->d_xtab); cudaFree(e->d_ytab);
@@ -635,6 +640,108 @@ extern "C" int pe_forward_frames(pe_engine* e, const uint8_t* const* frames, int
     }
     return pe_forward_frames_device(e, e->d_frames, n);
 }
+// bicubic weight table of OpenCV's fixed-point remap (initInterTab2D(INTER_CUBIC, fixpt)): a = -0.75, 15-bit shorts,
+// each 4x4 kernel normalised to sum 2^15 by nudging the largest/smallest central coefficient
+static void build_warp_tab(std::vector<short>& tab) {
+    tab.assign(32 * 32 * 16, 0);
+    float t1[32][4];
+    const float A = -0.75f, scale = 1.f / 32;
+    for (int i = 0; i < 32; i++) {
+        const float x = i * scale;
+        t1[i][0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+        t1[i][1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+        t1[i][2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+        t1[i][3] = 1.f - t1[i][0] - t1[i][1] - t1[i][2];
+    }
+    for (int i = 0; i < 32; i++)
+        for (int j = 0; j < 32; j++) {
+            short* w = tab.data() + (i * 32 + j) * 16;
+            int isum = 0;
+            for (int k = 0; k < 16; k++) {
+                long r = lrintf(t1[i][k / 4] * t1[j][k % 4] * 32768.f);
+                w[k] = (short)std::min(32767L, std::max(-32768L, r));
+                isum += w[k];
+            }
+            if (isum != 32768) {
+                int hi = 10, lo = 10;   // central 2x2 = indices 10, 11, 14, 15
+                const int cen[4] = {10, 11, 14, 15};
+                for (int c : cen) { if (w[c] < w[lo]) lo = c; else if (w[c] > w[hi]) hi = c; }
+                if (isum < 32768) w[hi] = (short)(w[hi] - (isum - 32768));
+                else w[lo] = (short)(w[lo] - (isum - 32768));
+            }
+        }
+}
+
+static int prepare_warp(pe_engine* e, int ow, int oh) {
+    if (e->warp_w == ow && e->warp_h == oh && e->d_wa) return PE_OK;
+    const int dw = e->cfg.disp_w, dh = e->cfg.disp_h;
+    // rtpose.cpp:474-480
+    const double s = (ow / (double)oh > dw / (double)dh) ? dw / (double)ow : dh / (double)oh;
+    double M[6] = {s, 0, 0, 0, s, 0};
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+    const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+    M[2] = b1; M[5] = b2;
+    std::vector<int> ad(dw), bd(dw), x0(dh), y0(dh);
+    for (int x = 0; x < dw; x++) { ad[x] = (int)lrint(M[0] * x * 1024); bd[x] = (int)lrint(M[3] * x * 1024); }
+    for (int y = 0; y < dh; y++) { x0[y] = (int)lrint((M[1] * y + M[2]) * 1024) + 16; y0[y] = (int)lrint((M[4] * y + M[5]) * 1024) + 16; }
+    if (!e->d_wa) {
+        std::vector<short> tab;
+        build_warp_tab(tab);
+        CK(e, cudaMalloc(&e->d_wa, dw * sizeof(int))); CK(e, cudaMalloc(&e->d_wb, dw * sizeof(int)));
+        CK(e, cudaMalloc(&e->d_wx0, dh * sizeof(int))); CK(e, cudaMalloc(&e->d_wy0, dh * sizeof(int)));
+        CK(e, cudaMalloc(&e->d_wtab, tab.size() * sizeof(short)));
+        CK(e, cudaMemcpy(e->d_wtab, tab.data(), tab.size() * sizeof(short), cudaMemcpyHostToDevice));
+    }
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaMemcpy(e->d_wa, ad.data(), dw * sizeof(int), cudaMemcpyHostToDevice));
+    CK(e, cudaMemcpy(e->d_wb, bd.data(), dw * sizeof(int), cudaMemcpyHostToDevice));
+    CK(e, cudaMemcpy(e->d_wx0, x0.data(), dh * sizeof(int), cudaMemcpyHostToDevice));
+    CK(e, cudaMemcpy(e->d_wy0, y0.data(), dh * sizeof(int), cudaMemcpyHostToDevice));
+    e->warp_w = ow; e->warp_h = oh; e->warp_scale = s;
+    return PE_OK;
+}
+
+extern "C" int pe_forward_camera_frames(pe_engine* e, const uint8_t* const* frames, int n, int orig_w, int orig_h, double* scale) {
+    int rc = check_n(e, n); if (rc) return rc;
+    if (!frames || orig_w <= 0 || orig_h <= 0) return fail(e, PE_ERR_INVALID, "bad raw frame arguments");
+    CK(e, cudaSetDevice(e->cfg.device));
+    rc = prepare_warp(e, orig_w, orig_h); if (rc) return rc;
+    if (scale) *scale = e->warp_scale;
+    const size_t fb = (size_t)orig_w * orig_h * 3;
+    if (e->raw_cap < fb * n) {
+        CK(e, cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_raw); e->d_raw = nullptr;
+        CK(e, cudaMalloc(&e->d_raw, fb * e->cfg.max_batch));
+        e->raw_cap = fb * e->cfg.max_batch;
+    }
+    bool pinned = true;
+    for (int i = 0; i < n && pinned; i++) {
+        cudaPointerAttributes at;
+        if (!frames[i]) return fail(e, PE_ERR_INVALID, "null frame %d", i);
+        if (cudaPointerGetAttributes(&at, frames[i]) != cudaSuccess || at.type != cudaMemoryTypeHost) { pinned = false; cudaGetLastError(); }
+    }
+    if (pinned) {
+        for (int i = 0; i < n; i++) CK(e, cudaMemcpyAsync(e->d_raw + i * fb, frames[i], fb, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        CK(e, cudaStreamSynchronize(e->stream));
+        if (e->h_raw_cap < fb * n) {
+            cudaFreeHost(e->h_raw); e->h_raw = nullptr;
+            CK(e, cudaMallocHost(&e->h_raw, fb * e->cfg.max_batch));
+            e->h_raw_cap = fb * e->cfg.max_batch;
+        }
+        for (int i = 0; i < n; i++) memcpy(e->h_raw + i * fb, frames[i], fb);
+        CK(e, cudaMemcpyAsync(e->d_raw, e->h_raw, fb * n, cudaMemcpyHostToDevice, e->stream));
+    }
+    WarpArgs w;
+    w.src = e->d_raw; w.dst = e->d_frames; w.sw = orig_w; w.sh = orig_h; w.dw = e->cfg.disp_w; w.dh = e->cfg.disp_h;
+    w.adelta = e->d_wa; w.bdelta = e->d_wb; w.x0 = e->d_wx0; w.y0 = e->d_wy0; w.tab = e->d_wtab;
+    e->launches += launch_warp_affine(w, n, e->stream);
+    return pe_forward_frames_device(e, e->d_frames, n);
+}
+
 extern "C" int pe_forward_net_input(pe_engine* e, const float* net_input, int n) {
     int rc = check_n(e, n); if (rc) return rc;
     if (!net_input) return fail(e, PE_ERR_INVALID, "null input");

@@ -47,6 +47,12 @@ struct PreArgs {
     int Wp, Hs;
 };
 int launch_preprocess(const PreArgs& a, cudaStream_t st);
+struct WarpArgs {
+    const uint8_t* src; uint8_t* dst; int sw, sh, dw, dh;
+    const int* adelta; const int* bdelta; const int* x0; const int* y0;   // OpenCV's fixed-point coordinate tables
+    const short* tab;                                                      // [32*32][16] bicubic weights
+};
+int launch_warp_affine(const WarpArgs& a, int nframes, cudaStream_t st);
 // planar fp32 net input [N][3][H][W] -> im2col'ed input
 int launch_input_from_planar(const float* planar, const PreArgs& a, int nimages, cudaStream_t st);
 

@@ -66,6 +66,42 @@ __global__ void __launch_bounds__(256) area_resize_kernel(PreArgs a) {
     dst[2] = (uint8_t)min(max(__float2int_rn(sum2), 0), 255);
 }
 
+// cv::warpAffine(frame, diag(s,s), display size, INTER_CUBIC, BORDER_CONSTANT 0) of rtpose.cpp:474-487, OpenCV's
+// fixed-point arithmetic (imgproc/imgwarp.cpp): source coordinates in 1/32 pixel from integer tables built on the host
+// exactly as OpenCV builds adelta/bdelta/X0/Y0, 16 bicubic (a = -0.75) weights as shorts summing to 2^15,
+// (sum + 2^14) >> 15, saturate.  Bit-exact against cv2 (tests/golden/warp_cv2.npz).
+__global__ void __launch_bounds__(256) warp_affine_cubic_kernel(WarpArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.dw * a.dh) return;
+    const int x = idx % a.dw, y = idx / a.dw, f = blockIdx.y;
+    const int X = (a.x0[y] + a.adelta[x]) >> 5, Y = (a.y0[y] + a.bdelta[x]) >> 5;
+    const int sx = (X >> 5) - 1, sy = (Y >> 5) - 1;
+    const short* w = a.tab + ((Y & 31) * 32 + (X & 31)) * 16;
+    const uint8_t* src = a.src + (size_t)f * a.sw * a.sh * 3;
+    int acc0 = 0, acc1 = 0, acc2 = 0;
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) {
+        const int yy = sy + k1;
+        if (yy < 0 || yy >= a.sh) continue;
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) {
+            const int xx = sx + k2;
+            if (xx < 0 || xx >= a.sw) continue;
+            const uint8_t* p = src + ((size_t)yy * a.sw + xx) * 3;
+            const int ww = w[k1 * 4 + k2];
+            acc0 += p[0] * ww; acc1 += p[1] * ww; acc2 += p[2] * ww;
+        }
+    }
+    uint8_t* d = a.dst + ((size_t)f * a.dw * a.dh + idx) * 3;
+    d[0] = (uint8_t)min(max((acc0 + (1 << 14)) >> 15, 0), 255);
+    d[1] = (uint8_t)min(max((acc1 + (1 << 14)) >> 15, 0), 255);
+    d[2] = (uint8_t)min(max((acc2 + (1 << 14)) >> 15, 0), 255);
+}
+int launch_warp_affine(const WarpArgs& a, int nframes, cudaStream_t st) {
+    warp_affine_cubic_kernel<<<dim3((a.dw * a.dh + 255) / 256, nframes), 256, 0, st>>>(a);
+    return 1;
+}
+
 __device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
     h = __float2bfloat16_rn(x);
     const float r = __fsub_rn(x, __bfloat162float(h));

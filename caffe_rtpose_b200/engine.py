@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
-    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free",
+    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
     L.pe_set_connect_params.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int]
     L.pe_forward_frames.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
     L.pe_forward_frames_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.pe_forward_camera_frames.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.pe_forward_net_input.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.pe_forward_maps.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.pe_fetch.argtypes = [C.c_void_p, C.c_int, _f32p, C.POINTER(C.c_int), C.c_void_p]
@@ -291,6 +292,17 @@ class PoseEngine:
         ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
         self._keep = frames
         self._ck(lib().pe_forward_frames(self._h, ptrs, len(frames)))
+
+    def forward_camera_frames(self, frames):
+        """frames: list of uint8 BGR HWC images of one common (arbitrary) size; returns frame.scale (rtpose.cpp:474-487)."""
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        h, w, _ = frames[0].shape
+        assert all(f.shape == (h, w, 3) for f in frames)
+        ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+        self._keep = frames
+        s = C.c_double()
+        self._ck(lib().pe_forward_camera_frames(self._h, ptrs, len(frames), w, h, C.byref(s)))
+        return s.value
 
     def forward_frames_device(self, dev_ptr, n):
         self._ck(lib().pe_forward_frames_device(self._h, C.c_void_p(dev_ptr), n))

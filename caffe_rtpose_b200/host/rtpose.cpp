@@ -38,7 +38,6 @@ static void define(const char* name, const char* dflt, const char* help, bool is
 static std::string F(const char* n) { return g_flags.at(n).value; }
 static int Fi(const char* n) { return atoi(F(n).c_str()); }
 static double Fd(const char* n) { return atof(F(n).c_str()); }
-static bool Fb(const char* n) { const std::string v = F(n); return v == "true" || v == "1"; }
 
 static void define_flags() {
     // names, defaults and help strings of rtpose.cpp:50-72
@@ -107,8 +106,8 @@ static int parse_flags(int argc, char** argv) {
 
 // ---------------------------------------------------------------------------------------------- frames
 struct Frame {
-    int index = 0, video_frame_number = 0;
-    double scale = 1.0;                      // display / original (rtpose.cpp:474-480); identity here
+    int index = 0, video_frame_number = 0, w = 0, h = 0;
+    double scale = 1.0;                      // display / original (rtpose.cpp:474-480), filled by the engine
     std::vector<uint8_t> bgr;                // display image, HWC BGR (decode buffer)
     std::shared_ptr<uint8_t> pinned;         // same image in page-locked memory (pe_host_alloc) for direct async DMA
     std::string stem;                        // for <stem>.json with --image_dir
@@ -249,11 +248,6 @@ static void producer() {
             const std::string& p = global.image_list[i];
             const bool ok = p.size() > 4 && p.substr(p.size() - 4) == ".ppm" ? read_ppm(p, w, h, fr.bgr) : read_bmp(p, w, h, fr.bgr);
             if (!ok) { LOG_ERROR("cannot decode %s (only 24-bit .bmp and P6 .ppm are supported without an image codec)", p.c_str()); continue; }
-            if (w != global.disp_w || h != global.disp_h) {
-                LOG_ERROR("%s is %dx%d but --resolution is %dx%d: the warpAffine rescale of rtpose.cpp:474-487 is not part of "
-                          "this path; pass --resolution -1x-1 or matching images", p.c_str(), w, h, global.disp_w, global.disp_h);
-                continue;
-            }
             const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
             fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
         }
@@ -262,6 +256,7 @@ static void producer() {
             fr.pinned = std::shared_ptr<uint8_t>((uint8_t*)ph, [](uint8_t* q) { pe_host_free(q); });
             std::vector<uint8_t>().swap(fr.bgr);
         }
+        fr.w = w; fr.h = h;
         fr.t_commit = now_s();
         while (global.input_queue.size() > 64 && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
         global.input_queue.push(std::move(fr));
@@ -296,28 +291,35 @@ static void worker(int tid) {
     LOG_INFO("GPU %d is ready (model %s, max_peaks %d)", device, nms_layer.GetNumParts() == 15 ? "MPI" : "COCO", nms_layer.GetMaxPeaks());
     const int P = nms_layer.GetNumParts();
     std::vector<float> joints((size_t)PE_MAX_PEOPLE * P * 3);
+    Frame pending;
+    bool pending_valid = false;
     while (!global.quit) {
         std::vector<Frame> frames;
         Frame fr;
-        while ((int)frames.size() < batch && global.input_queue.try_pop(&fr)) {
-            // drop frames that waited more than 0.1 s unless --no_frame_drops (rtpose.cpp:1107-1124); file and
-            // synthetic sources never drop (the reference's image_dir runs are meant to process every image)
-            const bool live = false;
-            if (live && !Fb("no_frame_drops") && now_s() - fr.t_commit > 0.1) {
-                std::lock_guard<std::mutex> l(global.mutex);
-                global.dropped_index.push(fr.index);
-                continue;
+        while ((int)frames.size() < batch) {
+            if (pending_valid) { fr = std::move(pending); pending_valid = false; }
+            else if (!global.input_queue.try_pop(&fr)) break;
+            if (!frames.empty() && (fr.w != frames[0].w || fr.h != frames[0].h)) {   // one forward = one frame size
+                pending = std::move(fr); pending_valid = true;
+                break;
             }
+            // The reference drops frames that waited more than 0.1 s unless --no_frame_drops (rtpose.cpp:1107-1124);
+            // that policy is for live capture.  File and synthetic sources (the only ones here) process every frame.
             frames.push_back(std::move(fr));
         }
         if (frames.empty()) {
-            if (global.producer_done && global.input_queue.size() == 0) break;
+            if (global.producer_done && global.input_queue.size() == 0 && !pending_valid) break;
             std::this_thread::sleep_for(std::chrono::microseconds(200));
             continue;
         }
         std::vector<const uint8_t*> ptrs;
         for (auto& f : frames) ptrs.push_back(f.pinned ? f.pinned.get() : f.bgr.data());
-        if (pe_forward_frames(e, ptrs.data(), (int)ptrs.size())) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break; }
+        int frc;
+        double scale = 1.0;
+        if (frames[0].w == global.disp_w && frames[0].h == global.disp_h) frc = pe_forward_frames(e, ptrs.data(), (int)ptrs.size());
+        else frc = pe_forward_camera_frames(e, ptrs.data(), (int)ptrs.size(), frames[0].w, frames[0].h, &scale);   // warpAffine on the GPU
+        for (auto& f : frames) f.scale = scale;
+        if (frc) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break; }
         for (size_t i = 0; i < frames.size(); i++) {
             int cnt = 0;
             if (pe_fetch(e, (int)i, joints.data(), &cnt, nullptr)) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break; }

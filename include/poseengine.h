@@ -98,6 +98,11 @@ int pe_set_connect_params(pe_engine* e, int min_subset_cnt, float min_subset_sco
  * warpAffine, rtpose.cpp:484).  Does H2D + the scale loop / INTER_AREA / pad / normalise of rtpose.cpp:508-518
  * on the GPU + net + resize + NMS + connectLimbs*. */
 int pe_forward_frames(pe_engine* e, const uint8_t* const* frames, int n);
+/* HOST camera/video frames of ANY size (orig_h x orig_w uint8 BGR): first the display image of rtpose.cpp:474-487 -
+ * uniform scale s = min(disp_w/cols, disp_h/rows), top-left anchored, cv::warpAffine INTER_CUBIC, black border - is
+ * produced on the GPU (OpenCV's fixed-point arithmetic, bit-exact), then as pe_forward_frames.  *scale receives
+ * frame.scale (the JSON writer multiplies joints by 1/scale, rtpose.cpp:1384,1399-1400). */
+int pe_forward_camera_frames(pe_engine* e, const uint8_t* const* frames, int n, int orig_w, int orig_h, double* scale);
 /* same, frames already resident in device memory (n consecutive disp_h*disp_w*3 images) */
 int pe_forward_frames_device(pe_engine* e, const void* d_frames, int n);
 /* HOST net input as the reference uploads it: n x num_scales x 3 x net_h x net_w fp32 planar

@@ -812,6 +812,99 @@ extern "C" int orc_resize_area_u8c3(const uint8_t* src, int sh, int sw, uint8_t*
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Display image: cv::warpAffine(frame, diag(s,s), display size, INTER_CUBIC, BORDER_CONSTANT 0)  (rtpose.cpp:474-487).
+// Third-party arithmetic (OpenCV imgproc/imgwarp.cpp: fixed-point coordinates AB_BITS=10 / INTER_BITS=5, bicubic
+// weights a=-0.75 as 15-bit shorts normalised to sum 32768, rounding (sum + 2^14) >> 15), restated and pinned to
+// cv2 4.13 fixtures (tests/golden/warp_cv2.npz).
+// ------------------------------------------------------------------------------------------------
+static const short* warp_cubic_tab() {
+    static short tab[32 * 32 * 16];
+    static bool init = false;
+    if (!init) {
+        float t1[32][4];
+        const float A = -0.75f, scale = 1.f / 32;
+        for (int i = 0; i < 32; i++) {
+            const float x = i * scale;
+            t1[i][0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+            t1[i][1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+            t1[i][2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+            t1[i][3] = 1.f - t1[i][0] - t1[i][1] - t1[i][2];
+        }
+        for (int i = 0; i < 32; i++)
+            for (int j = 0; j < 32; j++) {
+                short* w = tab + (i * 32 + j) * 16;
+                int isum = 0;
+                for (int k1 = 0; k1 < 4; k1++)
+                    for (int k2 = 0; k2 < 4; k2++) {
+                        const float v = t1[i][k1] * t1[j][k2];
+                        long r = lrintf(v * 32768.f);
+                        r = r < -32768 ? -32768 : (r > 32767 ? 32767 : r);
+                        w[k1 * 4 + k2] = (short)r;
+                        isum += (int)r;
+                    }
+                if (isum != 32768) {
+                    const int diff = isum - 32768;
+                    int Mi = 2 * 4 + 2, mi = 2 * 4 + 2;
+                    for (int k1 = 2; k1 < 4; k1++)
+                        for (int k2 = 2; k2 < 4; k2++) {
+                            if (w[k1 * 4 + k2] < w[mi]) mi = k1 * 4 + k2;
+                            else if (w[k1 * 4 + k2] > w[Mi]) Mi = k1 * 4 + k2;
+                        }
+                    if (diff < 0) w[Mi] = (short)(w[Mi] - diff);
+                    else w[mi] = (short)(w[mi] - diff);
+                }
+            }
+        init = true;
+    }
+    return tab;
+}
+
+// rtpose.cpp:474-480
+extern "C" double orc_display_scale(int cols, int rows, int disp_w, int disp_h) {
+    if (cols / (double)rows > disp_w / (double)disp_h) return disp_w / (double)cols;
+    return disp_h / (double)rows;
+}
+
+extern "C" void orc_warp_affine_cubic_u8c3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, double scale) {
+    double M[6] = {scale, 0, 0, 0, scale, 0};
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+    const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+    M[2] = b1; M[5] = b2;
+    const short* tab = warp_cubic_tab();
+    std::vector<int> adelta(dw), bdelta(dw);
+    for (int x = 0; x < dw; x++) { adelta[x] = (int)lrint(M[0] * x * 1024); bdelta[x] = (int)lrint(M[3] * x * 1024); }
+    const int round_delta = 1024 / 32 / 2;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < dh; y++) {
+        const int X0 = (int)lrint((M[1] * y + M[2]) * 1024) + round_delta, Y0 = (int)lrint((M[4] * y + M[5]) * 1024) + round_delta;
+        for (int x = 0; x < dw; x++) {
+            const int X = (X0 + adelta[x]) >> 5, Y = (Y0 + bdelta[x]) >> 5;
+            const int sx = (X >> 5) - 1, sy = (Y >> 5) - 1;
+            const short* w = tab + ((Y & 31) * 32 + (X & 31)) * 16;
+            int acc[3] = {0, 0, 0};
+            for (int k1 = 0; k1 < 4; k1++) {
+                const int yy = sy + k1;
+                if (yy < 0 || yy >= sh) continue;
+                for (int k2 = 0; k2 < 4; k2++) {
+                    const int xx = sx + k2;
+                    if (xx < 0 || xx >= sw) continue;
+                    const uint8_t* p = src + ((size_t)yy * sw + xx) * 3;
+                    const int ww = w[k1 * 4 + k2];
+                    acc[0] += p[0] * ww; acc[1] += p[1] * ww; acc[2] += p[2] * ww;
+                }
+            }
+            for (int c = 0; c < 3; c++) {
+                const int v = (acc[c] + (1 << 14)) >> 15;
+                dst[((size_t)y * dw + x) * 3 + c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+        }
+    }
+}
+
 // rtpose.cpp:508-511: float scale = START_SCALE - i*SCALE_GAP (double math, stored float);
 // target = 16*ceil(NET*scale/16)
 extern "C" void orc_scale_target(int net_w, int net_h, double start_scale, double scale_gap, int i, int* tw, int* th) {

@@ -100,6 +100,10 @@ int orc_connect(int model, const float* heatmap, const float* peaks, int max_pea
                 int disp_h, const OrcConnectParams* p, float* joints, double* subset_out, int subset_cap,
                 int* subset_rows);
 
+/* ---- display image (rtpose.cpp:474-487): uniform scale s, top-left anchored, cv::warpAffine INTER_CUBIC, black border */
+double orc_display_scale(int cols, int rows, int disp_w, int disp_h);
+void orc_warp_affine_cubic_u8c3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, double scale);
+
 /* ---- preprocess (rtpose.cpp:508-518, 239-269) */
 /* OpenCV INTER_AREA, 8UC3, downscale only. Returns 0, or -1 if unsupported (upscale). */
 int orc_resize_area_u8c3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw);

@@ -100,6 +100,9 @@ def lib():
     L.orc_connect.argtypes = [C.c_int, _f32p, _f32p] + [C.c_int] * 5 + [C.POINTER(ConnectParams), _f32p, C.c_void_p,
                                                                       C.c_int, C.POINTER(C.c_int)]
     L.orc_resize_area_u8c3.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
+    L.orc_display_scale.restype = C.c_double
+    L.orc_display_scale.argtypes = [C.c_int] * 4
+    L.orc_warp_affine_cubic_u8c3.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_double]
     L.orc_scale_target.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.orc_preprocess.argtypes = [_u8p] + [C.c_int] * 5 + [C.c_double, C.c_double, _f32p]
     L.orc_json.argtypes = [_f32p, C.c_int, C.c_int, C.c_double, C.c_char_p, C.c_int]
@@ -209,6 +212,15 @@ def resize_area(img, dh, dw):
     if rc:
         raise ValueError("orc_resize_area_u8c3: unsupported (upscale)")
     return out
+
+
+def display_image(frame, disp_w, disp_h):
+    """(display image, frame.scale) of rtpose.cpp:474-487."""
+    sh, sw, _ = frame.shape
+    s = lib().orc_display_scale(sw, sh, disp_w, disp_h)
+    out = np.empty((disp_h, disp_w, 3), np.uint8)
+    lib().orc_warp_affine_cubic_u8c3(np.ascontiguousarray(frame, np.uint8), sh, sw, out, disp_h, disp_w, s)
+    return out, s
 
 
 def scale_target(net_w, net_h, start_scale, scale_gap, i):

@@ -81,6 +81,22 @@ def test_cli_json_equals_python_path(tmp_path):
         got = (out / ("img%03d.json" % i)).read_text()
         assert got == eng.json(joints, 1.0)
     eng.close()
+    # frames whose size differs from --resolution go through the GPU warpAffine (rtpose.cpp:474-487); JSON carries 1/scale
+    big_dir = tmp_path / "big"
+    big_dir.mkdir()
+    big = synth.make_frame(77, 270, 480)
+    write_bmp(str(big_dir / "big.bmp"), big)
+    out2 = tmp_path / "json2"
+    r = run(["--image_dir", str(big_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
+             "--net_resolution", "160x96", "--write_json", str(out2), "--no_display"], timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
+    eng.set_weights(W)
+    sc = eng.forward_camera_frames([big])
+    cnt, joints, _ = eng.fetch(0)
+    assert abs(sc - 320 / 480.0) < 1e-12
+    assert (out2 / "big.json").read_text() == eng.json(joints, sc)
+    eng.close()
     # --resolution -1x-1 takes the size from the first image (rtpose.cpp:1683-1686); missing model file is an error
     r = run(["--image_dir", str(img_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "-1x-1",
              "--net_resolution", "%dx%d" % (net_w, net_h), "--no_display"], timeout=300)

@@ -183,3 +183,20 @@ def test_joint_coordinates_within_1e3_px(small, prec):
     scale = 320.0 / s["net_w"]                                            # joints are reported in display pixels
     assert np.abs(joints[:, :, :2] - oj[:, :, :2]).max() / scale < 1e-3
     assert np.abs(joints[:, :, 2] - oj[:, :, 2]).max() < 20 * TOL[prec]
+
+
+@pytest.mark.parametrize("sh,sw", [(270, 480), (150, 200), (192, 320), (400, 360)])
+def test_camera_frames_warp_affine_bit_exact(sh, sw):
+    """Frames of any size: the display image (warpAffine INTER_CUBIC, rtpose.cpp:474-487) and then the net input must equal
+    the oracle's (OpenCV fixed-point arithmetic restated, pinned to cv2) bit for bit; frame.scale feeds the JSON."""
+    net_w, net_h, disp_w, disp_h = 160, 96, 320, 192
+    eng = engine.PoseEngine(engine.COCO_18, net_w, net_h, disp_w, disp_h, precision=engine.PREC_FP32_SIMT, max_batch=2)
+    eng.set_weights(synth.make_weights(engine.COCO_18, "caffe"))
+    frames = [synth.make_frame(31, sh, sw), synth.make_frame(32, sh, sw)]
+    s = eng.forward_camera_frames(frames)
+    img = eng.fetch_blob("image")
+    for i, f in enumerate(frames):
+        disp, os_ = orc.display_image(f, disp_w, disp_h)
+        assert s == os_
+        assert np.array_equal(img[i:i + 1], orc.preprocess(disp, net_h, net_w, 1, 1.0, 0.3))
+    eng.close()

@@ -245,3 +245,26 @@ def test_json_format():
     assert t.startswith('{\n"version":0.1,\n"bodies":[\n{\n"joints":[1237.12,579.194,0.950805,0,0,0,')
     assert t.endswith("]\n}]\n}\n")
     assert orc.json_text(np.zeros((0, 18, 3), np.float32), 18) == '{\n"version":0.1,\n"bodies":[\n]\n}\n'
+
+
+def test_warp_affine_vs_cv2_fixture(golden_dir):
+    d = np.load(os.path.join(golden_dir, "warp_cv2.npz"))
+    n = len([k for k in d.files if k.startswith("src")])
+    assert n >= 5
+    for i in range(n):
+        dst = d["dst%d" % i]
+        out, s = orc.display_image(d["src%d" % i], dst.shape[1], dst.shape[0])
+        assert s == float(d["scale%d" % i]) and np.array_equal(out, dst)
+
+
+def test_warp_affine_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    for (sh, sw, dw, dh) in [(108, 192, 128, 72), (48, 64, 128, 72), (72, 128, 128, 72), (100, 100, 128, 72)]:
+        img = synth.make_frame(5, sh, sw)
+        out, s = orc.display_image(img, dw, dh)
+        M = np.eye(2, 3)
+        M[0, 0] = M[1, 1] = s
+        ref = cv2.warpAffine(img, M, (dw, dh), flags=cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT, borderValue=(0, 0, 0))
+        assert np.array_equal(out, ref)
+    same, s = orc.display_image(synth.make_frame(1, 72, 128), 128, 72)   # scale 1: identity
+    assert s == 1.0 and np.array_equal(same, synth.make_frame(1, 72, 128))

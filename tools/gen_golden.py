@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """Generate the committed golden fixtures under tests/golden/ (run in the BUILD container).
 
+  warp_cv2.npz        cv2.warpAffine(diag(s,s), INTER_CUBIC, BORDER_CONSTANT) outputs (rtpose.cpp:484); pins
+                      oracle.orc_warp_affine_cubic_u8c3.
   area_cv2.npz        cv2.resize(INTER_AREA) outputs (cv2 4.13 here == the OpenCV algorithm the reference
                       calls at rtpose.cpp:516) for small uint8 BGR images; pins oracle.orc_resize_area_u8c3.
   parse_<model>.npz   reference-pinned stage outputs on a seeded injected scene: stride-8 maps (float16-free,
@@ -33,6 +35,22 @@ def gen_area():
     print("area_cv2.npz", len(cases), "cases, cv2", cv2.__version__)
 
 
+def gen_warp():
+    import cv2
+    d = {}
+    cases = [(54, 96, 64, 36), (40, 60, 64, 36), (36, 64, 64, 36), (30, 40, 64, 36), (45, 45, 80, 48)]
+    for i, (sh, sw, dw, dh) in enumerate(cases):
+        img = synth.make_frame(200 + i, sh, sw)
+        s = dw / float(sw) if sw / float(sh) > dw / float(dh) else dh / float(sh)
+        M = np.eye(2, 3)
+        M[0, 0] = M[1, 1] = s
+        d["src%d" % i] = img
+        d["dst%d" % i] = cv2.warpAffine(img, M, (dw, dh), flags=cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT, borderValue=(0, 0, 0))
+        d["scale%d" % i] = np.float64(s)
+    np.savez_compressed(os.path.join(OUT, "warp_cv2.npz"), **d)
+    print("warp_cv2.npz", len(cases), "cases")
+
+
 def gen_parse(model, name, net_w, net_h, disp_w, disp_h, n_people, num_scales, seed):
     people = synth.make_people(model, n_people, net_w, net_h, seed=seed)
     maps = synth.make_maps(model, people, net_w, net_h, num_scales=num_scales, start_scale=1.0, scale_gap=0.15, seed=seed)
@@ -56,6 +74,7 @@ def gen_parse(model, name, net_w, net_h, disp_w, disp_h, n_people, num_scales, s
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_area()
+    gen_warp()
     gen_parse(orc.COCO_18, "coco", 320, 176, 640, 352, 6, 1, 11)
     gen_parse(orc.COCO_18, "coco_s3", 320, 176, 640, 352, 5, 3, 12)
     gen_parse(orc.MPI_15, "mpi", 240, 176, 480, 352, 4, 1, 13)
