@@ -139,8 +139,29 @@ static int build_pre_tables(pe_engine* e) {
         t.tw = tw; t.th = th; t.padw = (c.net_w - tw) / 2; t.padh = (c.net_h - th) / 2;
         const double inv_x = (double)tw / c.disp_w, inv_y = (double)th / c.disp_h;
         const double sx = 1. / inv_x, sy = 1. / inv_y;
-        if (!(tw == c.disp_w && th == c.disp_h) && (sx < 1 || sy < 1))
-            return fail(e, PE_ERR_INVALID, "INTER_AREA upscaling (display %dx%d -> %dx%d) is not supported", c.disp_w, c.disp_h, tw, th);
+        t.linear = !(tw == c.disp_w && th == c.disp_h) && (sx < 1 || sy < 1);
+        if (t.linear) {
+            // cv::resize leaves the area path when one axis enlarges: fixed-point bilinear, "area mode" positions
+            // (imgproc/resize.cpp: sx = floor(dx*scale), fx = (dx+1) - (sx+1)*inv_scale clipped to [0,1), 11-bit coefficients)
+            auto lin = [](int ssize, int dsize, std::vector<int>& tab) {
+                const double inv = (double)dsize / ssize, scale = 1. / inv;
+                tab.resize((size_t)dsize * 3);
+                for (int d = 0; d < dsize; d++) {
+                    int s0 = (int)floor(d * scale);
+                    float f = (float)((d + 1) - (s0 + 1) * inv);
+                    f = f <= 0 ? 0.f : f - floorf(f);
+                    if (s0 < 0) { f = 0; s0 = 0; }
+                    if (s0 >= ssize - 1) { f = 0; s0 = ssize - 1; }
+                    tab[d * 3] = s0;
+                    tab[d * 3 + 1] = (int)std::min(32767L, std::max(-32768L, lrintf((1.f - f) * 2048)));
+                    tab[d * 3 + 2] = (int)std::min(32767L, std::max(-32768L, lrintf(f * 2048)));
+                }
+            };
+            std::vector<int> lx, ly;
+            lin(c.disp_w, tw, lx);
+            lin(c.disp_h, th, ly);
+            if (upload(e, lx, &t.lin_x) || upload(e, ly, &t.lin_y)) return PE_ERR_CUDA;
+        }
         const int ix = (int)lrint(sx), iy = (int)lrint(sy);
         t.fast = fabs(sx - ix) < 2.220446049250313e-16 && fabs(sy - iy) < 2.220446049250313e-16;
         t.iscale_x = ix; t.iscale_y = iy;

@@ -35,7 +35,8 @@ int launch_post(const PostDev& pd, int nframes, cudaStream_t st);
 struct AreaTab {           // OpenCV INTER_AREA decimation tables for one scale, device pointers
     const int* x_ofs; const int* x_si; const float* x_alpha;   // per dst x: [x_ofs[dx], x_ofs[dx+1]) entries
     const int* y_ofs; const int* y_si; const float* y_alpha;
-    int tw, th, padw, padh, fast, iscale_x, iscale_y;
+    const int* lin_x; const int* lin_y;                       // linear "area mode" (an axis enlarges): [d][3] = src index, a0, a1
+    int tw, th, padw, padh, fast, iscale_x, iscale_y, linear;
 };
 struct PreArgs {
     const uint8_t* frames;    // [nframes][disp_h][disp_w][3] BGR

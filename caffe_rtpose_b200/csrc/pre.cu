@@ -26,6 +26,21 @@ __global__ void __launch_bounds__(256) area_resize_kernel(PreArgs a) {
         dst[0] = p[0]; dst[1] = p[1]; dst[2] = p[2];
         return;
     }
+    if (t.linear) {   // one axis enlarges: OpenCV's fixed-point bilinear with area-mode positions (11-bit coefficients)
+        const int* lx = t.lin_x + dx * 3;
+        const int* ly = t.lin_y + dy * 3;
+        const int x0 = lx[0], x1 = min(x0 + 1, a.disp_w - 1), y0 = ly[0], y1 = min(y0 + 1, a.disp_h - 1);
+        const uint8_t* r0 = src + (size_t)y0 * a.disp_w * 3;
+        const uint8_t* r1 = src + (size_t)y1 * a.disp_w * 3;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int h0 = r0[x0 * 3 + c] * lx[1] + r0[x1 * 3 + c] * lx[2];
+            const int h1 = r1[x0 * 3 + c] * lx[1] + r1[x1 * 3 + c] * lx[2];
+            const int v = ((ly[1] * (h0 >> 4)) >> 16) + ((ly[2] * (h1 >> 4)) >> 16);
+            dst[c] = (uint8_t)min(max((v + 2) >> 2, 0), 255);
+        }
+        return;
+    }
     if (t.fast) {  // integer ratios: resizeAreaFast_ (2x2 uses the (sum+2)>>2 SIMD specialisation)
         int s0 = 0, s1 = 0, s2 = 0;
         for (int yy = 0; yy < t.iscale_y; yy++)

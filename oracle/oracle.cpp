@@ -762,7 +762,43 @@ extern "C" int orc_resize_area_u8c3(const uint8_t* src, int sh, int sw, uint8_t*
     if (dh == sh && dw == sw) { memcpy(dst, src, (size_t)sh * sw * cn); return 0; }
     const double inv_x = (double)dw / sw, inv_y = (double)dh / sh;
     const double scale_x = 1. / inv_x, scale_y = 1. / inv_y;
-    if (scale_x < 1 || scale_y < 1) return -1;
+    if (scale_x < 1 || scale_y < 1) {
+        // cv::resize leaves the area path as soon as ONE axis enlarges: INTER_AREA then means the fixed-point bilinear
+        // resize (INTER_RESIZE_COEF_BITS = 11) with "area mode" sample positions on BOTH axes (imgproc/resize.cpp:
+        // sx = floor(dx*scale), fx = (dx+1) - (sx+1)*inv_scale clipped to [0,1); HResizeLinear + VResizeLinear<uchar>).
+        struct Lin { int s, a0, a1; };
+        auto tab = [](int ssize, int dsize, std::vector<Lin>& t) {
+            const double inv = (double)dsize / ssize, scale = 1. / inv;
+            t.resize(dsize);
+            for (int dx = 0; dx < dsize; dx++) {
+                int sx = (int)floor(dx * scale);
+                float fx = (float)((dx + 1) - (sx + 1) * inv);
+                fx = fx <= 0 ? 0.f : fx - floorf(fx);
+                if (sx < 0) { fx = 0; sx = 0; }
+                if (sx >= ssize - 1) { fx = 0; sx = ssize - 1; }
+                t[dx].s = sx;
+                t[dx].a0 = (int)std::min(32767L, std::max(-32768L, lrintf((1.f - fx) * 2048)));
+                t[dx].a1 = (int)std::min(32767L, std::max(-32768L, lrintf(fx * 2048)));
+            }
+        };
+        std::vector<Lin> tx, ty;
+        tab(sw, dw, tx);
+        tab(sh, dh, ty);
+        for (int dy = 0; dy < dh; dy++) {
+            const int y0 = ty[dy].s, y1 = std::min(y0 + 1, sh - 1);
+            for (int dx = 0; dx < dw; dx++) {
+                const int x0 = tx[dx].s, x1 = std::min(x0 + 1, sw - 1);
+                for (int c = 0; c < cn; c++) {
+                    const int h0 = src[((size_t)y0 * sw + x0) * cn + c] * tx[dx].a0 + src[((size_t)y0 * sw + x1) * cn + c] * tx[dx].a1;
+                    const int h1 = src[((size_t)y1 * sw + x0) * cn + c] * tx[dx].a0 + src[((size_t)y1 * sw + x1) * cn + c] * tx[dx].a1;
+                    const int v = ((ty[dy].a0 * (h0 >> 4)) >> 16) + ((ty[dy].a1 * (h1 >> 4)) >> 16);
+                    const int o = (v + 2) >> 2;
+                    dst[((size_t)dy * dw + dx) * cn + c] = (uint8_t)(o < 0 ? 0 : (o > 255 ? 255 : o));
+                }
+            }
+        }
+        return 0;
+    }
     const int iscale_x = (int)lrint(scale_x), iscale_y = (int)lrint(scale_y);
     const bool fast = fabs(scale_x - iscale_x) < 2.220446049250313e-16 && fabs(scale_y - iscale_y) < 2.220446049250313e-16;
     if (fast) {  // resizeAreaFast_<uchar,int>: integer sum, saturate_cast<uchar>(sum*scale) with float scale

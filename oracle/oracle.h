@@ -105,7 +105,8 @@ double orc_display_scale(int cols, int rows, int disp_w, int disp_h);
 void orc_warp_affine_cubic_u8c3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, double scale);
 
 /* ---- preprocess (rtpose.cpp:508-518, 239-269) */
-/* OpenCV INTER_AREA, 8UC3, downscale only. Returns 0, or -1 if unsupported (upscale). */
+/* cv::resize(..., INTER_AREA), 8UC3: area decimation when both axes shrink, OpenCV's fixed-point bilinear "area mode"
+ * as soon as one axis enlarges.  Returns 0. */
 int orc_resize_area_u8c3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw);
 void orc_scale_target(int net_w, int net_h, double start_scale, double scale_gap, int i, int* tw, int* th);
 /* display image (disp_h x disp_w x 3 BGR u8) -> num_scales x 3 x net_h x net_w floats */

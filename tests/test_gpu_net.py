@@ -30,6 +30,19 @@ def small():
     return dict(model=model, net_w=net_w, net_h=net_h, W=W, onet=onet, frames=frames, x=x, omaps=omaps)
 
 
+def test_preprocess_net_taller_than_display():
+    """C5-style geometry (992x736 net from 1280x720 frames): the y axis enlarges, so cv::resize(INTER_AREA) is OpenCV's
+    fixed-point bilinear area mode for scale 1.0 and the area decimation for the smaller scales."""
+    net_w, net_h, disp_w, disp_h, S = 496, 368, 640, 360, 2
+    eng = engine.PoseEngine(engine.COCO_18, net_w, net_h, disp_w, disp_h, num_scales=S, start_scale=1.0, scale_gap=0.15,
+                            precision=engine.PREC_FP32_SIMT)
+    eng.set_weights(synth.make_weights(engine.COCO_18, "caffe"))
+    f = synth.make_frame(9, disp_h, disp_w)
+    eng.forward_frames([f])
+    assert np.array_equal(eng.fetch_blob("image")[:S], orc.preprocess(f, net_h, net_w, S, 1.0, 0.15))
+    eng.close()
+
+
 @pytest.mark.parametrize("S,start,gap", [(1, 1.0, 0.3), (3, 1.0, 0.15)])
 def test_preprocess_bit_exact(S, start, gap):
     net_w, net_h, disp_w, disp_h = 320, 176, 640, 360

@@ -136,7 +136,8 @@ def test_inter_area_vs_cv2_fixture(golden_dir):
 def test_inter_area_live_cv2():
     cv2 = pytest.importorskip("cv2")
     img = synth.make_frame(3, 180, 320)
-    for dh, dw in [(92, 164), (80, 140), (90, 160), (60, 160)]:
+    # (184, 248): one axis enlarges -> OpenCV's fixed-point bilinear "area mode"; (200, 400): both enlarge
+    for dh, dw in [(92, 164), (80, 140), (90, 160), (60, 160), (184, 248), (200, 400)]:
         assert np.array_equal(orc.resize_area(img, dh, dw), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA))
 
 
