@@ -386,18 +386,25 @@ __global__ void __launch_bounds__(512) limb_greedy_kernel(PostDev pd) {
             }
             __syncthreads();
         }
+    const ModelDev& md = pd.md;
+    const int pa = md.limb_seq[2 * limb], pb = md.limb_seq[2 * limb + 1];
+    const float* peaks = pd.peaks + (size_t)frame * pd.p.num_parts * poff;
+    const int nA = min((int)peaks[pa * poff], MP), nB = min((int)peaks[pb * poff], MP);
+    // decode the loop position p -> (i, j) for every candidate in parallel, so the inherently sequential greedy scan below
+    // (up to max_peaks^2 candidates on noise maps) is a handful of instructions per candidate instead of a div/mod chain
+    for (int r = threadIdx.x; r < ncand; r += blockDim.x) {
+        const unsigned long long key = s_keys[r];
+        const unsigned p = (unsigned)(key & 0xffffffffu);
+        s_keys[r] = (key & 0xffffffff00000000ull) | ((unsigned long long)(p / nB + 1) << 16) | (unsigned long long)(p % nB + 1);
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const ModelDev& md = pd.md;
-        const int pa = md.limb_seq[2 * limb], pb = md.limb_seq[2 * limb + 1];
-        const float* peaks = pd.peaks + (size_t)frame * pd.p.num_parts * poff;
-        const int nA = min((int)peaks[pa * poff], MP), nB = min((int)peaks[pb * poff], MP);
         const int num = min(nA, nB);
         Conn* out = pd.conns + (size_t)lf * MP;
         int cnt = 0;
         for (int row = 0; row < ncand && cnt < num; row++) {
             const unsigned long long key = s_keys[row];
-            const int p = (int)(key & 0xffffffffu);
-            const int i = p / nB + 1, j = p % nB + 1;
+            const int i = (int)((key >> 16) & 0xffffu), j = (int)(key & 0xffffu);
             if (!occA[i - 1] && !occB[j - 1]) {
                 const unsigned ok = ~(unsigned)(key >> 32);
                 const unsigned u = (ok & 0x80000000u) ? (ok & 0x7fffffffu) : ~ok;
@@ -525,17 +532,36 @@ __global__ void __launch_bounds__(256) assemble_kernel(PostDev pd) {
         __syncthreads();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // Output (rtpose.cpp:1051-1073): rows that pass the count / mean-score test, in creation order, at most 96.
+    // Each thread owns a contiguous chunk of rows (order preserved), a block scan gives every kept row its slot.
+    {
+        __shared__ int s_scan[256];
         const int rows = s_rows;
         float* joints = pd.joints + (size_t)frame * PE_MAX_PEOPLE * P * 3;
-        int cnt = 0;
-        for (int i = 0; i < rows; i++) {
+        const int per = (rows + 255) / 256;
+        const int r0 = threadIdx.x * per, r1 = min(r0 + per, rows);
+        int kept = 0;
+        for (int i = r0; i < r1; i++) {
             const double* row = subset + (size_t)i * S_SIZE;
-            if (row[S_CNT] >= (double)pd.p.min_subset_cnt &&
-                __ddiv_rn(row[S_SCORE], row[S_CNT]) > (double)pd.p.min_subset_score) {
+            kept += (row[S_CNT] >= (double)pd.p.min_subset_cnt && __ddiv_rn(row[S_SCORE], row[S_CNT]) > (double)pd.p.min_subset_score) ? 1 : 0;
+        }
+        s_scan[threadIdx.x] = kept;
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {
+            int v = 0;
+            if ((int)threadIdx.x >= off) v = s_scan[threadIdx.x - off];
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        int slot = s_scan[threadIdx.x] - kept;
+        for (int i = r0; i < r1; i++) {
+            const double* row = subset + (size_t)i * S_SIZE;
+            if (!(row[S_CNT] >= (double)pd.p.min_subset_cnt && __ddiv_rn(row[S_SCORE], row[S_CNT]) > (double)pd.p.min_subset_score)) continue;
+            if (slot < PE_MAX_PEOPLE) {
                 for (int j = 0; j < P; j++) {
                     const int idx = (int)row[j];
-                    float* o = joints + (size_t)cnt * P * 3 + j * 3;
+                    float* o = joints + (size_t)slot * P * 3 + j * 3;
                     if (idx) {
                         o[2] = peaks[idx];
                         o[1] = __fdiv_rn(__fmul_rn(peaks[idx - 1], (float)pd.p.disp_h), (float)pd.p.net_h);
@@ -544,12 +570,13 @@ __global__ void __launch_bounds__(256) assemble_kernel(PostDev pd) {
                         o[0] = o[1] = o[2] = 0.f;
                     }
                 }
-                cnt++;
-                if (cnt == PE_MAX_PEOPLE) break;
             }
+            slot++;
         }
-        pd.num_people[frame] = cnt;
-        pd.subset_rows[frame] = rows;
+        if (threadIdx.x == 255) {
+            pd.num_people[frame] = min(s_scan[255], PE_MAX_PEOPLE);
+            pd.subset_rows[frame] = rows;
+        }
     }
 }
 
