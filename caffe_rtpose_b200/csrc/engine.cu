@@ -294,7 +294,6 @@ extern "C" int pe_create(const pe_config* cfg, pe_engine** out) {
     CKC(cudaMalloc(&pd.cand_count, sizeof(int) * (size_t)B * NL));
     pd.sort_stride = 1;
     while (pd.sort_stride < MP * MP) pd.sort_stride <<= 1;
-    CKC(cudaMalloc(&pd.sort_scratch, sizeof(unsigned long long) * (size_t)B * NL * pd.sort_stride));
     CKC(cudaMalloc(&pd.conns, sizeof(Conn) * (size_t)B * NL * MP));
     CKC(cudaMalloc(&pd.conn_count, sizeof(int) * (size_t)B * NL));
     CKC(cudaMemset(pd.conn_count, 0, sizeof(int) * (size_t)B * NL));
@@ -325,7 +324,7 @@ extern "C" void pe_destroy(pe_engine* e) {
     cudaFreeHost(e->h_frames); cudaFreeHost(e->h_planar); cudaFreeHost(e->h_maps);
     cudaFree(e->d_xtab); cudaFree(e->d_ytab);
     PostDev& pd = e->post;
-    cudaFree(pd.flags); cudaFree(pd.peaks); cudaFree(pd.cands); cudaFree(pd.cand_count); cudaFree(pd.sort_scratch); cudaFree(pd.conns);
+    cudaFree(pd.flags); cudaFree(pd.peaks); cudaFree(pd.cands); cudaFree(pd.cand_count); cudaFree(pd.conns);
     cudaFree(pd.conn_count); cudaFree(pd.subset); cudaFree(pd.subset_rows); cudaFree(pd.joints); cudaFree(pd.num_people);
     cudaFreeHost(e->h_joints); cudaFreeHost(e->h_num_people); cudaFreeHost(e->h_peaks);
     for (int i = 0; i < 16; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);

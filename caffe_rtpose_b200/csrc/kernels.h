@@ -19,7 +19,7 @@ struct PostDev {
     float* peaks;             // [frames][parts][max_peaks+1][3]
     Cand* cands;              // [frames][limbs][max_peaks^2]
     int* cand_count;          // [frames][limbs]
-    unsigned long long* sort_scratch; int sort_stride;   // [frames][limbs][pow2 >= max_peaks^2] sort keys (large case)
+    int sort_stride;          // next_pow2(max_peaks^2): sort keys per limb (dynamic shared memory of limb_greedy_kernel)
     Conn* conns;              // [frames][limbs][max_peaks]
     int* conn_count;          // [frames][limbs]
     double* subset;           // [frames][PE_MAX_SUBSET_ROWS][parts+3]

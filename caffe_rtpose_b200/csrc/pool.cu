@@ -36,16 +36,16 @@ __global__ void __launch_bounds__(256) pool_f32_kernel(PoolArgs a) {
 
 template <int PLANES>
 __global__ void __launch_bounds__(256) pool_bf16_kernel(PoolArgs a) {
-    const int cv = a.C / 8;  // 8 channels (16 bytes) per thread and plane
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long rows_out = (long long)a.N * a.Hso * a.Wpo;
-    if (idx >= rows_out * cv) return;
+    const unsigned cv = a.C / 8;  // 8 channels (16 bytes) per thread and plane
+    const int n = blockIdx.y;     // grid.y = image; 32-bit index math inside an image
+    const unsigned per_img = (unsigned)a.Hso * (unsigned)a.Wpo;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_img * cv) return;
     const int g = (int)(idx % cv);
-    const long long mo = idx / cv;
-    const int n = (int)(mo / ((long long)a.Hso * a.Wpo));
-    const int rem = (int)(mo % ((long long)a.Hso * a.Wpo));
-    const int yo = rem / a.Wpo, xo = rem % a.Wpo;
+    const unsigned rem = idx / cv;
+    const int yo = (int)(rem / (unsigned)a.Wpo), xo = (int)(rem % (unsigned)a.Wpo);
     if (xo >= a.Wo || yo >= a.Ho) return;
+    const long long mo = (long long)n * per_img + rem;
     // issue all window loads first (4 positions x PLANES x 16 B in flight per thread), then reduce
     uint4 v[4][PLANES];
     bool ok[4];
@@ -90,10 +90,11 @@ int launch_pool(const PoolArgs& a, cudaStream_t st) {
         const long long total = rows_out * (a.C / 4);
         pool_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
     } else {
-        const long long total = rows_out * (a.C / 8);
-        if (a.planes == 1) pool_bf16_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
-        else if (a.planes == 2) pool_bf16_kernel<2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
-        else pool_bf16_kernel<3><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+        const unsigned per = (unsigned)a.Hso * a.Wpo * (a.C / 8);
+        const dim3 grid((per + 255) / 256, a.N);
+        if (a.planes == 1) pool_bf16_kernel<1><<<grid, 256, 0, st>>>(a);
+        else if (a.planes == 2) pool_bf16_kernel<2><<<grid, 256, 0, st>>>(a);
+        else pool_bf16_kernel<3><<<grid, 256, 0, st>>>(a);
     }
     return 1;
 }

@@ -352,12 +352,8 @@ __device__ __forceinline__ unsigned order_key(float f) {  // monotone float -> u
     const unsigned u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-#define GREEDY_SMEM_KEYS 1024
 __global__ void __launch_bounds__(512) limb_greedy_kernel(PostDev pd) {
-    // 8 KB of keys in shared memory covers the usual case; the (rare) limb with more than 1024 candidates sorts in
-    // its global scratch slice.  Keeping the footprint small lets these CTAs share an SM with a resident
-    // persistent conv CTA (~201 KB) of the other worker handle instead of waiting for a free SM.
-    __shared__ unsigned long long s_small[GREEDY_SMEM_KEYS];
+    extern __shared__ unsigned long long s_keys[];   // next_pow2(max_peaks^2) keys: 32 KB for COCO, 4 KB for MPI
     __shared__ unsigned char occA[128], occB[128];
     const int limb = blockIdx.x, frame = blockIdx.y;
     const int MP = pd.p.max_peaks, poff = 3 * (MP + 1);
@@ -366,7 +362,6 @@ __global__ void __launch_bounds__(512) limb_greedy_kernel(PostDev pd) {
     const Cand* cands = pd.cands + (size_t)lf * MP * MP;
     int n2 = 1;
     while (n2 < ncand) n2 <<= 1;
-    unsigned long long* s_keys = n2 <= GREEDY_SMEM_KEYS ? s_small : pd.sort_scratch + (size_t)lf * pd.sort_stride;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) {
         unsigned long long k = ~0ull;
         if (i < ncand) k = ((unsigned long long)(~order_key(cands[i].conn)) << 32) | (unsigned)cands[i].p;
@@ -599,7 +594,7 @@ int launch_post(const PostDev& pd, int nframes, cudaStream_t st) {
     nms_flags_kernel<<<g1, 256, 0, st>>>(pd);
     nms_write_kernel<<<dim3(p.num_parts, nframes), 256, 0, st>>>(pd);
     paf_score_kernel<<<dim3((MP * MP + 127) / 128, p.num_limbs, nframes), 128, 0, st>>>(pd);
-    limb_greedy_kernel<<<dim3(p.num_limbs, nframes), 512, 0, st>>>(pd);
+    limb_greedy_kernel<<<dim3(p.num_limbs, nframes), 512, sizeof(unsigned long long) * pd.sort_stride, st>>>(pd);
     assemble_kernel<<<nframes, 256, 0, st>>>(pd);
     return 5;  // kernels launched
 }

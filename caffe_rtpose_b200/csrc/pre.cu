@@ -133,14 +133,15 @@ __global__ void __launch_bounds__(256) input_im2col_kernel(PreArgs a, const floa
     // hi plane and only the 32 channels that can be non-zero (27 used); everything else stays zero from init
     // (the engine clears the other planes when it switches from the planar-input path, see engine.cu).
     const int parts = (SRC == 0 && a.planes > 0) ? 4 : a.kp / 8;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long per_img = (long long)a.Hs * a.Wp;
-    if (idx >= per_img * nimages * parts) return;
-    const int part = (int)(idx % parts);
-    const long long m = idx / parts;
-    const int n = (int)(m / per_img);
-    const int rem = (int)(m % per_img);
-    const int y = rem / a.Wp, x = rem % a.Wp;
+    // grid.y = image; 32-bit index math inside an image (64-bit divisions cost hundreds of cycles on the GPU)
+    const int n = blockIdx.y;
+    const unsigned per_img = (unsigned)a.Hs * (unsigned)a.Wp;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_img * (unsigned)parts) return;
+    const int part = (int)(idx % (unsigned)parts);
+    const unsigned rem = idx / (unsigned)parts;
+    const int y = (int)(rem / (unsigned)a.Wp), x = (int)(rem % (unsigned)a.Wp);
+    const long long m = (long long)n * per_img + rem;
     if (x >= a.net_w || y >= a.net_h) return;  // gap rows stay zero
     const int s = n % a.S;
     const AreaTab& t = a.tab[SRC == 0 ? s : 0];
@@ -190,14 +191,14 @@ __global__ void __launch_bounds__(256) input_im2col_kernel(PreArgs a, const floa
 int launch_preprocess(const PreArgs& a, cudaStream_t st) {
     dim3 g((a.net_w * a.net_h + 255) / 256, a.S, a.nframes);
     area_resize_kernel<<<g, 256, 0, st>>>(a);
-    const long long work = (long long)a.Hs * a.Wp * a.nframes * a.S * (a.planes > 0 ? 4 : a.kp / 8);
-    input_im2col_kernel<0><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(a, nullptr, a.nframes * a.S);
+    const unsigned work = (unsigned)a.Hs * a.Wp * (a.planes > 0 ? 4 : a.kp / 8);
+    input_im2col_kernel<0><<<dim3((work + 255) / 256, a.nframes * a.S), 256, 0, st>>>(a, nullptr, a.nframes * a.S);
     return 2;
 }
 
 int launch_input_from_planar(const float* planar, const PreArgs& a, int nimages, cudaStream_t st) {
-    const long long work = (long long)a.Hs * a.Wp * nimages * (a.kp / 8);
-    input_im2col_kernel<1><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(a, planar, nimages);
+    const unsigned work = (unsigned)a.Hs * a.Wp * (a.kp / 8);
+    input_im2col_kernel<1><<<dim3((work + 255) / 256, nimages), 256, 0, st>>>(a, planar, nimages);
     return 1;
 }
 
