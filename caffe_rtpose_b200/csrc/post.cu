@@ -354,7 +354,6 @@ __device__ __forceinline__ unsigned order_key(float f) {  // monotone float -> u
 }
 __global__ void __launch_bounds__(512) limb_greedy_kernel(PostDev pd) {
     extern __shared__ unsigned long long s_keys[];   // next_pow2(max_peaks^2) keys: 32 KB for COCO, 4 KB for MPI
-    __shared__ unsigned char occA[128], occB[128];
     const int limb = blockIdx.x, frame = blockIdx.y;
     const int MP = pd.p.max_peaks, poff = 3 * (MP + 1);
     const int lf = frame * pd.p.num_limbs + limb;
@@ -367,7 +366,6 @@ __global__ void __launch_bounds__(512) limb_greedy_kernel(PostDev pd) {
         if (i < ncand) k = ((unsigned long long)(~order_key(cands[i].conn)) << 32) | (unsigned)cands[i].p;
         s_keys[i] = k;
     }
-    if (threadIdx.x < 128) { occA[threadIdx.x] = 0; occB[threadIdx.x] = 0; }
     __syncthreads();
     for (int k = 2; k <= n2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -393,25 +391,45 @@ __global__ void __launch_bounds__(512) limb_greedy_kernel(PostDev pd) {
         s_keys[r] = (key & 0xffffffff00000000ull) | ((unsigned long long)(p / nB + 1) << 16) | (unsigned long long)(p % nB + 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // Greedy one-to-one selection in sorted order (rtpose.cpp:953-980) by ONE WARP, 32 candidates per step: within a
+    // group the first candidate whose A and B are both still free is exactly the one the sequential scan would take
+    // next; accept it, update the occupancy masks, re-test the later lanes, repeat.  Same picks in the same order, but
+    // ~ncand/32 + #picks dependent steps instead of ncand.
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         const int num = min(nA, nB);
         Conn* out = pd.conns + (size_t)lf * MP;
+        unsigned long long ua0 = 0, ua1 = 0, ub0 = 0, ub1 = 0;   // occupancy bitmasks (max_peaks <= 128)
         int cnt = 0;
-        for (int row = 0; row < ncand && cnt < num; row++) {
-            const unsigned long long key = s_keys[row];
-            const int i = (int)((key >> 16) & 0xffffu), j = (int)(key & 0xffffu);
-            if (!occA[i - 1] && !occB[j - 1]) {
-                const unsigned ok = ~(unsigned)(key >> 32);
-                const unsigned u = (ok & 0x80000000u) ? (ok & 0x7fffffffu) : ~ok;
-                Conn c;
-                c.a = pa * poff + i * 3 + 2;
-                c.b = pb * poff + j * 3 + 2;
-                c.score = __uint_as_float(u);
-                out[cnt++] = c;
-                occA[i - 1] = 1; occB[j - 1] = 1;
+        for (int base = 0; base < ncand && cnt < num; base += 32) {
+            const int row = base + lane;
+            bool valid = row < ncand;
+            const unsigned long long key = valid ? s_keys[row] : 0ull;
+            const int i = (int)((key >> 16) & 0xffffu) - 1, j = (int)(key & 0xffffu) - 1;
+            while (cnt < num) {
+                const bool a_used = valid && (((i < 64 ? ua0 : ua1) >> (i & 63)) & 1ull);
+                const bool b_used = valid && (((j < 64 ? ub0 : ub1) >> (j & 63)) & 1ull);
+                const unsigned m = __ballot_sync(0xffffffffu, valid && !a_used && !b_used);
+                if (!m) break;
+                const int f = __ffs(m) - 1;
+                const int fi = __shfl_sync(0xffffffffu, i, f), fj = __shfl_sync(0xffffffffu, j, f);
+                const unsigned fhi = __shfl_sync(0xffffffffu, (unsigned)(key >> 32), f);
+                if (fi < 64) ua0 |= 1ull << fi; else ua1 |= 1ull << (fi - 64);
+                if (fj < 64) ub0 |= 1ull << fj; else ub1 |= 1ull << (fj - 64);
+                if (lane == 0) {
+                    const unsigned ok = ~fhi;
+                    const unsigned u = (ok & 0x80000000u) ? (ok & 0x7fffffffu) : ~ok;
+                    Conn c;
+                    c.a = pa * poff + (fi + 1) * 3 + 2;
+                    c.b = pb * poff + (fj + 1) * 3 + 2;
+                    c.score = __uint_as_float(u);
+                    out[cnt] = c;
+                }
+                cnt++;
+                if (lane == f) valid = false;
             }
         }
-        pd.conn_count[lf] = cnt;
+        if (lane == 0) pd.conn_count[lf] = cnt;
     }
 }
 
@@ -435,18 +453,33 @@ __global__ void __launch_bounds__(256) assemble_kernel(PostDev pd) {
     if (threadIdx.x == 0) s_rows = 0;
     __syncthreads();
 
+    // New rows of one limb are first described in shared memory by thread 0 (cheap, in reference order) and then
+    // written to the subset table by the whole CTA (21 doubles per row).
+    struct NewRow { int slot_a, slot_b; double va, vb, cnt, score; };
+    __shared__ NewRow s_new[128];
+    __shared__ int s_nnew;
+    if (threadIdx.x == 0) s_nnew = 0;
     auto append = [&](int slot_a, double va, int slot_b, double vb, double cnt, double score) {
         // called by thread 0 only
-        const int r = s_rows;
-        if (r < PE_MAX_SUBSET_ROWS) {
-            double* row = subset + (size_t)r * S_SIZE;
-            for (int q = 0; q < S_SIZE; q++) row[q] = 0.0;
-            row[slot_a] = va;
-            if (slot_b >= 0) row[slot_b] = vb;
-            row[S_CNT] = cnt;
-            row[S_SCORE] = score;
-            s_rows = r + 1;
+        const int r = s_nnew;
+        if (r < 128) { s_new[r] = NewRow{slot_a, slot_b, va, vb, cnt, score}; s_nnew = r + 1; }
+    };
+    auto flush = [&]() {   // called by all threads
+        __syncthreads();
+        const int n = s_nnew, base = s_rows;
+        for (int t = threadIdx.x; t < n * S_SIZE; t += blockDim.x) {
+            const int r = t / S_SIZE, q = t % S_SIZE;
+            const NewRow nr = s_new[r];
+            double v = 0.0;
+            if (q == nr.slot_a) v = nr.va;
+            else if (q == nr.slot_b) v = nr.vb;
+            else if (q == S_CNT) v = nr.cnt;
+            else if (q == S_SCORE) v = nr.score;
+            if (base + r < PE_MAX_SUBSET_ROWS) subset[(size_t)(base + r) * S_SIZE + q] = v;
         }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_rows = min(base + n, PE_MAX_SUBSET_ROWS); s_nnew = 0; }
+        __syncthreads();
     };
     // The reference walks connections (and, in the nA==0/nB==0 branches, peaks) one at a time over all rows.
     // Within one limb every connection has a distinct part-A peak and rows created during the limb carry that
@@ -478,7 +511,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(PostDev pd) {
                         const int off = part * poff + i * 3 + 2;
                         append(part, (double)off, -1, 0.0, 1.0, (double)peaks[off]);
                     }
-            __syncthreads();
+            flush();
             continue;
         }
         const int lf = frame * pd.p.num_limbs + k;
@@ -491,7 +524,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(PostDev pd) {
                     const double sc = __dadd_rn((double)__fadd_rn(peaks[c.a], peaks[c.b]), (double)c.score);
                     append(pa, (double)c.a, pb, (double)c.b, 2.0, sc);
                 }
-            __syncthreads();
+            flush();
             continue;
         }
         if (nc == 0) continue;
@@ -524,7 +557,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(PostDev pd) {
                     const double sc = __dadd_rn((double)__fadd_rn(peaks[c.a], peaks[c.b]), (double)c.score);
                     append(pa, (double)c.a, pb, (double)c.b, 2.0, sc);
                 }
-        __syncthreads();
+        flush();
     }
     __syncthreads();
     // Output (rtpose.cpp:1051-1073): rows that pass the count / mean-score test, in creation order, at most 96.
