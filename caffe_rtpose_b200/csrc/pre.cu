@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) input_im2col_kernel(PreArgs a, const floa
                 if (SRC == 0) {
                     const int oy = yy - t.padh, ox = xx - t.padw;
                     if (oy >= 0 && oy < t.th && ox >= 0 && ox < t.tw)
-                        val = __fsub_rn(__fdiv_rn((float)img[((size_t)oy * t.tw + ox) * 3 + c], 256.0f), 0.5f);
+                        val = __fsub_rn(__fmul_rn((float)img[((size_t)oy * t.tw + ox) * 3 + c], 0.00390625f), 0.5f);   // x/256 == x*2^-8 exactly
                 } else {
                     val = planar[((size_t)n * 3 + c) * a.net_h * a.net_w + (size_t)yy * a.net_w + xx];
                 }
