@@ -191,6 +191,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # the image's default prints "NCCL version ..." on stdout, next to the JSON line
     import torch
     from caffe_rtpose_b200 import engine, synth
 
