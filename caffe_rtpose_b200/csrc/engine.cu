@@ -479,6 +479,68 @@ extern "C" int pe_commit_weights(pe_engine* e) {
     e->committed = true;
     return PE_OK;
 }
+// ---------------------------------------------------------------------------------------------
+// One-time weight replica broadcast inside ONE process (rtpose.bin --num_gpu N).  The reference reads and parses the
+// .caffemodel once per GPU (rtpose.cpp:183-184); here engines[0]'s packed device buffer goes to every other GPU with
+// one grouped ncclBroadcast over NVLink.  This is the path's only collective.  NCCL is dlopen'ed (no link-time
+// dependency, and a process that already carries torch's NCCL keeps using that one).
+// ---------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+typedef struct ncclComm* pe_ncclComm_t;
+extern "C" int pe_broadcast_weights(pe_engine* const* engines, int n) {
+    if (!engines || n < 1 || !engines[0]) return PE_ERR_INVALID;
+    pe_engine* root = engines[0];
+    if (!root->committed) return fail(root, PE_ERR_STATE, "engines[0] has no committed weights to broadcast");
+    if (n == 1) return PE_OK;
+    for (int i = 1; i < n; i++) {
+        pe_engine* e = engines[i];
+        if (!e || e->cfg.model != root->cfg.model || e->cfg.precision != root->cfg.precision || e->cfg.net_w != root->cfg.net_w ||
+            e->cfg.net_h != root->cfg.net_h)
+            return fail(root, PE_ERR_INVALID, "engine %d is not a replica of engine 0 (model / precision / net size differ)", i);
+        if (!e->committed) {   // allocate the packed buffer + TMA maps with the same layout (values arrive by broadcast)
+            for (size_t l = 0; l < e->plan.convs.size(); l++) {
+                const ConvSpec& c = e->plan.convs[l];
+                e->hw[l].w.assign((size_t)c.cout * c.cin * c.k * c.k, 0.f);
+                e->hw[l].b.assign(c.cout, 0.f);
+                e->hw[l].set = true;
+            }
+            const int rc = pe_commit_weights(e);
+            if (rc) return rc;
+            for (auto& h : e->hw) { std::vector<float>().swap(h.w); }
+        }
+        if (e->packed_bytes != root->packed_bytes) return fail(root, PE_ERR_STATE, "packed layouts differ");
+    }
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(root, PE_ERR_STATE, "NCCL is not available (%s)", dlerror());
+    typedef int (*InitAllFn)(pe_ncclComm_t*, int, const int*);
+    typedef int (*BcastFn)(const void*, void*, size_t, int, int, pe_ncclComm_t, cudaStream_t);
+    typedef int (*VoidFn)(void);
+    typedef int (*DestroyFn)(pe_ncclComm_t);
+    typedef const char* (*ErrFn)(int);
+    InitAllFn init_all = (InitAllFn)dlsym(h, "ncclCommInitAll");
+    BcastFn bcast = (BcastFn)dlsym(h, "ncclBroadcast");
+    VoidFn gstart = (VoidFn)dlsym(h, "ncclGroupStart"), gend = (VoidFn)dlsym(h, "ncclGroupEnd");
+    DestroyFn destroy = (DestroyFn)dlsym(h, "ncclCommDestroy");
+    ErrFn errstr = (ErrFn)dlsym(h, "ncclGetErrorString");
+    if (!init_all || !bcast || !gstart || !gend || !destroy) return fail(root, PE_ERR_STATE, "NCCL symbols missing");
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; i++) devs[i] = engines[i]->cfg.device;
+    std::vector<pe_ncclComm_t> comms(n, nullptr);
+    int rc = init_all(comms.data(), n, devs.data());
+    if (rc) return fail(root, PE_ERR_CUDA, "ncclCommInitAll: %s", errstr ? errstr(rc) : "error");
+    gstart();
+    for (int i = 0; i < n && !rc; i++) {
+        cudaSetDevice(devs[i]);
+        rc = bcast(root->d_packed, engines[i]->d_packed, root->packed_bytes, 0 /*ncclChar*/, 0, comms[i], engines[i]->stream);
+    }
+    const int rc2 = gend();
+    for (int i = 0; i < n; i++) { cudaSetDevice(devs[i]); cudaStreamSynchronize(engines[i]->stream); }
+    for (int i = 0; i < n; i++) destroy(comms[i]);
+    if (rc || rc2) return fail(root, PE_ERR_CUDA, "ncclBroadcast: %s", errstr ? errstr(rc ? rc : rc2) : "error");
+    return PE_OK;
+}
+
 extern "C" size_t pe_packed_weights_bytes(const pe_engine* e) { return e ? e->packed_bytes : 0; }
 extern "C" void* pe_packed_weights_device_ptr(pe_engine* e) { return e ? e->d_packed : nullptr; }
 

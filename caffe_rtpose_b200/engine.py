@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
-    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames",
+    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights",
 ]
 
 
@@ -115,6 +115,7 @@ def lib():
     L.pe_packed_weights_bytes.restype = C.c_size_t
     L.pe_packed_weights_device_ptr.argtypes = [C.c_void_p]
     L.pe_packed_weights_device_ptr.restype = C.c_void_p
+    L.pe_broadcast_weights.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     _lib = L
     return L
 
@@ -467,3 +468,11 @@ def write_caffemodel(path, weights, table, legacy_v1=False, legacy_dims=False):
             net += _pb_len(100, _pb_len(1, ("relu_" + name).encode()) + _pb_len(2, b"ReLU"))   # blob-less layer, ignored
     with open(path, "wb") as f:
         f.write(net)
+
+
+def broadcast_weights(engines):
+    """engines[0]'s committed weights -> the other handles (one per GPU, same process) with one ncclBroadcast."""
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    rc = lib().pe_broadcast_weights(arr, len(engines))
+    if rc != 0:
+        raise PoseEngineError("pe_broadcast_weights failed (%d): %s" % (rc, lib().pe_last_error(engines[0]._h).decode()))

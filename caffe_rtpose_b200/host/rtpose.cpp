@@ -266,24 +266,49 @@ static void producer() {
     global.input_queue.wake();
 }
 
-static void worker(int tid) {
-    const int device = Fi("start_device") + tid, batch = std::max(1, Fi("batch"));
-    pe_config c;
-    memset(&c, 0, sizeof c);
-    c.device = device; c.model = global.model; c.net_w = global.net_w; c.net_h = global.net_h;
-    c.disp_w = global.disp_w; c.disp_h = global.disp_h; c.num_scales = Fi("num_scales");
-    c.start_scale = Fd("start_scale"); c.scale_gap = Fd("scale_gap"); c.max_batch = batch; c.precision = Fi("precision");
-    pe_engine* e = nullptr;
-    struct Done { ~Done() { global.finished++; global.output_queue.wake(); } } done_guard;   // every exit path counts
-    if (pe_create(&c, &e)) { LOG_ERROR("GPU %d: %s", device, pe_last_error(nullptr)); global.quit = true; global.input_queue.wake(); return; }
+static int load_weights(pe_engine* e, int device) {   // CopyTrainedLayersFrom (rtpose.cpp:184)
     LOG_INFO("GPU %d: copying to person net", device);
     int rc = 0;
     if (!F("random_init").empty()) random_weights(e, F("random_init"));
     else rc = pe_load_caffemodel(e, F("caffemodel").c_str());
     if (rc || pe_commit_weights(e)) {
         LOG_ERROR("GPU %d: cannot load %s: %s %s", device, F("caffemodel").c_str(), pe_caffemodel_last_error(), pe_last_error(e));
-        global.quit = true; global.input_queue.wake(); pe_destroy(e); return;
+        return 1;
     }
+    return 0;
+}
+
+// warmup() of every GPU (rtpose.cpp:173-237).  The reference parses the .caffemodel once per GPU; here GPU 0 loads and
+// packs it and the replicas receive the packed buffer by one ncclBroadcast (the path's only collective).
+static bool create_engines(int num_gpu, std::vector<pe_engine*>& engines) {
+    const int batch = std::max(1, Fi("batch"));
+    for (int tid = 0; tid < num_gpu; tid++) {
+        pe_config c;
+        memset(&c, 0, sizeof c);
+        c.device = Fi("start_device") + tid; c.model = global.model; c.net_w = global.net_w; c.net_h = global.net_h;
+        c.disp_w = global.disp_w; c.disp_h = global.disp_h; c.num_scales = Fi("num_scales");
+        c.start_scale = Fd("start_scale"); c.scale_gap = Fd("scale_gap"); c.max_batch = batch; c.precision = Fi("precision");
+        pe_engine* e = nullptr;
+        if (pe_create(&c, &e)) { LOG_ERROR("GPU %d: %s", c.device, pe_last_error(nullptr)); return false; }
+        engines.push_back(e);
+    }
+    if (load_weights(engines[0], Fi("start_device"))) return false;
+    if (num_gpu > 1) {
+        if (pe_broadcast_weights(engines.data(), num_gpu) == PE_OK) {
+            LOG_INFO("weights broadcast from GPU %d to %d replicas (%.1f MB, NCCL)", Fi("start_device"), num_gpu - 1,
+                     pe_packed_weights_bytes(engines[0]) / 1e6);
+        } else {
+            LOG_ERROR("weight broadcast unavailable (%s); every GPU loads the model itself", pe_last_error(engines[0]));
+            for (int tid = 1; tid < num_gpu; tid++)
+                if (load_weights(engines[tid], Fi("start_device") + tid)) return false;
+        }
+    }
+    return true;
+}
+
+static void worker(int tid, pe_engine* e) {
+    const int device = Fi("start_device") + tid, batch = std::max(1, Fi("batch"));
+    struct Done { ~Done() { global.finished++; global.output_queue.wake(); } } done_guard;   // every exit path counts
     caffe::NmsLayer<float> nms_layer(e);
     caffe::ImResizeLayer<float> resize_layer(e);
     resize_layer.SetStartScale((float)Fd("start_scale"));
@@ -329,7 +354,6 @@ static void worker(int tid) {
             global.output_queue.push(std::move(frames[i]));
         }
     }
-    pe_destroy(e);
 }
 
 // re-order by frame index (buffer_and_order, rtpose.cpp:1214-1273) and write JSON (displayFrame, :1383-1416)
@@ -434,12 +458,18 @@ int main(int argc, char** argv) {
         LOG_INFO("Selecting %s model: %d parts, %d limbs.", model == PE_MODEL_MPI_15 ? "MPI" : "COCO", global.num_parts, md->number_limb_sequence());
     }
     const int num_gpu = std::max(1, Fi("num_gpu"));
+    std::vector<pe_engine*> engines;
+    if (!create_engines(num_gpu, engines)) {
+        for (pe_engine* e : engines) pe_destroy(e);
+        return 1;
+    }
     std::vector<std::thread> workers;
-    for (int i = 0; i < num_gpu; i++) workers.emplace_back(worker, i);
+    for (int i = 0; i < num_gpu; i++) workers.emplace_back(worker, i, engines[i]);
     std::thread prod(producer);
     std::thread ord(orderer_and_writer, num_gpu);
     prod.join();
     for (auto& t : workers) t.join();
     ord.join();
+    for (pe_engine* e : engines) pe_destroy(e);
     return global.quit ? 1 : 0;
 }

@@ -153,6 +153,9 @@ double pe_conv_flops_per_scale(const pe_engine* e);
  * exports / imports the packed device buffer so that the host layer (NCCL via torch.distributed or
  * ncclBroadcast in rtpose.bin) can move it.  Returns size in bytes. */
 size_t pe_packed_weights_bytes(const pe_engine* e);
+/* single-process --num_gpu N: engines[0]'s committed weights -> engines[1..n-1] (one handle per GPU) with one grouped
+ * ncclBroadcast over NVLink instead of N file reads (rtpose.cpp:183-184).  The path's only collective. */
+int pe_broadcast_weights(pe_engine* const* engines, int n);
 void* pe_packed_weights_device_ptr(pe_engine* e);
 
 #ifdef __cplusplus
