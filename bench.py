@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=9, help="frames per forward per GPU (9 x 4165 rows = 1.98 waves of 128-row tiles on 148 SMs)")
-    ap.add_argument("--precision", type=int, default=2, help="0 fp32 SIMT, 1 bf16, 2 bf16x2 (parity mode), 3 bf16x3")
+    ap.add_argument("--precision", type=int, default=2, help="0 fp32 SIMT, 1 bf16, 2 f16x2 split (parity mode), 3 bf16x3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -370,7 +370,7 @@ def main():
             cpu["parity_note"] = note
         line = {"metric": "frames/sec at 656x368 COCO-18", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": {0: "f32", 1: "bf16", 2: "bf16x2 (split, fp32 accumulate)", 3: "bf16x3 (split, fp32 accumulate)"}[args.precision],
+                "vs_baseline": None, "dtype": {0: "f32", 1: "bf16", 2: "f16x2 (2 fp16 planes, 3 tcgen05 MMAs per MAC, fp32 accumulate)", 3: "bf16x3 (split, fp32 accumulate)"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": "C2: COCO 656x368, 1 scale, synthetic 720p stream, W-he random-init weights",
                            "frames_per_step_per_gpu": B, "precision_mode": args.precision, "sharding": "frames round-robin, one rank per GPU",

@@ -13,9 +13,9 @@
 //     mbarriers; a STAGES-deep ring overlaps loads with MMAs.
 //   * One elected thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32), M=128, N=BN,
 //     K=16 per instruction, accumulator in TMEM (BN columns x 128 lanes, fp32).
-//   * Split precision: activations and weights are stored as P bf16 "planes" whose sum is the fp32 value
-//     (hi / mid / lo).  For P planes the kernel issues the P(P+1)/2 cross products (i + j < P) into the same
-//     TMEM accumulator: P=1 plain bf16, P=2 ~2^-16 relative, P=3 ~fp32.  The accumulation itself is fp32.
+//   * Split precision: activations and weights are stored as P 16-bit "planes" whose sum is the fp32 value
+//     (hi / lo); the kernel issues the cross products hi*hi, hi*lo, lo*hi on the tensor core.  P=1 plain bf16,
+//     P=2 = parity mode on fp16 planes (kernels.h), ~1e-5 over the whole net.
 //   * Epilogue warps read TMEM with tcgen05.ld (32 lanes x 16 columns), add bias, ReLU, re-split into
 //     planes and store NHWC bf16 (channel-slice stores implement Concat), or - for the last stage - store
 //     the planar fp32 concat_stage7 blob directly (coalesced along x).
@@ -31,6 +31,7 @@
 
 #include "common.h"
 #include "conv_tc.h"
+#include "kernels.h"
 
 namespace pe {
 
@@ -39,10 +40,12 @@ struct TcArgs {
     __nv_bfloat16* out; int out_pitch, out_coff; long long out_plane;
     float* planar; int planar_C, planar_coff;
     int cout, relu;
+    const float* out_scale;                   // -> 2^-k in the packed buffer: the weights of this layer carry a factor 2^k (fp16 planes)
     int ksize, pad, kblocks_per_tap, cin_k;   // cin_k = channels per tap in the weight K ordering
     int W, H, Wp, Hs;
     long long M;
     int n_tiles_n; long long total_tiles;   // persistent window kernel: tile = (m_tile, n_tile), n fastest
+    int chunk_steps;                        // (channel block, filter row) steps per TMEM accumulation chunk (window kernel)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -127,8 +130,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // bits, and the base_offset field [49,52) must stay 0 (measured: setting it to (addr>>7)&7 gives wrong results).
 // instruction descriptor kind::f16 (InstrDescriptor): c_format F32 (bit 4), a/b format BF16 (bits 7,10),
 // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool f16 = false) {   // a/b format: 0 = F16, 1 = BF16
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -150,7 +153,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int B_BYTES = BN * 128;
     constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
     constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
-    constexpr uint32_t IDESC = umma_idesc(TC_BM, BN);
+    constexpr uint32_t IDESC = umma_idesc(TC_BM, BN, planes_are_fp16(PLANES));
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024 B
@@ -236,6 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             valid = (x < a.W) && (y < a.H);
         }
         const int cout8 = (a.cout + 7) & ~7;
+        const float out_scale = __ldg(a.out_scale);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
             uint32_t r[16];
@@ -246,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const int co = n0 + c0 + j;
-                    float t = __uint_as_float(r[j]) + (co < a.cout ? __ldg(a.bias + co) : 0.f);
+                    float t = __fmaf_rn(__uint_as_float(r[j]), out_scale, co < a.cout ? __ldg(a.bias + co) : 0.f);
                     if (a.relu) t = fmaxf(t, 0.f);
                     v[j] = t;
                 }
@@ -262,12 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 16; j += 2) {
                         float r0 = v[j], r1 = v[j + 1];
 #pragma unroll
-                        for (int p = 0; p < PLANES; p++) {
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(r0), h1 = __float2bfloat16_rn(r1);
-                            pk[p][j / 2] = pack_bf16(h0, h1);
-                            r0 = __fsub_rn(r0, __bfloat162float(h0));
-                            r1 = __fsub_rn(r1, __bfloat162float(h1));
-                        }
+                        for (int p = 0; p < PLANES; p++) pk[p][j / 2] = split_pair<planes_are_fp16(PLANES)>(r0, r1);
                     }
                     __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + n0 + c0;
 #pragma unroll
@@ -321,8 +320,9 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int B_SLOT = (ROWB ? 3 : 1) * B_TAP;          // ROWB: all taps of a filter row (ksize <= 3) share a slot
     constexpr int ACC_COLS = PLANES * BN;
     constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
-    constexpr uint32_t IDESC1 = umma_idesc(TC_BM, PLANES * BN);   // A_hi x [B_hi;B_lo]
-    constexpr uint32_t IDESC2 = umma_idesc(TC_BM, BN);            // A_lo x B_hi
+    constexpr bool F16 = planes_are_fp16(PLANES);
+    constexpr uint32_t IDESC1 = umma_idesc(TC_BM, PLANES * BN, F16);   // A_hi x [B_hi;B_lo]
+    constexpr uint32_t IDESC2 = umma_idesc(TC_BM, BN, F16);            // A_lo x B_hi
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -390,15 +390,26 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
-        int aw = 0, bt = 0, ti = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ti++) {
-            const int as = ti & 1;
-            mbar_wait(&tmem_empty[as], ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t acc = tmem_base + (uint32_t)(as * ACC_COLS);
+        // The tensor core adds every K=16 step into the fp32 TMEM accumulator with truncation, so a long chain drifts
+        // (measured: 1.9e-4 relative over the net with one accumulator, 5.7e-5 with hi*hi alone in its accumulator).
+        // The chain is therefore cut into CHUNKS of a.chunk_steps steps: every chunk starts from zero in one of the two
+        // TMEM buffers and the epilogue warps add the chunks in registers with round-to-nearest while the next chunk runs.
+        int aw = 0, bt = 0;
+        uint32_t ci = 0;
+        const int nsteps = a.kblocks_per_tap * ks, cs = a.chunk_steps;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int step = 0, as = 0;
+            uint32_t acc = 0;
             bool first = true;
             for (int kb = 0; kb < a.kblocks_per_tap; kb++)
                 for (int r = 0; r < ks; r++) {
+                    if (step % cs == 0) {
+                        as = (int)(ci & 1u);
+                        mbar_wait(&tmem_empty[as], ((ci >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+                        tc_fence_after();
+                        acc = tmem_base + (uint32_t)(as * ACC_COLS);
+                        first = true;
+                    }
                     const int sa_slot = aw % NA;
                     mbar_wait(&a_full[sa_slot], (uint32_t)(aw / NA) & 1u);
                     const uint32_t sa = smem_u32(smem_a + sa_slot * A_SLOT);
@@ -440,8 +451,9 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     umma_commit(&a_empty[sa_slot]);
                     aw++;
+                    step++;
+                    if (step % cs == 0 || step == nsteps) { umma_commit(&tmem_full[as]); ci++; }
                 }
-            umma_commit(&tmem_full[as]);
         }
     } else if (warp >= 2) {
         // ===== epilogue: 8 warps; warp w owns TMEM lanes 32*(w%4).. and the column half (w-2)/4 =====
@@ -453,13 +465,13 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool active_half = SPLIT || (warp - 2) / 4 == 0;
         const int per_img = a.Hs * a.Wp;
         const int cout8 = (a.cout + 7) & ~7;
-        int ti = 0;
-        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, ti++) {
+        const float out_scale = __ldg(a.out_scale);
+        uint32_t ci = 0;
+        const int nsteps = a.kblocks_per_tap * ks;
+        const int nchunks = (nsteps + a.chunk_steps - 1) / a.chunk_steps;
+        for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const long long m0 = (t / n_tiles_n) * TC_BM;
             const int n0 = (int)(t % n_tiles_n) * BN;
-            const int as = ti & 1;
-            mbar_wait(&tmem_full[as], (uint32_t)(ti >> 1) & 1u);
-            tc_fence_after();
             const long long m = m0 + quad * 32 + lane;
             bool valid = m < a.M;
             int n = 0, y = 0, x = 0;
@@ -469,67 +481,73 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 y = rem / a.Wp; x = rem % a.Wp;
                 valid = (x < a.W) && (y < a.H);
             }
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS + half * HALF);
-            if (active_half) {
-                uint32_t r[2][16], r2[2][16];
-                __syncwarp();
-                tmem_ld16_nowait(trow, r[0]);
-                if (PLANES == 2) tmem_ld16_nowait(trow + BN, r2[0]);
-                tmem_ld_wait();
+            // ---- sum the chunks of this tile in registers (fp32 round-to-nearest) ----
+            float accv[HALF];
+            for (int c = 0; c < nchunks; c++, ci++) {
+                const int as = (int)(ci & 1u);
+                mbar_wait(&tmem_full[as], (ci >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS + half * HALF);
+                if (active_half) {
+                    uint32_t r[2][16], r2[2][16];
+                    __syncwarp();
+                    tmem_ld16_nowait(trow, r[0]);
+                    if (PLANES == 2) tmem_ld16_nowait(trow + BN, r2[0]);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < NCHUNK; c++) {
-                    const int cur = c & 1;
-                    if (c + 1 < NCHUNK) {   // prefetch the next 16 columns while this chunk is converted and stored
-                        __syncwarp();
-                        tmem_ld16_nowait(trow + (uint32_t)((c + 1) * 16), r[cur ^ 1]);
-                        if (PLANES == 2) tmem_ld16_nowait(trow + (uint32_t)(BN + (c + 1) * 16), r2[cur ^ 1]);
-                    }
-                    const int cb = n0 + half * HALF + c * 16;   // first output channel of this chunk
-                    if (valid) {
-                        float v[16];
+                    for (int pc = 0; pc < NCHUNK; pc++) {
+                        const int cur = pc & 1;
+                        if (pc + 1 < NCHUNK) {   // next 16 columns in flight while these are added
+                            tmem_ld16_nowait(trow + (uint32_t)((pc + 1) * 16), r[cur ^ 1]);
+                            if (PLANES == 2) tmem_ld16_nowait(trow + (uint32_t)(BN + (pc + 1) * 16), r2[cur ^ 1]);
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
                             float tv = __uint_as_float(r[cur][j]);
-                            if (PLANES == 2) tv += __uint_as_float(r2[cur][j]);
-                            tv += s_bias[cb + j];
-                            if (a.relu) tv = fmaxf(tv, 0.f);
-                            v[j] = tv;
+                            if (PLANES == 2) tv = __fadd_rn(tv, __uint_as_float(r2[cur][j]));
+                            accv[pc * 16 + j] = (c == 0) ? tv : __fadd_rn(accv[pc * 16 + j], tv);
                         }
-                        if (a.planar) {
+                        if (pc + 1 < NCHUNK) tmem_ld_wait();
+                    }
+                }
+                __syncwarp();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);   // 8 epilogue warps -> accumulator free for chunk ci+2
+            }
+            // ---- bias, ReLU, re-split, store ----
+            if (active_half && valid) {
 #pragma unroll
-                            for (int j = 0; j < 16; j++)
-                                if (cb + j < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + cb + j) * a.H + y) * a.W + x] = v[j];
-                        } else {
-                            uint32_t pk[PLANES][8];
+                for (int pc = 0; pc < NCHUNK; pc++) {
+                    const int cb = n0 + half * HALF + pc * 16;   // first output channel of this piece
+                    float v[16];
 #pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                float r0 = v[j], r1 = v[j + 1];
+                    for (int j = 0; j < 16; j++) {
+                        float tv = __fmaf_rn(accv[pc * 16 + j], out_scale, s_bias[cb + j]);   // out_scale is a power of two: exact
+                        if (a.relu) tv = fmaxf(tv, 0.f);
+                        v[j] = tv;
+                    }
+                    if (a.planar) {
 #pragma unroll
-                                for (int p = 0; p < PLANES; p++) {
-                                    const __nv_bfloat162 h = __floats2bfloat162_rn(r0, r1);   // one packed conversion
-                                    const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
-                                    pk[p][j / 2] = hu;
-                                    if (p + 1 < PLANES) {
-                                        r0 = __fsub_rn(r0, __uint_as_float(hu << 16));
-                                        r1 = __fsub_rn(r1, __uint_as_float(hu & 0xffff0000u));
-                                    }
-                                }
-                            }
-                            __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + cb;
+                        for (int j = 0; j < 16; j++)
+                            if (cb + j < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + cb + j) * a.H + y) * a.W + x] = v[j];
+                    } else {
+                        uint32_t pk[PLANES][8];
 #pragma unroll
-                            for (int p = 0; p < PLANES; p++) {
-                                uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
-                                if (cb < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
-                                if (cb + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
-                            }
+                        for (int j = 0; j < 16; j += 2) {
+                            float r0 = v[j], r1 = v[j + 1];
+#pragma unroll
+                            for (int p = 0; p < PLANES; p++) pk[p][j / 2] = split_pair<F16>(r0, r1);   // one packed conversion
+                        }
+                        __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + cb;
+#pragma unroll
+                        for (int p = 0; p < PLANES; p++) {
+                            uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
+                            if (cb < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+                            if (cb + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
                         }
                     }
-                    if (c + 1 < NCHUNK) tmem_ld_wait();
                 }
             }
-            __syncwarp();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);   // 8 epilogue warps -> accumulator free for tile ti+2
         }
     }
     __syncthreads();
@@ -704,10 +722,11 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
     a.bias = d.bias;
     a.out = (__nv_bfloat16*)d.out; a.out_pitch = d.out_pitch; a.out_coff = d.out_coff; a.out_plane = d.out_plane;
     a.planar = d.planar; a.planar_C = d.planar_C; a.planar_coff = d.planar_coff;
-    a.cout = d.cout; a.relu = d.relu;
+    a.cout = d.cout; a.relu = d.relu; a.out_scale = d.out_scale;
     a.ksize = d.ksize; a.pad = d.pad; a.kblocks_per_tap = d.in_cused / TC_BK; a.cin_k = d.in_cused;
     a.W = d.geo.W; a.H = d.geo.H; a.Wp = d.geo.Wp; a.Hs = d.geo.Hs;
     a.M = (long long)nimg * d.geo.Hs * d.geo.Wp;
+    a.chunk_steps = 1 << 30;
     dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), (unsigned)(d.cout_pad / l.bn));
     static const int variant = env_int("PE_TC_VARIANT", 1);     // 1: window kernel, 0: one TMA tile per tap
     if (variant == 1 && d.planes <= 2) {
@@ -728,6 +747,15 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
         }
         a.n_tiles_n = d.cout_pad / bn;
         a.total_tiles = (long long)grid.x * a.n_tiles_n;
+        {   // accumulation chunk (see the MMA issuer): ~24-28 K=16 steps per chunk in the parity mode, whole tile otherwise
+            static const int chunk_env = env_int("PE_TC_CHUNK", -1);   // -1: default, 0: one chunk per tile, n: n steps
+            const int nsteps = a.kblocks_per_tap * a.ksize;
+            int cs = nsteps;
+            if (d.planes == 2) cs = a.ksize >= 7 ? 1 : (a.ksize >= 3 ? 2 : 4);
+            if (chunk_env == 0) cs = nsteps;
+            else if (chunk_env > 0) cs = chunk_env;
+            a.chunk_steps = cs < 1 ? 1 : (cs > nsteps ? nsteps : cs);
+        }
         grid = dim3((unsigned)(a.total_tiles < nsm ? a.total_tiles : nsm), 1, 1);
         switch (bn) {
             case 128: return launch_win_bn<128>(l, a, grid, st, bmap);

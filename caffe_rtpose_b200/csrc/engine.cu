@@ -395,6 +395,14 @@ static inline void split_bf16(float x, int planes, uint16_t* out) {
         r = r - hf;
     }
 }
+static inline void split_fp16(float x, int planes, uint16_t* out) {   // parity mode: IEEE fp16 planes (kernels.h)
+    float r = x;
+    for (int p = 0; p < planes; p++) {
+        const __half h = __float2half_rn(r);
+        out[p] = __half_as_ushort(h);
+        r = r - __half2float(h);
+    }
+}
 
 extern "C" int pe_commit_weights(pe_engine* e) {
     if (!e) return PE_ERR_INVALID;
@@ -413,7 +421,7 @@ extern "C" int pe_commit_weights(pe_engine* e) {
         e->w_off[i] = total;
         total = align256(total + K * e->cout_pad[i] * e->elem * (e->planes ? e->planes : 1));
         e->b_off[i] = total;
-        total = align256(total + (size_t)e->cout_pad[i] * 4);
+        total = align256(total + (size_t)(e->cout_pad[i] + 1) * 4);   // bias[cout_pad] + the layer's epilogue scale
     }
     std::vector<uint8_t> host(total, 0);
     for (size_t i = 0; i < nc; i++) {
@@ -421,6 +429,7 @@ extern "C" int pe_commit_weights(pe_engine* e) {
         const HostWeights& hw = e->hw[i];
         const int taps = c.im2col_input ? 1 : c.k * c.k, cp = e->cin_pad[i], cop = e->cout_pad[i];
         const size_t K = (size_t)taps * cp;
+        float wscale_inv = 1.f;
         auto src = [&](int co, int kk) -> float {  // engine K index -> Caffe weight (co, ci, r, s)
             if (c.im2col_input) {
                 if (kk >= 27) return 0.f;
@@ -439,15 +448,27 @@ extern "C" int pe_commit_weights(pe_engine* e) {
         } else {               // bf16 planes [P][cout_pad][K]  (K-major rows: the tcgen05 B operand)
             uint16_t* W = (uint16_t*)(host.data() + e->w_off[i]);
             const size_t plane = (size_t)cop * K;
+            // fp16 planes: scale the layer by 2^k so that max|w| lands in [2^13, 2^14) - small weights would otherwise
+            // put their lo plane into fp16 subnormals.  Exact (power of two); the epilogue multiplies by 2^-k.
+            float wscale = 1.f;
+            if (planes_are_fp16(e->planes)) {
+                float mx = 0.f;
+                for (float v : hw.w) mx = fmaxf(mx, fabsf(v));
+                int ex = 0;
+                if (mx > 0.f && mx < 3e38f) { frexpf(mx, &ex); wscale = ldexpf(1.f, std::max(-30, std::min(30, 14 - ex))); }
+            }
+            wscale_inv = 1.f / wscale;
             for (int co = 0; co < c.cout; co++)
                 for (size_t kk = 0; kk < K; kk++) {
                     uint16_t h[3];
-                    split_bf16(src(co, (int)kk), e->planes, h);
+                    if (planes_are_fp16(e->planes)) split_fp16(src(co, (int)kk) * wscale, e->planes, h);
+                    else split_bf16(src(co, (int)kk), e->planes, h);
                     for (int p = 0; p < e->planes; p++) W[p * plane + (size_t)co * K + kk] = h[p];
                 }
         }
         float* B = (float*)(host.data() + e->b_off[i]);
         for (int co = 0; co < c.cout; co++) B[co] = hw.b[co];
+        B[cop] = wscale_inv;   // travels with the packed buffer (weight broadcast)
     }
     if (e->d_packed) { cudaFree(e->d_packed); e->d_packed = nullptr; }
     CK(e, cudaMalloc(&e->d_packed, total));
@@ -463,7 +484,7 @@ extern "C" int pe_commit_weights(pe_engine* e) {
             d.in = e->acts[c.in_act]; d.in_pitch = e->plan.acts[c.in_act].C; d.in_cused = c.in_cused; d.in_plane = e->act_plane[c.in_act];
             d.w = (char*)e->d_packed + e->w_off[i]; d.bias = (const float*)((char*)e->d_packed + e->b_off[i]);
             d.cout = c.cout; d.cout_pad = e->cout_pad[i]; d.ksize = c.im2col_input ? 1 : c.k; d.pad = c.im2col_input ? 0 : c.pad;
-            d.relu = c.relu; d.planes = e->planes; d.geo = g;
+            d.relu = c.relu; d.planes = e->planes; d.geo = g; d.out_scale = d.bias + e->cout_pad[i];
             if (c.out_act >= 0) {
                 d.out = e->acts[c.out_act]; d.out_pitch = e->plan.acts[c.out_act].C; d.out_coff = c.out_coff; d.out_plane = e->act_plane[c.out_act];
                 d.planar = nullptr; d.planar_C = 0; d.planar_coff = 0;

@@ -4,6 +4,36 @@
 
 namespace pe {
 
+// 16-bit "plane" formats of the tcgen05 conv stack.  The parity mode (2 planes) stores IEEE fp16 planes: 11 + 11
+// significant bits, so hi*hi + hi*lo + lo*hi carries ~2^-22 (bf16 planes: 8 + 8 bits, ~2^-17 - measured 2.2e-5 over
+// the net with exact accumulation vs 3e-6 for fp16).  fp16's range (65504) is ample for this net (inputs in
+// [-0.5, 0.5], activations O(1-100)); the 1- and 3-plane modes keep bf16.
+__host__ __device__ constexpr bool planes_are_fp16(int planes) { return planes == 2; }
+#ifdef __CUDACC__
+template <bool F16> __device__ __forceinline__ float plane_to_float(uint16_t h) {
+    return F16 ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
+}
+template <bool F16> __device__ __forceinline__ uint16_t float_to_plane(float x) {
+    return F16 ? __half_as_ushort(__float2half_rn(x)) : __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+// two floats -> packed pair of plane values (low half = a) and the residuals a - hi(a), b - hi(b)
+template <bool F16> __device__ __forceinline__ uint32_t split_pair(float& a, float& b) {
+    if (F16) {
+        const __half2 h = __floats2half2_rn(a, b);
+        a = __fsub_rn(a, __low2float(h));
+        b = __fsub_rn(b, __high2float(h));
+        return *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+        a = __fsub_rn(a, __uint_as_float(hu << 16));
+        b = __fsub_rn(b, __uint_as_float(hu & 0xffff0000u));
+        return hu;
+    }
+}
+#endif
+
+
 struct AxisTap { int i0, i1, i2, i3; float d; };
 struct Cand { float conn; int p; };
 struct Conn { int a, b; float score; };

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) pool_bf16_kernel(PoolArgs a) {
         for (int w = 0; w < 4; w++) {
             float sum = 0.f;
 #pragma unroll
-            for (int p = 0; p < PLANES; p++) sum += __uint_as_float((uint32_t)((const uint16_t*)&v[w][p])[j] << 16);
+            for (int p = 0; p < PLANES; p++) sum += plane_to_float<planes_are_fp16(PLANES)>(((const uint16_t*)&v[w][p])[j]);
             if (ok[w] && sum > best) { best = sum; bw = w; }
         }
 #pragma unroll
@@ -131,7 +131,10 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const void* act, int p
     const long long m = ((long long)n * g.Hs + y) * g.Wp + x;
     float v = 0.f;
     if (planes == 0) v = ((const float*)act)[m * pitch + coff + ch];
-    else for (int p = 0; p < planes; p++) v += __bfloat162float(((const __nv_bfloat16*)act)[p * plane + m * pitch + coff + ch]);
+    else for (int p = 0; p < planes; p++) {
+        const uint16_t h = ((const uint16_t*)act)[p * plane + m * pitch + coff + ch];
+        v += planes_are_fp16(planes) ? plane_to_float<true>(h) : plane_to_float<false>(h);
+    }
     out[idx] = v;
 }
 int launch_act_to_nchw(const void* act, int pitch, int coff, int c, long long plane, int planes, const Geo& g,

@@ -117,11 +117,11 @@ int launch_warp_affine(const WarpArgs& a, int nframes, cudaStream_t st) {
     return 1;
 }
 
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
-    h = __float2bfloat16_rn(x);
-    const float r = __fsub_rn(x, __bfloat162float(h));
-    m = __float2bfloat16_rn(r);
-    l = __float2bfloat16_rn(__fsub_rn(r, __bfloat162float(m)));
+template <bool F16> __device__ __forceinline__ void split3(float x, uint16_t& h, uint16_t& m, uint16_t& l) {
+    h = float_to_plane<F16>(x);
+    const float r = __fsub_rn(x, plane_to_float<F16>(h));
+    m = float_to_plane<F16>(r);
+    l = float_to_plane<F16>(__fsub_rn(r, plane_to_float<F16>(m)));
 }
 
 // SRC = 0: uint8 resized images (pad + normalise here);  SRC = 1: planar fp32 net input (already padded/normalised)
@@ -129,7 +129,7 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16&
 // the im2col'ed input is written with coalesced 16/32-byte vector stores.
 template <int SRC>
 __global__ void __launch_bounds__(256) input_im2col_kernel(PreArgs a, const float* planar, int nimages) {
-    // uint8 pixels normalised by /256-0.5 are exact in bf16 (8 significant bits), so the SRC=0 path fills only the
+    // uint8 pixels normalised by /256-0.5 are exact in bf16 (8 significant bits) and in fp16, so the SRC=0 path fills only the
     // hi plane and only the 32 channels that can be non-zero (27 used); everything else stays zero from init
     // (the engine clears the other planes when it switches from the planar-input path, see engine.cu).
     const int parts = (SRC == 0 && a.planes > 0) ? 4 : a.kp / 8;
@@ -174,12 +174,12 @@ __global__ void __launch_bounds__(256) input_im2col_kernel(PreArgs a, const floa
         uint32_t pk[3][4];
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-            __nv_bfloat16 h0, m0, l0, h1, m1, l1;
-            split3(v[j], h0, m0, l0);
-            split3(v[j + 1], h1, m1, l1);
-            pk[0][j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            pk[1][j / 2] = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
-            pk[2][j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            uint16_t h0, m0, l0, h1, m1, l1;
+            if (planes_are_fp16(a.planes)) { split3<true>(v[j], h0, m0, l0); split3<true>(v[j + 1], h1, m1, l1); }
+            else { split3<false>(v[j], h0, m0, l0); split3<false>(v[j + 1], h1, m1, l1); }
+            pk[0][j / 2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            pk[1][j / 2] = (uint32_t)m0 | ((uint32_t)m1 << 16);
+            pk[2][j / 2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
         }
         __nv_bfloat16* o0 = (__nv_bfloat16*)a.out + (size_t)m * a.kp + part * 8;
         const int np = SRC == 0 ? 1 : a.planes;

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "libposeengine.so")
 
 MPI_15, COCO_18 = 0, 1
 PREC_FP32_SIMT, PREC_BF16X1, PREC_BF16X2, PREC_BF16X3 = 0, 1, 2, 3
+PREC_F16X2 = PREC_BF16X2   # the parity mode: 2 fp16 planes, chunked round-to-nearest accumulation (poseengine.h)
 MAX_PEOPLE = 96
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")

@@ -29,8 +29,13 @@ extern "C" {
 /* arithmetic of the convolution stack */
 #define PE_PREC_FP32_SIMT 0 /* fp32 FFMA implicit GEMM (CUDA cores) - the exact-fp32 debugging reference */
 #define PE_PREC_BF16X1 1    /* tcgen05 bf16 x bf16 -> fp32 (fast, NOT parity grade) */
-#define PE_PREC_BF16X2 2    /* tcgen05, activations/weights split in 2 bf16 planes, 3 MMAs (~2^-16) */
-#define PE_PREC_BF16X3 3    /* tcgen05, 3 planes, 6 MMAs (~fp32) */
+#define PE_PREC_F16X2 2     /* tcgen05 PARITY mode: activations/weights split in 2 fp16 planes (11+11 bits), 3 MMAs
+                             * hi*hi + hi*lo + lo*hi, fp32 accumulation cut into chunks that are summed in registers with
+                             * round-to-nearest (the tensor core's own fp32 accumulate truncates): ~1e-5 of the map range
+                             * over the whole net, i.e. the level at which two fp32 implementations differ */
+#define PE_PREC_BF16X2 PE_PREC_F16X2 /* historical name of the parity mode (its planes were bf16 at first) */
+#define PE_PREC_BF16X3 3    /* tcgen05, 3 bf16 planes, 6 MMAs into one accumulator (baseline kernel; LESS accurate than
+                             * mode 2 because of the accumulate truncation - kept for A/B measurements) */
 
 #define PE_MAX_PEOPLE 96   /* RENDER_MAX_PEOPLE, renderFunctions.h:6 / rtpose.cpp:88 */
 

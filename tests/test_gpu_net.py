@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 # max |engine - oracle| / max |oracle| on the stride-8 maps.  fp32 reorders sums (BLAS vs GPU): ~5e-6.
 # bf16x2: operands carry 16 significand bits and the tensor core accumulates in truncated fp32: ~2e-4.
 # bf16x1 is the non-parity "fast" mode and only sanity-checked.
-TOL = {engine.PREC_FP32_SIMT: 5e-5, engine.PREC_BF16X2: 1e-3, engine.PREC_BF16X3: 1e-3, engine.PREC_BF16X1: 6e-2}
+# measured on B200 (tools/gpu_diag.py): SIMT 5e-6, parity mode 8e-6 (160x96) / 1.1e-5 (656x368), bf16x3 4e-4, bf16x1 2e-2
+TOL = {engine.PREC_FP32_SIMT: 5e-5, engine.PREC_BF16X2: 1e-4, engine.PREC_BF16X3: 1e-3, engine.PREC_BF16X1: 6e-2}
 
 
 def rel(a, b):
