@@ -57,6 +57,9 @@ struct pe_engine {
     int warp_w = 0, warp_h = 0; double warp_scale = 1.0;
     int *d_wa = nullptr, *d_wb = nullptr, *d_wx0 = nullptr, *d_wy0 = nullptr; short* d_wtab = nullptr;
     bool input_lo_dirty = false;
+    // renderers: canvas, uint8 image, heat-map scratch (allocated on first pe_render); display frames of the last forward
+    float* d_canvas = nullptr; uint8_t* d_render_u8 = nullptr; uint8_t* d_render_src = nullptr; float* d_heat = nullptr; size_t heat_cap = 0;
+    const uint8_t* last_frames = nullptr;
     // CUDA graphs of the steady-state forward (92 conv + pool/copy + 5 parse kernels + result copies), one per batch
     // size; the first forward of a size runs eagerly, the second is captured, later ones replay.  Invalidated by
     // any setter whose value is baked into kernel arguments.
@@ -323,6 +326,7 @@ extern "C" void pe_destroy(pe_engine* e) {
     cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_resized); cudaFree(e->d_planar); cudaFree(e->d_maps);
     cudaFreeHost(e->h_frames); cudaFreeHost(e->h_planar); cudaFreeHost(e->h_maps);
     cudaFree(e->d_xtab); cudaFree(e->d_ytab);
+    cudaFree(e->d_canvas); cudaFree(e->d_render_u8); cudaFree(e->d_render_src); cudaFree(e->d_heat);
     PostDev& pd = e->post;
     cudaFree(pd.flags); cudaFree(pd.peaks); cudaFree(pd.cands); cudaFree(pd.cand_count); cudaFree(pd.conns);
     cudaFree(pd.conn_count); cudaFree(pd.subset); cudaFree(pd.subset_rows); cudaFree(pd.joints); cudaFree(pd.num_people);
@@ -718,6 +722,7 @@ extern "C" int pe_forward_frames_device(pe_engine* e, const void* d_frames, int 
         e->input_lo_dirty = false;
     }
     e->launches += launch_preprocess(a, e->stream);
+    e->last_frames = (const uint8_t*)d_frames;
     return run_net(e, n);
 }
 extern "C" int pe_forward_frames(pe_engine* e, const uint8_t* const* frames, int n) {
@@ -857,6 +862,7 @@ extern "C" int pe_forward_net_input(pe_engine* e, const float* net_input, int n)
     a.nframes = n;
     e->launches += launch_input_from_planar(e->d_planar, a, n * e->cfg.num_scales, e->stream);
     e->input_lo_dirty = e->planes > 0;
+    e->last_frames = nullptr;
     return run_net(e, n);
 }
 extern "C" int pe_forward_maps(pe_engine* e, const float* maps8, int n) {
@@ -867,7 +873,74 @@ extern "C" int pe_forward_maps(pe_engine* e, const float* maps8, int n) {
     CK(e, cudaStreamSynchronize(e->stream));
     memcpy(e->h_maps, maps8, cnt * sizeof(float));
     CK(e, cudaMemcpyAsync(e->d_maps, e->h_maps, cnt * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    e->last_frames = nullptr;
     return run_post_and_return(e, n);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// renderers: render() of rtpose.cpp:271-300 on the canvas of frame `idx`
+// ---------------------------------------------------------------------------------------------
+extern "C" int pe_render(pe_engine* e, int idx, int part_to_show, int googly_eyes, const uint8_t* display_bgr, float* canvas,
+                         uint8_t* bgr) {
+    if (!e) return PE_ERR_INVALID;
+    if (idx < 0 || idx >= e->last_n) return fail(e, PE_ERR_INVALID, "frame index %d outside the last forward (n=%d)", idx, e->last_n);
+    const int P = e->mt->num_parts, W = e->cfg.disp_w, H = e->cfg.disp_h, nw = e->cfg.net_w, nh = e->cfg.net_h;
+    const int max_show = e->cfg.model == PE_MODEL_MPI_15 ? e->mt->num_maps : P + 2 + e->mt->num_limbs;   // COCO: 0..39
+    if (part_to_show < 0 || part_to_show > max_show)
+        return fail(e, PE_ERR_INVALID, "part_to_show=%d outside [0, %d]", part_to_show, max_show);
+    if (!display_bgr && !e->last_frames)
+        return fail(e, PE_ERR_STATE, "the last forward had no display frame (net-input / map path): pass display_bgr");
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t px = (size_t)W * H;
+    if (!e->d_canvas) {
+        CK(e, cudaMalloc(&e->d_canvas, px * 3 * sizeof(float)));
+        CK(e, cudaMalloc(&e->d_render_u8, px * 3));
+        CK(e, cudaMalloc(&e->d_render_src, px * 3));
+    }
+    const uint8_t* src = e->last_frames ? e->last_frames + (size_t)idx * px * 3 : nullptr;
+    if (display_bgr) {
+        CK(e, cudaMemcpyAsync(e->d_render_src, display_bgr, px * 3, cudaMemcpyHostToDevice, e->stream));
+        src = e->d_render_src;
+    }
+    e->launches += launch_canvas_fill(src, e->d_canvas, W, H, e->stream);   // process_and_pad_image(normalize = 0), rtpose.cpp:349,1127
+    const PostDev& pd = e->post;
+    const float* poses = pd.joints + (size_t)idx * PE_MAX_PEOPLE * P * 3;
+    auto heat = [&](int ch0, int nch) -> int {   // the channels a heat-map view reads, from the stride-8 maps
+        const size_t need = (size_t)nch * nw * nh * sizeof(float);
+        if (need > e->heat_cap) {
+            cudaFree(e->d_heat); e->d_heat = nullptr; e->heat_cap = 0;
+            CK(e, cudaMalloc(&e->d_heat, need));
+            e->heat_cap = need;
+        }
+        e->launches += launch_fullres_fill(pd, idx, ch0, nch, e->d_heat, e->stream);
+        return PE_OK;
+    };
+    int rc = PE_OK;
+    if (part_to_show == 0) {
+        e->launches += launch_skeleton(e->cfg.model, e->d_canvas, W, H, poses, pd.num_people + idx, googly_eyes, e->stream);
+    } else if (e->cfg.model == PE_MODEL_MPI_15) {                 // render_mpi_parts: channel part_to_show-1
+        if ((rc = heat(part_to_show - 1, 1))) return rc;
+        e->launches += launch_heat_view(e->d_canvas, W, H, e->d_heat, nw, nh, 0, part_to_show - 1, 1, e->stream);
+    } else if (part_to_show - 1 < P) {                            // render_coco_parts: one part map
+        if ((rc = heat(part_to_show - 1, 1))) return rc;
+        e->launches += launch_heat_view(e->d_canvas, W, H, e->d_heat, nw, nh, 1, part_to_show - 1, 1, e->stream);
+    } else if (part_to_show - 1 == P) {                           // all part maps, nearest neighbour (heatmap2)
+        if ((rc = heat(0, P))) return rc;
+        e->launches += launch_heat_view(e->d_canvas, W, H, e->d_heat, nw, nh, 2, 0, P, e->stream);
+    } else {                                                      // render_coco_aff (rtpose.cpp:286-296)
+        int aff_part = ((part_to_show - 1) - P - 1) * 2, accum = 1;
+        if (aff_part == 0) accum = e->mt->num_limbs; else aff_part -= 2;
+        aff_part += 1 + P;
+        if ((rc = heat(aff_part, 2 * accum))) return rc;
+        e->launches += launch_heat_view(e->d_canvas, W, H, e->d_heat, nw, nh, 3, aff_part, 2 * accum, e->stream);
+    }
+    if (bgr) e->launches += launch_canvas_to_u8(e->d_canvas, e->d_render_u8, W, H, e->stream);   // postProcessFrame, rtpose.cpp:1286-1296
+    if (canvas) CK(e, cudaMemcpyAsync(canvas, e->d_canvas, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (bgr) CK(e, cudaMemcpyAsync(bgr, e->d_render_u8, px * 3, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaGetLastError());
+    return PE_OK;
 }
 
 extern "C" int pe_sync(pe_engine* e) {

@@ -61,6 +61,14 @@ struct PostDev {
 void launch_axis_tables(AxisTap* xtab, AxisTap* ytab, const PostParams& p, cudaStream_t st);
 int launch_post(const PostDev& pd, int nframes, cudaStream_t st);
 
+// ---- renderers (render.cu)
+int launch_canvas_fill(const uint8_t* bgr, float* canvas, int w, int h, cudaStream_t st);
+int launch_canvas_to_u8(const float* canvas, uint8_t* bgr, int w, int h, cudaStream_t st);
+int launch_fullres_fill(const PostDev& pd, int frame, int ch0, int nch, float* out, cudaStream_t st);
+int launch_skeleton(int model, float* canvas, int w, int h, const float* poses, const int* num_people, int googly, cudaStream_t st);
+// mode 0: MPI part map, 1: COCO part map, 2: COCO all parts, 3: COCO PAF (render.cu)
+int launch_heat_view(float* canvas, int w, int h, float* heat, int w_net, int h_net, int mode, int part, int nch, cudaStream_t st);
+
 // ---- preprocessing (pre.cu)
 struct AreaTab {           // OpenCV INTER_AREA decimation tables for one scale, device pointers
     const int* x_ofs; const int* x_si; const float* x_alpha;   // per dst x: [x_ofs[dx], x_ofs[dx+1]) entries

@@ -17,24 +17,9 @@
 // compiler emits for connectLimbs*, so results are bit-identical to the oracle (tests/test_gpu_post.py).
 #include "common.h"
 #include "kernels.h"
+#include "fullres.cuh"
 
 namespace pe {
-
-// ------------------------------------------------------------------------------------------------
-// cubic_interpolation (imresize_layer.cu:8-18) with nvcc's contraction pattern (see oracle.cpp)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float cubic_ref(float v0, float v1, float v2, float v3, float d) {
-    const float h = __fmul_rn(0.5f, v0);
-    const float a = __fmaf_rn(v3, 0.5f, __fmaf_rn(v2, -1.5f, __fmaf_rn(v1, 1.5f, -h)));
-    const float t1 = __fmul_rn(__fmul_rn(__fmul_rn(a, d), d), d);
-    const double b = __fma_rn((double)v3, -0.5, __fma_rn((double)v2, 2.0, (double)__fmaf_rn(v1, -2.5f, v0)));
-    const double dd = (double)d;
-    double acc = __fma_rn(dd, __dmul_rn(dd, b), (double)t1);
-    const float t3 = __fmul_rn(d, __fmaf_rn(v2, 0.5f, -h));
-    acc = __dadd_rn(acc, (double)t3);
-    acc = __dadd_rn(acc, (double)v1);
-    return __double2float_rn(acc);
-}
 
 // Per-scale, per-output-coordinate source taps of imresize_cubic_kernel (imresize_layer.cu:110-140).
 // Built once per (net size, scales) by axis_table_kernel with the kernel's own arithmetic.
@@ -58,45 +43,6 @@ __global__ void axis_table_kernel(AxisTap* tab, int t, int ori, int num_scales, 
     a.i1 = n1 + pad;
     a.i2 = n2 + pad;
     tab[(size_t)n * t + x] = a;
-}
-
-struct FullRes {
-    const float* maps;     // this frame: [S][C][h8][w8]
-    const AxisTap* xt;     // [S][net_w]
-    const AxisTap* yt;     // [S][net_h]
-    int S, C, h8, w8, net_w, net_h;
-    float inv_div;         // (float)S
-};
-
-// resized_map[c][y][x] of the reference, evaluated from the stride-8 maps
-__device__ __forceinline__ float fullres_at(const FullRes& fr, int c, int y, int x) {
-    float sum = 0.f;
-    const size_t plane = (size_t)fr.h8 * fr.w8;
-    for (int n = 0; n < fr.S; n++) {
-        const AxisTap ax = fr.xt[n * fr.net_w + x];
-        const AxisTap ay = fr.yt[n * fr.net_h + y];
-        const float* s = fr.maps + ((size_t)n * fr.C + c) * plane;
-        const float* r0 = s + (size_t)ay.i0 * fr.w8;
-        const float* r1 = s + (size_t)ay.i1 * fr.w8;
-        const float* r2 = s + (size_t)ay.i2 * fr.w8;
-        const float* r3 = s + (size_t)ay.i3 * fr.w8;
-        const float t0 = cubic_ref(__ldg(r0 + ax.i0), __ldg(r0 + ax.i1), __ldg(r0 + ax.i2), __ldg(r0 + ax.i3), ax.d);
-        const float t1 = cubic_ref(__ldg(r1 + ax.i0), __ldg(r1 + ax.i1), __ldg(r1 + ax.i2), __ldg(r1 + ax.i3), ax.d);
-        const float t2 = cubic_ref(__ldg(r2 + ax.i0), __ldg(r2 + ax.i1), __ldg(r2 + ax.i2), __ldg(r2 + ax.i3), ax.d);
-        const float t3 = cubic_ref(__ldg(r3 + ax.i0), __ldg(r3 + ax.i1), __ldg(r3 + ax.i2), __ldg(r3 + ax.i3), ax.d);
-        sum = __fadd_rn(sum, cubic_ref(t0, t1, t2, t3, ay.d));
-    }
-    return __fdiv_rn(sum, fr.inv_div);
-}
-
-__device__ __forceinline__ FullRes make_fullres(const PostDev& pd, int frame) {
-    FullRes fr;
-    fr.S = pd.p.num_scales; fr.C = pd.p.num_maps; fr.h8 = pd.p.h8; fr.w8 = pd.p.w8;
-    fr.net_w = pd.p.net_w; fr.net_h = pd.p.net_h;
-    fr.maps = pd.maps + (size_t)frame * fr.S * fr.C * fr.h8 * fr.w8;
-    fr.xt = pd.xtab; fr.yt = pd.ytab;
-    fr.inv_div = (float)fr.S;
-    return fr;
 }
 
 // ------------------------------------------------------------------------------------------------

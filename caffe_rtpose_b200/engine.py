@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
-    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights",
+    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render",
 ]
 
 
@@ -117,6 +117,7 @@ def lib():
     L.pe_packed_weights_device_ptr.argtypes = [C.c_void_p]
     L.pe_packed_weights_device_ptr.restype = C.c_void_p
     L.pe_broadcast_weights.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.pe_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -305,6 +306,20 @@ class PoseEngine:
         s = C.c_double()
         self._ck(lib().pe_forward_camera_frames(self._h, ptrs, len(frames), w, h, C.byref(s)))
         return s.value
+
+    def render(self, idx=0, part_to_show=0, googly_eyes=False, display_bgr=None, want_canvas=False):
+        """render() of rtpose.cpp:271-300 on frame idx of the last forward; returns the uint8 BGR image
+        (disp_h, disp_w, 3) and, if want_canvas, also the float planar canvas (3, disp_h, disp_w)."""
+        H, W = self.cfg.disp_h, self.cfg.disp_w
+        img = np.zeros((H, W, 3), np.uint8)
+        canvas = np.zeros((3, H, W), np.float32) if want_canvas else None
+        src = None
+        if display_bgr is not None:
+            src = np.ascontiguousarray(display_bgr, np.uint8)
+            assert src.shape == (H, W, 3), src.shape
+        self._ck(lib().pe_render(self._h, idx, part_to_show, 1 if googly_eyes else 0, src.ctypes.data if src is not None else None,
+                                 canvas.ctypes.data if want_canvas else None, img.ctypes.data))
+        return (img, canvas) if want_canvas else img
 
     def forward_frames_device(self, dev_ptr, n):
         self._ck(lib().pe_forward_frames_device(self._h, C.c_void_p(dev_ptr), n))

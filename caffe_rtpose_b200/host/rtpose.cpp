@@ -5,7 +5,8 @@
 //
 // Supported sources: --image_dir with .bmp (24-bit) and .ppm (P6) files, or --synthetic N procedural frames.
 // .jpg/.png/--video/--camera need an image/video codec and are rejected with an explicit message.  Display,
-// keyboard handling and --write_frames (rendering) are not part of this path.
+// keyboard handling is not part of this path.  --write_frames renders on the GPU (pe_render) and
+// writes lossless .bmp files (no JPEG encoder here; the reference writes quality-98 .jpg), without the putText overlays.
 #include <dirent.h>
 #include <math.h>
 #include <stdio.h>
@@ -43,7 +44,7 @@ static void define_flags() {
     // names, defaults and help strings of rtpose.cpp:50-72
     define("fullscreen", "false", "Run in fullscreen mode (press f during runtime to toggle)", true);
     define("part_to_show", "0", "Part to show from the start.");
-    define("write_frames", "", "Write frames with format prefix%06d.jpg");
+    define("write_frames", "", "Write frames with format prefix%06d.jpg  [this build: prefix%06d.bmp, lossless - no JPEG encoder]");
     define("no_frame_drops", "false", "Dont drop frames.", true);
     define("write_json", "", "Write joint data with json format as prefix%06d.json");
     define("camera", "0", "The camera index for VideoCapture.");
@@ -113,6 +114,7 @@ struct Frame {
     std::string stem;                        // for <stem>.json with --image_dir
     int num_people = 0;
     std::vector<float> joints;
+    std::vector<uint8_t> rendered;           // --write_frames: display image with overlays (pe_render), HWC BGR
     double t_commit = 0, t_done = 0;
 };
 
@@ -162,6 +164,24 @@ static bool read_bmp(const std::string& path, int& w, int& h, std::vector<uint8_
         if (fread(row.data(), 1, stride, f) != stride) { fclose(f); return false; }
         const int dy = bh < 0 ? y : h - 1 - y;   // bottom-up unless the height is negative
         memcpy(&bgr[(size_t)dy * w * 3], row.data(), (size_t)w * 3);
+    }
+    fclose(f);
+    return true;
+}
+
+static bool write_bmp(const std::string& path, int w, int h, const uint8_t* bgr) {   // 24-bit, bottom-up
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const uint32_t stride = ((uint32_t)w * 3 + 3) & ~3u, size = 54 + stride * (uint32_t)h;
+    uint8_t hd[54] = {'B', 'M'};
+    auto put32 = [&](int o, uint32_t v) { hd[o] = v & 255; hd[o + 1] = (v >> 8) & 255; hd[o + 2] = (v >> 16) & 255; hd[o + 3] = (v >> 24) & 255; };
+    put32(2, size); put32(10, 54); put32(14, 40); put32(18, (uint32_t)w); put32(22, (uint32_t)h);
+    hd[26] = 1; hd[28] = 24; put32(34, stride * (uint32_t)h); put32(38, 2835); put32(42, 2835);
+    fwrite(hd, 1, 54, f);
+    std::vector<uint8_t> row(stride, 0);
+    for (int y = h - 1; y >= 0; y--) {
+        memcpy(row.data(), bgr + (size_t)y * w * 3, (size_t)w * 3);
+        fwrite(row.data(), 1, stride, f);
     }
     fclose(f);
     return true;
@@ -350,6 +370,12 @@ static void worker(int tid, pe_engine* e) {
             if (pe_fetch(e, (int)i, joints.data(), &cnt, nullptr)) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break; }
             frames[i].num_people = cnt;
             frames[i].joints.assign(joints.begin(), joints.begin() + (size_t)cnt * P * 3);
+            if (!F("write_frames").empty()) {   // render() + postProcessFrame (rtpose.cpp:271-300, 1286-1296) on the GPU
+                frames[i].rendered.resize((size_t)global.disp_w * global.disp_h * 3);
+                if (pe_render(e, (int)i, Fi("part_to_show"), 0, nullptr, nullptr, frames[i].rendered.data())) {
+                    LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break;
+                }
+            }
             frames[i].t_done = now_s();
             global.output_queue.push(std::move(frames[i]));
         }
@@ -374,6 +400,12 @@ static void orderer_and_writer(int num_workers) {
             pe_write_json(fr.joints.data(), fr.num_people, global.num_parts, fr.scale, buf.data(), need + 1);
             FILE* f = fopen(fname, "wb");
             if (f) { fwrite(buf.data(), 1, (size_t)need, f); fclose(f); }
+        }
+        if (!F("write_frames").empty() && !fr.rendered.empty()) {   // displayFrame :1363-1380 (.jpg there, .bmp here)
+            char fname[1024];
+            if (F("image_dir").empty()) snprintf(fname, sizeof fname, "%s/frame%06d.bmp", F("write_frames").c_str(), fr.video_frame_number);
+            else snprintf(fname, sizeof fname, "%s/%s.bmp", F("write_frames").c_str(), fr.stem.c_str());
+            if (!write_bmp(fname, global.disp_w, global.disp_h, fr.rendered.data())) LOG_ERROR("cannot write %s", fname);
         }
         written++;
         if (written % 30 == 0) {   // the reference prints FPS every 30 frames (:1421-1441)
@@ -419,7 +451,7 @@ int main(int argc, char** argv) {
         LOG_ERROR("camera/video capture needs a video codec that this build does not have; use --image_dir (.bmp/.ppm) or --synthetic N");
         return 1;
     }
-    if (!F("write_frames").empty()) LOG_ERROR("--write_frames needs the renderer + a JPEG encoder (SURVEY.md 8f rank 2); ignoring");
+    if (!F("write_frames").empty()) LOG_INFO("--write_frames: writing lossless .bmp files (no JPEG encoder in this build), no text overlays");
     if (sscanf(F("resolution").c_str(), "%dx%d", &global.disp_w, &global.disp_h) != 2) { LOG_ERROR("Error, resolution format (%s) invalid, should be e.g., 960x540", F("resolution").c_str()); return 1; }
     if (sscanf(F("net_resolution").c_str(), "%dx%d", &global.net_w, &global.net_h) != 2) { LOG_ERROR("Error, net resolution format (%s) invalid, should be e.g., 656x368 (multiples of 16)", F("net_resolution").c_str()); return 1; }
     if (!F("image_dir").empty()) {   // readImageDirIfFlagEnabled (rtpose.cpp:1732-1755): sorted list of image files
@@ -444,6 +476,7 @@ int main(int argc, char** argv) {
     if (global.disp_w <= 0 || global.disp_h <= 0) { LOG_ERROR("Invalid resolution without video/images: %dx%d", global.disp_w, global.disp_h); return 1; }
     LOG_INFO("Display resolution: %dx%d", global.disp_w, global.disp_h);
     LOG_INFO("Net resolution: %dx%d", global.net_w, global.net_h);
+    if (!F("write_frames").empty() && !ensure_dir(F("write_frames"))) { LOG_ERROR("Could not write to or create directory %s", F("write_frames").c_str()); return 1; }
     if (!F("write_json").empty() && !ensure_dir(F("write_json"))) { LOG_ERROR("Could not write to or create directory %s", F("write_json").c_str()); return 1; }
 
     int model = model_from_prototxt(F("caffeproto"));

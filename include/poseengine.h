@@ -136,6 +136,18 @@ void pe_host_free(void* p);
 /* JSON writer of displayFrame (rtpose.cpp:1383-1416).  Returns the text length (writes if < cap). */
 int pe_write_json(const float* joints, int num_people, int num_parts, double frame_scale, char* buf, int cap);
 
+/* ---- renderers: render() (rtpose.cpp:271-300) + render_mpi_parts / render_coco_parts / render_coco_aff
+ * (src/rtpose/renderFunctions.cu:331-389, 978-1080) on the display frame `idx` of the last forward, followed by the
+ * float -> uint8 conversion of postProcessFrame (rtpose.cpp:1286-1296).  part_to_show as --part_to_show / the UI keys:
+ * 0 = skeletons; MPI: k>0 = heat map of channel k-1; COCO: 1..18 = part heat map, 19 = all parts, 20 = all PAFs,
+ * 21..39 = one PAF.  display_bgr: HOST uint8 BGR disp_h x disp_w, or NULL = the frame given to the last
+ * pe_forward_frames / _frames_device / _camera_frames (still on the device).  Outputs (either may be NULL): canvas =
+ * 3 x disp_h x disp_w float planar BGR (Frame::data_for_mat after render), bgr = disp_h x disp_w x 3 uint8
+ * (Frame::data_for_wrap).  The cv::putText overlays of displayFrame (rtpose.cpp:1317-1353) are not drawn (= --no_text).
+ * Synchronous. */
+int pe_render(pe_engine* e, int idx, int part_to_show, int googly_eyes, const uint8_t* display_bgr, float* canvas,
+              uint8_t* bgr);
+
 /* ---- model descriptor tables (modelDescriptorFactory.cpp:6-28,30-55) */
 int pe_model_num_parts(int model);
 int pe_model_num_limbs(int model);

@@ -11,6 +11,7 @@ the resulting shared objects are kept under oracle/_ref/ (git-ignored, travels t
   libref_cpm.so   nvcc  src/caffe/cpm/layers/imresize_layer.cu:8-18,97-155
                         src/caffe/cpm/layers/nms_layer.cu:13-113
                         (sm_100a; default -fmad, as the reference Makefile:410 passes no fmad flag)
+  libref_render.so nvcc src/rtpose/renderFunctions.cu:4-329, 394-975 (the six render kernels + colour helpers)
 
 Flags: the reference Makefile (:326,405,409) uses `-O3 -march=native -std=c++11`; we drop
 -march=native so that the host arithmetic is the portable SSE2 one (no machine-dependent FMA
@@ -123,6 +124,22 @@ def build_cpm(tmp, keep_sass=False):
     return out
 
 
+def build_render(tmp, keep_sass=False):
+    tu = ('#include "%s"\n' % os.path.join(HERE, "ref_render_prelude.cuh")
+          + lines("src/rtpose/renderFunctions.cu", [(4, 329), (394, 975)])
+          + '#include "%s"\n' % os.path.join(HERE, "ref_render_launch.cuh"))
+    src = os.path.join(tmp, "ref_render_tu.cu")
+    open(src, "w").write(tu)
+    out = os.path.join(OUT, "libref_render.so")
+    cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+           "-shared", "-w", src, "-o", out]
+    subprocess.check_call(cmd)
+    if keep_sass:
+        sass = subprocess.check_output(["cuobjdump", "-sass", out]).decode()
+        open(os.path.join(OUT, "ref_render.sass"), "w").write(sass)
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         print("build_ref: %s absent - keeping prebuilt oracle/_ref" % REF)
@@ -133,6 +150,7 @@ def main():
         print("built", build_host(tmp))
         if shutil.which("nvcc"):
             print("built", build_cpm(tmp, keep_sass="--sass" in sys.argv))
+            print("built", build_render(tmp, keep_sass="--sass" in sys.argv))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return 0

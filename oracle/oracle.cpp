@@ -978,6 +978,300 @@ extern "C" int orc_preprocess(const uint8_t* disp, int disp_h, int disp_w, int n
 // ------------------------------------------------------------------------------------------------
 // JSON (rtpose.cpp:1383-1416); default ostream formatting == "%g" (6 significant digits)
 // ------------------------------------------------------------------------------------------------
+// =====================================================================================================
+// Renderers (TEST ONLY): CPU restatement of render() (examples/rtpose/rtpose.cpp:271-300) and of the six kernels of
+// src/rtpose/renderFunctions.cu.  The reference runs these on the GPU only; float vs double promotions follow the
+// kernels statement by statement, sums of products are evaluated WITHOUT fusing (the GPU build of the reference fuses
+// some of them and its sinf/cosf/atan2f differ from libm in the last place), so GPU parity against this restatement is
+// "equal up to 1e-3 on the float canvas except at shape borders"; the bit-level pin is the reference's own kernels
+// compiled into oracle/_ref/libref_render.so (tests/test_gpu_render.py).
+// =====================================================================================================
+namespace {
+
+const int kLimbMpi[] = {0, 1, 2, 3, 3, 4, 5, 6, 6, 7, 8, 9, 9, 10, 11, 12, 12, 13};                       // renderFunctions.cu:7
+const int kLimbCoco[] = {1, 2, 1, 5, 2, 3, 3, 4, 5, 6, 6, 7, 1, 8, 8, 9, 9, 10, 1, 11, 11, 12, 12, 13,
+                         1, 0, 0, 14, 14, 16, 0, 15, 15, 17};                                               // :9 (NOEAR)
+const int kColor9[] = {255, 0, 0, 255, 170, 0, 170, 255, 0, 0, 255, 0, 0, 255, 170, 0, 170, 255, 0, 0, 255, 170, 0, 255, 255, 0, 170};   // :145-153
+const int kColor18[] = {255, 0, 0, 255, 85, 0, 255, 170, 0, 255, 255, 0, 170, 255, 0, 85, 255, 0, 0, 255, 0, 0, 255, 85, 0, 255, 170,
+                        0, 255, 255, 0, 170, 255, 0, 85, 255, 0, 0, 255, 85, 0, 255, 170, 0, 255, 255, 0, 255, 255, 0, 170, 255, 0, 85};   // :461-479
+
+struct Bgr { float b, g, r; };
+
+inline void mix(Bgr& px, float alpha, float cb, float cg, float cr) {   // b = (1-alpha)*b + alpha*colour
+    px.b = (1 - alpha) * px.b + alpha * cb;
+    px.g = (1 - alpha) * px.g + alpha * cg;
+    px.r = (1 - alpha) * px.r + alpha * cr;
+}
+
+// one limb ellipse test (renderFunctions.cu:181-205 / 513-530): returns judge, or -1 when a joint is missing
+inline bool limb_judge(const float* pose, int pa, int pb, float thr, int x, int y, float b_sqrt, bool head, float* judge_out) {
+    const float x_a = pose[pa * 3], x_b = pose[pb * 3], y_a = pose[pa * 3 + 1], y_b = pose[pb * 3 + 1];
+    if (!(pose[pa * 3 + 2] > thr && pose[pb * 3 + 2] > thr)) return false;
+    const float x_p = (x_a + x_b) / 2, y_p = (y_a + y_b) / 2;
+    const float angle = atan2f(y_b - y_a, x_b - x_a);
+    const float sine = sinf(angle), cosine = cosf(angle);
+    float a_sqrt = (x_a - x_p) * (x_a - x_p) + (y_a - y_p) * (y_a - y_p);
+    if (head) { a_sqrt = (float)(a_sqrt * 1.2); b_sqrt = a_sqrt; }   // MPI limb 0 (:189-193)
+    const float A = cosine * (x - x_p) + sine * (y - y_p);
+    const float B = sine * (x - x_p) - cosine * (y - y_p);
+    *judge_out = A * A / a_sqrt + B * B / b_sqrt;
+    return true;
+}
+
+void skeleton_mpi(float* canvas, int w, int h, const float* poses, int num_people) {   // render_pose_29parts :124-240
+    const int NP = 15;
+    const float thr = 0.0f, radius = 3 * h / 200.0f, stick = h / 60.0f;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            Bgr px = {canvas[y * w + x], canvas[w * h + y * w + x], canvas[2 * w * h + y * w + x]};
+            for (int p = 0; p < num_people; p++) {
+                const float* pose = poses + p * NP * 3;
+                for (int l = 0; l < 9; l++) {
+                    float judge;
+                    if (!limb_judge(pose, kLimbMpi[2 * l], kLimbMpi[2 * l + 1], thr, x, y, stick * stick, l == 0, &judge)) continue;
+                    const float minV = l == 0 ? 0.8f : 0.f;
+                    if (judge >= minV && judge <= 1) mix(px, 0.6f, (float)kColor9[l * 3 + 2], (float)kColor9[l * 3 + 1], (float)kColor9[l * 3]);
+                }
+                for (int i = 0; i < NP; i++) {
+                    const float jx = pose[i * 3], jy = pose[i * 3 + 1];
+                    if (pose[i * 3 + 2] > thr && (x - jx) * (x - jx) + (y - jy) * (y - jy) <= radius * radius) {
+                        px.b = (float)(0.6 * px.b + 0.4 * kColor9[(i % 9) * 3 + 2]);   // double arithmetic (:218-220)
+                        px.g = (float)(0.6 * px.g + 0.4 * kColor9[(i % 9) * 3 + 1]);
+                        px.r = (float)(0.6 * px.r + 0.4 * kColor9[(i % 9) * 3]);
+                    }
+                }
+            }
+            canvas[y * w + x] = px.b; canvas[w * h + y * w + x] = px.g; canvas[2 * w * h + y * w + x] = px.r;
+        }
+}
+
+void skeleton_coco(float* canvas, int w, int h, const float* poses, int num_people, bool googly) {   // :394-636
+    const int NP = 18;
+    const float thr = 0.01f, radius = 2 * h / 200.0f, stick = h / 120.0f;
+    std::vector<float> minx(num_people), miny(num_people), maxx(num_people), maxy(num_people), scale(num_people);
+    for (int p = 0; p < num_people; p++) {   // per-person box and size factor (:410-444)
+        float mnx = (float)w, mny = (float)h, mxx = 0, mxy = 0;
+        for (int part = 0; part < NP; part++) {
+            const float jx = poses[p * NP * 3 + part * 3], jy = poses[p * NP * 3 + part * 3 + 1];
+            if (poses[p * NP * 3 + part * 3 + 2] > thr) {
+                if (jx < mnx) mnx = jx;
+                if (jx > mxx) mxx = jx;
+                if (jy < mny) mny = jy;
+                if (jy > mxy) mxy = jy;
+            }
+        }
+        float s = (float)(((mxx - mnx) + (mxy - mny)) / 2.0);
+        if (s < 200) { s = s / 200; if (s < 0.33) s = (float)0.33; } else s = 1.0f;
+        maxx[p] = mxx + 50; maxy[p] = mxy + 50; minx[p] = mnx - 50; miny[p] = mny - 50; scale[p] = s;
+    }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            Bgr px = {canvas[y * w + x], canvas[w * h + y * w + x], canvas[2 * w * h + y * w + x]};
+            for (int p = 0; p < num_people; p++) {
+                if (x > maxx[p] || x < minx[p] || y > maxy[p] || y < miny[p]) continue;
+                const float* pose = poses + p * NP * 3;
+                const float sc = scale[p];
+                for (int l = 0; l < 17; l++) {
+                    float judge;
+                    if (!limb_judge(pose, kLimbCoco[2 * l], kLimbCoco[2 * l + 1], thr, x, y, sc * sc * stick * stick, false, &judge)) continue;
+                    if (judge >= 0 && judge <= 1) mix(px, 0.5f, (float)kColor18[(l % 18) * 3 + 2], (float)kColor18[(l % 18) * 3 + 1], (float)kColor18[(l % 18) * 3]);
+                }
+                for (int i = 0; i < NP; i++) {
+                    const float jx = pose[i * 3], jy = pose[i * 3 + 1];
+                    if (!(pose[i * 3 + 2] > thr)) continue;
+                    const float dist2 = (x - jx) * (x - jx) + (y - jy) * (y - jy);
+                    float cb = (float)kColor18[(i % 18) * 3 + 2], cg = (float)kColor18[(i % 18) * 3 + 1], cr = (float)kColor18[(i % 18) * 3];
+                    if (googly && (i == 14 || i == 15)) {   // :589-611
+                        const float maxr2 = (float)(sc * sc * 2.5 * 2.5 * radius * radius);
+                        const float minr2 = (float)(sc * sc * (2.5 * radius - 2) * (2.5 * radius - 2));
+                        cb = cg = cr = 0;
+                        if (dist2 <= maxr2) {
+                            if (dist2 <= minr2) cb = cg = cr = 255;
+                            if (dist2 <= minr2 * 0.6) {
+                                const float dist3 = (x - 4 - jx) * (x - 4 - jx) + (y - jy + 4) * (y - jy + 4);
+                                if (dist3 > 3.75 * 3.75) cb = cg = cr = 0;
+                            }
+                            mix(px, 0.9f, cb, cg, cr);
+                        }
+                    } else {
+                        const float maxr2 = sc * sc * radius * radius;
+                        if (dist2 >= 0 && dist2 <= maxr2) mix(px, 0.6f, cb, cg, cr);
+                    }
+                }
+            }
+            canvas[y * w + x] = px.b; canvas[w * h + y * w + x] = px.g; canvas[2 * w * h + y * w + x] = px.r;
+        }
+}
+
+void jet(float* c, float v, float vmin, float vmax) {   // getColor :11-44; c = {b, g, r}
+    c[0] = c[1] = c[2] = 255;
+    if (v < vmin) v = vmin;
+    if (v > vmax) v = vmax;
+    const float dv = vmax - vmin;
+    if (v < (vmin + 0.125 * dv)) { c[0] = (float)(256 * (0.5 + (v * 4))); c[1] = c[2] = 0; }
+    else if (v < (vmin + 0.375 * dv)) { c[0] = 255; c[1] = (float)(256 * (v - 0.125) * 4); c[2] = 0; }
+    else if (v < (vmin + 0.625 * dv)) { c[0] = (float)(256 * (-4 * v + 2.5)); c[1] = 255; c[2] = (float)(256 * (4 * (v - 0.375))); }
+    else if (v < (vmin + 0.875 * dv)) { c[0] = 0; c[1] = (float)(256 * (-4 * v + 3.5)); c[2] = 255; }
+    else { c[0] = 0; c[1] = 0; c[2] = (float)(256 * (-4 * v + 4.5)); }
+}
+
+void wheel(float* c, float v) {   // getColor2 :46-94 with vmin 0, vmax 1
+    if (v < 0) v = 0;
+    if (v > 1) v = 1;
+    v = 55 * v;
+    const int RY = 15, YG = 6, GC = 4, CB = 11, BM = 13, MR = 6;
+    if (v < RY) { c[0] = 255; c[1] = 255 * (v / RY); c[2] = 0; }
+    else if (v < RY + YG) { c[0] = 255 - 255 * ((v - RY) / YG); c[1] = 255; c[2] = 0; }
+    else if (v < RY + YG + GC) { c[0] = 0; c[1] = 255; c[2] = 255 * ((v - RY - YG) / GC); }
+    else if (v < RY + YG + GC + CB) { c[0] = 0; c[1] = 255 - 255 * ((v - RY - YG - GC) / CB); c[2] = 255; }
+    else if (v < RY + YG + GC + CB + BM) { c[0] = 255 * ((v - RY - YG - GC - CB) / BM); c[1] = 0; c[2] = 255; }
+    else if (v < RY + YG + GC + CB + BM + MR) { c[0] = 255; c[1] = 0; c[2] = 255 - 255 * ((v - RY - YG - GC - CB - BM) / MR); }
+    else { c[0] = 255; c[1] = 0; c[2] = 0; }
+}
+
+void vec_color(float* c, float x, float y) {   // getColorXY :96-112
+    float rad = sqrtf(x * x + y * y);
+    const float a = (float)(atan2f(-y, -x) / M_PI);
+    float fk = (float)((a + 1) / 2.0);
+    if (std::isnan(fk)) fk = 0;
+    if (rad > 1) rad = 1;
+    wheel(c, fk);
+    for (int k = 0; k < 3; k++) c[k] = 255 * (rad * (c[k] / 255));
+}
+
+float cubic_render(float v0, float v1, float v2, float v3, float dx) {   // :114-122, float/double mix as written there
+    return (float)((-0.5f * v0 + 1.5f * v1 - 1.5f * v2 + 0.5f * v3) * dx * dx * dx + (v0 - 2.5f * v1 + 2.0 * v2 - 0.5 * v3) * dx * dx +
+                   (-0.5f * v0 + 0.5f * v2) * dx + v1);
+}
+
+struct HeatTaps { int xn[4], yn[4]; float dx, dy; bool inside; };
+HeatTaps heat_taps(int x, int y, int w_canvas, int h_canvas, int w_net, int h_net) {   // :263-285 (identical in all four views)
+    HeatTaps t;
+    const float h_inv = (float)h_net / (float)h_canvas, w_inv = (float)w_net / (float)w_canvas;
+    const float xb = (float)(w_inv * x + (0.5 * w_inv - 0.5)), yb = (float)(h_inv * y + (0.5 * h_inv - 0.5));
+    t.inside = xb >= 0 && xb < w_net && yb >= 0 && yb < h_net;
+    auto axis = [](float on, int n, int* nei, float* d) {
+        nei[1] = int(on + 1e-5);
+        nei[1] = nei[1] < 0 ? 0 : nei[1];
+        nei[0] = nei[1] - 1 < 0 ? nei[1] : nei[1] - 1;
+        nei[2] = nei[1] + 1 >= n ? n - 1 : nei[1] + 1;
+        nei[3] = nei[2] + 1 >= n ? n - 1 : nei[2] + 1;
+        *d = on - nei[1];
+    };
+    axis(xb, w_net, t.xn, &t.dx);
+    axis(yb, h_net, t.yn, &t.dy);
+    return t;
+}
+
+// mode 0: render_pose_29parts_heatmap :242-329; 1: ..._coco_heatmap :638-724; 2: ..._coco_heatmap2 :726-836 (in_part = 0);
+// 3: ..._coco_affinity :838-975
+void heat_view(float* canvas, int w, int h, int w_net, int h_net, const float* heat, int mode, int part, int accum) {
+    const int off2 = w_net * h_net;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            Bgr px = {canvas[y * w + x], canvas[w * h + y * w + x], canvas[2 * w * h + y * w + x]};
+            const HeatTaps t = heat_taps(x, y, w, h, w_net, h_net);
+            if (mode == 0 || mode == 1) {
+                const int NP = mode == 0 ? 15 : 18;
+                float value = (part == NP - 1) ? 1.f : 0.f;
+                if (t.inside) {
+                    const float* src = heat + (size_t)part * off2;
+                    float tmp[4];
+                    for (int i = 0; i < 4; i++)
+                        tmp[i] = cubic_render(src[t.yn[i] * w_net + t.xn[0]], src[t.yn[i] * w_net + t.xn[1]], src[t.yn[i] * w_net + t.xn[2]],
+                                              src[t.yn[i] * w_net + t.xn[3]], t.dx);
+                    value = cubic_render(tmp[0], tmp[1], tmp[2], tmp[3], t.dy);
+                }
+                float c[3];
+                if (mode == 0) {
+                    if (part < 16) jet(c, value, 0, 1); else jet(c, value, -1, 1);
+                    px.b = (float)(0.5 * px.b + 0.5 * c[0]); px.g = (float)(0.5 * px.g + 0.5 * c[1]); px.r = (float)(0.5 * px.r + 0.5 * c[2]);
+                } else {
+                    if (part < NP + 1) jet(c, value, 0, 1); else jet(c, value, -1, 1);
+                    mix(px, 0.7f, c[2], c[1], c[0]);
+                }
+            } else if (mode == 2) {
+                float c[3] = {0, 0, 0};
+                if (t.inside)
+                    for (int p2 = 0; p2 < 18; p2++) {
+                        const float value = heat[(size_t)p2 * off2 + t.yn[1] * w_net + t.xn[1]];
+                        for (int k = 0; k < 3; k++) c[k] += value * kColor18[(p2 % 18) * 3 + k];
+                    }
+                mix(px, 0.7f, c[2], c[1], c[0]);
+            } else {
+                float c[3] = {0, 0, 0};
+                if (t.inside)
+                    for (int p2 = part; p2 < part + accum * 2; p2 += 2) {
+                        const float* h0 = heat + (size_t)p2 * off2;
+                        const float* h1 = heat + (size_t)(p2 + 1) * off2;
+                        float value, value2;
+                        if (accum == 1) {   // bilinear (:912-935)
+                            auto bil = [&](const float* m) {
+                                const float a = m[t.yn[1] * w_net + t.xn[1]], b = m[t.yn[1] * w_net + t.xn[2]];
+                                const float cc = m[t.yn[2] * w_net + t.xn[1]], d = m[t.yn[2] * w_net + t.xn[2]];
+                                return (1 - t.dx) * (1 - t.dy) * a + (t.dx) * (1 - t.dy) * b + (1 - t.dx) * (t.dy) * cc + (t.dx) * (t.dy) * d;
+                            };
+                            value = bil(h0); value2 = bil(h1);
+                        } else {
+                            value = h0[t.yn[1] * w_net + t.xn[1]];
+                            value2 = h1[t.yn[1] * w_net + t.xn[1]];
+                        }
+                        float c2[3];
+                        vec_color(c2, value, value2);
+                        for (int k = 0; k < 3; k++) c[k] += c2[k];
+                    }
+                for (int k = 0; k < 3; k++) if (c[k] > 255) c[k] = 255;
+                mix(px, 0.7f, c[2], c[1], c[0]);
+            }
+            canvas[y * w + x] = px.b; canvas[w * h + y * w + x] = px.g; canvas[2 * w * h + y * w + x] = px.r;
+        }
+}
+
+}  // namespace
+
+// process_and_pad_image(..., normalize = 0) for an image of the canvas size (rtpose.cpp:239-269, :349)
+extern "C" void orc_canvas_from_u8(const uint8_t* bgr, int h, int w, float* canvas) {
+    for (int c = 0; c < 3; c++)
+        for (int i = 0; i < h * w; i++) canvas[(size_t)c * h * w + i] = float(bgr[(size_t)i * 3 + c]);
+}
+// postProcessFrame (rtpose.cpp:1286-1296)
+extern "C" void orc_canvas_to_u8(const float* canvas, int h, int w, uint8_t* bgr) {
+    for (int c = 0; c < 3; c++)
+        for (int i = 0; i < h * w; i++) {
+            int value = int(canvas[(size_t)c * h * w + i] + 0.5);
+            value = value < 0 ? 0 : (value > 255 ? 255 : value);
+            bgr[(size_t)i * 3 + c] = (unsigned char)value;
+        }
+}
+// render() (rtpose.cpp:271-300) + launchers (renderFunctions.cu:331-389, 978-1080).  heatmaps: the full-resolution
+// resized_map (num_maps x h_net x w_net), only read when part_to_show > 0.  Returns 0, or -1 for a bad part_to_show.
+extern "C" int orc_render(int model, float* canvas, int w_canvas, int h_canvas, int w_net, int h_net, const float* heatmaps,
+                          const float* poses, int num_people, int part_to_show, int googly_eyes) {
+    const ModelDesc& md = model_desc(model);
+    const int NP = md.num_parts;
+    if (part_to_show < 0) return -1;
+    if (NP == 15) {
+        if (part_to_show == 0) { if (num_people != 0) skeleton_mpi(canvas, w_canvas, h_canvas, poses, num_people); }
+        else { if (part_to_show - 1 >= NP + 1 + 2 * md.num_limbs) return -1; heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 0, part_to_show - 1, 0); }
+        return 0;
+    }
+    if (part_to_show - 1 <= NP) {
+        if (part_to_show == 0) { if (num_people != 0) skeleton_coco(canvas, w_canvas, h_canvas, poses, num_people, googly_eyes != 0); }
+        else if (part_to_show - 1 == NP) heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 2, 0, 0);
+        else heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 1, part_to_show - 1, 0);
+        return 0;
+    }
+    int aff_part = ((part_to_show - 1) - NP - 1) * 2, accum = 1;
+    if (aff_part == 0) accum = 19; else aff_part -= 2;
+    aff_part += 1 + NP;
+    if (aff_part + 2 * accum > NP + 1 + 2 * md.num_limbs) return -1;
+    heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 3, aff_part, accum);
+    return 0;
+}
+
 extern "C" int orc_json(const float* joints, int num_people, int num_parts, double frame_scale, char* buf, int cap) {
     std::string s;
     char t[64];

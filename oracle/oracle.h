@@ -113,6 +113,13 @@ void orc_scale_target(int net_w, int net_h, double start_scale, double scale_gap
 int orc_preprocess(const uint8_t* disp, int disp_h, int disp_w, int net_h, int net_w, int num_scales,
                    double start_scale, double scale_gap, float* out);
 
+/* ---- renderers: render() rtpose.cpp:271-300 + src/rtpose/renderFunctions.cu (GPU-only in the reference).  canvas: 3 x h x w float
+ * planar BGR in/out; heatmaps: full-resolution resized_map (num_maps x h_net x w_net), read when part_to_show > 0. */
+void orc_canvas_from_u8(const uint8_t* bgr, int h, int w, float* canvas);
+void orc_canvas_to_u8(const float* canvas, int h, int w, uint8_t* bgr);
+int orc_render(int model, float* canvas, int w_canvas, int h_canvas, int w_net, int h_net, const float* heatmaps,
+               const float* poses, int num_people, int part_to_show, int googly_eyes);
+
 /* ---- JSON (rtpose.cpp:1383-1416).  Returns bytes written (excluding NUL), or needed size if > cap. */
 int orc_json(const float* joints, int num_people, int num_parts, double frame_scale, char* buf, int cap);
 

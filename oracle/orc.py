@@ -106,6 +106,9 @@ def lib():
     L.orc_scale_target.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.orc_preprocess.argtypes = [_u8p] + [C.c_int] * 5 + [C.c_double, C.c_double, _f32p]
     L.orc_json.argtypes = [_f32p, C.c_int, C.c_int, C.c_double, C.c_char_p, C.c_int]
+    L.orc_canvas_from_u8.argtypes = [_u8p, C.c_int, C.c_int, _f32p]
+    L.orc_canvas_to_u8.argtypes = [_f32p, C.c_int, C.c_int, _u8p]
+    L.orc_render.argtypes = [C.c_int, _f32p] + [C.c_int] * 4 + [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int]
     L.orc_process_frame.argtypes = [C.c_void_p, C.c_int, _u8p] + [C.c_int] * 5 + [C.c_double, C.c_double, C.c_float,
                                                                                 C.POINTER(ConnectParams), _f32p,
                                                                                 C.c_void_p, C.c_void_p]
@@ -333,6 +336,7 @@ def flops(model, h, w):
 # ------------------------------------------------------------------------------------------ oracle/_ref
 _ref_host = None
 _ref_cpm = None
+_ref_render = None
 
 
 def ref_host():
@@ -364,6 +368,76 @@ def ref_cpm():
         R.ref_nms_host.argtypes = [_f32p, _f32p] + [C.c_int] * 5 + [C.c_float]
         _ref_cpm = R
     return _ref_cpm
+
+
+def canvas_from_u8(bgr):
+    """process_and_pad_image(normalize=0) of a display-sized image: uint8 HWC -> float planar (rtpose.cpp:239-269)."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    out = np.zeros((3, h, w), np.float32)
+    lib().orc_canvas_from_u8(bgr, h, w, out)
+    return out
+
+
+def canvas_to_u8(canvas):
+    """postProcessFrame (rtpose.cpp:1286-1296): float planar canvas -> uint8 HWC."""
+    canvas = np.ascontiguousarray(canvas, np.float32)
+    _, h, w = canvas.shape
+    out = np.zeros((h, w, 3), np.uint8)
+    lib().orc_canvas_to_u8(canvas, h, w, out)
+    return out
+
+
+def _poses(poses, num_people, P):
+    buf = np.zeros((max(num_people, 1), P, 3), np.float32)
+    if num_people:
+        buf[:num_people] = np.asarray(poses, np.float32).reshape(-1, P, 3)[:num_people]
+    return buf
+
+
+def render(model, canvas, net_w, net_h, full, poses, num_people, part_to_show=0, googly_eyes=False):
+    """CPU restatement of render() + renderFunctions.cu; returns the rendered float canvas (copy)."""
+    out = np.ascontiguousarray(canvas, np.float32).copy()
+    _, h, w = out.shape
+    P = 15 if model == MPI_15 else 18
+    fp = None
+    if full is not None:
+        full = np.ascontiguousarray(full, np.float32)
+        fp = full.ctypes.data
+    rc = lib().orc_render(model, out, w, h, net_w, net_h, fp, _poses(poses, num_people, P), num_people, part_to_show,
+                          1 if googly_eyes else 0)
+    if rc != 0:
+        raise ValueError("part_to_show %d out of range" % part_to_show)
+    return out
+
+
+def ref_render_lib():
+    """The reference's own render kernels compiled for sm_100a (needs a GPU to call)."""
+    global _ref_render
+    if _ref_render is None:
+        p = os.path.join(HERE, "_ref", "libref_render.so")
+        if not os.path.exists(p):
+            return None
+        R = C.CDLL(p)
+        R.ref_render_host.argtypes = [_f32p] + [C.c_int] * 4 + [C.c_void_p, C.c_int, _f32p] + [C.c_int] * 4
+        _ref_render = R
+    return _ref_render
+
+
+def ref_render(model, canvas, net_w, net_h, full, poses, num_people, part_to_show=0, googly_eyes=False):
+    R = ref_render_lib()
+    out = np.ascontiguousarray(canvas, np.float32).copy()
+    _, h, w = out.shape
+    P = 15 if model == MPI_15 else 18
+    fp, nm = None, 0
+    if full is not None:
+        full = np.ascontiguousarray(full, np.float32)
+        fp, nm = full.ctypes.data, full.shape[0]
+    rc = R.ref_render_host(out, w, h, net_w, net_h, fp, nm, _poses(poses, num_people, P), num_people, P, part_to_show,
+                           1 if googly_eyes else 0)
+    if rc != 0:
+        raise RuntimeError("ref_render_host failed")
+    return out
 
 
 def ref_connect(model, full, peaks, disp_w, disp_h, params):

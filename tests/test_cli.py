@@ -49,6 +49,14 @@ def write_bmp(path, bgr):
         f.write(rows)
 
 
+def read_bmp(path):
+    d = open(path, "rb").read()
+    off, w, h = struct.unpack_from("<I", d, 10)[0], struct.unpack_from("<i", d, 18)[0], struct.unpack_from("<i", d, 22)[0]
+    stride = (w * 3 + 3) & ~3
+    rows = [np.frombuffer(d, np.uint8, w * 3, off + y * stride).reshape(w, 3) for y in range(h - 1, -1, -1)]
+    return np.stack(rows)
+
+
 def write_ppm(path, bgr):
     h, w, _ = bgr.shape
     with open(path, "wb") as f:
@@ -71,7 +79,8 @@ def test_cli_json_equals_python_path(tmp_path):
         (write_bmp if i % 2 == 0 else write_ppm)(str(img_dir / ("img%03d.%s" % (i, "bmp" if i % 2 == 0 else "ppm"))), f)
     out = tmp_path / "json"
     r = run(["--image_dir", str(img_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "%dx%d" % (disp_w, disp_h),
-             "--net_resolution", "%dx%d" % (net_w, net_h), "--write_json", str(out), "--no_display", "--num_gpu", "1"], timeout=300)
+             "--net_resolution", "%dx%d" % (net_w, net_h), "--write_json", str(out), "--no_display", "--num_gpu", "1",
+             "--write_frames", str(tmp_path / "rendered"), "--part_to_show", "2"], timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
     eng.set_weights(W)
@@ -80,6 +89,8 @@ def test_cli_json_equals_python_path(tmp_path):
         cnt, joints, _ = eng.fetch(0)
         got = (out / ("img%03d.json" % i)).read_text()
         assert got == eng.json(joints, 1.0)
+        # --write_frames: the rendered display image (heat map of part 1 here), lossless .bmp instead of the reference's .jpg
+        assert np.array_equal(read_bmp(str(tmp_path / "rendered" / ("img%03d.bmp" % i))), eng.render(0, 2))
     eng.close()
     # frames whose size differs from --resolution go through the GPU warpAffine (rtpose.cpp:474-487); JSON carries 1/scale
     big_dir = tmp_path / "big"

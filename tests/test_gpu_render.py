@@ -1,0 +1,94 @@
+"""Renderers on the GPU (pe_render, csrc/render.cu) against
+  (1) the reference's OWN render kernels (src/rtpose/renderFunctions.cu) compiled for sm_100a into
+      oracle/_ref/libref_render.so and launched with the reference's geometry - the bit-level pin, and
+  (2) the CPU restatement in oracle/ (libm trigonometry, unfused sums) - equal up to shape-border pixels.
+Inputs are injected stride-8 maps, so joints and the full-resolution maps are bit-identical on both sides."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from caffe_rtpose_b200 import engine, synth
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+STATS = {}
+
+
+def scene(model, net_w, net_h, disp_w, disp_h, n_people, seed, S=1):
+    people = synth.make_people(model, n_people, net_w, net_h, seed=seed)
+    maps8 = synth.make_maps(model, people, net_w, net_h, num_scales=S, start_scale=1.0, scale_gap=0.15, seed=seed)
+    eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, num_scales=S, start_scale=1.0, scale_gap=0.15,
+                            precision=engine.PREC_FP32_SIMT)
+    eng.forward_maps(maps8)
+    cnt, joints, _ = eng.fetch(0)
+    full = orc.imresize(maps8, net_h, net_w, 1.0, 0.15)
+    frame = synth.make_frame(seed, disp_h, disp_w)
+    return eng, cnt, joints, full, frame
+
+
+def compare(tag, got_canvas, got_img, want_canvas, exact_expected):
+    diff = np.abs(got_canvas - want_canvas)
+    px_bad = float((diff.max(0) > 1e-3).mean())
+    img_bad = float((got_img != orc.canvas_to_u8(want_canvas)).any(2).mean())
+    STATS[tag] = {"bit_exact": bool(np.array_equal(got_canvas, want_canvas)), "max_abs": float(diff.max()),
+                  "pixels_off_1e-3": px_bad, "u8_pixels_differ": img_bad}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(STATS, open(os.path.join(ROOT, "gpurun_out", "render_parity.json"), "w"), indent=1, sort_keys=True)
+    if exact_expected:
+        assert px_bad <= 1e-4 and img_bad <= 1e-4, (tag, STATS[tag])
+    else:
+        assert px_bad <= 2e-3 and img_bad <= 2e-3, (tag, STATS[tag])
+
+
+@pytest.mark.parametrize("model,net_w,net_h,disp_w,disp_h,parts", [
+    (engine.COCO_18, 320, 176, 640, 352, [(0, 0), (0, 1), (1, 0), (18, 0), (19, 0), (20, 0), (21, 0), (39, 0)]),
+    (engine.MPI_15, 240, 176, 480, 352, [(0, 0), (1, 0), (15, 0), (16, 0), (17, 0), (44, 0)]),
+    (engine.COCO_18, 656, 368, 1280, 720, [(0, 1), (5, 0), (20, 0)]),
+])
+def test_render_vs_reference_kernels_and_oracle(model, net_w, net_h, disp_w, disp_h, parts):
+    if orc.ref_render_lib() is None:
+        pytest.skip("oracle/_ref/libref_render.so not built")
+    eng, cnt, joints, full, frame = scene(model, net_w, net_h, disp_w, disp_h, 7, seed=21)
+    assert cnt >= 3
+    canvas0 = orc.canvas_from_u8(frame)
+    for part, googly in parts:
+        img, canvas = eng.render(0, part, bool(googly), display_bgr=frame, want_canvas=True)
+        tag = "m%d_%dx%d_p%d_g%d" % (model, disp_w, disp_h, part, googly)
+        ref = orc.ref_render(model, canvas0, net_w, net_h, full, joints, cnt, part, bool(googly))
+        compare(tag + "_ref", canvas, img, ref, True)
+        cpu = orc.render(model, canvas0, net_w, net_h, full, joints, cnt, part, bool(googly))
+        compare(tag + "_cpu", canvas, img, cpu, False)
+        assert np.array_equal(img, orc.canvas_to_u8(canvas))   # the uint8 conversion itself is exact
+    eng.close()
+
+
+def test_render_from_resident_frame_and_errors():
+    model, net_w, net_h, disp_w, disp_h = engine.COCO_18, 160, 96, 320, 192
+    W = synth.make_weights(model, "he")
+    eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_F16X2, max_batch=2)
+    eng.set_weights(W)
+    frames = [synth.make_frame(i, disp_h, disp_w) for i in range(2)]
+    eng.forward_frames(frames)
+    for idx in range(2):
+        a = eng.render(idx, 0)                              # display frame still on the device
+        b = eng.render(idx, 0, display_bgr=frames[idx])     # same frame passed explicitly
+        assert np.array_equal(a, b)
+        h = eng.render(idx, 3)
+        assert h.shape == (disp_h, disp_w, 3) and (h != frames[idx]).any()
+    cnt, joints, _ = eng.fetch(0)
+    if cnt == 0:   # noise maps rarely give persons: the skeleton view must then return the frame itself
+        assert np.array_equal(eng.render(0, 0), frames[0])
+    with pytest.raises(engine.PoseEngineError):
+        eng.render(0, 40)
+    with pytest.raises(engine.PoseEngineError):
+        eng.render(2, 0)
+    people = synth.make_people(model, 3, net_w, net_h, seed=5)
+    eng.forward_maps(synth.make_maps(model, people, net_w, net_h, seed=5))
+    with pytest.raises(engine.PoseEngineError):             # no display frame on the map-injection path
+        eng.render(0, 0)
+    assert eng.render(0, 0, display_bgr=frames[0]).shape == (disp_h, disp_w, 3)
+    eng.close()

@@ -269,3 +269,42 @@ def test_warp_affine_live_cv2():
         assert np.array_equal(out, ref)
     same, s = orc.display_image(synth.make_frame(1, 72, 128), 128, 72)   # scale 1: identity
     assert s == 1.0 and np.array_equal(same, synth.make_frame(1, 72, 128))
+
+
+# ---- renderers (render() rtpose.cpp:271-300, renderFunctions.cu): GPU-only in the reference, so the CPU suite holds
+# regression vectors of the restatement + its invariants; the bit-level pin against the reference's own kernels
+# (oracle/_ref/libref_render.so) is tests/test_gpu_render.py.
+@pytest.mark.parametrize("name", ["coco", "mpi"])
+def test_render_goldens(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, "parse_%s.npz" % name))
+    r = np.load(os.path.join(golden_dir, "render_%s.npz" % name))
+    model, net_w, net_h, disp_w, disp_h, S, _ = [int(v) for v in g["meta"]]
+    full = orc.imresize(g["maps"], net_h, net_w, float(g["start_scale"]), float(g["scale_gap"]))
+    canvas = np.full((3, disp_h, disp_w), 96.0, np.float32)
+    for key in r.files:
+        part, googly = int(key.split("_")[0][1:]), int(key.split("_")[1][1:])
+        img = orc.canvas_to_u8(orc.render(model, canvas, net_w, net_h, full, g["joints"], len(g["joints"]), part, bool(googly)))
+        assert (img != r[key]).any(2).mean() < 1e-4, key   # libm sinf/cosf may move a border pixel between glibc builds
+
+
+def test_render_invariants():
+    model, w, h = orc.COCO_18, 96, 64
+    canvas = orc.canvas_from_u8(synth.make_frame(3, h, w))
+    joints = np.zeros((1, 18, 3), np.float32)
+    # no people / no confident joint: the skeleton view leaves the canvas untouched (renderFunctions.cu:1006, :437)
+    assert np.array_equal(orc.render(model, canvas, 48, 32, None, joints, 0, 0), canvas)
+    assert np.array_equal(orc.render(model, canvas, 48, 32, None, joints, 1, 0), canvas)
+    # one limb (neck-right shoulder): an ellipse around the segment in the limb's colour, alpha 0.5, plus two joint discs
+    joints[0, 1] = (30, 30, 1.0)
+    joints[0, 2] = (60, 30, 1.0)
+    out = orc.render(model, canvas, 48, 32, None, joints, 1, 0)
+    changed = np.argwhere((out != canvas).any(0))
+    assert len(changed) > 0 and changed[:, 1].min() >= 29 and changed[:, 1].max() <= 61 and abs(changed[:, 0].mean() - 30) < 1
+    mid = out[:, 30, 45]
+    assert np.allclose(mid, 0.5 * canvas[:, 30, 45] + 0.5 * np.array([0, 0, 255], np.float32))   # colour 0 = (r 255, g 0, b 0)
+    # float canvas -> uint8: int(v + 0.5) with clamping (rtpose.cpp:1291-1293)
+    c = np.zeros((3, 1, 4), np.float32)
+    c[0, 0] = (-3.0, 0.49, 0.5, 300.0)
+    assert orc.canvas_to_u8(c)[0, :, 0].tolist() == [0, 0, 1, 255]
+    with pytest.raises(ValueError):
+        orc.render(model, canvas, 48, 32, np.zeros((57, 32, 48), np.float32), joints, 1, 40)

@@ -71,6 +71,24 @@ def gen_parse(model, name, net_w, net_h, disp_w, disp_h, n_people, num_scales, s
     print("parse_%s.npz" % name, "people", cnt, "subset rows", len(subset), "peaks/part max", int(peaks[:, 0, 0].max()))
 
 
+RENDER_CASES = {"coco": [(0, 1), (1, 0), (19, 0), (20, 0), (25, 0)], "mpi": [(0, 0), (3, 0), (20, 0)]}   # (part_to_show, googly)
+
+
+def gen_render(name):
+    """Renderer regression vectors of the ORACLE (the reference renders on the GPU only; the bit-level pin is
+    oracle/_ref/libref_render.so in tests/test_gpu_render.py): flat grey canvas + the persons of parse_<name>.npz."""
+    g = np.load(os.path.join(OUT, "parse_%s.npz" % name))
+    model, net_w, net_h, disp_w, disp_h, S, _ = [int(v) for v in g["meta"]]
+    full = orc.imresize(g["maps"], net_h, net_w, float(g["start_scale"]), float(g["scale_gap"]))
+    canvas = np.full((3, disp_h, disp_w), 96.0, np.float32)
+    d = {}
+    for part, googly in RENDER_CASES[name]:
+        out = orc.render(model, canvas, net_w, net_h, full, g["joints"], len(g["joints"]), part, bool(googly))
+        d["p%d_g%d" % (part, googly)] = orc.canvas_to_u8(out)
+    np.savez_compressed(os.path.join(OUT, "render_%s.npz" % name), **d)
+    print("render_%s.npz" % name, {k: int((v != 96).any(2).sum()) for k, v in d.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_area()
@@ -78,6 +96,8 @@ def main():
     gen_parse(orc.COCO_18, "coco", 320, 176, 640, 352, 6, 1, 11)
     gen_parse(orc.COCO_18, "coco_s3", 320, 176, 640, 352, 5, 3, 12)
     gen_parse(orc.MPI_15, "mpi", 240, 176, 480, 352, 4, 1, 13)
+    gen_render("coco")
+    gen_render("mpi")
 
 
 if __name__ == "__main__":

@@ -115,10 +115,34 @@ def timing(prec, batch=1, net_w=656, net_h=368, iters=5):
         traceback.print_exc()
 
 
+def render_diag():
+    """wall time of pe_render (canvas fill + overlay kernel(s) + uint8 conversion + 2.8 MB D2H) at 1280x720."""
+    try:
+        model, net_w, net_h = engine.COCO_18, 656, 368
+        people = synth.make_people(model, 20, net_w, net_h, seed=4)
+        maps8 = synth.make_maps(model, people, net_w, net_h, seed=4)
+        eng = engine.PoseEngine(model, net_w, net_h, 1280, 720, precision=engine.PREC_FP32_SIMT)
+        eng.forward_maps(maps8)
+        cnt, _, _ = eng.fetch(0)
+        frame = synth.make_frame(0)
+        for part in (0, 5, 19, 20, 25):
+            eng.render(0, part, display_bgr=frame)
+            t = time.time()
+            for _ in range(20):
+                eng.render(0, part, display_bgr=frame)
+            print("render 1280x720 people=%d part_to_show=%d: %.3f ms per frame (incl. 2.8 MB H2D + 2.8 MB D2H, synchronous)" % (
+                cnt, part, (time.time() - t) / 20 * 1e3), flush=True)
+        eng.close()
+    except Exception:
+        traceback.print_exc()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("post", "all"):
         post_diag()
+    if what in ("render",):
+        render_diag()
     if what in ("simt", "all"):
         conv_diag([engine.PREC_FP32_SIMT])
     precs = [int(v) for v in os.environ.get("DIAG_PRECS", "1,2").split(",")]
