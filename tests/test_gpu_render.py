@@ -38,10 +38,10 @@ def compare(tag, got_canvas, got_img, want_canvas, exact_expected):
                   "pixels_off_1e-3": px_bad, "u8_pixels_differ": img_bad}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(STATS, open(os.path.join(ROOT, "gpurun_out", "render_parity.json"), "w"), indent=1, sort_keys=True)
-    if exact_expected:
-        assert px_bad <= 1e-4 and img_bad <= 1e-4, (tag, STATS[tag])
-    else:
-        assert px_bad <= 2e-3 and img_bad <= 2e-3, (tag, STATS[tag])
+    if exact_expected:   # the reference's own kernels: measured bit-identical on B200 for every view (profiles/r1m_render_parity.json)
+        assert STATS[tag]["bit_exact"], (tag, STATS[tag])
+    else:                # CPU restatement: measured max 2.3e-4 on the float canvas, <= 1.2e-5 of the uint8 pixels differ
+        assert diff.max() <= 2e-3 and img_bad <= 1e-4, (tag, STATS[tag])
 
 
 @pytest.mark.parametrize("model,net_w,net_h,disp_w,disp_h,parts", [
