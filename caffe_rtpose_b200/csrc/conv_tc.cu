@@ -751,7 +751,8 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
             static const int chunk_env = env_int("PE_TC_CHUNK", -1);   // -1: default, 0: one chunk per tile, n: n steps
             const int nsteps = a.kblocks_per_tap * a.ksize;
             int cs = nsteps;
-            if (d.planes == 2) cs = a.ksize >= 7 ? 1 : (a.ksize >= 3 ? 2 : 4);
+            static const int chunk_mul = env_int("PE_TC_CHUNK_MUL", 1);   // experiments: longer chunks
+            if (d.planes == 2) cs = (a.ksize >= 7 ? 1 : (a.ksize >= 3 ? 2 : 4)) * (chunk_mul < 1 ? 1 : chunk_mul);
             if (chunk_env == 0) cs = nsteps;
             else if (chunk_env > 0) cs = chunk_env;
             a.chunk_steps = cs < 1 ? 1 : (cs > nsteps ? nsteps : cs);

@@ -8,7 +8,11 @@ namespace pe {
 // significant bits, so hi*hi + hi*lo + lo*hi carries ~2^-22 (bf16 planes: 8 + 8 bits, ~2^-17 - measured 2.2e-5 over
 // the net with exact accumulation vs 3e-6 for fp16).  fp16's range (65504) is ample for this net (inputs in
 // [-0.5, 0.5], activations O(1-100)); the 1- and 3-plane modes keep bf16.
+#ifdef PE_PARITY_PLANES_BF16   // A/B build: parity mode on bf16 planes (8 + 8 bits, 2.1e-5 over the net), see DESIGN.md section 3
+__host__ __device__ constexpr bool planes_are_fp16(int) { return false; }
+#else
 __host__ __device__ constexpr bool planes_are_fp16(int planes) { return planes == 2; }
+#endif
 #ifdef __CUDACC__
 template <bool F16> __device__ __forceinline__ float plane_to_float(uint16_t h) {
     return F16 ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
