@@ -143,7 +143,7 @@ int pe_write_json(const float* joints, int num_people, int num_parts, double fra
  * 21..39 = one PAF.  display_bgr: HOST uint8 BGR disp_h x disp_w, or NULL = the frame given to the last
  * pe_forward_frames / _frames_device / _camera_frames (still on the device).  Outputs (either may be NULL): canvas =
  * 3 x disp_h x disp_w float planar BGR (Frame::data_for_mat after render), bgr = disp_h x disp_w x 3 uint8
- * (Frame::data_for_wrap).  The cv::putText overlays of displayFrame (rtpose.cpp:1317-1353) are not drawn (= --no_text).
+ * (Frame::data_for_wrap).  After pe_forward_frames_device the caller's device buffer must still be valid.  The cv::putText overlays of displayFrame (rtpose.cpp:1317-1353) are not drawn (= --no_text).
  * Synchronous. */
 int pe_render(pe_engine* e, int idx, int part_to_show, int googly_eyes, const uint8_t* display_bgr, float* canvas,
               uint8_t* bgr);
