@@ -1,0 +1,201 @@
+// Baseline JPEG (JFIF) encoder for --write_frames: the reference writes the rendered frame with
+// cv::imwrite(..., {CV_IMWRITE_JPEG_QUALITY, 98}) (examples/rtpose/rtpose.cpp:1363-1380); this image has no libjpeg /
+// OpenCV for C++, so the encoder is written out here: ITU-T T.81 baseline sequential DCT, 8-bit, YCbCr 4:2:0 (the
+// libjpeg default that cv::imwrite uses), Annex K quantisation tables scaled with libjpeg's quality rule, Annex K
+// Huffman tables.  The byte stream is a standard JFIF file; it is NOT bit-identical to libjpeg's output (different DCT
+// rounding), which no test of the reference depends on.  Host code, no GPU.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/poseengine.h"
+
+namespace {
+
+const uint8_t kZigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                             35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+// T.81 Annex K.1 (natural order)
+const uint8_t kQLum[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56, 14, 17, 22, 29, 51, 87, 80, 62,
+                           18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+const uint8_t kQChr[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                           99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+// T.81 Annex K.3: BITS (codes per length 1..16) and HUFFVAL
+const uint8_t kDcLumBits[16] = {0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0};
+const uint8_t kDcChrBits[16] = {0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0};
+const uint8_t kDcVal[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+const uint8_t kAcLumBits[16] = {0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d};
+const uint8_t kAcLumVal[162] = {
+    0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71, 0x14, 0x32, 0x81, 0x91, 0xa1, 0x08,
+    0x23, 0x42, 0xb1, 0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72, 0x82, 0x09, 0x0a, 0x16, 0x17, 0x18, 0x19, 0x1a, 0x25, 0x26, 0x27, 0x28,
+    0x29, 0x2a, 0x34, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59,
+    0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89,
+    0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6,
+    0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2,
+    0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+const uint8_t kAcChrBits[16] = {0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77};
+const uint8_t kAcChrVal[162] = {
+    0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22, 0x32, 0x81, 0x08, 0x14, 0x42, 0x91,
+    0xa1, 0xb1, 0xc1, 0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1, 0x0a, 0x16, 0x24, 0x34, 0xe1, 0x25, 0xf1, 0x17, 0x18, 0x19, 0x1a, 0x26,
+    0x27, 0x28, 0x29, 0x2a, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58,
+    0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x82, 0x83, 0x84, 0x85, 0x86, 0x87,
+    0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4,
+    0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda,
+    0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+
+struct Huff { uint16_t code[256]; uint8_t len[256]; };
+void build_huff(const uint8_t* bits, const uint8_t* vals, Huff& h) {   // T.81 Annex C
+    memset(&h, 0, sizeof h);
+    int k = 0;
+    uint16_t code = 0;
+    for (int l = 1; l <= 16; l++) {
+        for (int i = 0; i < bits[l - 1]; i++) { h.code[vals[k]] = code++; h.len[vals[k]] = (uint8_t)l; k++; }
+        code <<= 1;
+    }
+}
+
+struct BitWriter {
+    std::vector<uint8_t>& out;
+    uint32_t acc = 0;
+    int n = 0;
+    explicit BitWriter(std::vector<uint8_t>& o) : out(o) {}
+    void put(uint32_t bits, int len) {
+        acc = (acc << len) | (bits & ((1u << len) - 1u));
+        n += len;
+        while (n >= 8) {
+            const uint8_t b = (uint8_t)(acc >> (n - 8));
+            out.push_back(b);
+            if (b == 0xFF) out.push_back(0);   // byte stuffing
+            n -= 8;
+        }
+    }
+    void flush() { if (n) put(0x7F, 8 - n); }   // pad with ones
+};
+
+void fdct8x8(const float* in, double* out) {   // separable DCT-II, orthonormal JPEG scaling
+    static double c[8][8];
+    static bool init = false;
+    if (!init) {
+        for (int u = 0; u < 8; u++)
+            for (int x = 0; x < 8; x++) c[u][x] = (u == 0 ? sqrt(0.125) : 0.5) * cos((2 * x + 1) * u * M_PI / 16.0);
+        init = true;
+    }
+    double tmp[64];
+    for (int y = 0; y < 8; y++)
+        for (int u = 0; u < 8; u++) {
+            double s = 0;
+            for (int x = 0; x < 8; x++) s += c[u][x] * in[y * 8 + x];
+            tmp[y * 8 + u] = s;
+        }
+    for (int v = 0; v < 8; v++)
+        for (int u = 0; u < 8; u++) {
+            double s = 0;
+            for (int y = 0; y < 8; y++) s += c[v][y] * tmp[y * 8 + u];
+            out[v * 8 + u] = s;
+        }
+}
+
+inline int bit_size(int v) { int a = v < 0 ? -v : v, n = 0; while (a) { n++; a >>= 1; } return n; }
+
+void encode_block(const float* px, const uint8_t* q, int& dc_pred, const Huff& dc, const Huff& ac, BitWriter& bw) {
+    double f[64];
+    fdct8x8(px, f);
+    int z[64];
+    for (int i = 0; i < 64; i++) {
+        const int nat = kZigzag[i];
+        int v = (int)lrint(f[nat] / q[nat]);
+        const int lo = i == 0 ? -1024 : -1023;   // 8-bit baseline coefficient range (T.81 F.1.2): DC diff fits 11 bits, AC 10
+        z[i] = v < lo ? lo : (v > 1023 ? 1023 : v);
+    }
+    const int diff = z[0] - dc_pred;
+    dc_pred = z[0];
+    int s = bit_size(diff);
+    bw.put(dc.code[s], dc.len[s]);
+    if (s) bw.put((uint32_t)(diff < 0 ? diff - 1 : diff), s);
+    int run = 0;
+    for (int i = 1; i < 64; i++) {
+        if (z[i] == 0) { run++; continue; }
+        while (run > 15) { bw.put(ac.code[0xF0], ac.len[0xF0]); run -= 16; }
+        s = bit_size(z[i]);
+        const int sym = (run << 4) | s;
+        bw.put(ac.code[sym], ac.len[sym]);
+        bw.put((uint32_t)(z[i] < 0 ? z[i] - 1 : z[i]), s);
+        run = 0;
+    }
+    if (run) bw.put(ac.code[0], ac.len[0]);   // EOB
+}
+
+void put16(std::vector<uint8_t>& o, int v) { o.push_back((uint8_t)(v >> 8)); o.push_back((uint8_t)v); }
+
+}  // namespace
+
+// BGR uint8 HWC image -> JFIF bytes.  Returns the length (writes if <= cap), or -1 for bad arguments.
+extern "C" long long pe_encode_jpeg(const uint8_t* bgr, int w, int h, int quality, uint8_t* buf, long long cap) {
+    if (!bgr || w <= 0 || h <= 0 || w > 65535 || h > 65535) return -1;
+    quality = quality < 1 ? 1 : (quality > 100 ? 100 : quality);
+    const int scale = quality < 50 ? 5000 / quality : 200 - quality * 2;   // libjpeg jpeg_quality_scaling
+    uint8_t ql[64], qc[64];
+    for (int i = 0; i < 64; i++) {
+        int a = (kQLum[i] * scale + 50) / 100, b = (kQChr[i] * scale + 50) / 100;
+        ql[i] = (uint8_t)(a < 1 ? 1 : (a > 255 ? 255 : a));
+        qc[i] = (uint8_t)(b < 1 ? 1 : (b > 255 ? 255 : b));
+    }
+    std::vector<uint8_t> o;
+    o.reserve((size_t)w * h / 2 + 1024);
+    o.push_back(0xFF); o.push_back(0xD8);                                           // SOI
+    const uint8_t app0[] = {0xFF, 0xE0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0};
+    o.insert(o.end(), app0, app0 + sizeof app0);
+    for (int t = 0; t < 2; t++) {                                                    // DQT (zigzag order)
+        o.push_back(0xFF); o.push_back(0xDB); put16(o, 67); o.push_back((uint8_t)t);
+        for (int i = 0; i < 64; i++) o.push_back((t ? qc : ql)[kZigzag[i]]);
+    }
+    o.push_back(0xFF); o.push_back(0xC0); put16(o, 17); o.push_back(8); put16(o, h); put16(o, w); o.push_back(3);   // SOF0
+    o.push_back(1); o.push_back(0x22); o.push_back(0);                               // Y  2x2, table 0
+    o.push_back(2); o.push_back(0x11); o.push_back(1);                               // Cb 1x1, table 1
+    o.push_back(3); o.push_back(0x11); o.push_back(1);                               // Cr
+    const uint8_t* bits[4] = {kDcLumBits, kAcLumBits, kDcChrBits, kAcChrBits};
+    const uint8_t* vals[4] = {kDcVal, kAcLumVal, kDcVal, kAcChrVal};
+    const int nval[4] = {12, 162, 12, 162};
+    const uint8_t cls[4] = {0x00, 0x10, 0x01, 0x11};
+    for (int t = 0; t < 4; t++) {                                                    // DHT
+        o.push_back(0xFF); o.push_back(0xC4); put16(o, 19 + nval[t]); o.push_back(cls[t]);
+        o.insert(o.end(), bits[t], bits[t] + 16);
+        o.insert(o.end(), vals[t], vals[t] + nval[t]);
+    }
+    const uint8_t sos[] = {0xFF, 0xDA, 0, 12, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0};
+    o.insert(o.end(), sos, sos + sizeof sos);
+    Huff hdl, hal, hdc, hac;
+    build_huff(kDcLumBits, kDcVal, hdl); build_huff(kAcLumBits, kAcLumVal, hal);
+    build_huff(kDcChrBits, kDcVal, hdc); build_huff(kAcChrBits, kAcChrVal, hac);
+    BitWriter bw(o);
+    int pred[3] = {0, 0, 0};
+    float Y[4][64], Cb[64], Cr[64], yy[16][16], cb[16][16], cr[16][16];
+    for (int my = 0; my < h; my += 16)
+        for (int mx = 0; mx < w; mx += 16) {
+            for (int y = 0; y < 16; y++)
+                for (int x = 0; x < 16; x++) {
+                    const int sy = my + y < h ? my + y : h - 1, sx = mx + x < w ? mx + x : w - 1;   // edge replication
+                    const uint8_t* p = bgr + ((size_t)sy * w + sx) * 3;
+                    const float B = p[0], G = p[1], R = p[2];
+                    yy[y][x] = 0.299f * R + 0.587f * G + 0.114f * B - 128.f;
+                    cb[y][x] = -0.168736f * R - 0.331264f * G + 0.5f * B;
+                    cr[y][x] = 0.5f * R - 0.418688f * G - 0.081312f * B;
+                }
+            for (int b = 0; b < 4; b++)
+                for (int y = 0; y < 8; y++)
+                    for (int x = 0; x < 8; x++) Y[b][y * 8 + x] = yy[(b >> 1) * 8 + y][(b & 1) * 8 + x];
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++) {                                         // 2x2 box for the 4:2:0 chroma
+                    Cb[y * 8 + x] = 0.25f * (cb[2 * y][2 * x] + cb[2 * y][2 * x + 1] + cb[2 * y + 1][2 * x] + cb[2 * y + 1][2 * x + 1]);
+                    Cr[y * 8 + x] = 0.25f * (cr[2 * y][2 * x] + cr[2 * y][2 * x + 1] + cr[2 * y + 1][2 * x] + cr[2 * y + 1][2 * x + 1]);
+                }
+            for (int b = 0; b < 4; b++) encode_block(Y[b], ql, pred[0], hdl, hal, bw);
+            encode_block(Cb, qc, pred[1], hdc, hac, bw);
+            encode_block(Cr, qc, pred[2], hdc, hac, bw);
+        }
+    bw.flush();
+    o.push_back(0xFF); o.push_back(0xD9);                                           // EOI
+    if (buf && (long long)o.size() <= cap) memcpy(buf, o.data(), o.size());
+    return (long long)o.size();
+}

@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
-    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render",
+    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg",
 ]
 
 
@@ -118,6 +118,8 @@ def lib():
     L.pe_packed_weights_device_ptr.restype = C.c_void_p
     L.pe_broadcast_weights.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.pe_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pe_encode_jpeg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
+    L.pe_encode_jpeg.restype = C.c_longlong
     _lib = L
     return L
 
@@ -492,3 +494,15 @@ def broadcast_weights(engines):
     rc = lib().pe_broadcast_weights(arr, len(engines))
     if rc != 0:
         raise PoseEngineError("pe_broadcast_weights failed (%d): %s" % (rc, lib().pe_last_error(engines[0]._h).decode()))
+
+
+def encode_jpeg(bgr, quality=98):
+    """Baseline JFIF bytes of a uint8 BGR HWC image (what --write_frames stores; cv::imwrite quality 98 in the reference)."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    n = lib().pe_encode_jpeg(bgr.ctypes.data, w, h, quality, None, 0)
+    if n < 0:
+        raise PoseEngineError("pe_encode_jpeg: bad arguments")
+    buf = np.zeros(n, np.uint8)
+    lib().pe_encode_jpeg(bgr.ctypes.data, w, h, quality, buf.ctypes.data, n)
+    return buf.tobytes()

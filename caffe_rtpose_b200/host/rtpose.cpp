@@ -6,7 +6,7 @@
 // Supported sources: --image_dir with .bmp (24-bit) and .ppm (P6) files, or --synthetic N procedural frames.
 // .jpg/.png/--video/--camera need an image/video codec and are rejected with an explicit message.  Display,
 // keyboard handling is not part of this path.  --write_frames renders on the GPU (pe_render) and
-// writes lossless .bmp files (no JPEG encoder here; the reference writes quality-98 .jpg), without the putText overlays.
+// writes quality-98 .jpg files like the reference (pe_encode_jpeg; --frame_format bmp for lossless), without the putText overlays.
 #include <dirent.h>
 #include <math.h>
 #include <stdio.h>
@@ -44,7 +44,8 @@ static void define_flags() {
     // names, defaults and help strings of rtpose.cpp:50-72
     define("fullscreen", "false", "Run in fullscreen mode (press f during runtime to toggle)", true);
     define("part_to_show", "0", "Part to show from the start.");
-    define("write_frames", "", "Write frames with format prefix%06d.jpg  [this build: prefix%06d.bmp, lossless - no JPEG encoder]");
+    define("write_frames", "", "Write frames with format prefix%06d.jpg");
+    define("frame_format", "jpg", "[extension] jpg (quality 98, as the reference) or bmp (lossless) for --write_frames");
     define("no_frame_drops", "false", "Dont drop frames.", true);
     define("write_json", "", "Write joint data with json format as prefix%06d.json");
     define("camera", "0", "The camera index for VideoCapture.");
@@ -401,11 +402,23 @@ static void orderer_and_writer(int num_workers) {
             FILE* f = fopen(fname, "wb");
             if (f) { fwrite(buf.data(), 1, (size_t)need, f); fclose(f); }
         }
-        if (!F("write_frames").empty() && !fr.rendered.empty()) {   // displayFrame :1363-1380 (.jpg there, .bmp here)
+        if (!F("write_frames").empty() && !fr.rendered.empty()) {   // displayFrame :1363-1380 (cv::imwrite, JPEG quality 98)
+            const bool bmp = F("frame_format") == "bmp";
             char fname[1024];
-            if (F("image_dir").empty()) snprintf(fname, sizeof fname, "%s/frame%06d.bmp", F("write_frames").c_str(), fr.video_frame_number);
-            else snprintf(fname, sizeof fname, "%s/%s.bmp", F("write_frames").c_str(), fr.stem.c_str());
-            if (!write_bmp(fname, global.disp_w, global.disp_h, fr.rendered.data())) LOG_ERROR("cannot write %s", fname);
+            if (F("image_dir").empty()) snprintf(fname, sizeof fname, "%s/frame%06d.%s", F("write_frames").c_str(), fr.video_frame_number, bmp ? "bmp" : "jpg");
+            else snprintf(fname, sizeof fname, "%s/%s.%s", F("write_frames").c_str(), fr.stem.c_str(), bmp ? "bmp" : "jpg");
+            bool ok;
+            if (bmp) {
+                ok = write_bmp(fname, global.disp_w, global.disp_h, fr.rendered.data());
+            } else {
+                const long long need = pe_encode_jpeg(fr.rendered.data(), global.disp_w, global.disp_h, 98, nullptr, 0);
+                std::vector<uint8_t> jb((size_t)std::max(need, 0LL));
+                ok = need > 0 && pe_encode_jpeg(fr.rendered.data(), global.disp_w, global.disp_h, 98, jb.data(), need) == need;
+                FILE* f = ok ? fopen(fname, "wb") : nullptr;
+                ok = f != nullptr;
+                if (f) { fwrite(jb.data(), 1, jb.size(), f); fclose(f); }
+            }
+            if (!ok) LOG_ERROR("cannot write %s", fname);
         }
         written++;
         if (written % 30 == 0) {   // the reference prints FPS every 30 frames (:1421-1441)
@@ -451,7 +464,7 @@ int main(int argc, char** argv) {
         LOG_ERROR("camera/video capture needs a video codec that this build does not have; use --image_dir (.bmp/.ppm) or --synthetic N");
         return 1;
     }
-    if (!F("write_frames").empty()) LOG_INFO("--write_frames: writing lossless .bmp files (no JPEG encoder in this build), no text overlays");
+    if (F("frame_format") != "jpg" && F("frame_format") != "bmp") { LOG_ERROR("--frame_format must be jpg or bmp"); return 1; }
     if (sscanf(F("resolution").c_str(), "%dx%d", &global.disp_w, &global.disp_h) != 2) { LOG_ERROR("Error, resolution format (%s) invalid, should be e.g., 960x540", F("resolution").c_str()); return 1; }
     if (sscanf(F("net_resolution").c_str(), "%dx%d", &global.net_w, &global.net_h) != 2) { LOG_ERROR("Error, net resolution format (%s) invalid, should be e.g., 656x368 (multiples of 16)", F("net_resolution").c_str()); return 1; }
     if (!F("image_dir").empty()) {   // readImageDirIfFlagEnabled (rtpose.cpp:1732-1755): sorted list of image files

@@ -148,6 +148,11 @@ int pe_write_json(const float* joints, int num_people, int num_parts, double fra
 int pe_render(pe_engine* e, int idx, int part_to_show, int googly_eyes, const uint8_t* display_bgr, float* canvas,
               uint8_t* bgr);
 
+/* cv::imwrite(fname, frame, {CV_IMWRITE_JPEG_QUALITY, 98}) of displayFrame (rtpose.cpp:1363-1380): baseline JFIF encoder
+ * (YCbCr 4:2:0, Annex K tables, libjpeg quality scaling) for the uint8 BGR image pe_render returns.  Host code.  Returns the
+ * byte count (the stream is written when it fits in cap), -1 on bad arguments. */
+long long pe_encode_jpeg(const uint8_t* bgr, int w, int h, int quality, uint8_t* buf, long long cap);
+
 /* ---- model descriptor tables (modelDescriptorFactory.cpp:6-28,30-55) */
 int pe_model_num_parts(int model);
 int pe_model_num_limbs(int model);

@@ -160,3 +160,34 @@ int main() {
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout.split("\n")
     assert out[0] == "18 19 %s %s" % (orc.lib().orc_model_map_name(orc.COCO_18, 19).decode(), orc.lib().orc_model_map_name(orc.COCO_18, 31).decode())
     assert out[1] == "oor" and out[2] == "rte"
+
+
+def test_jpeg_encoder_decodes_like_libjpeg_at_same_quality():
+    """pe_encode_jpeg (--write_frames, rtpose.cpp:1363-1380 uses cv::imwrite quality 98): a standard JFIF stream that
+    OpenCV's libjpeg decodes, with the same quality/size trade-off as cv2.imencode at the same setting."""
+    import cv2
+    from caffe_rtpose_b200 import synth
+
+    def psnr(a, b):
+        d = a.astype(np.float64) - b.astype(np.float64)
+        return 10 * np.log10(255.0 ** 2 / max(np.mean(d * d), 1e-12))
+
+    for h, w in [(192, 320), (100, 75), (17, 33), (8, 8), (1, 1)]:
+        img = synth.make_frame(3, h, w)
+        if min(h, w) > 8:
+            img = cv2.GaussianBlur(img, (0, 0), 3)   # camera-like content; pure noise is chroma-subsampled away by any JPEG
+        for q in (98, 75, 30):
+            data = engine.encode_jpeg(img, q)
+            assert data[:2] == b"\xff\xd8" and data[-2:] == b"\xff\xd9"
+            dec = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+            assert dec is not None and dec.shape == img.shape
+            ok, ref = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q])
+            rdec = cv2.imdecode(ref, cv2.IMREAD_COLOR)
+            assert psnr(dec, img) > psnr(rdec, img) - 0.5, (h, w, q)
+            assert len(data) < 1.25 * len(ref) + 64, (h, w, q)
+    # extreme block contrast at quality 100 stays inside the baseline coefficient range
+    chk = (np.indices((16, 16)).sum(0) % 2 * 255).astype(np.uint8)[:, :, None].repeat(3, 2)
+    dec = cv2.imdecode(np.frombuffer(engine.encode_jpeg(chk, 100), np.uint8), cv2.IMREAD_COLOR)
+    assert psnr(dec, chk) > 30
+    with pytest.raises(engine.PoseEngineError):
+        engine.encode_jpeg(np.zeros((0, 4, 3), np.uint8))

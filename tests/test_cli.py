@@ -37,6 +37,8 @@ def test_flag_errors():
     assert r.returncode == 1 and "codec" in r.stderr
     r = run(["--synthetic", "2", "--resolution", "abc", "--model", "COCO"])
     assert r.returncode == 1 and "resolution format" in r.stderr
+    r = run(["--synthetic", "2", "--model", "COCO", "--frame_format", "png"])
+    assert r.returncode == 1 and "frame_format" in r.stderr
 
 
 def write_bmp(path, bgr):
@@ -89,8 +91,8 @@ def test_cli_json_equals_python_path(tmp_path):
         cnt, joints, _ = eng.fetch(0)
         got = (out / ("img%03d.json" % i)).read_text()
         assert got == eng.json(joints, 1.0)
-        # --write_frames: the rendered display image (heat map of part 1 here), lossless .bmp instead of the reference's .jpg
-        assert np.array_equal(read_bmp(str(tmp_path / "rendered" / ("img%03d.bmp" % i))), eng.render(0, 2))
+        # --write_frames: the rendered display image (heat map of part 1 here) as quality-98 JPEG, like the reference
+        assert (tmp_path / "rendered" / ("img%03d.jpg" % i)).read_bytes() == engine.encode_jpeg(eng.render(0, 2), 98)
     eng.close()
     # frames whose size differs from --resolution go through the GPU warpAffine (rtpose.cpp:474-487); JSON carries 1/scale
     big_dir = tmp_path / "big"
@@ -107,6 +109,15 @@ def test_cli_json_equals_python_path(tmp_path):
     cnt, joints, _ = eng.fetch(0)
     assert abs(sc - 320 / 480.0) < 1e-12
     assert (out2 / "big.json").read_text() == eng.json(joints, sc)
+    eng.close()
+    # lossless frames on request
+    r = run(["--image_dir", str(big_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
+             "--net_resolution", "160x96", "--no_display", "--write_frames", str(tmp_path / "bmp"), "--frame_format", "bmp"], timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
+    eng.set_weights(W)
+    eng.forward_camera_frames([big])
+    assert np.array_equal(read_bmp(str(tmp_path / "bmp" / "big.bmp")), eng.render(0, 0))
     eng.close()
     # --resolution -1x-1 takes the size from the first image (rtpose.cpp:1683-1686); missing model file is an error
     r = run(["--image_dir", str(img_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "-1x-1",
