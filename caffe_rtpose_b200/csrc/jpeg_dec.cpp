@@ -1,0 +1,386 @@
+// Baseline JPEG decoder for --image_dir: the reference reads its input images with cv::imread
+// (examples/rtpose/rtpose.cpp:302-391, getFrameFromDir), i.e. libjpeg with its defaults.  No libjpeg / OpenCV for C++ in
+// this image, so the decoder is written out here and follows libjpeg's DEFAULT decompression arithmetic exactly, so that
+// a frame decoded here equals cv::imread's bytes (tests/test_abi.py compares with cv2):
+//   * Huffman sequential DCT, 8-bit (SOF0 / SOF1), restart intervals, 8- and 16-bit quantisation tables;
+//   * the "islow" integer inverse DCT (13-bit constants, 2 extra bits after pass 1, Loeffler-Ligtenberg-Moschytz);
+//   * "fancy" triangle-filter chroma upsampling for 2x1 and 2x2 subsampling (3/4-1/4 weights, libjpeg's rounding biases),
+//     plain replication when the chroma plane is at most 2 samples wide;
+//   * YCbCr -> RGB with libjpeg's 16-bit fixed-point tables.
+// Not handled (reported as PE_ERR_INVALID by the caller): progressive / arithmetic / lossless / 12-bit files, CMYK,
+// chroma sampling other than 4:4:4 / 4:2:2 / 4:2:0, non-interleaved colour scans.  EXIF orientation is ignored (as in
+// the OpenCV 2.4 / 3.0 the reference was written for).  Host code, no GPU.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/poseengine.h"
+
+namespace {
+
+const uint8_t kZigzagNat[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct HuffTab {
+    bool set = false;
+    uint8_t bits[17] = {0};
+    uint8_t vals[256] = {0};
+    int mincode[17], maxcode[18], valptr[17];
+    uint8_t look_len[512];   // 9-bit lookahead: code length (0 = longer than 9 bits)
+    uint8_t look_sym[512];
+    void build() {
+        int code = 0, k = 0;
+        for (int l = 1; l <= 16; l++) {
+            valptr[l] = k;
+            mincode[l] = code;
+            code += bits[l];
+            k += bits[l];
+            maxcode[l] = bits[l] ? code - 1 : -1;
+            code <<= 1;
+        }
+        maxcode[17] = 0x7fffffff;
+        memset(look_len, 0, sizeof look_len);
+        k = 0;
+        code = 0;
+        for (int l = 1; l <= 9; l++) {
+            for (int i = 0; i < bits[l]; i++, k++, code++) {
+                const int first = code << (9 - l);
+                for (int f = 0; f < (1 << (9 - l)); f++) { look_len[first + f] = (uint8_t)l; look_sym[first + f] = vals[k]; }
+            }
+            code <<= 1;
+        }
+        set = true;
+    }
+};
+
+struct BitReader {
+    const uint8_t* p; const uint8_t* end;
+    uint32_t acc = 0;
+    int n = 0;
+    bool hit_marker = false;
+    void fill() {
+        while (n <= 24) {
+            uint32_t b = 0;
+            if (!hit_marker && p < end) {
+                b = *p;
+                if (b == 0xFF) {
+                    if (p + 1 < end && p[1] == 0) p += 2;
+                    else { hit_marker = true; b = 0; }   // a marker: feed zeros (libjpeg does the same past the data)
+                } else {
+                    p++;
+                }
+            }
+            acc |= b << (24 - n);
+            n += 8;
+        }
+    }
+    inline int peek(int k) { if (n < k) fill(); return (int)(acc >> (32 - k)); }
+    inline void skip(int k) { acc <<= k; n -= k; }
+    inline int get(int k) { if (k == 0) return 0; const int v = peek(k); skip(k); return v; }
+    void reset() { acc = 0; n = 0; hit_marker = false; }
+};
+
+inline int huff_decode(BitReader& br, const HuffTab& t) {
+    const int look = br.peek(9);
+    const int l = t.look_len[look];
+    if (l) { br.skip(l); return t.look_sym[look]; }
+    int code = br.peek(16);
+    for (int len = 10; len <= 16; len++) {
+        const int c = code >> (16 - len);
+        if (t.maxcode[len] >= 0 && c <= t.maxcode[len] && c >= t.mincode[len]) {
+            br.skip(len);
+            return t.vals[t.valptr[len] + c - t.mincode[len]];
+        }
+    }
+    br.skip(16);
+    return 0;   // corrupt data: libjpeg warns and returns 0
+}
+inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+
+// ---- jpeg_idct_islow: dequantise + inverse DCT of one block into 8 rows of the component plane
+constexpr int CONST_BITS = 13, PASS1_BITS = 2;
+constexpr int F_0_298631336 = 2446, F_0_390180644 = 3196, F_0_541196100 = 4433, F_0_765366865 = 6270, F_0_899976223 = 7373, F_1_175875602 = 9633,
+              F_1_501321110 = 12299, F_1_847759065 = 15137, F_1_961570560 = 16069, F_2_053119869 = 16819, F_2_562915447 = 20995, F_3_072711026 = 25172;
+inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+inline uint8_t range_limit(int x) { x += 128; return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+
+inline void idct_1d(const int* in, int stride, int shift_in_is_pass1, int* o) {
+    // even part
+    int z2 = in[2 * stride], z3 = in[6 * stride];
+    int z1 = (z2 + z3) * F_0_541196100;
+    int tmp2 = z1 + z3 * (-F_1_847759065);
+    int tmp3 = z1 + z2 * F_0_765366865;
+    z2 = in[0];
+    z3 = in[4 * stride];
+    int tmp0 = (z2 + z3) << CONST_BITS;
+    int tmp1 = (z2 - z3) << CONST_BITS;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    // odd part
+    tmp0 = in[7 * stride]; tmp1 = in[5 * stride]; tmp2 = in[3 * stride]; tmp3 = in[1 * stride];
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * F_1_175875602;
+    tmp0 *= F_0_298631336; tmp1 *= F_2_053119869; tmp2 *= F_3_072711026; tmp3 *= F_1_501321110;
+    z1 *= -F_0_899976223; z2 *= -F_2_562915447; z3 *= -F_1_961570560; z4 *= -F_0_390180644;
+    z3 += z5; z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    (void)shift_in_is_pass1;
+    o[0] = tmp10 + tmp3; o[7] = tmp10 - tmp3; o[1] = tmp11 + tmp2; o[6] = tmp11 - tmp2;
+    o[2] = tmp12 + tmp1; o[5] = tmp12 - tmp1; o[3] = tmp13 + tmp0; o[4] = tmp13 - tmp0;
+}
+
+void idct_islow(const short* coef, const uint16_t* quant, uint8_t* out, int out_stride) {
+    int deq[64], ws[64], o[8];
+    for (int i = 0; i < 64; i++) deq[i] = (int)coef[i] * (int)quant[i];
+    for (int c = 0; c < 8; c++) {   // pass 1: columns
+        idct_1d(deq + c, 8, 1, o);
+        for (int r = 0; r < 8; r++) ws[r * 8 + c] = descale(o[r], CONST_BITS - PASS1_BITS);
+    }
+    for (int r = 0; r < 8; r++) {   // pass 2: rows
+        idct_1d(ws + r * 8, 1, 0, o);
+        for (int c = 0; c < 8; c++) out[r * out_stride + c] = range_limit(descale(o[c], CONST_BITS + PASS1_BITS + 3));
+    }
+}
+
+struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pw = 0, ph = 0, dw = 0, dh = 0; std::vector<uint8_t> plane; int pred = 0; };
+
+inline uint16_t rd16(const uint8_t* p) { return (uint16_t)((p[0] << 8) | p[1]); }
+
+// libjpeg jdsample.c: h2v1_fancy_upsample / h2v2_fancy_upsample / replication fallbacks; in: dw x dh real samples
+void upsample(const Comp& c, int hmax, int vmax, int W, int H, std::vector<uint8_t>& out) {
+    out.assign((size_t)W * H, 0);
+    const int hs = hmax / c.h, vs = vmax / c.v;
+    const uint8_t* src = c.plane.data();
+    const int pw = c.pw, dw = c.dw, dh = c.dh;
+    auto row = [&](int r) { r = r < 0 ? 0 : (r >= dh ? dh - 1 : r); return src + (size_t)r * pw; };
+    if (hs == 1 && vs == 1) {
+        for (int y = 0; y < H; y++) memcpy(&out[(size_t)y * W], row(y), W);
+        return;
+    }
+    std::vector<uint8_t> line((size_t)2 * dw + 2);
+    const bool fancy = dw > 2;
+    for (int y = 0; y < H; y++) {
+        if (vs == 1) {   // h2v1
+            const uint8_t* in = row(y);
+            if (fancy) {
+                int inv = in[0];
+                line[0] = (uint8_t)inv;
+                line[1] = (uint8_t)((inv * 3 + in[1] + 2) >> 2);
+                for (int x = 1; x < dw - 1; x++) {
+                    inv = in[x] * 3;
+                    line[2 * x] = (uint8_t)((inv + in[x - 1] + 1) >> 2);
+                    line[2 * x + 1] = (uint8_t)((inv + in[x + 1] + 2) >> 2);
+                }
+                inv = in[dw - 1];
+                line[2 * (dw - 1)] = (uint8_t)((inv * 3 + in[dw - 2] + 1) >> 2);
+                line[2 * (dw - 1) + 1] = (uint8_t)inv;
+            } else {
+                for (int x = 0; x < dw; x++) line[2 * x] = line[2 * x + 1] = in[x];
+            }
+        } else {         // h2v2
+            const int r = y >> 1;
+            const uint8_t* in0 = row(r);
+            if (fancy) {
+                const uint8_t* in1 = (y & 1) ? row(r + 1) : row(r - 1);   // the nearer row weighs 3, the other 1
+                int thiscol = in0[0] * 3 + in1[0], nextcol = in0[1] * 3 + in1[1], lastcol;
+                line[0] = (uint8_t)((thiscol * 4 + 8) >> 4);
+                line[1] = (uint8_t)((thiscol * 3 + nextcol + 7) >> 4);
+                lastcol = thiscol; thiscol = nextcol;
+                for (int x = 1; x < dw - 1; x++) {
+                    nextcol = in0[x + 1] * 3 + in1[x + 1];
+                    line[2 * x] = (uint8_t)((thiscol * 3 + lastcol + 8) >> 4);
+                    line[2 * x + 1] = (uint8_t)((thiscol * 3 + nextcol + 7) >> 4);
+                    lastcol = thiscol; thiscol = nextcol;
+                }
+                line[2 * (dw - 1)] = (uint8_t)((thiscol * 3 + lastcol + 8) >> 4);
+                line[2 * (dw - 1) + 1] = (uint8_t)((thiscol * 4 + 7) >> 4);
+            } else {
+                for (int x = 0; x < dw; x++) line[2 * x] = line[2 * x + 1] = in0[x];
+            }
+        }
+        memcpy(&out[(size_t)y * W], line.data(), W);
+    }
+}
+
+}  // namespace
+
+// JPEG bytes -> uint8 BGR HWC.  Returns 0 and the size in *w, *h (pixels are written when bgr != NULL and cap suffices),
+// -1 = not a JPEG / truncated / corrupt header, -2 = a JPEG this decoder does not handle (see the top of this file).
+extern "C" int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* h, uint8_t* bgr, long long cap) {
+    if (!data || size < 4 || data[0] != 0xFF || data[1] != 0xD8) return -1;
+    uint16_t quant[4][64];
+    bool quant_set[4] = {false, false, false, false};
+    HuffTab dc[4], ac[4];
+    std::vector<Comp> comps;
+    int W = 0, H = 0, restart = 0;
+    const uint8_t* p = data + 2;
+    const uint8_t* end = data + size;
+    bool have_sof = false;
+    while (true) {
+        while (p < end && *p != 0xFF) p++;
+        while (p < end && *p == 0xFF) p++;
+        if (p >= end) return -1;
+        const int m = *p++;
+        if (m == 0xD9) return -1;   // EOI before any scan
+        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (p + 2 > end) return -1;
+        const int len = rd16(p);
+        if (len < 2 || p + len > end) return -1;
+        const uint8_t* s = p + 2;
+        const uint8_t* se = p + len;
+        if (m == 0xDB) {                                   // DQT
+            while (s < se) {
+                const int pq = *s >> 4, tq = *s & 15;
+                s++;
+                if (tq > 3 || s + (pq ? 128 : 64) > se) return -1;
+                for (int i = 0; i < 64; i++) { quant[tq][kZigzagNat[i]] = pq ? rd16(s + 2 * i) : s[i]; }
+                s += pq ? 128 : 64;
+                quant_set[tq] = true;
+            }
+        } else if (m == 0xC4) {                            // DHT
+            while (s < se) {
+                const int tc = *s >> 4, th = *s & 15;
+                s++;
+                if (tc > 1 || th > 3 || s + 16 > se) return -1;
+                HuffTab& t = tc ? ac[th] : dc[th];
+                int n = 0;
+                for (int l = 1; l <= 16; l++) { t.bits[l] = s[l - 1]; n += s[l - 1]; }
+                s += 16;
+                if (n > 256 || s + n > se) return -1;
+                memcpy(t.vals, s, n);
+                s += n;
+                t.build();
+            }
+        } else if (m == 0xC0 || m == 0xC1) {               // SOF0 / SOF1: Huffman sequential
+            if (len < 8 || s[0] != 8) return -2;
+            H = rd16(s + 1); W = rd16(s + 3);
+            const int nc = s[5];
+            if (W <= 0 || H <= 0) return -1;
+            if ((nc != 1 && nc != 3) || len < 8 + 3 * nc) return -2;
+            comps.resize(nc);
+            for (int i = 0; i < nc; i++) {
+                comps[i].id = s[6 + 3 * i]; comps[i].h = s[7 + 3 * i] >> 4; comps[i].v = s[7 + 3 * i] & 15; comps[i].tq = s[8 + 3 * i];
+                if (comps[i].tq > 3) return -1;
+            }
+            have_sof = true;
+        } else if ((m >= 0xC2 && m <= 0xCF) && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return -2;                                     // progressive, lossless, arithmetic, hierarchical
+        } else if (m == 0xDD) {                            // DRI
+            if (len < 4) return -1;
+            restart = rd16(s);
+        } else if (m == 0xDA) {                            // SOS
+            if (!have_sof) return -1;
+            const int ns = s[0];
+            if (ns != (int)comps.size() || len < 6 + 2 * ns) return -2;   // non-interleaved colour scans are not handled
+            for (int i = 0; i < ns; i++) {
+                const int cid = s[1 + 2 * i];
+                Comp* c = nullptr;
+                for (auto& cc : comps) if (cc.id == cid) c = &cc;
+                if (!c) return -1;
+                c->td = s[2 + 2 * i] >> 4; c->ta = s[2 + 2 * i] & 15;
+                if (c->td > 3 || c->ta > 3 || !dc[c->td].set || !ac[c->ta].set || !quant_set[c->tq]) return -1;
+            }
+            p += len;
+            break;
+        }
+        p += len;
+    }
+    if (w) *w = W;
+    if (h) *h = H;
+    if (!bgr) return 0;
+    if (cap < (long long)W * H * 3) return -1;
+    const int nc = (int)comps.size();
+    int hmax = 1, vmax = 1;
+    if (nc == 1) { comps[0].h = comps[0].v = 1; }
+    for (auto& c : comps) { hmax = c.h > hmax ? c.h : hmax; vmax = c.v > vmax ? c.v : vmax; }
+    if (nc == 3) {
+        const Comp& y = comps[0];
+        if (comps[1].h != 1 || comps[1].v != 1 || comps[2].h != 1 || comps[2].v != 1) return -2;
+        if (!((y.h == 1 && y.v == 1) || (y.h == 2 && y.v == 1) || (y.h == 2 && y.v == 2))) return -2;
+    }
+    const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+    for (auto& c : comps) {
+        c.pw = mcux * c.h * 8; c.ph = mcuy * c.v * 8;
+        c.dw = (W * c.h + hmax - 1) / hmax; c.dh = (H * c.v + vmax - 1) / vmax;   // real (downsampled) samples
+        c.plane.assign((size_t)c.pw * c.ph, 0);
+        c.pred = 0;
+    }
+    BitReader br;
+    br.p = p; br.end = end;
+    short coef[64];
+    int until_restart = restart;
+    for (int my = 0; my < mcuy; my++)
+        for (int mx = 0; mx < mcux; mx++) {
+            if (restart && until_restart == 0) {   // RSTn: byte-align, skip the marker, reset predictions
+                const uint8_t* q = br.p;
+                // the reader may have consumed stuffed bytes ahead; resynchronise on the next RST marker in the stream
+                while (q + 1 < end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
+                if (q + 1 >= end) return -1;
+                br.p = q + 2;
+                br.reset();
+                for (auto& c : comps) c.pred = 0;
+                until_restart = restart;
+            }
+            for (auto& c : comps)
+                for (int by = 0; by < c.v; by++)
+                    for (int bx = 0; bx < c.h; bx++) {
+                        memset(coef, 0, sizeof coef);
+                        int s = huff_decode(br, dc[c.td]);
+                        if (s > 15) return -1;
+                        int diff = s ? extend(br.get(s), s) : 0;
+                        c.pred += diff;
+                        coef[0] = (short)c.pred;
+                        for (int k = 1; k < 64;) {
+                            const int rs = huff_decode(br, ac[c.ta]);
+                            const int r = rs >> 4;
+                            s = rs & 15;
+                            if (s == 0) { if (r != 15) break; k += 16; continue; }
+                            k += r;
+                            if (k > 63) break;
+                            coef[kZigzagNat[k]] = (short)extend(br.get(s), s);
+                            k++;
+                        }
+                        uint8_t* out = c.plane.data() + (size_t)((my * c.v + by) * 8) * c.pw + (size_t)(mx * c.h + bx) * 8;
+                        idct_islow(coef, quant[c.tq], out, c.pw);
+                    }
+            if (restart) until_restart--;
+        }
+    if (nc == 1) {
+        const Comp& c = comps[0];
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                const uint8_t g = c.plane[(size_t)y * c.pw + x];
+                uint8_t* o = bgr + ((size_t)y * W + x) * 3;
+                o[0] = o[1] = o[2] = g;
+            }
+        return 0;
+    }
+    std::vector<uint8_t> cb, cr;
+    upsample(comps[1], hmax, vmax, W, H, cb);
+    upsample(comps[2], hmax, vmax, W, H, cr);
+    // jdcolor.c build_ycc_rgb_table: SCALEBITS 16, FIX(x) = (int)(x * 65536 + 0.5)
+    static int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
+    static bool tabs = false;
+    if (!tabs) {
+        for (int i = 0; i < 256; i++) {
+            const int x = i - 128;
+            cr_r[i] = (91881 * x + 32768) >> 16;      // FIX(1.40200)
+            cb_b[i] = (116130 * x + 32768) >> 16;     // FIX(1.77200)
+            cr_g[i] = -46802 * x;                     // FIX(0.71414)
+            cb_g[i] = -22554 * x + 32768;             // FIX(0.34414), includes ONE_HALF
+        }
+        tabs = true;
+    }
+    auto clamp = [](int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
+    const Comp& yc = comps[0];
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int Y = yc.plane[(size_t)y * yc.pw + x], b = cb[(size_t)y * W + x], r = cr[(size_t)y * W + x];
+            uint8_t* o = bgr + ((size_t)y * W + x) * 3;
+            o[2] = clamp(Y + cr_r[r]);
+            o[1] = clamp(Y + ((cb_g[b] + cr_g[r]) >> 16));
+            o[0] = clamp(Y + cb_b[b]);
+        }
+    return 0;
+}

@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
-    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg",
+    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg", "pe_decode_jpeg",
 ]
 
 
@@ -120,6 +120,7 @@ def lib():
     L.pe_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pe_encode_jpeg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
     L.pe_encode_jpeg.restype = C.c_longlong
+    L.pe_decode_jpeg.argtypes = [C.c_char_p, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_longlong]
     _lib = L
     return L
 
@@ -506,3 +507,16 @@ def encode_jpeg(bgr, quality=98):
     buf = np.zeros(n, np.uint8)
     lib().pe_encode_jpeg(bgr.ctypes.data, w, h, quality, buf.ctypes.data, n)
     return buf.tobytes()
+
+
+def decode_jpeg(data):
+    """uint8 BGR HWC pixels of a baseline JPEG, bit-identical to cv::imread / libjpeg defaults (what --image_dir feeds)."""
+    w, h = C.c_int(), C.c_int()
+    rc = lib().pe_decode_jpeg(data, len(data), C.byref(w), C.byref(h), None, 0)
+    if rc != 0:
+        raise PoseEngineError("pe_decode_jpeg: %s" % ("not a JPEG / truncated" if rc == -1 else "unsupported JPEG variant (progressive, 12-bit, CMYK, sampling)"))
+    out = np.zeros((h.value, w.value, 3), np.uint8)
+    rc = lib().pe_decode_jpeg(data, len(data), C.byref(w), C.byref(h), out.ctypes.data, out.size)
+    if rc != 0:
+        raise PoseEngineError("pe_decode_jpeg failed (%d)" % rc)
+    return out

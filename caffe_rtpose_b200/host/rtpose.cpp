@@ -45,6 +45,7 @@ static void define_flags() {
     define("fullscreen", "false", "Run in fullscreen mode (press f during runtime to toggle)", true);
     define("part_to_show", "0", "Part to show from the start.");
     define("write_frames", "", "Write frames with format prefix%06d.jpg");
+    define("probe_image", "", "[extension] decode this image file, print WxH and an FNV-1a hash of the BGR pixels, exit (no GPU)");
     define("frame_format", "jpg", "[extension] jpg (quality 98, as the reference) or bmp (lossless) for --write_frames");
     define("no_frame_drops", "false", "Dont drop frames.", true);
     define("write_json", "", "Write joint data with json format as prefix%06d.json");
@@ -170,6 +171,35 @@ static bool read_bmp(const std::string& path, int& w, int& h, std::vector<uint8_
     return true;
 }
 
+static bool read_jpg(const std::string& path, int& w, int& h, std::vector<uint8_t>& bgr) {   // cv::imread of a .jpg (pe_decode_jpeg)
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> data((size_t)std::max(n, 0L));
+    const bool rd = n > 0 && fread(data.data(), 1, (size_t)n, f) == (size_t)n;
+    fclose(f);
+    if (!rd) return false;
+    int rc = pe_decode_jpeg(data.data(), n, &w, &h, nullptr, 0);
+    if (rc == 0) { bgr.resize((size_t)w * h * 3); rc = pe_decode_jpeg(data.data(), n, &w, &h, bgr.data(), (long long)bgr.size()); }
+    if (rc == -2) LOG_ERROR("%s: JPEG variant not handled (progressive / 12-bit / CMYK / unusual chroma sampling)", path.c_str());
+    return rc == 0;
+}
+
+static std::string lower_ext(const std::string& p) {
+    const size_t dot = p.find_last_of('.');
+    std::string e = dot == std::string::npos ? "" : p.substr(dot);
+    for (auto& c : e) c = (char)tolower((unsigned char)c);
+    return e;
+}
+static bool read_image(const std::string& p, int& w, int& h, std::vector<uint8_t>& bgr) {
+    const std::string e = lower_ext(p);
+    if (e == ".ppm") return read_ppm(p, w, h, bgr);
+    if (e == ".jpg" || e == ".jpeg") return read_jpg(p, w, h, bgr);
+    return read_bmp(p, w, h, bgr);
+}
+
 static bool write_bmp(const std::string& path, int w, int h, const uint8_t* bgr) {   // 24-bit, bottom-up
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) return false;
@@ -267,8 +297,8 @@ static void producer() {
             synthetic_frame(i, w, h, fr.bgr);
         } else {
             const std::string& p = global.image_list[i];
-            const bool ok = p.size() > 4 && p.substr(p.size() - 4) == ".ppm" ? read_ppm(p, w, h, fr.bgr) : read_bmp(p, w, h, fr.bgr);
-            if (!ok) { LOG_ERROR("cannot decode %s (only 24-bit .bmp and P6 .ppm are supported without an image codec)", p.c_str()); continue; }
+            const bool ok = read_image(p, w, h, fr.bgr);
+            if (!ok) { LOG_ERROR("cannot decode %s (supported: baseline .jpg, 24-bit .bmp, P6 .ppm)", p.c_str()); continue; }
             const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
             fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
         }
@@ -460,6 +490,15 @@ static bool ensure_dir(const std::string& d) {
 int main(int argc, char** argv) {
     define_flags();
     if (parse_flags(argc, argv)) return 1;
+    if (!F("probe_image").empty()) {
+        int w = 0, h = 0;
+        std::vector<uint8_t> px;
+        if (!read_image(F("probe_image"), w, h, px)) { LOG_ERROR("cannot decode %s", F("probe_image").c_str()); return 1; }
+        uint64_t hash = 1469598103934665603ull;
+        for (uint8_t b : px) { hash ^= b; hash *= 1099511628211ull; }
+        printf("%dx%d %016llx\n", w, h, (unsigned long long)hash);
+        return 0;
+    }
     if (!F("video").empty() || (F("image_dir").empty() && Fi("synthetic") <= 0)) {
         LOG_ERROR("camera/video capture needs a video codec that this build does not have; use --image_dir (.bmp/.ppm) or --synthetic N");
         return 1;
@@ -474,15 +513,16 @@ int main(int argc, char** argv) {
             const std::string n = ent->d_name;
             const size_t dot = n.find_last_of('.');
             const std::string ext = dot == std::string::npos ? "" : n.substr(dot);
-            if (ext == ".bmp" || ext == ".ppm") global.image_list.push_back(F("image_dir") + "/" + n);
-            else if (ext == ".jpg" || ext == ".png") LOG_ERROR("skipping %s: no JPEG/PNG codec in this build", n.c_str());
+            const std::string le = lower_ext(n);
+            if (le == ".bmp" || le == ".ppm" || le == ".jpg" || le == ".jpeg") global.image_list.push_back(F("image_dir") + "/" + n);
+            else if (le == ".png") LOG_ERROR("skipping %s: no PNG decoder in this build", n.c_str());
         }
         closedir(d);
         std::sort(global.image_list.begin(), global.image_list.end());
         if (global.disp_w == -1 && !global.image_list.empty()) {   // --resolution -1x-1: take it from the first image (:1683-1686)
             std::vector<uint8_t> tmp;
             const std::string& p = global.image_list[0];
-            if (!(p.substr(p.size() - 4) == ".ppm" ? read_ppm(p, global.disp_w, global.disp_h, tmp) : read_bmp(p, global.disp_w, global.disp_h, tmp))) return 1;
+            if (!read_image(p, global.disp_w, global.disp_h, tmp)) return 1;
             LOG_INFO("Setting display resolution from first image: %dx%d", global.disp_w, global.disp_h);
         }
     }

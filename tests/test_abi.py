@@ -191,3 +191,40 @@ def test_jpeg_encoder_decodes_like_libjpeg_at_same_quality():
     assert psnr(dec, chk) > 30
     with pytest.raises(engine.PoseEngineError):
         engine.encode_jpeg(np.zeros((0, 4, 3), np.uint8))
+
+
+def _jpeg_variants(cv2, q):
+    v = [("420", [cv2.IMWRITE_JPEG_QUALITY, q]), ("optimised-huffman", [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_OPTIMIZE, 1]),
+         ("restart-3", [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, 3])]
+    if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+        v += [("444", [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]),
+              ("422", [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422])]
+    return v
+
+
+def test_jpeg_decoder_equals_cv_imread_bit_for_bit():
+    """pe_decode_jpeg feeds --image_dir where the reference calls cv::imread (rtpose.cpp:302-391): same pixels as OpenCV's
+    libjpeg for baseline files - sizes that are not multiples of the MCU, 4:2:0 / 4:2:2 / 4:4:4, grey, optimised Huffman
+    tables, restart intervals, and the stream of our own encoder."""
+    import cv2
+    from caffe_rtpose_b200 import synth
+
+    for h, w in [(192, 320), (100, 75), (17, 33), (8, 8), (1, 1), (16, 16), (31, 47), (3, 5), (2, 4), (5, 3)]:
+        noise = synth.make_frame(3, h, w)
+        for img in (noise, cv2.GaussianBlur(noise, (0, 0), 2) if min(h, w) > 8 else noise):
+            for q in (98, 75, 20):
+                for name, params in _jpeg_variants(cv2, q):
+                    ok, enc = cv2.imencode(".jpg", img, params)
+                    assert ok
+                    assert np.array_equal(engine.decode_jpeg(enc.tobytes()), cv2.imdecode(enc, cv2.IMREAD_COLOR)), (h, w, q, name)
+        ok, enc = cv2.imencode(".jpg", noise[:, :, 0], [cv2.IMWRITE_JPEG_QUALITY, 90])
+        assert np.array_equal(engine.decode_jpeg(enc.tobytes()), cv2.imdecode(enc, cv2.IMREAD_COLOR))
+        own = engine.encode_jpeg(noise, 98)
+        assert np.array_equal(engine.decode_jpeg(own), cv2.imdecode(np.frombuffer(own, np.uint8), cv2.IMREAD_COLOR))
+    ok, enc = cv2.imencode(".jpg", synth.make_frame(1, 64, 64), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(engine.PoseEngineError, match="unsupported"):
+        engine.decode_jpeg(enc.tobytes())
+    with pytest.raises(engine.PoseEngineError, match="not a JPEG"):
+        engine.decode_jpeg(b"BM" + bytes(100))
+    with pytest.raises(engine.PoseEngineError):
+        engine.decode_jpeg(enc.tobytes()[:40])

@@ -59,6 +59,34 @@ def read_bmp(path):
     return np.stack(rows)
 
 
+def fnv1a(px):
+    h = 1469598103934665603
+    for b in px.tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def test_image_readers_without_gpu(tmp_path):
+    """--image_dir file formats through rtpose.bin's own readers (--probe_image: decode, print size + pixel hash, exit):
+    .jpg equals cv::imread (cv2), .bmp / .ppm round-trip."""
+    import cv2
+    img = synth.make_frame(9, 45, 70)
+    ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
+    (tmp_path / "a.JPG").write_bytes(enc.tobytes())
+    want = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+    r = run(["--probe_image", str(tmp_path / "a.JPG")])
+    assert r.returncode == 0 and r.stdout.split() == ["70x45", "%016x" % fnv1a(want)], (r.stdout, r.stderr)
+    write_bmp(str(tmp_path / "b.bmp"), img)
+    write_ppm(str(tmp_path / "c.ppm"), img)
+    for f in ("b.bmp", "c.ppm"):
+        r = run(["--probe_image", str(tmp_path / f)])
+        assert r.returncode == 0 and r.stdout.split() == ["70x45", "%016x" % fnv1a(img)], f
+    ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    (tmp_path / "p.jpg").write_bytes(enc.tobytes())
+    r = run(["--probe_image", str(tmp_path / "p.jpg")])
+    assert r.returncode == 1 and "not handled" in r.stderr
+
+
 def write_ppm(path, bgr):
     h, w, _ = bgr.shape
     with open(path, "wb") as f:
