@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
-    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg", "pe_decode_jpeg",
+    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg", "pe_decode_jpeg", "pe_decode_png",
 ]
 
 
@@ -121,6 +121,7 @@ def lib():
     L.pe_encode_jpeg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
     L.pe_encode_jpeg.restype = C.c_longlong
     L.pe_decode_jpeg.argtypes = [C.c_char_p, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_longlong]
+    L.pe_decode_png.argtypes = L.pe_decode_jpeg.argtypes
     _lib = L
     return L
 
@@ -519,4 +520,15 @@ def decode_jpeg(data):
     rc = lib().pe_decode_jpeg(data, len(data), C.byref(w), C.byref(h), out.ctypes.data, out.size)
     if rc != 0:
         raise PoseEngineError("pe_decode_jpeg failed (%d)" % rc)
+    return out
+
+
+def decode_png(data):
+    """uint8 BGR HWC pixels of a PNG as cv::imread(IMREAD_COLOR) returns them."""
+    w, h = C.c_int(), C.c_int()
+    if lib().pe_decode_png(data, len(data), C.byref(w), C.byref(h), None, 0) != 0:
+        raise PoseEngineError("pe_decode_png: not a PNG / corrupt")
+    out = np.zeros((h.value, w.value, 3), np.uint8)
+    if lib().pe_decode_png(data, len(data), C.byref(w), C.byref(h), out.ctypes.data, out.size) != 0:
+        raise PoseEngineError("pe_decode_png: corrupt image data")
     return out

@@ -171,9 +171,25 @@ static bool read_bmp(const std::string& path, int& w, int& h, std::vector<uint8_
     return true;
 }
 
-static bool read_jpg(const std::string& path, int& w, int& h, std::vector<uint8_t>& bgr) {   // cv::imread of a .jpg (pe_decode_jpeg)
+static std::string lower_ext(const std::string& p) {
+    const size_t dot = p.find_last_of('.');
+    std::string e = dot == std::string::npos ? "" : p.substr(dot);
+    for (auto& c : e) c = (char)tolower((unsigned char)c);
+    return e;
+}
+
+// cv::imread (rtpose.cpp:302-391): the decoder is chosen by the file's signature, not its name
+static bool read_image(const std::string& path, int& w, int& h, std::vector<uint8_t>& bgr) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) return false;
+    uint8_t magic[8] = {0};
+    const size_t got = fread(magic, 1, 8, f);
+    const bool jpg = got >= 2 && magic[0] == 0xFF && magic[1] == 0xD8;
+    const bool png = got >= 8 && magic[0] == 0x89 && magic[1] == 'P' && magic[2] == 'N' && magic[3] == 'G';
+    if (!jpg && !png) {
+        fclose(f);
+        return got >= 2 && magic[0] == 'P' && magic[1] == '6' ? read_ppm(path, w, h, bgr) : read_bmp(path, w, h, bgr);
+    }
     fseek(f, 0, SEEK_END);
     const long n = ftell(f);
     fseek(f, 0, SEEK_SET);
@@ -181,23 +197,11 @@ static bool read_jpg(const std::string& path, int& w, int& h, std::vector<uint8_
     const bool rd = n > 0 && fread(data.data(), 1, (size_t)n, f) == (size_t)n;
     fclose(f);
     if (!rd) return false;
-    int rc = pe_decode_jpeg(data.data(), n, &w, &h, nullptr, 0);
-    if (rc == 0) { bgr.resize((size_t)w * h * 3); rc = pe_decode_jpeg(data.data(), n, &w, &h, bgr.data(), (long long)bgr.size()); }
+    auto dec = jpg ? pe_decode_jpeg : pe_decode_png;
+    int rc = dec(data.data(), n, &w, &h, nullptr, 0);
+    if (rc == 0) { bgr.resize((size_t)w * h * 3); rc = dec(data.data(), n, &w, &h, bgr.data(), (long long)bgr.size()); }
     if (rc == -2) LOG_ERROR("%s: JPEG variant not handled (progressive / 12-bit / CMYK / unusual chroma sampling)", path.c_str());
     return rc == 0;
-}
-
-static std::string lower_ext(const std::string& p) {
-    const size_t dot = p.find_last_of('.');
-    std::string e = dot == std::string::npos ? "" : p.substr(dot);
-    for (auto& c : e) c = (char)tolower((unsigned char)c);
-    return e;
-}
-static bool read_image(const std::string& p, int& w, int& h, std::vector<uint8_t>& bgr) {
-    const std::string e = lower_ext(p);
-    if (e == ".ppm") return read_ppm(p, w, h, bgr);
-    if (e == ".jpg" || e == ".jpeg") return read_jpg(p, w, h, bgr);
-    return read_bmp(p, w, h, bgr);
 }
 
 static bool write_bmp(const std::string& path, int w, int h, const uint8_t* bgr) {   // 24-bit, bottom-up
@@ -298,7 +302,7 @@ static void producer() {
         } else {
             const std::string& p = global.image_list[i];
             const bool ok = read_image(p, w, h, fr.bgr);
-            if (!ok) { LOG_ERROR("cannot decode %s (supported: baseline .jpg, 24-bit .bmp, P6 .ppm)", p.c_str()); continue; }
+            if (!ok) { LOG_ERROR("cannot decode %s (supported: baseline .jpg, .png, 24-bit .bmp, P6 .ppm)", p.c_str()); continue; }
             const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
             fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
         }
@@ -514,8 +518,8 @@ int main(int argc, char** argv) {
             const size_t dot = n.find_last_of('.');
             const std::string ext = dot == std::string::npos ? "" : n.substr(dot);
             const std::string le = lower_ext(n);
-            if (le == ".bmp" || le == ".ppm" || le == ".jpg" || le == ".jpeg") global.image_list.push_back(F("image_dir") + "/" + n);
-            else if (le == ".png") LOG_ERROR("skipping %s: no PNG decoder in this build", n.c_str());
+            // the reference lists .jpg / .png / .bmp (rtpose.cpp:1743); .jpeg, .ppm and upper-case names are accepted as well
+            if (le == ".jpg" || le == ".png" || le == ".bmp" || le == ".jpeg" || le == ".ppm") global.image_list.push_back(F("image_dir") + "/" + n);
         }
         closedir(d);
         std::sort(global.image_list.begin(), global.image_list.end());

@@ -159,6 +159,10 @@ long long pe_encode_jpeg(const uint8_t* bgr, int w, int h, int quality, uint8_t*
  * cap >= w*h*3.  -1: not a JPEG / truncated; -2: progressive, arithmetic-coded, 12-bit, CMYK or unusual chroma sampling. */
 int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* h, uint8_t* bgr, long long cap);
 
+/* same for .png (the third format the reference lists, rtpose.cpp:1743): inflate + PNG filters / Adam7 / all colour types and
+ * bit depths, converted as cv::imread(IMREAD_COLOR) does (8-bit BGR, alpha dropped, 16-bit -> high byte). */
+int pe_decode_png(const uint8_t* data, long long size, int* w, int* h, uint8_t* bgr, long long cap);
+
 /* ---- model descriptor tables (modelDescriptorFactory.cpp:6-28,30-55) */
 int pe_model_num_parts(int model);
 int pe_model_num_limbs(int model);

@@ -228,3 +228,124 @@ def test_jpeg_decoder_equals_cv_imread_bit_for_bit():
         engine.decode_jpeg(b"BM" + bytes(100))
     with pytest.raises(engine.PoseEngineError):
         engine.decode_jpeg(enc.tobytes()[:40])
+
+
+def _png_chunk(tag, body):
+    import struct
+    import zlib
+    return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body) & 0xFFFFFFFF)
+
+
+def _png_filter_row(kind, cur, prev, bpp):
+    cur = np.frombuffer(cur, np.uint8).astype(np.int32)
+    prev = np.frombuffer(prev, np.uint8).astype(np.int32)
+    left = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+    upleft = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+    if kind == 0:
+        pred = 0
+    elif kind == 1:
+        pred = left
+    elif kind == 2:
+        pred = prev
+    elif kind == 3:
+        pred = (left + prev) // 2
+    else:
+        p = left + prev - upleft
+        pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - upleft)
+        pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, upleft))
+    return bytes([kind]) + ((cur - pred) & 255).astype(np.uint8).tobytes()
+
+
+def _make_png(samples, depth, ctype, palette=None, interlace=False, idat_split=1, trns=None, level=6):
+    """samples: (H, W, channels) integer array of raw sample values at `depth` bits; filters cycle 0..4 over the rows."""
+    import struct
+    import zlib
+    H, W, ch = samples.shape
+
+    def pack_rows(sub):
+        h, w, _ = sub.shape
+        out, prev = b"", None
+        bits = ch * depth
+        bpp = max(bits // 8, 1)
+        for y in range(h):
+            v = sub[y].reshape(-1)
+            if depth == 16:
+                row = v.astype(">u2").tobytes()
+            elif depth == 8:
+                row = v.astype(np.uint8).tobytes()
+            else:
+                per = 8 // depth
+                pad = (-len(v)) % per
+                vv = np.concatenate([v, np.zeros(pad, v.dtype)]).reshape(-1, per)
+                row = bytes(int(sum(int(s) << ((per - 1 - i) * depth) for i, s in enumerate(r))) for r in vv)
+            if prev is None:
+                prev = bytes(len(row))
+            out += _png_filter_row(y % 5, row, prev, bpp)
+            prev = row
+        return out
+
+    if not interlace:
+        raw = pack_rows(samples)
+    else:
+        raw = b""
+        for xs, ys, dx, dy in [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]:
+            sub = samples[ys::dy, xs::dx]
+            if sub.shape[0] and sub.shape[1]:
+                raw += pack_rows(sub)
+    z = zlib.compress(raw, level)
+    n = max(len(z) // idat_split, 1)
+    out = b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, ctype, 0, 0, 1 if interlace else 0))
+    if palette is not None:
+        out += _png_chunk(b"PLTE", np.asarray(palette, np.uint8).tobytes())
+    if trns is not None:
+        out += _png_chunk(b"tRNS", bytes(trns))
+    for i in range(0, len(z), n):
+        out += _png_chunk(b"IDAT", z[i:i + n])
+    return out + _png_chunk(b"IEND", b"")
+
+
+def test_png_decoder_equals_cv_imread():
+    """pe_decode_png feeds --image_dir where the reference calls cv::imread on .png files (rtpose.cpp:1743, :302-391): the
+    same 8-bit BGR pixels as OpenCV's libpng path, for the files cv2 can write (8/16-bit BGR, BGRA, grey, bilevel, every zlib
+    strategy/level) and for hand-built palette, low-bit-depth, grey+alpha, Adam7-interlaced, all-filter, split-IDAT files."""
+    import cv2
+    from caffe_rtpose_b200 import synth
+
+    def same(data, what):
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        assert ref is not None, what
+        assert np.array_equal(engine.decode_png(data), ref), what
+
+    for h, w in [(72, 128), (17, 33), (1, 1), (5, 3), (9, 8)]:
+        img = synth.make_frame(3, h, w)
+        img = cv2.GaussianBlur(img, (0, 0), 2) if min(h, w) > 8 else img
+        for lvl in (0, 1, 9):
+            same(cv2.imencode(".png", img, [cv2.IMWRITE_PNG_COMPRESSION, lvl])[1].tobytes(), ("bgr8", h, w, lvl))
+        for strat in (cv2.IMWRITE_PNG_STRATEGY_FILTERED, cv2.IMWRITE_PNG_STRATEGY_HUFFMAN_ONLY, cv2.IMWRITE_PNG_STRATEGY_RLE, cv2.IMWRITE_PNG_STRATEGY_FIXED):
+            same(cv2.imencode(".png", img, [cv2.IMWRITE_PNG_STRATEGY, strat])[1].tobytes(), ("strategy", strat))
+        same(cv2.imencode(".png", img[:, :, 0])[1].tobytes(), "grey8")
+        same(cv2.imencode(".png", np.dstack([img, img[:, :, 0]]))[1].tobytes(), "bgra8")
+        im16 = img.astype(np.uint16) * 257 + (img[:, :, ::-1].astype(np.uint16) % 200)
+        same(cv2.imencode(".png", im16)[1].tobytes(), "bgr16")
+        same(cv2.imencode(".png", im16[:, :, 0])[1].tobytes(), "grey16")
+        same(cv2.imencode(".png", (img[:, :, 0] > 128).astype(np.uint8) * 255, [cv2.IMWRITE_PNG_BILEVEL, 1])[1].tobytes(), "bilevel")
+    rng = np.random.default_rng(5)
+    for h, w in [(13, 21), (8, 8), (1, 7), (20, 3)]:
+        for interlace in (False, True):
+            for depth in (1, 2, 4, 8):
+                pal = rng.integers(0, 256, (1 << depth, 3))
+                idx = rng.integers(0, 1 << depth, (h, w, 1))
+                same(_make_png(idx, depth, 3, palette=pal, interlace=interlace), ("palette", depth, interlace, h, w))
+                same(_make_png(idx, depth, 3, palette=pal, interlace=interlace, trns=[0, 128]), ("palette+tRNS", depth))
+                same(_make_png(idx, depth, 0, interlace=interlace), ("grey", depth, interlace))
+            for depth in (8, 16):
+                top = 1 << depth
+                same(_make_png(rng.integers(0, top, (h, w, 3)), depth, 2, interlace=interlace, idat_split=3), ("rgb", depth, interlace))
+                same(_make_png(rng.integers(0, top, (h, w, 4)), depth, 6, interlace=interlace), ("rgba", depth, interlace))
+                same(_make_png(rng.integers(0, top, (h, w, 2)), depth, 4, interlace=interlace, level=0), ("grey+alpha", depth, interlace))
+                same(_make_png(rng.integers(0, top, (h, w, 1)), depth, 0, interlace=interlace), ("grey", depth, interlace))
+    with pytest.raises(engine.PoseEngineError):
+        engine.decode_png(b"\x89PNG\r\n\x1a\n" + bytes(40))
+    good = cv2.imencode(".png", synth.make_frame(1, 16, 16))[1].tobytes()
+    with pytest.raises(engine.PoseEngineError):
+        engine.decode_png(good[:len(good) // 2])

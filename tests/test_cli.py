@@ -68,7 +68,7 @@ def fnv1a(px):
 
 def test_image_readers_without_gpu(tmp_path):
     """--image_dir file formats through rtpose.bin's own readers (--probe_image: decode, print size + pixel hash, exit):
-    .jpg equals cv::imread (cv2), .bmp / .ppm round-trip."""
+    .jpg equals cv::imread (cv2), .png / .bmp / .ppm round-trip."""
     import cv2
     img = synth.make_frame(9, 45, 70)
     ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
@@ -76,6 +76,9 @@ def test_image_readers_without_gpu(tmp_path):
     want = cv2.imdecode(enc, cv2.IMREAD_COLOR)
     r = run(["--probe_image", str(tmp_path / "a.JPG")])
     assert r.returncode == 0 and r.stdout.split() == ["70x45", "%016x" % fnv1a(want)], (r.stdout, r.stderr)
+    (tmp_path / "d.png").write_bytes(cv2.imencode(".png", img)[1].tobytes())
+    r = run(["--probe_image", str(tmp_path / "d.png")])
+    assert r.returncode == 0 and r.stdout.split() == ["70x45", "%016x" % fnv1a(img)], (r.stdout, r.stderr)
     write_bmp(str(tmp_path / "b.bmp"), img)
     write_ppm(str(tmp_path / "c.ppm"), img)
     for f in ("b.bmp", "c.ppm"):
