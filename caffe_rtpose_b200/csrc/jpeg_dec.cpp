@@ -2,14 +2,15 @@
 // (examples/rtpose/rtpose.cpp:302-391, getFrameFromDir), i.e. libjpeg with its defaults.  No libjpeg / OpenCV for C++ in
 // this image, so the decoder is written out here and follows libjpeg's DEFAULT decompression arithmetic exactly, so that
 // a frame decoded here equals cv::imread's bytes (tests/test_abi.py compares with cv2):
-//   * Huffman sequential DCT, 8-bit (SOF0 / SOF1), restart intervals, 8- and 16-bit quantisation tables;
+//   * Huffman sequential (SOF0 / SOF1) and progressive (SOF2: spectral selection + successive approximation) DCT, 8-bit,
+//     interleaved and non-interleaved scans, restart intervals, 8- and 16-bit quantisation tables;
 //   * the "islow" integer inverse DCT (13-bit constants, 2 extra bits after pass 1, Loeffler-Ligtenberg-Moschytz);
 //   * "fancy" triangle-filter chroma upsampling for 2x1 and 2x2 subsampling (3/4-1/4 weights, libjpeg's rounding biases),
 //     plain replication when the chroma plane is at most 2 samples wide;
 //   * YCbCr -> RGB with libjpeg's 16-bit fixed-point tables.
-// Not handled (reported as PE_ERR_INVALID by the caller): progressive / arithmetic / lossless / 12-bit files, CMYK,
-// chroma sampling other than 4:4:4 / 4:2:2 / 4:2:0, non-interleaved colour scans.  EXIF orientation is ignored (as in
-// the OpenCV 2.4 / 3.0 the reference was written for).  Host code, no GPU.
+// Not handled (return code -2): arithmetic-coded / lossless / hierarchical / 12-bit files, CMYK, chroma sampling other
+// than 4:4:4 / 4:2:2 / 4:2:0.  EXIF orientation is ignored (as in the OpenCV 2.4 / 3.0 the reference was written for).
+// Host code, no GPU.
 #include <stdint.h>
 #include <string.h>
 
@@ -143,7 +144,18 @@ void idct_islow(const short* coef, const uint16_t* quant, uint8_t* out, int out_
     }
 }
 
-struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pw = 0, ph = 0, dw = 0, dh = 0; std::vector<uint8_t> plane; int pred = 0; };
+struct Comp {
+    int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
+    int pw = 0, ph = 0;     // plane size in samples, padded to whole MCUs
+    int dw = 0, dh = 0;     // real (downsampled) samples
+    int bw = 0, bh = 0;     // blocks per row / column of the padded plane
+    int nbw = 0, nbh = 0;   // blocks that cover the real samples (extent of a non-interleaved scan)
+    std::vector<uint8_t> plane;
+    std::vector<short> coef;   // [bh][bw][64], natural order
+    uint16_t q[64];
+    bool q_latched = false;
+    int pred = 0;
+};
 
 inline uint16_t rd16(const uint8_t* p) { return (uint16_t)((p[0] << 8) | p[1]); }
 
@@ -203,30 +215,118 @@ void upsample(const Comp& c, int hmax, int vmax, int W, int H, std::vector<uint8
     }
 }
 
+
+// One block of a scan (T.81 F.2.2 sequential, G.1.2 progressive; decode_mcu_* of libjpeg's jdhuff.c / jdphuff.c)
+struct ScanParams { int Ss, Se, Ah, Al; bool progressive; };
+inline bool decode_block(BitReader& br, Comp& c, const HuffTab* dc, const HuffTab* ac, short* blk, const ScanParams& sp, int& eobrun) {
+    if (!sp.progressive) {
+        int s = huff_decode(br, dc[c.td]);
+        if (s > 15) return false;
+        c.pred += s ? extend(br.get(s), s) : 0;
+        blk[0] = (short)c.pred;
+        for (int k = 1; k < 64;) {
+            const int rs = huff_decode(br, ac[c.ta]);
+            const int r = rs >> 4;
+            s = rs & 15;
+            if (s == 0) { if (r != 15) break; k += 16; continue; }
+            k += r;
+            if (k > 63) break;
+            blk[kZigzagNat[k]] = (short)extend(br.get(s), s);
+            k++;
+        }
+        return true;
+    }
+    if (sp.Ss == 0) {
+        if (sp.Ah == 0) {   // DC first
+            const int s = huff_decode(br, dc[c.td]);
+            if (s > 15) return false;
+            c.pred += s ? extend(br.get(s), s) : 0;
+            blk[0] = (short)(c.pred * (1 << sp.Al));
+        } else if (br.get(1)) {   // DC refinement
+            blk[0] = (short)(blk[0] | (1 << sp.Al));
+        }
+        return true;
+    }
+    if (sp.Ah == 0) {       // AC first
+        if (eobrun > 0) { eobrun--; return true; }
+        for (int k = sp.Ss; k <= sp.Se; k++) {
+            const int rs = huff_decode(br, ac[c.ta]);
+            const int r = rs >> 4, s = rs & 15;
+            if (s) {
+                k += r;
+                if (k > 63) return false;
+                blk[kZigzagNat[k]] = (short)(extend(br.get(s), s) * (1 << sp.Al));
+            } else if (r == 15) {
+                k += 15;
+            } else {
+                eobrun = 1 << r;
+                if (r) eobrun += br.get(r);
+                eobrun--;
+                break;
+            }
+        }
+        return true;
+    }
+    // AC refinement
+    const int p1 = 1 << sp.Al, m1 = -(1 << sp.Al);
+    int k = sp.Ss;
+    if (eobrun == 0) {
+        for (; k <= sp.Se; k++) {
+            const int rs = huff_decode(br, ac[c.ta]);
+            int r = rs >> 4, s = rs & 15;
+            if (s) {
+                s = br.get(1) ? p1 : m1;   // a newly non-zero coefficient is always +-1 at this bit
+            } else if (r != 15) {
+                eobrun = 1 << r;
+                if (r) eobrun += br.get(r);
+                break;
+            }
+            do {   // skip r still-zero coefficients, correcting the already non-zero ones on the way
+                short* co = blk + kZigzagNat[k];
+                if (*co != 0) {
+                    if (br.get(1) && (*co & p1) == 0) *co = (short)(*co + (*co >= 0 ? p1 : m1));
+                } else if (--r < 0) {
+                    break;
+                }
+                k++;
+            } while (k <= sp.Se);
+            if (s) { if (k > 63) return false; blk[kZigzagNat[k]] = (short)s; }
+        }
+    }
+    if (eobrun > 0) {
+        for (; k <= sp.Se; k++) {
+            short* co = blk + kZigzagNat[k];
+            if (*co != 0 && br.get(1) && (*co & p1) == 0) *co = (short)(*co + (*co >= 0 ? p1 : m1));
+        }
+        eobrun--;
+    }
+    return true;
+}
+
 }  // namespace
 
 // JPEG bytes -> uint8 BGR HWC.  Returns 0 and the size in *w, *h (pixels are written when bgr != NULL and cap suffices),
-// -1 = not a JPEG / truncated / corrupt header, -2 = a JPEG this decoder does not handle (see the top of this file).
+// -1 = not a JPEG / truncated / corrupt, -2 = a JPEG this decoder does not handle (see the top of this file).
 extern "C" int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* h, uint8_t* bgr, long long cap) {
     if (!data || size < 4 || data[0] != 0xFF || data[1] != 0xD8) return -1;
     uint16_t quant[4][64];
     bool quant_set[4] = {false, false, false, false};
     HuffTab dc[4], ac[4];
     std::vector<Comp> comps;
-    int W = 0, H = 0, restart = 0;
+    int W = 0, H = 0, restart = 0, hmax = 1, vmax = 1, mcux = 0, mcuy = 0;
     const uint8_t* p = data + 2;
     const uint8_t* end = data + size;
-    bool have_sof = false;
-    while (true) {
+    bool have_sof = false, progressive = false, any_scan = false, eoi = false;
+    while (!eoi) {
         while (p < end && *p != 0xFF) p++;
         while (p < end && *p == 0xFF) p++;
-        if (p >= end) return -1;
+        if (p >= end) break;                               // no EOI: libjpeg warns and uses what it has
         const int m = *p++;
-        if (m == 0xD9) return -1;   // EOI before any scan
-        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
-        if (p + 2 > end) return -1;
+        if (m == 0xD9) { eoi = true; break; }
+        if (m == 0x00 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (p + 2 > end) break;
         const int len = rd16(p);
-        if (len < 2 || p + len > end) return -1;
+        if (len < 2 || p + len > end) { if (any_scan) break; return -1; }
         const uint8_t* s = p + 2;
         const uint8_t* se = p + len;
         if (m == 0xDB) {                                   // DQT
@@ -234,7 +334,7 @@ extern "C" int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* 
                 const int pq = *s >> 4, tq = *s & 15;
                 s++;
                 if (tq > 3 || s + (pq ? 128 : 64) > se) return -1;
-                for (int i = 0; i < 64; i++) { quant[tq][kZigzagNat[i]] = pq ? rd16(s + 2 * i) : s[i]; }
+                for (int i = 0; i < 64; i++) quant[tq][kZigzagNat[i]] = pq ? rd16(s + 2 * i) : s[i];
                 s += pq ? 128 : 64;
                 quant_set[tq] = true;
             }
@@ -252,7 +352,8 @@ extern "C" int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* 
                 s += n;
                 t.build();
             }
-        } else if (m == 0xC0 || m == 0xC1) {               // SOF0 / SOF1: Huffman sequential
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {  // SOF0 / SOF1 sequential, SOF2 progressive (Huffman)
+            if (have_sof) return -1;
             if (len < 8 || s[0] != 8) return -2;
             H = rd16(s + 1); W = rd16(s + 3);
             const int nc = s[5];
@@ -261,91 +362,112 @@ extern "C" int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* 
             comps.resize(nc);
             for (int i = 0; i < nc; i++) {
                 comps[i].id = s[6 + 3 * i]; comps[i].h = s[7 + 3 * i] >> 4; comps[i].v = s[7 + 3 * i] & 15; comps[i].tq = s[8 + 3 * i];
-                if (comps[i].tq > 3) return -1;
+                if (comps[i].tq > 3 || comps[i].h < 1 || comps[i].v < 1) return -1;
             }
+            if (nc == 1) { comps[0].h = comps[0].v = 1; }
+            for (auto& c : comps) { hmax = c.h > hmax ? c.h : hmax; vmax = c.v > vmax ? c.v : vmax; }
+            if (nc == 3) {
+                const Comp& y = comps[0];
+                if (comps[1].h != 1 || comps[1].v != 1 || comps[2].h != 1 || comps[2].v != 1) return -2;
+                if (!((y.h == 1 && y.v == 1) || (y.h == 2 && y.v == 1) || (y.h == 2 && y.v == 2))) return -2;
+            }
+            progressive = m == 0xC2;
             have_sof = true;
-        } else if ((m >= 0xC2 && m <= 0xCF) && m != 0xC4 && m != 0xC8 && m != 0xCC) {
-            return -2;                                     // progressive, lossless, arithmetic, hierarchical
+            if (w) *w = W;
+            if (h) *h = H;
+            if (!bgr) return 0;
+            if (cap < (long long)W * H * 3) return -1;
+            mcux = (W + 8 * hmax - 1) / (8 * hmax); mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+            for (auto& c : comps) {
+                c.bw = mcux * c.h; c.bh = mcuy * c.v;
+                c.pw = c.bw * 8; c.ph = c.bh * 8;
+                c.dw = (W * c.h + hmax - 1) / hmax; c.dh = (H * c.v + vmax - 1) / vmax;
+                c.nbw = (c.dw + 7) / 8; c.nbh = (c.dh + 7) / 8;
+                c.coef.assign((size_t)c.bw * c.bh * 64, 0);
+            }
+        } else if ((m >= 0xC3 && m <= 0xCF) && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return -2;                                     // lossless, arithmetic, hierarchical
         } else if (m == 0xDD) {                            // DRI
             if (len < 4) return -1;
             restart = rd16(s);
-        } else if (m == 0xDA) {                            // SOS
+        } else if (m == 0xDA) {                            // SOS: decode one scan into the coefficient arrays
             if (!have_sof) return -1;
             const int ns = s[0];
-            if (ns != (int)comps.size() || len < 6 + 2 * ns) return -2;   // non-interleaved colour scans are not handled
+            if (ns < 1 || ns > (int)comps.size() || len < 6 + 2 * ns) return -1;
+            std::vector<Comp*> sc;
             for (int i = 0; i < ns; i++) {
                 const int cid = s[1 + 2 * i];
                 Comp* c = nullptr;
                 for (auto& cc : comps) if (cc.id == cid) c = &cc;
                 if (!c) return -1;
                 c->td = s[2 + 2 * i] >> 4; c->ta = s[2 + 2 * i] & 15;
-                if (c->td > 3 || c->ta > 3 || !dc[c->td].set || !ac[c->ta].set || !quant_set[c->tq]) return -1;
+                if (c->td > 3 || c->ta > 3) return -1;
+                if (!c->q_latched) {   // libjpeg latches a component's table at its first scan
+                    if (!quant_set[c->tq]) return -1;
+                    memcpy(c->q, quant[c->tq], sizeof c->q);
+                    c->q_latched = true;
+                }
+                sc.push_back(c);
             }
-            p += len;
-            break;
+            ScanParams sp;
+            sp.Ss = s[1 + 2 * ns]; sp.Se = s[2 + 2 * ns]; sp.Ah = s[3 + 2 * ns] >> 4; sp.Al = s[3 + 2 * ns] & 15;
+            sp.progressive = progressive;
+            if (progressive) {
+                if (sp.Ss > sp.Se || sp.Se > 63 || sp.Al > 13 || (sp.Ss == 0 && sp.Se != 0) || (sp.Ss > 0 && ns != 1)) return -1;
+            } else {
+                sp.Ss = 0; sp.Se = 63; sp.Ah = sp.Al = 0;
+            }
+            for (Comp* c : sc) {
+                const bool need_dc = !progressive || sp.Ss == 0, need_ac = !progressive || sp.Ss > 0;
+                if ((need_dc && sp.Ah == 0 && !dc[c->td].set) || (need_ac && !ac[c->ta].set)) return -1;
+                c->pred = 0;
+            }
+            BitReader br;
+            br.p = p + len; br.end = end;
+            int eobrun = 0, until_restart = restart;
+            // interleaved: MCUs of h x v blocks per component over the padded grid; single component: its real blocks
+            const int units_x = ns > 1 ? mcux : sc[0]->nbw, units_y = ns > 1 ? mcuy : sc[0]->nbh;
+            bool ok = true;
+            for (int uy = 0; uy < units_y && ok; uy++)
+                for (int ux = 0; ux < units_x && ok; ux++) {
+                    if (restart && until_restart == 0) {   // RSTn: resynchronise on the marker, reset predictions and EOB run
+                        const uint8_t* q = br.p;
+                        while (q + 1 < end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
+                        if (q + 1 >= end) { ok = false; break; }
+                        br.p = q + 2;
+                        br.reset();
+                        for (Comp* c : sc) c->pred = 0;
+                        eobrun = 0;
+                        until_restart = restart;
+                    }
+                    for (Comp* c : sc) {
+                        const int nbx = ns > 1 ? c->h : 1, nby = ns > 1 ? c->v : 1;
+                        for (int by = 0; by < nby && ok; by++)
+                            for (int bx = 0; bx < nbx && ok; bx++) {
+                                const int col = ux * nbx + bx, rowb = uy * nby + by;
+                                ok = decode_block(br, *c, dc, ac, &c->coef[((size_t)rowb * c->bw + col) * 64], sp, eobrun);
+                            }
+                    }
+                    if (restart) until_restart--;
+                }
+            if (!ok) return -1;
+            any_scan = true;
+            p = br.p;       // the reader stops at the next marker
+            continue;
         }
         p += len;
     }
-    if (w) *w = W;
-    if (h) *h = H;
+    if (!have_sof) return -1;
     if (!bgr) return 0;
-    if (cap < (long long)W * H * 3) return -1;
-    const int nc = (int)comps.size();
-    int hmax = 1, vmax = 1;
-    if (nc == 1) { comps[0].h = comps[0].v = 1; }
-    for (auto& c : comps) { hmax = c.h > hmax ? c.h : hmax; vmax = c.v > vmax ? c.v : vmax; }
-    if (nc == 3) {
-        const Comp& y = comps[0];
-        if (comps[1].h != 1 || comps[1].v != 1 || comps[2].h != 1 || comps[2].v != 1) return -2;
-        if (!((y.h == 1 && y.v == 1) || (y.h == 2 && y.v == 1) || (y.h == 2 && y.v == 2))) return -2;
-    }
-    const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
-    for (auto& c : comps) {
-        c.pw = mcux * c.h * 8; c.ph = mcuy * c.v * 8;
-        c.dw = (W * c.h + hmax - 1) / hmax; c.dh = (H * c.v + vmax - 1) / vmax;   // real (downsampled) samples
+    if (!any_scan) return -1;
+    for (auto& c : comps) {   // inverse DCT of every block (a component without any scan decodes as mid-grey, like libjpeg)
+        if (!c.q_latched) { if (!quant_set[c.tq]) return -1; memcpy(c.q, quant[c.tq], sizeof c.q); }
         c.plane.assign((size_t)c.pw * c.ph, 0);
-        c.pred = 0;
+        for (int by = 0; by < c.bh; by++)
+            for (int bx = 0; bx < c.bw; bx++)
+                idct_islow(&c.coef[((size_t)by * c.bw + bx) * 64], c.q, c.plane.data() + (size_t)by * 8 * c.pw + (size_t)bx * 8, c.pw);
     }
-    BitReader br;
-    br.p = p; br.end = end;
-    short coef[64];
-    int until_restart = restart;
-    for (int my = 0; my < mcuy; my++)
-        for (int mx = 0; mx < mcux; mx++) {
-            if (restart && until_restart == 0) {   // RSTn: byte-align, skip the marker, reset predictions
-                const uint8_t* q = br.p;
-                // the reader may have consumed stuffed bytes ahead; resynchronise on the next RST marker in the stream
-                while (q + 1 < end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
-                if (q + 1 >= end) return -1;
-                br.p = q + 2;
-                br.reset();
-                for (auto& c : comps) c.pred = 0;
-                until_restart = restart;
-            }
-            for (auto& c : comps)
-                for (int by = 0; by < c.v; by++)
-                    for (int bx = 0; bx < c.h; bx++) {
-                        memset(coef, 0, sizeof coef);
-                        int s = huff_decode(br, dc[c.td]);
-                        if (s > 15) return -1;
-                        int diff = s ? extend(br.get(s), s) : 0;
-                        c.pred += diff;
-                        coef[0] = (short)c.pred;
-                        for (int k = 1; k < 64;) {
-                            const int rs = huff_decode(br, ac[c.ta]);
-                            const int r = rs >> 4;
-                            s = rs & 15;
-                            if (s == 0) { if (r != 15) break; k += 16; continue; }
-                            k += r;
-                            if (k > 63) break;
-                            coef[kZigzagNat[k]] = (short)extend(br.get(s), s);
-                            k++;
-                        }
-                        uint8_t* out = c.plane.data() + (size_t)((my * c.v + by) * 8) * c.pw + (size_t)(mx * c.h + bx) * 8;
-                        idct_islow(coef, quant[c.tq], out, c.pw);
-                    }
-            if (restart) until_restart--;
-        }
+    const int nc = (int)comps.size();
     if (nc == 1) {
         const Comp& c = comps[0];
         for (int y = 0; y < H; y++)

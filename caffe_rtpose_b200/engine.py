@@ -511,11 +511,11 @@ def encode_jpeg(bgr, quality=98):
 
 
 def decode_jpeg(data):
-    """uint8 BGR HWC pixels of a baseline JPEG, bit-identical to cv::imread / libjpeg defaults (what --image_dir feeds)."""
+    """uint8 BGR HWC pixels of a baseline JPEG, bit-identical to cv::imread / libjpeg defaults (baseline and progressive; what --image_dir feeds)."""
     w, h = C.c_int(), C.c_int()
     rc = lib().pe_decode_jpeg(data, len(data), C.byref(w), C.byref(h), None, 0)
     if rc != 0:
-        raise PoseEngineError("pe_decode_jpeg: %s" % ("not a JPEG / truncated" if rc == -1 else "unsupported JPEG variant (progressive, 12-bit, CMYK, sampling)"))
+        raise PoseEngineError("pe_decode_jpeg: %s" % ("not a JPEG / truncated" if rc == -1 else "unsupported JPEG variant (arithmetic / lossless / 12-bit / CMYK / unusual sampling)"))
     out = np.zeros((h.value, w.value, 3), np.uint8)
     rc = lib().pe_decode_jpeg(data, len(data), C.byref(w), C.byref(h), out.ctypes.data, out.size)
     if rc != 0:

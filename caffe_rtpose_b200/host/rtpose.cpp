@@ -200,7 +200,7 @@ static bool read_image(const std::string& path, int& w, int& h, std::vector<uint
     auto dec = jpg ? pe_decode_jpeg : pe_decode_png;
     int rc = dec(data.data(), n, &w, &h, nullptr, 0);
     if (rc == 0) { bgr.resize((size_t)w * h * 3); rc = dec(data.data(), n, &w, &h, bgr.data(), (long long)bgr.size()); }
-    if (rc == -2) LOG_ERROR("%s: JPEG variant not handled (progressive / 12-bit / CMYK / unusual chroma sampling)", path.c_str());
+    if (rc == -2) LOG_ERROR("%s: JPEG variant not handled (arithmetic-coded / lossless / 12-bit / CMYK / unusual chroma sampling)", path.c_str());
     return rc == 0;
 }
 
@@ -302,7 +302,7 @@ static void producer() {
         } else {
             const std::string& p = global.image_list[i];
             const bool ok = read_image(p, w, h, fr.bgr);
-            if (!ok) { LOG_ERROR("cannot decode %s (supported: baseline .jpg, .png, 24-bit .bmp, P6 .ppm)", p.c_str()); continue; }
+            if (!ok) { LOG_ERROR("cannot decode %s (supported: .jpg, .png, 24-bit .bmp, P6 .ppm)", p.c_str()); continue; }
             const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
             fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
         }

@@ -153,10 +153,10 @@ int pe_render(pe_engine* e, int idx, int part_to_show, int googly_eyes, const ui
  * byte count (the stream is written when it fits in cap), -1 on bad arguments. */
 long long pe_encode_jpeg(const uint8_t* bgr, int w, int h, int quality, uint8_t* buf, long long cap);
 
-/* cv::imread of getFrameFromDir (rtpose.cpp:302-391) for .jpg files: baseline (Huffman, 8-bit) JPEG decoder that follows
+/* cv::imread of getFrameFromDir (rtpose.cpp:302-391) for .jpg files: Huffman 8-bit JPEG decoder (baseline and progressive) that follows
  * libjpeg's default arithmetic (islow IDCT, fancy chroma upsampling, fixed-point YCbCr->RGB), so the pixels equal what
  * cv::imread returns.  Returns 0 and the image size in *w, *h; pixels (uint8 BGR HWC) are written when bgr != NULL and
- * cap >= w*h*3.  -1: not a JPEG / truncated; -2: progressive, arithmetic-coded, 12-bit, CMYK or unusual chroma sampling. */
+ * cap >= w*h*3.  -1: not a JPEG / truncated; -2: arithmetic-coded, lossless, 12-bit, CMYK or unusual chroma sampling. */
 int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* h, uint8_t* bgr, long long cap);
 
 /* same for .png (the third format the reference lists, rtpose.cpp:1743): inflate + PNG filters / Adam7 / all colour types and

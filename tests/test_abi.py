@@ -194,18 +194,20 @@ def test_jpeg_encoder_decodes_like_libjpeg_at_same_quality():
 
 
 def _jpeg_variants(cv2, q):
-    v = [("420", [cv2.IMWRITE_JPEG_QUALITY, q]), ("optimised-huffman", [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_OPTIMIZE, 1]),
-         ("restart-3", [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, 3])]
+    base = [cv2.IMWRITE_JPEG_QUALITY, q]
+    prog = base + [cv2.IMWRITE_JPEG_PROGRESSIVE, 1]
+    v = [("420", base), ("optimised-huffman", base + [cv2.IMWRITE_JPEG_OPTIMIZE, 1]), ("restart-3", base + [cv2.IMWRITE_JPEG_RST_INTERVAL, 3]),
+         ("progressive", prog), ("progressive+restart", prog + [cv2.IMWRITE_JPEG_RST_INTERVAL, 2])]
     if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
-        v += [("444", [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]),
-              ("422", [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422])]
+        for name, f in (("444", cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444), ("422", cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422)):
+            v += [(name, base + [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, f]), ("progressive-" + name, prog + [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, f])]
     return v
 
 
 def test_jpeg_decoder_equals_cv_imread_bit_for_bit():
     """pe_decode_jpeg feeds --image_dir where the reference calls cv::imread (rtpose.cpp:302-391): same pixels as OpenCV's
-    libjpeg for baseline files - sizes that are not multiples of the MCU, 4:2:0 / 4:2:2 / 4:4:4, grey, optimised Huffman
-    tables, restart intervals, and the stream of our own encoder."""
+    libjpeg for baseline AND progressive files - sizes that are not multiples of the MCU, 4:2:0 / 4:2:2 / 4:4:4, grey,
+    optimised Huffman tables, restart intervals, and the stream of our own encoder."""
     import cv2
     from caffe_rtpose_b200 import synth
 
@@ -217,13 +219,15 @@ def test_jpeg_decoder_equals_cv_imread_bit_for_bit():
                     ok, enc = cv2.imencode(".jpg", img, params)
                     assert ok
                     assert np.array_equal(engine.decode_jpeg(enc.tobytes()), cv2.imdecode(enc, cv2.IMREAD_COLOR)), (h, w, q, name)
-        ok, enc = cv2.imencode(".jpg", noise[:, :, 0], [cv2.IMWRITE_JPEG_QUALITY, 90])
-        assert np.array_equal(engine.decode_jpeg(enc.tobytes()), cv2.imdecode(enc, cv2.IMREAD_COLOR))
+        for params in ([cv2.IMWRITE_JPEG_QUALITY, 90], [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_PROGRESSIVE, 1]):
+            ok, enc = cv2.imencode(".jpg", noise[:, :, 0], params)
+            assert np.array_equal(engine.decode_jpeg(enc.tobytes()), cv2.imdecode(enc, cv2.IMREAD_COLOR))
         own = engine.encode_jpeg(noise, 98)
         assert np.array_equal(engine.decode_jpeg(own), cv2.imdecode(np.frombuffer(own, np.uint8), cv2.IMREAD_COLOR))
-    ok, enc = cv2.imencode(".jpg", synth.make_frame(1, 64, 64), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    ok, enc = cv2.imencode(".jpg", synth.make_frame(1, 64, 64))
+    arith = enc.tobytes().replace(b"\xff\xc0", b"\xff\xc9", 1)   # SOF9 = arithmetic coding: a variant that is not handled
     with pytest.raises(engine.PoseEngineError, match="unsupported"):
-        engine.decode_jpeg(enc.tobytes())
+        engine.decode_jpeg(arith)
     with pytest.raises(engine.PoseEngineError, match="not a JPEG"):
         engine.decode_jpeg(b"BM" + bytes(100))
     with pytest.raises(engine.PoseEngineError):

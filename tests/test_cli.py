@@ -87,6 +87,10 @@ def test_image_readers_without_gpu(tmp_path):
     ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
     (tmp_path / "p.jpg").write_bytes(enc.tobytes())
     r = run(["--probe_image", str(tmp_path / "p.jpg")])
+    assert r.returncode == 0 and r.stdout.split() == ["70x45", "%016x" % fnv1a(cv2.imdecode(enc, cv2.IMREAD_COLOR))]
+    ok, enc = cv2.imencode(".jpg", img)
+    (tmp_path / "q.jpg").write_bytes(enc.tobytes().replace(b"\xff\xc0", b"\xff\xc9", 1))   # arithmetic-coded: not handled
+    r = run(["--probe_image", str(tmp_path / "q.jpg")])
     assert r.returncode == 1 and "not handled" in r.stderr
 
 
