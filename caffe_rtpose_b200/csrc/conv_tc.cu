@@ -310,7 +310,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // MMA rings run straight through tile boundaries, and the TMEM accumulator is double-buffered (2 x P*BN
 // columns) so the epilogue of tile i overlaps the main loop of tile i+1 - this removes the per-tile
 // prologue/epilogue latency that dominated the short-K layers (conv1_x, conv2_x).
-template <int BN, int PLANES, int NA, int NB, int ROWB>
+template <int BN, int PLANES, int NA, int NB, int ROWB, int EPI>
 __global__ void __launch_bounds__(TCW_THREADS, 1)
 conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     static_assert(PLANES == 1 || PLANES == 2, "window kernel supports 1 or 2 planes");
@@ -482,8 +482,11 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 valid = (x < a.W) && (y < a.H);
             }
             // ---- sum the chunks of this tile in registers (fp32 round-to-nearest) ----
+            // EPI == 1 (experimental, PE_TC_EPI=1): the LAST chunk is not drained into accv but streamed piece by piece through
+            // bias / ReLU / split / store, so TMEM loads overlap the global stores as in the pre-chunking epilogue.
             float accv[HALF];
-            for (int c = 0; c < nchunks; c++, ci++) {
+            const int ndrain = EPI == 1 ? nchunks - 1 : nchunks;
+            for (int c = 0; c < ndrain; c++, ci++) {
                 const int as = (int)(ci & 1u);
                 mbar_wait(&tmem_full[as], (ci >> 1) & 1u);
                 tc_fence_after();
@@ -515,6 +518,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);   // 8 epilogue warps -> accumulator free for chunk ci+2
             }
             // ---- bias, ReLU, re-split, store ----
+            if (EPI == 0) {
             if (active_half && valid) {
 #pragma unroll
                 for (int pc = 0; pc < NCHUNK; pc++) {
@@ -547,6 +551,66 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                 }
+            }
+            } else {
+                const int as = (int)(ci & 1u);
+                mbar_wait(&tmem_full[as], (ci >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS + half * HALF);
+                if (active_half) {
+                    uint32_t r[2][16], r2[2][16];
+                    __syncwarp();
+                    tmem_ld16_nowait(trow, r[0]);
+                    if (PLANES == 2) tmem_ld16_nowait(trow + BN, r2[0]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int pc = 0; pc < NCHUNK; pc++) {
+                        const int cur = pc & 1;
+                        if (pc + 1 < NCHUNK) {   // prefetch the next 16 columns while this piece is converted and stored
+                            __syncwarp();
+                            tmem_ld16_nowait(trow + (uint32_t)((pc + 1) * 16), r[cur ^ 1]);
+                            if (PLANES == 2) tmem_ld16_nowait(trow + (uint32_t)(BN + (pc + 1) * 16), r2[cur ^ 1]);
+                        }
+                        const int cb = n0 + half * HALF + pc * 16;
+                        if (valid) {
+                            float v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                float tv = __uint_as_float(r[cur][j]);
+                                if (PLANES == 2) tv = __fadd_rn(tv, __uint_as_float(r2[cur][j]));
+                                if (nchunks > 1) tv = __fadd_rn(accv[pc * 16 + j], tv);
+                                tv = __fmaf_rn(tv, out_scale, s_bias[cb + j]);
+                                if (a.relu) tv = fmaxf(tv, 0.f);
+                                v[j] = tv;
+                            }
+                        if (a.planar) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                if (cb + j < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + cb + j) * a.H + y) * a.W + x] = v[j];
+                        } else {
+                            uint32_t pk[PLANES][8];
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                float r0 = v[j], r1 = v[j + 1];
+#pragma unroll
+                                for (int p = 0; p < PLANES; p++) pk[p][j / 2] = split_pair<F16>(r0, r1);   // one packed conversion
+                            }
+                            __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + cb;
+#pragma unroll
+                            for (int p = 0; p < PLANES; p++) {
+                                uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
+                                if (cb < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+                                if (cb + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
+                            }
+                        }
+                        }
+                        if (pc + 1 < NCHUNK) { __syncwarp(); tmem_ld_wait(); }
+                    }
+                }
+                __syncwarp();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                ci++;
             }
         }
     }
@@ -614,9 +678,14 @@ static int launch_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t 
     }
 }
 
-template <int BN, int PLANES, int NA, int NB, int ROWB>
-static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
-    auto kern = conv_tcw_kernel<BN, PLANES, NA, NB, ROWB>;
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int BN, int PLANES, int NA, int NB, int ROWB, int EPI>
+static int launch_win_epi(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
+    auto kern = conv_tcw_kernel<BN, PLANES, NA, NB, ROWB, EPI>;
     const int smem = NA * PLANES * TCW_A_BYTES + NB * (ROWB ? 3 : 1) * PLANES * BN * 128 + 1024;
     static std::atomic<unsigned long long> attr_done{0};   // bit d: attribute set on device d (it is per device)
     int dev = 0;
@@ -629,6 +698,12 @@ static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStr
     kern<<<grid, TCW_THREADS, smem, st>>>(maps[2], maps[bmap], a);
     return 1;
 }
+template <int BN, int PLANES, int NA, int NB, int ROWB>
+static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
+    static const int epi = env_int("PE_TC_EPI", 0);   // 1: experimental streamed-last-chunk epilogue (A/B, tools/ab_bench.sh)
+    if (epi == 1) return launch_win_epi<BN, PLANES, NA, NB, ROWB, 1>(l, a, grid, st, bmap);
+    return launch_win_epi<BN, PLANES, NA, NB, ROWB, 0>(l, a, grid, st, bmap);
+}
 template <int BN>
 static int launch_win_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
     if (BN <= 64 && l.d.ksize <= 3) {   // narrow-N layers (conv1_x, the 1x1 heads): filter-row B slots
@@ -639,10 +714,6 @@ static int launch_win_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStrea
     return launch_win_inst<BN, 2, 2, (BN >= 128 ? 4 : 6), 0>(l, a, grid, st, bmap);
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
 
 int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
     EncodeTiledFn enc = get_encode();

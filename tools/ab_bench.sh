@@ -3,7 +3,8 @@
 # every "ENV=VALUE" variant given on the command line.  Example (≈2 GPU-minutes per variant):
 #   gpurun --timeout 600 -- 'tools/ab_bench.sh PE_TC_CHUNK_MUL=1 PE_TC_CHUNK=0 PE_TC_CHUNK_MUL=2'
 # Knobs: PE_TC_CHUNK (0 = one TMEM chain per tile, n = n steps per chunk), PE_TC_CHUNK_MUL (multiplier of the default
-# chunk sizes), PE_TC_NARROW (0 = never pick 64/32-wide tiles), PE_TC_VARIANT (0 = baseline one-tile-per-tap kernel),
+# chunk sizes), PE_TC_EPI (1 = streamed-last-chunk epilogue, written at the end of round 1 and NOT yet run on a GPU: check
+# `tools/gpu_diag.py tc` and tests/test_gpu_net.py with it before trusting its fps), PE_TC_NARROW (0 = never pick 64/32-wide tiles), PE_TC_VARIANT (0 = baseline one-tile-per-tap kernel),
 # PE_GRAPH (0 = no CUDA graphs).
 export DIAG_PRECS=${DIAG_PRECS:-2}
 mkdir -p gpurun_out
