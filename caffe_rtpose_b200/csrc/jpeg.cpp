@@ -74,13 +74,14 @@ struct BitWriter {
 };
 
 void fdct8x8(const float* in, double* out) {   // separable DCT-II, orthonormal JPEG scaling
-    static double c[8][8];
-    static bool init = false;
-    if (!init) {
+    struct Basis { double c[8][8]; };
+    static const Basis basis = [] {   // thread-safe one-time initialisation
+        Basis b;
         for (int u = 0; u < 8; u++)
-            for (int x = 0; x < 8; x++) c[u][x] = (u == 0 ? sqrt(0.125) : 0.5) * cos((2 * x + 1) * u * M_PI / 16.0);
-        init = true;
-    }
+            for (int x = 0; x < 8; x++) b.c[u][x] = (u == 0 ? sqrt(0.125) : 0.5) * cos((2 * x + 1) * u * M_PI / 16.0);
+        return b;
+    }();
+    const double (*c)[8] = basis.c;
     double tmp[64];
     for (int y = 0; y < 8; y++)
         for (int u = 0; u < 8; u++) {

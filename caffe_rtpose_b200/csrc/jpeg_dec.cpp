@@ -482,27 +482,27 @@ extern "C" int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* 
     upsample(comps[1], hmax, vmax, W, H, cb);
     upsample(comps[2], hmax, vmax, W, H, cr);
     // jdcolor.c build_ycc_rgb_table: SCALEBITS 16, FIX(x) = (int)(x * 65536 + 0.5)
-    static int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
-    static bool tabs = false;
-    if (!tabs) {
+    struct ColorTab { int cr_r[256], cb_b[256], cr_g[256], cb_g[256]; };
+    static const ColorTab ct = [] {   // thread-safe one-time initialisation
+        ColorTab t;
         for (int i = 0; i < 256; i++) {
             const int x = i - 128;
-            cr_r[i] = (91881 * x + 32768) >> 16;      // FIX(1.40200)
-            cb_b[i] = (116130 * x + 32768) >> 16;     // FIX(1.77200)
-            cr_g[i] = -46802 * x;                     // FIX(0.71414)
-            cb_g[i] = -22554 * x + 32768;             // FIX(0.34414), includes ONE_HALF
+            t.cr_r[i] = (91881 * x + 32768) >> 16;      // FIX(1.40200)
+            t.cb_b[i] = (116130 * x + 32768) >> 16;     // FIX(1.77200)
+            t.cr_g[i] = -46802 * x;                     // FIX(0.71414)
+            t.cb_g[i] = -22554 * x + 32768;             // FIX(0.34414), includes ONE_HALF
         }
-        tabs = true;
-    }
+        return t;
+    }();
     auto clamp = [](int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
     const Comp& yc = comps[0];
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) {
             const int Y = yc.plane[(size_t)y * yc.pw + x], b = cb[(size_t)y * W + x], r = cr[(size_t)y * W + x];
             uint8_t* o = bgr + ((size_t)y * W + x) * 3;
-            o[2] = clamp(Y + cr_r[r]);
-            o[1] = clamp(Y + ((cb_g[b] + cr_g[r]) >> 16));
-            o[0] = clamp(Y + cb_b[b]);
+            o[2] = clamp(Y + ct.cr_r[r]);
+            o[1] = clamp(Y + ((ct.cb_g[b] + ct.cr_g[r]) >> 16));
+            o[0] = clamp(Y + ct.cb_b[b]);
         }
     return 0;
 }
