@@ -58,7 +58,7 @@ bool parse_blob(Reader r, Blob& b) {
             const size_t n = (size_t)(d.end - d.p) / 4;
             const size_t old = b.data.size();
             b.data.resize(old + n);
-            memcpy(b.data.data() + old, d.p, n * 4);
+            if (n) memcpy(b.data.data() + old, d.p, n * 4);
         } else if (f == 5 && wt == 5) {     // unpacked repeated float
             if (r.end - r.p < 4) return false;
             float v; memcpy(&v, r.p, 4); r.p += 4; b.data.push_back(v);

@@ -30,12 +30,13 @@ struct HuffTab {
     int mincode[17], maxcode[18], valptr[17];
     uint8_t look_len[512];   // 9-bit lookahead: code length (0 = longer than 9 bits)
     uint8_t look_sym[512];
-    void build() {
+    bool build() {   // false: the code lengths over-subscribe the code space (corrupt DHT)
         int code = 0, k = 0;
         for (int l = 1; l <= 16; l++) {
             valptr[l] = k;
             mincode[l] = code;
             code += bits[l];
+            if (code > (1 << l)) return false;
             k += bits[l];
             maxcode[l] = bits[l] ? code - 1 : -1;
             code <<= 1;
@@ -52,6 +53,7 @@ struct HuffTab {
             code <<= 1;
         }
         set = true;
+        return true;
     }
 };
 
@@ -103,43 +105,44 @@ inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 :
 constexpr int CONST_BITS = 13, PASS1_BITS = 2;
 constexpr int F_0_298631336 = 2446, F_0_390180644 = 3196, F_0_541196100 = 4433, F_0_765366865 = 6270, F_0_899976223 = 7373, F_1_175875602 = 9633,
               F_1_501321110 = 12299, F_1_847759065 = 15137, F_1_961570560 = 16069, F_2_053119869 = 16819, F_2_562915447 = 20995, F_3_072711026 = 25172;
-inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
-inline uint8_t range_limit(int x) { x += 128; return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+typedef long long jlong;   // libjpeg's JLONG is `long` (64-bit on LP64): corrupt data must not overflow the intermediates
+inline jlong descale(jlong x, int n) { return (x + ((jlong)1 << (n - 1))) >> n; }
+inline uint8_t range_limit(jlong x) { x += 128; return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
 
-inline void idct_1d(const int* in, int stride, int shift_in_is_pass1, int* o) {
+inline void idct_1d(const int* in, int stride, jlong* o) {
     // even part
-    int z2 = in[2 * stride], z3 = in[6 * stride];
-    int z1 = (z2 + z3) * F_0_541196100;
-    int tmp2 = z1 + z3 * (-F_1_847759065);
-    int tmp3 = z1 + z2 * F_0_765366865;
+    jlong z2 = in[2 * stride], z3 = in[6 * stride];
+    jlong z1 = (z2 + z3) * F_0_541196100;
+    jlong tmp2 = z1 + z3 * (-F_1_847759065);
+    jlong tmp3 = z1 + z2 * F_0_765366865;
     z2 = in[0];
     z3 = in[4 * stride];
-    int tmp0 = (z2 + z3) << CONST_BITS;
-    int tmp1 = (z2 - z3) << CONST_BITS;
-    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    jlong tmp0 = (z2 + z3) * (1 << CONST_BITS);
+    jlong tmp1 = (z2 - z3) * (1 << CONST_BITS);
+    const jlong tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
     // odd part
     tmp0 = in[7 * stride]; tmp1 = in[5 * stride]; tmp2 = in[3 * stride]; tmp3 = in[1 * stride];
     z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
-    int z4 = tmp1 + tmp3;
-    const int z5 = (z3 + z4) * F_1_175875602;
+    jlong z4 = tmp1 + tmp3;
+    const jlong z5 = (z3 + z4) * F_1_175875602;
     tmp0 *= F_0_298631336; tmp1 *= F_2_053119869; tmp2 *= F_3_072711026; tmp3 *= F_1_501321110;
     z1 *= -F_0_899976223; z2 *= -F_2_562915447; z3 *= -F_1_961570560; z4 *= -F_0_390180644;
     z3 += z5; z4 += z5;
     tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
-    (void)shift_in_is_pass1;
     o[0] = tmp10 + tmp3; o[7] = tmp10 - tmp3; o[1] = tmp11 + tmp2; o[6] = tmp11 - tmp2;
     o[2] = tmp12 + tmp1; o[5] = tmp12 - tmp1; o[3] = tmp13 + tmp0; o[4] = tmp13 - tmp0;
 }
 
 void idct_islow(const short* coef, const uint16_t* quant, uint8_t* out, int out_stride) {
-    int deq[64], ws[64], o[8];
+    int deq[64], ws[64];
+    jlong o[8];
     for (int i = 0; i < 64; i++) deq[i] = (int)coef[i] * (int)quant[i];
     for (int c = 0; c < 8; c++) {   // pass 1: columns
-        idct_1d(deq + c, 8, 1, o);
-        for (int r = 0; r < 8; r++) ws[r * 8 + c] = descale(o[r], CONST_BITS - PASS1_BITS);
+        idct_1d(deq + c, 8, o);
+        for (int r = 0; r < 8; r++) ws[r * 8 + c] = (int)descale(o[r], CONST_BITS - PASS1_BITS);
     }
     for (int r = 0; r < 8; r++) {   // pass 2: rows
-        idct_1d(ws + r * 8, 1, 0, o);
+        idct_1d(ws + r * 8, 1, o);
         for (int c = 0; c < 8; c++) out[r * out_stride + c] = range_limit(descale(o[c], CONST_BITS + PASS1_BITS + 3));
     }
 }
@@ -350,7 +353,7 @@ extern "C" int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* 
                 if (n > 256 || s + n > se) return -1;
                 memcpy(t.vals, s, n);
                 s += n;
-                t.build();
+                if (!t.build()) return -1;
             }
         } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {  // SOF0 / SOF1 sequential, SOF2 progressive (Huffman)
             if (have_sof) return -1;

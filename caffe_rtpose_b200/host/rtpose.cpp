@@ -199,6 +199,7 @@ static bool read_image(const std::string& path, int& w, int& h, std::vector<uint
     if (!rd) return false;
     auto dec = jpg ? pe_decode_jpeg : pe_decode_png;
     int rc = dec(data.data(), n, &w, &h, nullptr, 0);
+    if (rc == 0 && (long long)w * h > (1LL << 28)) { LOG_ERROR("%s: %dx%d is larger than this build accepts", path.c_str(), w, h); return false; }
     if (rc == 0) { bgr.resize((size_t)w * h * 3); rc = dec(data.data(), n, &w, &h, bgr.data(), (long long)bgr.size()); }
     if (rc == -2) LOG_ERROR("%s: JPEG variant not handled (arithmetic-coded / lossless / 12-bit / CMYK / unusual chroma sampling)", path.c_str());
     return rc == 0;

@@ -4,6 +4,7 @@ descriptor tables) match the oracle and the reference's own modelDescriptorFacto
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -353,3 +354,34 @@ def test_png_decoder_equals_cv_imread():
     good = cv2.imencode(".png", synth.make_frame(1, 16, 16))[1].tobytes()
     with pytest.raises(engine.PoseEngineError):
         engine.decode_png(good[:len(good) // 2])
+
+
+def test_parsers_survive_corrupt_files(tmp_path):
+    """The three parsers that read untrusted files (JPEG, PNG, .caffemodel) under AddressSanitizer + UBSan on thousands of
+    mutated files: they must accept or reject, never read out of bounds / overflow / crash."""
+    import cv2
+    from caffe_rtpose_b200 import synth
+    img = cv2.GaussianBlur(synth.make_frame(2, 61, 83), (0, 0), 1.5)
+    files = []
+    for name, params in [("a.jpg", [cv2.IMWRITE_JPEG_QUALITY, 80]), ("b.jpg", [cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_PROGRESSIVE, 1]),
+                         ("c.jpg", [cv2.IMWRITE_JPEG_QUALITY, 60, cv2.IMWRITE_JPEG_RST_INTERVAL, 2]), ("d.png", []),
+                         ("e.png", [cv2.IMWRITE_PNG_BILEVEL, 1])]:
+        data = cv2.imencode("." + name.split(".")[1], img[:, :, 0] if name == "e.png" else img, params)[1].tobytes()
+        (tmp_path / name).write_bytes(data)
+        files.append(str(tmp_path / name))
+    rng = np.random.default_rng(1)
+    W = {"conv1_1": (rng.standard_normal((4, 3, 3, 3)).astype(np.float32), np.zeros(4, np.float32)),
+         "conv1_2": (rng.standard_normal((5, 4, 1, 1)).astype(np.float32), np.ones(5, np.float32))}
+    engine.write_caffemodel(str(tmp_path / "m.caffemodel"), W, [("conv1_1", 4, 3, 3), ("conv1_2", 5, 4, 1)])
+    files.append(str(tmp_path / "m.caffemodel"))
+    src = os.path.join(ROOT, "caffe_rtpose_b200", "csrc")
+    exe = str(tmp_path / "fuzz_codecs")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                        "-I", os.path.join(ROOT, "include"), "-I", src, "-I", "/usr/local/cuda/include",
+                        os.path.join(ROOT, "tests", "fuzz", "fuzz_codecs.cpp"), os.path.join(src, "jpeg_dec.cpp"), os.path.join(src, "png_dec.cpp"),
+                        os.path.join(src, "caffemodel.cpp"), "-o", exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, "1500"] + files, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
+    acc, rej = [int(v) for v in r.stdout.split()[1::2]]
+    assert acc > 500 and rej > 500   # the mutations are neither all harmless nor all fatal
