@@ -137,7 +137,7 @@ static bool read_ppm(const std::string& path, int& w, int& h, std::vector<uint8_
     }
     w = vals[0]; h = vals[1]; maxv = vals[2];
     fgetc(f);
-    if (maxv != 255 || w <= 0 || h <= 0) { fclose(f); return false; }
+    if (maxv != 255 || w <= 0 || h <= 0 || (long long)w * h > (1LL << 28)) { fclose(f); return false; }
     std::vector<uint8_t> rgb((size_t)w * h * 3);
     const bool ok = fread(rgb.data(), 1, rgb.size(), f) == rgb.size();
     fclose(f);
@@ -156,7 +156,7 @@ static bool read_bmp(const std::string& path, int& w, int& h, std::vector<uint8_
     const int32_t bw = (int32_t)(hd[18] | (hd[19] << 8) | (hd[20] << 16) | ((uint32_t)hd[21] << 24));
     const int32_t bh = (int32_t)(hd[22] | (hd[23] << 8) | (hd[24] << 16) | ((uint32_t)hd[25] << 24));
     const int bpp = hd[28] | (hd[29] << 8), comp = hd[30];
-    if (bpp != 24 || comp != 0 || bw <= 0 || bh == 0) { fclose(f); return false; }
+    if (bpp != 24 || comp != 0 || bw <= 0 || bh == 0 || bh == INT32_MIN || (long long)bw * (bh < 0 ? -(long long)bh : bh) > (1LL << 28)) { fclose(f); return false; }
     w = bw; h = bh < 0 ? -bh : bh;
     const size_t stride = ((size_t)w * 3 + 3) & ~(size_t)3;
     std::vector<uint8_t> row(stride);
