@@ -39,6 +39,7 @@ static void define(const char* name, const char* dflt, const char* help, bool is
 static std::string F(const char* n) { return g_flags.at(n).value; }
 static int Fi(const char* n) { return atoi(F(n).c_str()); }
 static double Fd(const char* n) { return atof(F(n).c_str()); }
+static bool Fb(const char* n) { const std::string v = F(n); return v == "true" || v == "1"; }
 
 static void define_flags() {
     // names, defaults and help strings of rtpose.cpp:50-72
@@ -46,6 +47,8 @@ static void define_flags() {
     define("part_to_show", "0", "Part to show from the start.");
     define("write_frames", "", "Write frames with format prefix%06d.jpg");
     define("probe_image", "", "[extension] decode this image file, print WxH and an FNV-1a hash of the BGR pixels, exit (no GPU)");
+    define("num_producers", "1", "[extension] decoder threads for --image_dir / --synthetic (the reference has one)");
+    define("decode_bench", "false", "[extension] run only the producer stage (decode + queue), print frames/s, exit (no GPU)", true);
     define("frame_format", "jpg", "[extension] jpg (quality 98, as the reference) or bmp (lossless) for --write_frames");
     define("no_frame_drops", "false", "Dont drop frames.", true);
     define("write_json", "", "Write joint data with json format as prefix%06d.json");
@@ -322,6 +325,80 @@ static void producer() {
     global.input_queue.wake();
 }
 
+// [extension] --num_producers N > 1.  The reference decodes on ONE thread (getFrameFromDir, rtpose.cpp:302-391); a 720p JPEG
+// takes ~12 ms here, i.e. ~80 frames/s per thread against ~740 frames/s that one GPU consumes, so the producer stage is
+// what scales with threads.  N threads take file indices from a shared counter; order is restored downstream by the
+// re-orderer through Frame::index, and a file that fails to decode becomes a dropped index (as dropped frames do).
+static void producer_mt(int nthreads) {
+    const int n_syn = Fi("synthetic");
+    const int total = n_syn > 0 ? n_syn : (int)global.image_list.size(), start = Fi("start_frame");
+    std::atomic<int> next{start};
+    auto body = [&]() {
+        while (!global.quit) {
+            const int i = next++;
+            if (i >= total) break;
+            Frame fr;
+            fr.index = i - start; fr.video_frame_number = i;
+            int w = global.disp_w, h = global.disp_h;
+            if (n_syn > 0) {
+                synthetic_frame(i, w, h, fr.bgr);
+            } else {
+                const std::string& p = global.image_list[i];
+                if (!read_image(p, w, h, fr.bgr)) {
+                    LOG_ERROR("cannot decode %s (supported: .jpg, .png, 24-bit .bmp, P6 .ppm)", p.c_str());
+                    std::lock_guard<std::mutex> l(global.mutex);
+                    global.dropped_index.push(fr.index);
+                    continue;
+                }
+                const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
+                fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
+            }
+            if (void* ph = pe_host_alloc(fr.bgr.size())) {
+                memcpy(ph, fr.bgr.data(), fr.bgr.size());
+                fr.pinned = std::shared_ptr<uint8_t>((uint8_t*)ph, [](uint8_t* q) { pe_host_free(q); });
+                std::vector<uint8_t>().swap(fr.bgr);
+            }
+            fr.w = w; fr.h = h;
+            fr.t_commit = now_s();
+            while (global.input_queue.size() > 64 && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+            global.input_queue.push(std::move(fr));
+            global.produced++;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back(body);
+    for (auto& t : th) t.join();
+    global.producer_done = true;
+    global.input_queue.wake();
+}
+static void run_producers() {
+    const int n = Fi("num_producers");
+    if (n > 1) producer_mt(n); else producer();
+}
+
+// [extension] --decode_bench: the producer stage alone (decode + queue, no GPU): frames/s of --image_dir with --num_producers
+static int decode_bench() {
+    std::atomic<long long> bytes{0};
+    std::atomic<int> frames{0};
+    std::vector<int> order;
+    const double t0 = now_s();
+    std::thread prod(run_producers);
+    while (true) {
+        Frame fr;
+        if (global.input_queue.try_pop(&fr)) { frames++; bytes += (long long)fr.w * fr.h * 3; order.push_back(fr.index); continue; }
+        if (global.producer_done && global.input_queue.size() == 0) break;
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+    }
+    prod.join();
+    const double dt = now_s() - t0;
+    std::sort(order.begin(), order.end());
+    bool contiguous = true;   // every index once, gaps only where a file was dropped
+    for (size_t i = 1; i < order.size(); i++) contiguous = contiguous && order[i] != order[i - 1];
+    printf("decoded %d frames (%.1f MB) with %d producer(s) in %.3f s: %.1f frames/s, dropped %d, indices_unique %d\n", (int)frames,
+           bytes / 1e6, std::max(1, Fi("num_producers")), dt, frames / std::max(dt, 1e-9), (int)global.dropped_index.size(), contiguous ? 1 : 0);
+    return 0;
+}
+
 static int load_weights(pe_engine* e, int device) {   // CopyTrainedLayersFrom (rtpose.cpp:184)
     LOG_INFO("GPU %d: copying to person net", device);
     int rc = 0;
@@ -548,6 +625,7 @@ int main(int argc, char** argv) {
         global.num_parts = md->get_number_parts();
         LOG_INFO("Selecting %s model: %d parts, %d limbs.", model == PE_MODEL_MPI_15 ? "MPI" : "COCO", global.num_parts, md->number_limb_sequence());
     }
+    if (Fb("decode_bench")) return decode_bench();
     const int num_gpu = std::max(1, Fi("num_gpu"));
     std::vector<pe_engine*> engines;
     if (!create_engines(num_gpu, engines)) {
@@ -556,7 +634,7 @@ int main(int argc, char** argv) {
     }
     std::vector<std::thread> workers;
     for (int i = 0; i < num_gpu; i++) workers.emplace_back(worker, i, engines[i]);
-    std::thread prod(producer);
+    std::thread prod(run_producers);
     std::thread ord(orderer_and_writer, num_gpu);
     prod.join();
     for (auto& t : workers) t.join();

@@ -94,6 +94,21 @@ def test_image_readers_without_gpu(tmp_path):
     assert r.returncode == 1 and "not handled" in r.stderr
 
 
+def test_multi_producer_decode_stage_without_gpu(tmp_path):
+    """--num_producers N (extension): N decoder threads feed the queue, every file index exactly once, an undecodable file
+    becomes a dropped index; --decode_bench runs this stage alone."""
+    import cv2
+    for i in range(12):
+        cv2.imwrite(str(tmp_path / ("f%02d.jpg" % i)), synth.make_frame(i, 90, 160), [cv2.IMWRITE_JPEG_QUALITY, 85])
+    (tmp_path / "f05.jpg").write_bytes(b"\xff\xd8 not a jpeg")
+    for n in (1, 4):
+        r = run(["--image_dir", str(tmp_path), "--decode_bench", "--num_producers", str(n), "--model", "COCO", "--resolution", "160x90"])
+        assert r.returncode == 0, r.stderr
+        out = r.stdout.strip().splitlines()[-1]
+        assert out.startswith("decoded 11 frames") and "indices_unique 1" in out and ("with %d producer" % n) in out, out
+        assert ("dropped 1" in out) == (n > 1)   # the single-thread path skips the file without consuming an index
+
+
 def write_ppm(path, bgr):
     h, w, _ = bgr.shape
     with open(path, "wb") as f:
