@@ -138,11 +138,23 @@ void idct_islow(const short* coef, const uint16_t* quant, uint8_t* out, int out_
     jlong o[8];
     for (int i = 0; i < 64; i++) deq[i] = (int)coef[i] * (int)quant[i];
     for (int c = 0; c < 8; c++) {   // pass 1: columns
+        if ((deq[8 + c] | deq[16 + c] | deq[24 + c] | deq[32 + c] | deq[40 + c] | deq[48 + c] | deq[56 + c]) == 0) {
+            // libjpeg's shortcut for a column without AC terms; the general formula gives the same value (dc << PASS1_BITS)
+            const int dcv = deq[c] * (1 << PASS1_BITS);
+            for (int r = 0; r < 8; r++) ws[r * 8 + c] = dcv;
+            continue;
+        }
         idct_1d(deq + c, 8, o);
         for (int r = 0; r < 8; r++) ws[r * 8 + c] = (int)descale(o[r], CONST_BITS - PASS1_BITS);
     }
     for (int r = 0; r < 8; r++) {   // pass 2: rows
-        idct_1d(ws + r * 8, 1, o);
+        const int* w = ws + r * 8;
+        if ((w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) {   // same shortcut, again value-identical
+            const uint8_t v = range_limit(descale((jlong)w[0], PASS1_BITS + 3));
+            for (int c = 0; c < 8; c++) out[r * out_stride + c] = v;
+            continue;
+        }
+        idct_1d(w, 1, o);
         for (int c = 0; c < 8; c++) out[r * out_stride + c] = range_limit(descale(o[c], CONST_BITS + PASS1_BITS + 3));
     }
 }
