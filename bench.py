@@ -4,8 +4,9 @@
   python bench.py --gpus N --steps K --warmup W            one rank per GPU (torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle) on the host cores
 
-Workload (config.workload = "C2"): COCO model, net 656x368, 1 scale, synthetic 1280x720 uint8 BGR stream
-(72 distinct frames, 199 MB > L2), random-init "W-he" weights, B frames per forward.
+Workload (config.workload = "C2", the default): COCO model, net 656x368, 1 scale, synthetic 1280x720 uint8 BGR
+stream (72 distinct frames, 199 MB > L2), random-init "W-he" weights, B frames per forward.
+`--workload C1|C3|C5` times the other BASELINE.json configs the same way (extra lines for BASELINE.md section 5).
 A step = one forward of B frames per GPU through the whole path: INTER_AREA/pad/normalise, the 92-conv
 stack, fused resize+NMS, PAF integral + greedy assignment + assembly, results to pinned host memory.
 
@@ -14,7 +15,8 @@ stack, fused resize+NMS, PAF integral + greedy assignment + assembly, results to
             joints/peaks inside the timed region, two handles per GPU so copies overlap compute
   roofline  conv stack (tcgen05 kernel, all its launches of one step): algorithmic FLOPs / device time
             from CUDA events on the engine stream, vs the measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline  the oracle (Caffe CPU arithmetic, im2col + OpenBLAS sgemm, all host cores) on one full frame
+  cpu_baseline  the oracle (Caffe CPU arithmetic, im2col + OpenBLAS sgemm, best host thread count) on one full frame
+`--impl reference` times the same oracle on FULL frames of the same workload (one frame per step).
 Frames are sharded one-per-GPU; the only collective is the init broadcast of the packed weights (NCCL).
 """
 import argparse
@@ -31,8 +33,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NET_W, NET_H, DISP_W, DISP_H = 656, 368, 1280, 720
-N_FRAMES = 72
+# BASELINE.json configs that fit one GPU.  C2 is the configuration the metric is quoted on (the default and the only
+# one the driver runs); the others are extra lines for BASELINE.md section 5 (`--workload C3` ...).
+#            model   net_w net_h disp_w disp_h S  start gap  frames/step  distinct frames   description
+WORKLOADS = {
+    "C1": ("MPI_15", 496, 368, 640, 480, 1, 1.0, 0.3, 12, 96, "C1: MPI 496x368, 1 scale, synthetic 640x480 stream, W-he random-init weights"),
+    "C2": ("COCO_18", 656, 368, 1280, 720, 1, 1.0, 0.3, 9, 72, "C2: COCO 656x368, 1 scale, synthetic 720p stream, W-he random-init weights"),
+    "C3": ("COCO_18", 656, 368, 1280, 720, 3, 1.0, 0.15, 3, 72, "C3: COCO 656x368, 3 scales (1.0/0.85/0.70), synthetic 720p stream, W-he random-init weights"),
+    "C5": ("COCO_18", 992, 736, 1920, 1080, 4, 1.0, 0.15, 1, 24, "C5 per GPU: COCO 992x736, 4 scales (gap 0.15), synthetic 1080p stream, W-he random-init weights"),
+}
 
 
 def parse():
@@ -41,7 +50,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--batch", type=int, default=9, help="frames per forward per GPU (9 x 4165 rows = 1.98 waves of 128-row tiles on 148 SMs)")
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS), help="BASELINE.json config (default C2 = the metric's config)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per forward per GPU (default: per workload; C2: 9 x 4165 rows = 1.98 waves of 128-row tiles on 148 SMs)")
     ap.add_argument("--precision", type=int, default=2, help="0 fp32 SIMT, 1 bf16, 2 f16x2 split (parity mode), 3 bf16x3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -107,80 +117,110 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows), "samples_under_load": len(sm)}
 
 
-def cpu_baseline_full_frame(model, weights, frame):
-    """The oracle (reference CPU path restated) on ONE full frame with every host core; ~10-30 s of CPU work."""
-    from oracle import orc
-    net = orc.Net(model)
-    net.set_weights(weights)
-    band = np.ascontiguousarray(frame[:192])
-    net.process_frame(band, 96, NET_W)  # warm-up on a band (BLAS threads, page faults)
+class Workload:
+    def __init__(self, name):
+        (m, self.net_w, self.net_h, self.disp_w, self.disp_h, self.S, self.start, self.gap, self.batch, self.n_frames,
+         self.desc) = WORKLOADS[name]
+        self.name = name
+        self.model_name = m
+
+    def model(self, mod):
+        return getattr(mod, self.model_name)
+
+    def metric(self):
+        return "frames/sec at %dx%d %s" % (self.net_w, self.net_h, "COCO-18" if self.model_name == "COCO_18" else "MPI-15")
+
+
+def tune_threads(net, wl, synth, orc):
+    """OpenBLAS on these GEMM shapes is SLOWER with all 128 threads than with 16-32 (fork/join cost): try a few thread
+    counts up to every core on a band of a frame and keep the fastest."""
     cores = os.cpu_count() or 1
+    band_h = 96 if wl.net_h >= 96 else wl.net_h
+    disp_band = max(16, int(round(wl.disp_h * band_h / float(wl.net_h))))
+    band = np.ascontiguousarray(synth.make_frame(1000, wl.disp_h, wl.disp_w)[:disp_band])
+    net.process_frame(band, band_h, wl.net_w, wl.S, wl.start, wl.gap)   # warm-up (BLAS threads, page faults)
     best_t, best_n = None, cores
-    for nthr in sorted({cores, max(cores // 2, 1), max(cores // 4, 1), min(cores, 16)}, reverse=True):
-        orc.lib().orc_set_threads(nthr)   # OpenBLAS fork/join cost: fewer threads can be faster; keep the best
+    for nthr in sorted({cores, max(cores // 2, 1), max(cores // 4, 1), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+        orc.lib().orc_set_threads(nthr)
         t = time.time()
-        net.process_frame(band, 96, NET_W)
+        net.process_frame(band, band_h, wl.net_w, wl.S, wl.start, wl.gap)
         t = time.time() - t
         if best_t is None or t < best_t:
             best_t, best_n = t, nthr
     orc.lib().orc_set_threads(best_n)
+    return best_n, cores
+
+
+def cpu_baseline_full_frame(wl, weights, frame):
+    """The oracle (reference CPU path restated) on ONE full frame of the workload; ~5-60 s of CPU work."""
+    from caffe_rtpose_b200 import synth
+    from oracle import orc
+    net = orc.Net(wl.model(orc))
+    net.set_weights(weights)
+    best_n, cores = tune_threads(net, wl, synth, orc)
     t = time.time()
-    cnt, joints, peaks, _ = net.process_frame(frame, NET_H, NET_W)
+    cnt, joints, peaks, _ = net.process_frame(frame, wl.net_h, wl.net_w, wl.S, wl.start, wl.gap)
     dt = time.time() - t
     return {"value": 1.0 / dt, "unit": "frames/s", "cores": best_n, "kind": "port",
-            "sample": "1 full 1280x720 frame (net 656x368, 1 scale, whole path incl. resize/NMS/connect), %.1f s; im2col + "
-                      "OpenBLAS sgemm with %d threads (fastest of the counts tried on 656x96 bands; %d cores available)"
-                      % (dt, best_n, cores)}, (cnt, joints, peaks)
+            "sample": "1 full %dx%d frame (net %dx%d, %d scale(s), whole path incl. resize/NMS/connect), %.1f s; im2col + "
+                      "OpenBLAS sgemm with %d threads (fastest of the counts tried on a band; %d cores available)"
+                      % (wl.disp_w, wl.disp_h, wl.net_w, wl.net_h, wl.S, dt, best_n, cores)}, (cnt, joints, peaks)
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path = the oracle port (the reference
     cannot be built here: no glog/gflags/boost/OpenCV-C++/protoc; its Forward_cpu for Nms/ImResize are
-    different algorithms - SURVEY.md section 0).  One step = one 656x48 BAND of a frame (13% of a frame) through
-    the whole path; frames/s is scaled by the band fraction.  Rank 0 only."""
+    different algorithms - SURVEY.md section 0).  SAME workload as the engine arm: one step = one FULL frame through
+    the whole CPU path (the engine arm's step is `frames_per_step_per_gpu` such frames; the metric is frames/s).
+    Rank 0 only."""
     if rank != 0:
         return
     from caffe_rtpose_b200 import synth
     from oracle import orc
-    model = orc.COCO_18
-    W = synth.make_weights(model, "he")
+    wl = Workload(args.workload)
+    model = wl.model(orc)
     net = orc.Net(model)
-    net.set_weights(W)
-    band_h = 48
-    disp_band = 96
-    frames = [np.ascontiguousarray(synth.make_frame(i)[:disp_band]) for i in range(4)]
-    frac = band_h / float(NET_H)
-    # "all the host threads it can use": OpenBLAS on the small per-band GEMMs is SLOWER with 128 threads than with
-    # 16-32 (fork/join cost), so pick the best-performing thread count up to all cores on one band each
-    cores = os.cpu_count() or 1
-    net.process_frame(frames[0], band_h, NET_W)
-    best_t, best_n = None, cores
-    for nthr in sorted({cores, max(cores // 2, 1), max(cores // 4, 1), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
-        orc.lib().orc_set_threads(nthr)
-        t = time.time()
-        net.process_frame(frames[1], band_h, NET_W)
-        t = time.time() - t
-        if best_t is None or t < best_t:
-            best_t, best_n = t, nthr
-    orc.lib().orc_set_threads(best_n)
+    net.set_weights(synth.make_weights(model, "he"))
+    best_n, cores = tune_threads(net, wl, synth, orc)
+    frames = [synth.make_frame(i, wl.disp_h, wl.disp_w) for i in range(4)]
     for i in range(args.warmup):
-        net.process_frame(frames[i % 4], band_h, NET_W)
+        net.process_frame(frames[i % 4], wl.net_h, wl.net_w, wl.S, wl.start, wl.gap)
     t0 = time.time()
     for i in range(args.steps):
-        net.process_frame(frames[i % 4], band_h, NET_W)
+        net.process_frame(frames[i % 4], wl.net_h, wl.net_w, wl.S, wl.start, wl.gap)
     dt = time.time() - t0
-    fps = args.steps * frac / dt
-    line = {"metric": "frames/sec at 656x368 COCO-18", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+    fps = args.steps / dt
+    line = {"metric": wl.metric(), "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "C2: COCO 656x368, 1 scale, synthetic 720p stream, W-he random-init weights",
-                       "step": "one 656x48 band (13.04% of a frame) through the whole CPU path; value scaled to full frames"},
+            "config": {"workload": wl.desc, "step": "one full frame through the whole CPU path (bounded sample of the engine arm's step)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": best_n, "kind": "port",
-                             "sample": "%d steps x one 656x48 band of a 1280x720 frame, scaled by 48/368; %d BLAS/OpenMP threads "
-                                       "(fastest of the counts tried, %d cores available)" % (args.steps, best_n, cores)},
+                             "sample": "%d steps x one full %dx%d frame (net %dx%d, %d scale(s)); %d BLAS/OpenMP threads "
+                                       "(fastest of the counts tried, %d cores available)"
+                                       % (args.steps, wl.disp_w, wl.disp_h, wl.net_w, wl.net_h, wl.S, best_n, cores)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def parity_note(wl, eng, frame, ref):
+    """Engine vs oracle on one frame at the default thresholds (the asserting version is tests/test_gpu_bench_parity.py)."""
+    ocnt, ojoints, opeaks = ref
+    eng.forward_frames([frame])
+    cnt, joints, peaks = eng.fetch(0)
+    mp = peaks.shape[1] - 1
+    note = "frame 0: people engine/oracle %d/%d, peak counts per part identical: %s" % (
+        cnt, ocnt, bool(np.array_equal(peaks[:, 0, 0], opeaks[:, 0, 0])))
+    if np.array_equal(peaks[:, 0, 0], opeaks[:, 0, 0]):
+        n = np.minimum(peaks[:, 0, 0], mp).astype(int)
+        d = max([float(np.abs(peaks[p, 1:1 + n[p], :2] - opeaks[p, 1:1 + n[p], :2]).max()) for p in range(len(n)) if n[p]] or [0.0])
+        note += ", max peak offset %.1e px" % d
+    if cnt == ocnt and cnt > 0 and np.array_equal(joints[:, :, 2] > 0, ojoints[:, :, 2] > 0):
+        d = float(np.abs(joints[:, :, :2] - ojoints[:, :, :2]).max()) * wl.net_w / wl.disp_w
+        note += "; identical part->person assignment for all %d persons, max joint offset %.1e net px (bar: 1e-3)" % (cnt, d)
+    else:
+        note += "; person assignment differs"
+    return note
 
 
 def main():
@@ -191,11 +231,13 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
-    if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # the image's default prints "NCCL version ..." on stdout, next to the JSON line
+    # NCCL's own log (communicator ranks, transports) is NOT silenced; it goes to stderr so that stdout carries the
+    # JSON line only
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     from caffe_rtpose_b200 import engine, synth
 
+    wl = Workload(args.workload)
     torch.cuda.set_device(local_rank)
     # nvidia-smi takes ~1 s to deliver its first sample: start it now, keep only the samples whose arrival time
     # falls inside the two timed regions (device-resident loop, end-to-end loop)
@@ -206,13 +248,14 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    model = engine.COCO_18
-    B = args.batch
+    model = wl.model(engine)
+    B = args.batch or wl.batch
+    n_frames = max(wl.n_frames // B, 2) * B
 
     # ---- engines: two handles per GPU (as the reference runs one Net per worker thread) so that the H2D of
     # one batch overlaps the compute of the other in the end-to-end loop
-    engs = [engine.PoseEngine(model, NET_W, NET_H, DISP_W, DISP_H, device=local_rank, max_batch=B, precision=args.precision)
-            for _ in range(2)]
+    engs = [engine.PoseEngine(model, wl.net_w, wl.net_h, wl.disp_w, wl.disp_h, num_scales=wl.S, start_scale=wl.start, scale_gap=wl.gap,
+                              device=local_rank, max_batch=B, precision=args.precision) for _ in range(2)]
     table = synth.conv_table(model)
     if rank == 0:
         W = synth.make_weights(model, "he")
@@ -231,14 +274,14 @@ def main():
             dist.broadcast(t, src=0)
         torch.cuda.synchronize()
 
-    # ---- frames: 64 distinct synthetic 720p frames, sharded round-robin over ranks; pinned host + device copies
-    frame_bytes = DISP_H * DISP_W * 3
-    host = torch.empty((N_FRAMES, DISP_H, DISP_W, 3), dtype=torch.uint8, pin_memory=True)
+    # ---- frames: distinct synthetic frames, sharded round-robin over ranks; pinned host + device copies
+    frame_bytes = wl.disp_h * wl.disp_w * 3
+    host = torch.empty((n_frames, wl.disp_h, wl.disp_w, 3), dtype=torch.uint8, pin_memory=True)
     hnp = host.numpy()
-    for i in range(N_FRAMES):
-        hnp[i] = synth.make_frame(rank * N_FRAMES + i)
+    for i in range(n_frames):
+        hnp[i] = synth.make_frame(rank * n_frames + i, wl.disp_h, wl.disp_w)
     dev = host.cuda(non_blocking=False)
-    nb = N_FRAMES // B
+    nb = n_frames // B
 
     def batch_dev(i):
         return dev.data_ptr() + (i % nb) * B * frame_bytes
@@ -332,49 +375,31 @@ def main():
         step_ms = ms_dev / args.steps
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
-        if os.path.exists(tp):   # dram__bytes_read+write per launch from the committed ncu capture of this same workload
+        if os.path.exists(tp):   # dram__bytes_read+write per launch from the committed ncu capture of this same workload and build
             tj = json.load(open(tp))
-            if tj.get("batch") == B and tj.get("precision") == args.precision:
+            if tj.get("batch") == B and tj.get("precision") == args.precision and tj.get("workload", "C2") == wl.name:
                 traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, avg over the 92 launches of a step)",
+                    "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, avg over the conv launches of a step)",
                     "traffic_source": traffic_src, "peak_source": "%s (bf16 dense, sustained)" % how,
-                    "kernel": "pe::conv_tcw_kernel<BN,PLANES,NA,NB,ROWB> (persistent tcgen05/TMEM/TMA implicit GEMM), %d launches per step" % len(conv),
+                    "kernel": "pe::conv_tc{w,p}_kernel (persistent tcgen05/TMEM/TMA implicit GEMM), %d launches per step" % len(conv),
                     "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "avg_launch_us": 1e3 * conv_ms / len(conv),
                     "share_of_step": conv_ms / step_ms, "other_layer_ms_per_step": other_ms,
                     "note": "algorithmic FLOPs (2*Cout*Cin*k^2*H*W); precision mode %d issues %d tensor-core MMAs per "
-                            "algorithmic MAC" % (args.precision, {0: 0, 1: 1, 2: 3, 3: 6}[args.precision])}
+                            "algorithmic MAC; kernel time = sum over the conv launches of one step, CUDA events on the engine "
+                            "stream between launches (serialised: no overlap between consecutive layers is credited)"
+                            % (args.precision, {0: 0, 1: 1, 2: 3, 3: 6}[args.precision])}
         cpu = None
         if not args.no_cpu_baseline:
-            cpu, (ocnt, ojoints, opeaks) = cpu_baseline_full_frame(model, W, hnp[0])
-            e1 = engs[1]
-            e1.forward_frames([hnp[0]])
-            cnt, joints, peaks = e1.fetch(0)
-            note = "frame 0: people engine/oracle %d/%d, peaks found %d/%d" % (
-                cnt, ocnt, int(peaks[:, 0, 0].sum()), int(opeaks[:, 0, 0].sum()))
-            if ocnt > 0:   # person-level match: same parts present and every joint within 1e-3 net px (display px / scale)
-                sc = DISP_W / float(NET_W)
-                same = 0
-                worst = 0.0
-                for oj in ojoints:
-                    for ej in joints:
-                        if np.array_equal(ej[:, 2] > 0, oj[:, 2] > 0):
-                            d = float(np.abs(ej[:, :2] - oj[:, :2]).max()) / sc
-                            if d < 1e-3:
-                                same += 1
-                                worst = max(worst, d)
-                                break
-                note += ("; %d/%d oracle persons reproduced with identical part assignment and all joints within 1e-3 px "
-                         "(max %.1e px); random-init maps are noise, so the remainder trace to NMS decisions whose margin is "
-                         "below fp reorder noise (the oracle's own BLAS order is not pinned by the reference)" % (same, ocnt, worst))
-            cpu["parity_note"] = note
-        line = {"metric": "frames/sec at 656x368 COCO-18", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            cpu, ref = cpu_baseline_full_frame(wl, W, hnp[0])
+            cpu["parity_note"] = parity_note(wl, engs[1], hnp[0], ref)
+        line = {"metric": wl.metric(), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {0: "f32", 1: "bf16", 2: "f16x2 (2 fp16 planes, 3 tcgen05 MMAs per MAC, fp32 accumulate)", 3: "bf16x3 (split, fp32 accumulate)"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": "C2: COCO 656x368, 1 scale, synthetic 720p stream, W-he random-init weights",
+                "config": {"workload": wl.desc,
                            "frames_per_step_per_gpu": B, "precision_mode": args.precision, "sharding": "frames round-robin, one rank per GPU",
-                           "l2": "72 distinct frames (199 MB) cycled > 126 MB L2; activations of one step >> L2",
+                           "l2": "%d distinct frames (%d MB) cycled > 126 MB L2; activations of one step >> L2" % (n_frames, n_frames * frame_bytes // 1000000),
                            "collective": "init broadcast of packed weights only (NCCL)" if world > 1 else "none"},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": d2h,

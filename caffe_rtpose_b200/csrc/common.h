@@ -60,15 +60,21 @@ struct OpRef { int type, idx; };                      // 0 conv, 1 pool, 2 copy
 struct BlobRef { std::string name; int act, coff, c; };
 
 struct NetPlan {
-    int model, c_l1, c_l2, kp_input;
+    int model = 0, c_l1 = 0, c_l2 = 0, kp_input = 0;
+    // nms_param / imresize_param of the prototxt (caffe.proto:1471-1484); rtpose.cpp overrides threshold and scales at run time
+    float nms_threshold = 0.5f; int nms_max_peaks = 20, nms_num_parts = 15;
+    float resize_start_scale = 1.f, resize_scale_gap = 0.1f;
     std::vector<ActSpec> acts;
     std::vector<ConvSpec> convs;
     std::vector<PoolSpec> pools;
     std::vector<CopySpec> copies;
     std::vector<OpRef> order;
     std::vector<BlobRef> blobs;
-    int input_act;
+    int input_act = 0;
 };
+struct NetDef;
+// plan from a parsed prototxt / built-in definition; -1 and a message when the graph is outside the supported family
+int build_plan_from_net(const NetDef& net, int kp_input, int cpad, NetPlan& out, std::string& err);
 // kp_input: channel pitch of the im2col'ed network input (27 -> 32 for SIMT, 64 for tcgen05)
 // cpad: channel granularity of every activation (16 SIMT / 64 tcgen05)
 NetPlan build_plan(int model, int kp_input, int cpad);

@@ -23,6 +23,7 @@
 //     (each owns the TMEM lane quadrant warp_id % 4).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <atomic>
@@ -132,6 +133,28 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool f16 = false) {   // a/b format: 0 = F16, 1 = BF16
     return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// One lane of a CONVERGED warp.  The MMA-issuing warp runs its loop with all 32 lanes (barrier waits, index math) and
+// only the issue itself under elect_one(): the compiler then keeps descriptors in uniform registers and emits plain
+// UTCHMMA.  With the role guarded by `lane == 0` it wrapped every UTCHMMA in an ELECT / BRA.U.ANY uniformisation loop
+// plus R2UR moves, ~115 SASS instructions per filter tap, and the single issuing thread - not the tensor pipe - set the
+// pace (ncu r2a: issuer never blocked on a barrier, tensor pipe 74 % on the 7x7 layers, 65 % on 3x3).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// Programmatic dependent launch (PDL): a conv kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream drains.  Everything before pdl_wait() - barrier init, TMEM allocation,
+// tensor-map prefetch, bias staging, L2 prefetch of the first weight tiles - overlaps the predecessor's tail;
+// pdl_wait() returns once the predecessor grid has completed and its writes are visible.  pdl_launch_dependents()
+// lets the NEXT kernel's CTAs be scheduled as soon as SMs free up.  No-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -310,7 +333,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // MMA rings run straight through tile boundaries, and the TMEM accumulator is double-buffered (2 x P*BN
 // columns) so the epilogue of tile i overlaps the main loop of tile i+1 - this removes the per-tile
 // prologue/epilogue latency that dominated the short-K layers (conv1_x, conv2_x).
-template <int BN, int PLANES, int NA, int NB, int ROWB, int EPI>
+template <int BN, int PLANES, int NA, int NB, int ROWB>
 __global__ void __launch_bounds__(TCW_THREADS, 1)
 conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     static_assert(PLANES == 1 || PLANES == 2, "window kernel supports 1 or 2 planes");
@@ -348,10 +371,16 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    if (warp == 0 && lane == 0 && blockIdx.x < total_tiles) {   // weights do not depend on the previous kernel: warm L2 with the first taps
+        const int n0 = (int)(blockIdx.x % n_tiles_n) * BN;
+        for (int q = 0; q < (ks < 4 ? ks : 4); q++) tma_prefetch_3d(&tmB, q * a.cin_k, n0, 0);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer: windows and per-tap weight tiles in consumption order =====
@@ -388,8 +417,8 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp runs the loop converged, one elected lane issues (see elect_one) =====
         // The tensor core adds every K=16 step into the fp32 TMEM accumulator with truncation, so a long chain drifts
         // (measured: 1.9e-4 relative over the net with one accumulator, 5.7e-5 with hi*hi alone in its accumulator).
         // The chain is therefore cut into CHUNKS of a.chunk_steps steps: every chunk starts from zero in one of the two
@@ -397,62 +426,71 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int aw = 0, bt = 0;
         uint32_t ci = 0;
         const int nsteps = a.kblocks_per_tap * ks, cs = a.chunk_steps;
+        const uint32_t sa_base = smem_u32(smem_a), sb_base = smem_u32(smem_b);
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             int step = 0, as = 0;
             uint32_t acc = 0;
-            bool first = true;
+            uint32_t first = 0;   // accumulate flag of the next hi*hi MMA (0 at the start of a chunk)
             for (int kb = 0; kb < a.kblocks_per_tap; kb++)
                 for (int r = 0; r < ks; r++) {
                     if (step % cs == 0) {
                         as = (int)(ci & 1u);
                         mbar_wait(&tmem_empty[as], ((ci >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
-                        tc_fence_after();
                         acc = tmem_base + (uint32_t)(as * ACC_COLS);
-                        first = true;
+                        first = 0;
                     }
                     const int sa_slot = aw % NA;
                     mbar_wait(&a_full[sa_slot], (uint32_t)(aw / NA) & 1u);
-                    const uint32_t sa = smem_u32(smem_a + sa_slot * A_SLOT);
                     // descriptors are built once per operand; K steps and row shifts only move the 14-bit start address
-                    const uint64_t dA0 = umma_desc(sa), dA1 = umma_desc(sa + TCW_A_BYTES);
+                    const uint64_t dA0 = umma_desc(sa_base + sa_slot * A_SLOT), dA1 = dA0 + (uint64_t)(TCW_A_BYTES >> 4);
                     if (ROWB) {
                         const int sb_slot = bt % NB;
                         mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
                         tc_fence_after();
-                        const uint64_t dB = umma_desc(smem_u32(smem_b + sb_slot * B_SLOT));
-                        for (int q = 0; q < ks; q++) {
+                        const uint64_t dB = umma_desc(sb_base + sb_slot * B_SLOT);
+                        if (elect_one()) {
+                            for (int q = 0; q < ks; q++) {
 #pragma unroll
-                            for (int k = 0; k < TC_BK / 16; k++) {
-                                const uint64_t db = dB + (uint64_t)(q * (B_TAP >> 4) + k * 2);
-                                umma_bf16(acc, dA0 + (uint64_t)(q * 8 + k * 2), db, IDESC1, first ? 0u : 1u);
-                                if (PLANES == 2) umma_bf16(acc + BN, dA1 + (uint64_t)(q * 8 + k * 2), db, IDESC2, 1u);
-                                first = false;
+                                for (int k = 0; k < TC_BK / 16; k++) {
+                                    const uint64_t db = dB + (uint64_t)(q * (B_TAP >> 4) + k * 2);
+                                    umma_bf16(acc, dA0 + (uint64_t)(q * 8 + k * 2), db, IDESC1, (q | k) ? 1u : first);
+                                    if (PLANES == 2) umma_bf16(acc + BN, dA1 + (uint64_t)(q * 8 + k * 2), db, IDESC2, 1u);
+                                }
                             }
+                            umma_commit(&b_empty[sb_slot]);
                         }
-                        umma_commit(&b_empty[sb_slot]);
+                        __syncwarp();
+                        first = 1;
                         bt++;
                     } else {
                         for (int q = 0; q < ks; q++) {
                             const int sb_slot = bt % NB;
                             mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
                             tc_fence_after();
-                            const uint64_t dB = umma_desc(smem_u32(smem_b + sb_slot * B_SLOT));
+                            const uint64_t dB = umma_desc(sb_base + sb_slot * B_SLOT);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < TC_BK / 16; k++) {
-                                // row-shifted view of the window: start address + q rows (q*128 B = q*8 units); the swizzle
-                                // phase follows the absolute smem address (verified on B200: base_offset must stay 0)
-                                umma_bf16(acc, dA0 + (uint64_t)(q * 8 + k * 2), dB + (uint64_t)(k * 2), IDESC1, first ? 0u : 1u);
-                                if (PLANES == 2) umma_bf16(acc + BN, dA1 + (uint64_t)(q * 8 + k * 2), dB + (uint64_t)(k * 2), IDESC2, 1u);
-                                first = false;
+                                for (int k = 0; k < TC_BK / 16; k++) {
+                                    // row-shifted view of the window: start address + q rows (q*128 B = q*8 units); the swizzle
+                                    // phase follows the absolute smem address (verified on B200: base_offset must stay 0)
+                                    umma_bf16(acc, dA0 + (uint64_t)(q * 8 + k * 2), dB + (uint64_t)(k * 2), IDESC1, k ? 1u : first);
+                                    if (PLANES == 2) umma_bf16(acc + BN, dA1 + (uint64_t)(q * 8 + k * 2), dB + (uint64_t)(k * 2), IDESC2, 1u);
+                                }
+                                umma_commit(&b_empty[sb_slot]);
                             }
-                            umma_commit(&b_empty[sb_slot]);
+                            __syncwarp();
+                            first = 1;
                             bt++;
                         }
                     }
-                    umma_commit(&a_empty[sa_slot]);
-                    aw++;
                     step++;
-                    if (step % cs == 0 || step == nsteps) { umma_commit(&tmem_full[as]); ci++; }
+                    if (elect_one()) {
+                        umma_commit(&a_empty[sa_slot]);
+                        if (step % cs == 0 || step == nsteps) umma_commit(&tmem_full[as]);
+                    }
+                    __syncwarp();
+                    if (step % cs == 0 || step == nsteps) ci++;
+                    aw++;
                 }
         }
     } else if (warp >= 2) {
@@ -482,10 +520,8 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 valid = (x < a.W) && (y < a.H);
             }
             // ---- sum the chunks of this tile in registers (fp32 round-to-nearest) ----
-            // EPI == 1 (experimental, PE_TC_EPI=1): the LAST chunk is not drained into accv but streamed piece by piece through
-            // bias / ReLU / split / store, so TMEM loads overlap the global stores as in the pre-chunking epilogue.
             float accv[HALF];
-            const int ndrain = EPI == 1 ? nchunks - 1 : nchunks;
+            const int ndrain = nchunks;
             for (int c = 0; c < ndrain; c++, ci++) {
                 const int as = (int)(ci & 1u);
                 mbar_wait(&tmem_full[as], (ci >> 1) & 1u);
@@ -518,7 +554,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);   // 8 epilogue warps -> accumulator free for chunk ci+2
             }
             // ---- bias, ReLU, re-split, store ----
-            if (EPI == 0) {
+            {
             if (active_half && valid) {
 #pragma unroll
                 for (int pc = 0; pc < NCHUNK; pc++) {
@@ -552,65 +588,6 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             }
-            } else {
-                const int as = (int)(ci & 1u);
-                mbar_wait(&tmem_full[as], (ci >> 1) & 1u);
-                tc_fence_after();
-                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS + half * HALF);
-                if (active_half) {
-                    uint32_t r[2][16], r2[2][16];
-                    __syncwarp();
-                    tmem_ld16_nowait(trow, r[0]);
-                    if (PLANES == 2) tmem_ld16_nowait(trow + BN, r2[0]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int pc = 0; pc < NCHUNK; pc++) {
-                        const int cur = pc & 1;
-                        if (pc + 1 < NCHUNK) {   // prefetch the next 16 columns while this piece is converted and stored
-                            __syncwarp();
-                            tmem_ld16_nowait(trow + (uint32_t)((pc + 1) * 16), r[cur ^ 1]);
-                            if (PLANES == 2) tmem_ld16_nowait(trow + (uint32_t)(BN + (pc + 1) * 16), r2[cur ^ 1]);
-                        }
-                        const int cb = n0 + half * HALF + pc * 16;
-                        if (valid) {
-                            float v[16];
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                float tv = __uint_as_float(r[cur][j]);
-                                if (PLANES == 2) tv = __fadd_rn(tv, __uint_as_float(r2[cur][j]));
-                                if (nchunks > 1) tv = __fadd_rn(accv[pc * 16 + j], tv);
-                                tv = __fmaf_rn(tv, out_scale, s_bias[cb + j]);
-                                if (a.relu) tv = fmaxf(tv, 0.f);
-                                v[j] = tv;
-                            }
-                        if (a.planar) {
-#pragma unroll
-                            for (int j = 0; j < 16; j++)
-                                if (cb + j < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + cb + j) * a.H + y) * a.W + x] = v[j];
-                        } else {
-                            uint32_t pk[PLANES][8];
-#pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                float r0 = v[j], r1 = v[j + 1];
-#pragma unroll
-                                for (int p = 0; p < PLANES; p++) pk[p][j / 2] = split_pair<F16>(r0, r1);   // one packed conversion
-                            }
-                            __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + cb;
-#pragma unroll
-                            for (int p = 0; p < PLANES; p++) {
-                                uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
-                                if (cb < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
-                                if (cb + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
-                            }
-                        }
-                        }
-                        if (pc + 1 < NCHUNK) { __syncwarp(); tmem_ld_wait(); }
-                    }
-                }
-                __syncwarp();
-                tc_fence_before();
-                if (lane == 0) mbar_arrive(&tmem_empty[as]);
-                ci++;
             }
         }
     }
@@ -618,6 +595,305 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster (one TPC) compute ONE 256-row tile.  Each CTA stages its own
+// 128(+k-1)-row A window and only HALF of every weight tile (rows [rank*BN/2, rank*BN/2 + BN/2) of B_hi and of B_lo):
+// the tensor core of each SM reads the other half from its partner.  Per SM this halves the weight bytes pulled from
+// L2 and held in shared memory (16 KB per tap instead of 32 KB at BN = 128 -> 7 B slots + 3 A windows) and it halves
+// the B bytes each MMA reads from shared memory, which is what bounded the single-CTA kernel (M=128 x N=128 reads
+// 8 KB per 64 cycles).  With that bottleneck gone the three partial products are three plain M=256 x N=BN MMAs:
+//   H += A_hi x B_hi   (large terms; chunked, see below)      C += A_hi x B_lo      C += A_lo x B_hi
+// TMEM (per CTA: its 128 rows): H0 | H1 | C0 | C1, BN columns each.  The hi*hi chain is cut into chunks that alternate
+// between H0 and H1 and are summed in registers with round-to-nearest by the epilogue warps (tensor-core accumulation
+// truncates); the cross terms are 2^-11 smaller, so their chain runs over the whole tile in C[tile & 1] and is drained
+// once.  Only the leader CTA (cluster rank 0) issues MMAs; both CTAs run a TMA producer and 8 epilogue warps.
+// Barriers: a_full/b_full live in the leader (the peer's TMA completes its bytes there, cp.async.bulk.tensor
+// .cta_group::2), a_empty/b_empty/h_full/c_full exist in both CTAs and are signalled by multicast tcgen05.commit,
+// h_empty/c_empty live in the leader and collect the 16 epilogue warps of the pair.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {   // warps arrive reconverged; the non-.aligned forms tolerate stragglers anyway
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar) {   // arrives on this barrier offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+constexpr int TCP_BM = 256;   // rows per pair tile
+
+template <int BN, int NA, int NB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCW_THREADS, 1)
+conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    constexpr int A_SLOT = 2 * TCW_A_BYTES;                 // hi + lo window of this CTA's 128 rows
+    constexpr int B_HALF = (BN / 2) * 128;                  // this CTA's rows of one plane of one tap
+    constexpr int B_TAP = 2 * B_HALF;                       // [B_hi half ; B_lo half]
+    constexpr int TMEM_COLS = 4 * BN <= 32 ? 32 : (4 * BN <= 64 ? 64 : (4 * BN <= 128 ? 128 : (4 * BN <= 256 ? 256 : 512)));
+    constexpr uint32_t IDESC = umma_idesc(TCP_BM, BN, true);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + NA * A_SLOT;
+    __shared__ __align__(8) uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB];
+    __shared__ __align__(8) uint64_t h_full[2], h_empty[2], c_full[2], c_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_bias[512];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int ks = a.ksize;
+    for (int i = threadIdx.x; i < 512; i += TCW_THREADS) s_bias[i] = (i < a.cout) ? a.bias[i] : 0.f;
+    const int n_tiles_n = a.n_tiles_n;
+    const long long total_tiles = a.total_tiles;
+    const long long tile0 = blockIdx.x >> 1, tile_stride = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], 16); mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {   // the same warp of both CTAs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0 && tile0 < total_tiles) {   // weights do not depend on the previous kernel: warm L2 with the first taps
+        const int n0 = (int)(tile0 % n_tiles_n) * BN + (int)rank * (BN / 2);
+        for (int q = 0; q < (ks < 4 ? ks : 4); q++) tma_prefetch_3d(&tmB, q * a.cin_k, n0, 0);
+    }
+    tc_fence_before();
+    cluster_sync_all();      // barrier inits and the TMEM allocation of both CTAs are visible to the pair
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t tm_h = tmem_base, tm_c = tmem_base + 2 * BN;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer (both CTAs): own A window, own half of every weight tile; bytes land on the leader's barriers =====
+        int aw = 0, bt = 0;
+        for (long long t = tile0; t < total_tiles; t += tile_stride) {
+            const long long m0 = (t / n_tiles_n) * TCP_BM + (long long)rank * TC_BM;
+            const int n0 = (int)(t % n_tiles_n) * BN + (int)rank * (BN / 2);
+            for (int kb = 0; kb < a.kblocks_per_tap; kb++)
+                for (int r = 0; r < ks; r++) {
+                    {
+                        const int s = aw % NA;
+                        mbar_wait(&a_empty[s], ((uint32_t)(aw / NA) & 1u) ^ 1u);
+                        if (rank == 0) mbar_expect_tx(&a_full[s], 2 * A_SLOT);
+                        const int row0 = (int)(m0 + (long long)(r - a.pad) * a.Wp - a.pad);
+                        tma_load_3d_2sm(smem_a + s * A_SLOT, &tmA, mapa_u32(smem_u32(&a_full[s]), 0), kb * TC_BK, row0, 0);
+                        aw++;
+                    }
+                    for (int q = 0; q < ks; q++) {
+                        const int s = bt % NB;
+                        mbar_wait(&b_empty[s], ((uint32_t)(bt / NB) & 1u) ^ 1u);
+                        if (rank == 0) mbar_expect_tx(&b_full[s], 2 * B_TAP);
+                        const int tap = r * ks + q;
+                        tma_load_3d_2sm(smem_b + s * B_TAP, &tmB, mapa_u32(smem_u32(&b_full[s]), 0), tap * a.cin_k + kb * TC_BK, n0, 0);   // box {64, BN/2, 2}
+                        bt++;
+                    }
+                }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===== MMA issuer (leader CTA only): converged warp, one elected lane issues =====
+        int aw = 0, bt = 0;
+        uint32_t ci = 0, ti = 0;
+        const int nsteps = a.kblocks_per_tap * ks, cs = a.chunk_steps;
+        const uint32_t sa_base = smem_u32(smem_a), sb_base = smem_u32(smem_b);
+        for (long long t = tile0; t < total_tiles; t += tile_stride, ti++) {
+            const uint32_t cbuf = ti & 1u;
+            mbar_wait(&c_empty[cbuf], ((ti >> 1) & 1u) ^ 1u);       // both CTAs' epilogues have drained this cross accumulator
+            const uint32_t accC = tm_c + cbuf * BN;
+            uint32_t accH = tm_h;
+            int step = 0, hs = 0;
+            uint32_t firstH = 0, firstC = 0;   // accumulate flags of the next H / C MMA
+            for (int kb = 0; kb < a.kblocks_per_tap; kb++)
+                for (int r = 0; r < ks; r++) {
+                    if (step % cs == 0) {
+                        hs = (int)(ci & 1u);
+                        mbar_wait(&h_empty[hs], ((ci >> 1) & 1u) ^ 1u);
+                        accH = tm_h + (uint32_t)(hs * BN);
+                        firstH = 0;
+                    }
+                    const int sa_slot = aw % NA;
+                    mbar_wait(&a_full[sa_slot], (uint32_t)(aw / NA) & 1u);
+                    const uint64_t dA0 = umma_desc(sa_base + sa_slot * A_SLOT), dA1 = dA0 + (uint64_t)(TCW_A_BYTES >> 4);
+                    for (int q = 0; q < ks; q++) {
+                        const int sb_slot = bt % NB;
+                        mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
+                        tc_fence_after();
+                        const uint64_t dBh = umma_desc(sb_base + sb_slot * B_TAP), dBl = dBh + (uint64_t)(B_HALF >> 4);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; k++) {
+                                const uint64_t ao = (uint64_t)(q * 8 + k * 2), bo = (uint64_t)(k * 2);
+                                umma_f16_2sm(accH, dA0 + ao, dBh + bo, IDESC, k ? 1u : firstH);
+                                umma_f16_2sm(accC, dA0 + ao, dBl + bo, IDESC, k ? 1u : firstC);
+                                umma_f16_2sm(accC, dA1 + ao, dBh + bo, IDESC, 1u);
+                            }
+                            umma_commit_mc(&b_empty[sb_slot]);
+                        }
+                        __syncwarp();
+                        firstH = 1; firstC = 1;
+                        bt++;
+                    }
+                    step++;
+                    const bool chunk_end = step % cs == 0 || step == nsteps;
+                    if (elect_one()) {
+                        umma_commit_mc(&a_empty[sa_slot]);
+                        if (chunk_end) umma_commit_mc(&h_full[hs]);
+                        if (step == nsteps) umma_commit_mc(&c_full[cbuf]);
+                    }
+                    __syncwarp();
+                    if (chunk_end) ci++;
+                    aw++;
+                }
+        }
+    } else if (warp >= 2) {
+        // ===== epilogue (both CTAs): 8 warps; warp w owns TMEM lanes 32*(w%4).. (this CTA's rows) and column half (w-2)/4 =====
+        constexpr bool SPLIT = (BN / 2) % 16 == 0;
+        constexpr int HALF = SPLIT ? BN / 2 : BN;
+        constexpr int NCHUNK = HALF / 16;
+        const int quad = warp & 3;
+        const int half = SPLIT ? (warp - 2) / 4 : 0;
+        const bool active_half = SPLIT || (warp - 2) / 4 == 0;
+        const int per_img = a.Hs * a.Wp;
+        const int cout8 = (a.cout + 7) & ~7;
+        const float out_scale = __ldg(a.out_scale);
+        const uint32_t h_empty_leader = mapa_u32(smem_u32(&h_empty[0]), 0), c_empty_leader = mapa_u32(smem_u32(&c_empty[0]), 0);
+        uint32_t ci = 0, ti = 0;
+        const int nsteps = a.kblocks_per_tap * ks;
+        const int nchunks = (nsteps + a.chunk_steps - 1) / a.chunk_steps;
+        for (long long t = tile0; t < total_tiles; t += tile_stride, ti++) {
+            const long long m0 = (t / n_tiles_n) * TCP_BM + (long long)rank * TC_BM;
+            const int n0 = (int)(t % n_tiles_n) * BN;
+            const long long m = m0 + quad * 32 + lane;
+            bool valid = m < a.M;
+            int n = 0, y = 0, x = 0;
+            if (valid) {
+                n = (int)(m / per_img);
+                const int rem = (int)(m % per_img);
+                y = rem / a.Wp; x = rem % a.Wp;
+                valid = (x < a.W) && (y < a.H);
+            }
+            float accv[HALF];
+            // ---- hi*hi chunks, summed in registers with round-to-nearest ----
+            for (int c = 0; c < nchunks; c++, ci++) {
+                const int hs = (int)(ci & 1u);
+                mbar_wait(&h_full[hs], (ci >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tm_h + ((uint32_t)(quad * 32) << 16) + (uint32_t)(hs * BN + half * HALF);
+                if (active_half) {
+                    uint32_t r[2][16];
+                    __syncwarp();
+                    tmem_ld16_nowait(trow, r[0]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int pc = 0; pc < NCHUNK; pc++) {
+                        const int cur = pc & 1;
+                        if (pc + 1 < NCHUNK) tmem_ld16_nowait(trow + (uint32_t)((pc + 1) * 16), r[cur ^ 1]);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float tv = __uint_as_float(r[cur][j]);
+                            accv[pc * 16 + j] = (c == 0) ? tv : __fadd_rn(accv[pc * 16 + j], tv);
+                        }
+                        if (pc + 1 < NCHUNK) tmem_ld_wait();
+                    }
+                }
+                __syncwarp();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive_cluster(h_empty_leader + (uint32_t)(hs * 8));
+            }
+            // ---- cross terms of the whole tile, then bias / ReLU / re-split / store piece by piece ----
+            {
+                const uint32_t cbuf = ti & 1u;
+                mbar_wait(&c_full[cbuf], (ti >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tm_c + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cbuf * BN + half * HALF);
+                if (active_half) {
+                    uint32_t r[2][16];
+                    __syncwarp();
+                    tmem_ld16_nowait(trow, r[0]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int pc = 0; pc < NCHUNK; pc++) {
+                        const int cur = pc & 1;
+                        if (pc + 1 < NCHUNK) { __syncwarp(); tmem_ld16_nowait(trow + (uint32_t)((pc + 1) * 16), r[cur ^ 1]); }
+                        const int cb = n0 + half * HALF + pc * 16;   // first output channel of this piece
+                        if (valid) {
+                            float v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                float tv = __fadd_rn(accv[pc * 16 + j], __uint_as_float(r[cur][j]));
+                                tv = __fmaf_rn(tv, out_scale, s_bias[cb + j]);   // out_scale is a power of two: exact
+                                if (a.relu) tv = fmaxf(tv, 0.f);
+                                v[j] = tv;
+                            }
+                            if (a.planar) {
+#pragma unroll
+                                for (int j = 0; j < 16; j++)
+                                    if (cb + j < a.cout) a.planar[(((size_t)n * a.planar_C + a.planar_coff + cb + j) * a.H + y) * a.W + x] = v[j];
+                            } else {
+                                uint32_t pk[2][8];
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2) {
+                                    float r0 = v[j], r1 = v[j + 1];
+#pragma unroll
+                                    for (int p = 0; p < 2; p++) pk[p][j / 2] = split_pair<true>(r0, r1);
+                                }
+                                __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + cb;
+#pragma unroll
+                                for (int p = 0; p < 2; p++) {
+                                    uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
+                                    if (cb < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+                                    if (cb + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
+                                }
+                            }
+                        }
+                        if (pc + 1 < NCHUNK) { __syncwarp(); tmem_ld_wait(); }
+                    }
+                }
+                __syncwarp();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive_cluster(c_empty_leader + (uint32_t)(cbuf * 8));
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();      // no CTA of the pair exits (or frees TMEM) while its partner can still signal it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -683,9 +959,24 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-template <int BN, int PLANES, int NA, int NB, int ROWB, int EPI>
-static int launch_win_epi(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
-    auto kern = conv_tcw_kernel<BN, PLANES, NA, NB, ROWB, EPI>;
+// Launch with the programmatic-stream-serialization attribute (PDL, see pdl_wait): back-to-back conv kernels overlap the
+// next one's prologue with the previous one's tail.  PE_TC_PDL=0 launches plainly.
+template <typename Kern>
+static int launch_pdl(Kern kern, dim3 grid, int smem, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a) {
+    static const int pdl = env_int("PE_TC_PDL", 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TCW_THREADS, 1, 1); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, ma, mb, a);
+    return 1;
+}
+
+template <int BN, int PLANES, int NA, int NB, int ROWB>
+static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
+    auto kern = conv_tcw_kernel<BN, PLANES, NA, NB, ROWB>;
     const int smem = NA * PLANES * TCW_A_BYTES + NB * (ROWB ? 3 : 1) * PLANES * BN * 128 + 1024;
     static std::atomic<unsigned long long> attr_done{0};   // bit d: attribute set on device d (it is per device)
     int dev = 0;
@@ -695,15 +986,26 @@ static int launch_win_epi(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStre
         attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
-    kern<<<grid, TCW_THREADS, smem, st>>>(maps[2], maps[bmap], a);
-    return 1;
+    return launch_pdl(kern, grid, smem, st, maps[2], maps[bmap], a);
 }
-template <int BN, int PLANES, int NA, int NB, int ROWB>
-static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
-    static const int epi = env_int("PE_TC_EPI", 0);   // 1: experimental streamed-last-chunk epilogue (A/B, tools/ab_bench.sh)
-    if (epi == 1) return launch_win_epi<BN, PLANES, NA, NB, ROWB, 1>(l, a, grid, st, bmap);
-    return launch_win_epi<BN, PLANES, NA, NB, ROWB, 0>(l, a, grid, st, bmap);
+template <int BN>
+static int launch_pair(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
+    constexpr int NA = 3;
+    constexpr int B_TAP = BN * 128;
+    constexpr int NB = (120 * 1024) / B_TAP >= 12 ? 12 : (120 * 1024) / B_TAP;   // BN = 128: 7 slots
+    auto kern = conv_tcp_kernel<BN, NA, NB>;
+    const int smem = NA * 2 * TCW_A_BYTES + NB * B_TAP + 1024;
+    static std::atomic<unsigned long long> attr_done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_done.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+    const CUtensorMap* maps = (const CUtensorMap*)l.maps;
+    return launch_pdl(kern, grid, smem, st, maps[2], maps[bmap], a);
 }
+
 template <int BN>
 static int launch_win_bn(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
     if (BN <= 64 && l.d.ksize <= 3) {   // narrow-N layers (conv1_x, the 1x1 heads): filter-row B slots
@@ -722,7 +1024,7 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
     out.d = d;
     out.bn = tc_bn(d.cout_pad);
     CUtensorMap* maps = nullptr;
-    if (posix_memalign((void**)&maps, 64, 6 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
+    if (posix_memalign((void**)&maps, 64, 10 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
     const int taps = d.ksize * d.ksize;
     const cuuint64_t K = (cuuint64_t)taps * d.in_cused;
     {   // A: [planes][M][pitch] bf16, box {64, 128, 1}
@@ -776,6 +1078,19 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(B narrow) failed: " + std::to_string((int)r); free(maps); return -1; }
     }
+    // pair kernel (cta_group::2): each CTA of the pair loads HALF of the N rows of both planes, box {64, bn/2, 2}
+    for (int v = 0; v < 3 && d.planes == 2; v++) {
+        const int bn = v == 0 ? out.bn : (v == 1 ? 64 : 32);
+        if (v > 0 && out.bn != 128) break;
+        cuuint64_t dims[3] = {K, (cuuint64_t)d.cout_pad, (cuuint64_t)d.planes};
+        cuuint64_t strides[2] = {K * 2, K * 2 * (cuuint64_t)d.cout_pad};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)(bn / 2), 2};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&maps[6 + v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d.w, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(B pair) failed: " + std::to_string((int)r); free(maps); return -1; }
+    }
     out.maps = maps;
     out.stages = pick_stages(out.bn, d.planes);
     out.smem_bytes = out.stages * stage_bytes(out.bn, d.planes) + 1024;
@@ -806,6 +1121,36 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
         // Tile width: 128 output channels per CTA is the efficient shape, but a single frame at the 46x82 level has
         // only 33 row tiles for 148 SMs.  Pick the width that maximises (CTAs that can run at once) x (relative
         // efficiency of that MMA shape: the A operand is re-read per N tile, so narrow tiles are smem-bound).
+        static const int pair = env_int("PE_TC_PAIR", 0);   // 1: CTA-pair kernel (cta_group::2) for the fp16-plane parity mode
+        if (pair && d.planes == 2 && planes_are_fp16(2) && nsm >= 2) {
+            const long long mt = (a.M + TCP_BM - 1) / TCP_BM;
+            const int npairs = nsm / 2;
+            int bn = l.bn, bmap = 6;
+            if (l.bn == 128) {   // same trade-off as below, in units of CTA pairs
+                const double s128 = (double)std::min<long long>(mt * (d.cout_pad / 128), npairs) * 1.00;
+                const double s64 = (double)std::min<long long>(mt * (d.cout_pad / 64), npairs) * 0.80;
+                const double s32 = (double)std::min<long long>(mt * (d.cout_pad / 32), npairs) * 0.55;
+                if (s64 > s128 && s64 >= s32) { bn = 64; bmap = 7; }
+                else if (s32 > s128 && s32 > s64) { bn = 32; bmap = 8; }
+            }
+            a.n_tiles_n = d.cout_pad / bn;
+            a.total_tiles = mt * a.n_tiles_n;
+            const int nsteps = a.kblocks_per_tap * a.ksize;
+            static const int chunk_env = env_int("PE_TC_CHUNK", -1);
+            static const int chunk_mul = env_int("PE_TC_CHUNK_MUL", 1);
+            int cs = (a.ksize >= 7 ? 1 : (a.ksize >= 3 ? 2 : 4)) * (chunk_mul < 1 ? 1 : chunk_mul);
+            if (chunk_env == 0) cs = nsteps;
+            else if (chunk_env > 0) cs = chunk_env;
+            a.chunk_steps = cs < 1 ? 1 : (cs > nsteps ? nsteps : cs);
+            grid = dim3((unsigned)(2 * std::min<long long>(a.total_tiles, npairs)), 1, 1);
+            switch (bn) {
+                case 128: return launch_pair<128>(l, a, grid, st, bmap);
+                case 64: return launch_pair<64>(l, a, grid, st, bmap);
+                case 48: return launch_pair<48>(l, a, grid, st, bmap);
+                case 32: return launch_pair<32>(l, a, grid, st, bmap);
+                default: return launch_pair<16>(l, a, grid, st, bmap);
+            }
+        }
         int bn = l.bn, bmap = 3;
         if (l.bn == 128) {
             static const int narrow = env_int("PE_TC_NARROW", 1);

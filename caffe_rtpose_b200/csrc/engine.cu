@@ -15,6 +15,7 @@
 #include "common.h"
 #include "kernels.h"
 #include "conv_tc.h"
+#include "prototxt.h"
 
 using namespace pe;
 
@@ -26,6 +27,7 @@ struct pe_engine {
     pe_config cfg;
     NetPlan plan;
     const ModelTables* mt = nullptr;
+    ModelTables mt_own;     // model tables with the prototxt's nms max_peaks
     Geo geo[4];
     int planes = 0;         // 0: fp32 SIMT, else bf16 planes
     int elem = 4;
@@ -191,9 +193,66 @@ static void set_post_params(pe_engine* e) {
     p.num_scales = c.num_scales;
 }
 
-extern "C" int pe_create(const pe_config* cfg, pe_engine** out) {
-    if (!cfg || !out) return fail(nullptr, PE_ERR_INVALID, "null argument");
+// Host-only view of the execution plan a prototxt (or, with path == NULL, the built-in graph of `model`) produces: one
+// line per op, "conv <name> cout cin k relu level in_act in_cused out_act out_coff planar_coff", "pool <name> in out",
+// "copy src dst channels", then "nms threshold max_peaks num_parts" and "resize start_scale scale_gap".  No GPU needed.
+extern "C" int pe_plan_describe(int model, const char* prototxt_path, char* buf, int cap) {
+    NetDef net;
+    std::string err;
+    if (prototxt_path) {
+        if (parse_prototxt_file(prototxt_path, net, err)) return -fail(nullptr, PE_ERR_IO, "%s: %s", prototxt_path, err.c_str());
+    } else {
+        if (model != PE_MODEL_MPI_15 && model != PE_MODEL_COCO_18) return -fail(nullptr, PE_ERR_INVALID, "unknown model %d", model);
+        net = builtin_netdef(model, 6);
+    }
+    NetPlan p;
+    if (build_plan_from_net(net, 64, 64, p, err)) return -fail(nullptr, PE_ERR_INVALID, "%s", err.c_str());
+    std::string s = "model " + std::to_string(p.model) + "\n";
+    char t[512];
+    for (const OpRef& op : p.order) {
+        if (op.type == 0) {
+            const ConvSpec& c = p.convs[op.idx];
+            snprintf(t, sizeof t, "conv %s %d %d %d %d %d %d %d %d %d %d\n", c.name.c_str(), c.cout, c.cin, c.k, c.relu, c.level, c.in_act, c.in_cused,
+                     c.out_act, c.out_coff, c.planar_coff);
+        } else if (op.type == 1) {
+            snprintf(t, sizeof t, "pool %s %d %d\n", p.pools[op.idx].name.c_str(), p.pools[op.idx].in_act, p.pools[op.idx].out_act);
+        } else {
+            snprintf(t, sizeof t, "copy %d %d %d\n", p.copies[op.idx].src_act, p.copies[op.idx].dst_act, p.copies[op.idx].channels);
+        }
+        s += t;
+    }
+    snprintf(t, sizeof t, "nms %g %d %d\nresize %g %g\n", p.nms_threshold, p.nms_max_peaks, p.nms_num_parts, p.resize_start_scale, p.resize_scale_gap);
+    s += t;
+    if (buf && (int)s.size() < cap) memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+static int create_impl(const pe_config* cfg, const char* prototxt_path, pe_engine** out);
+extern "C" int pe_create(const pe_config* cfg, pe_engine** out) { return create_impl(cfg, nullptr, out); }
+// new caffe::Net(proto, TEST): the graph comes from the deploy prototxt (rtpose.cpp:183, net.cpp:30-50); cfg->model may be
+// -1, the model then follows the Nms layer's num_parts as in rtpose.cpp:212-229.
+extern "C" int pe_create_from_prototxt(const pe_config* cfg, const char* prototxt_path, pe_engine** out) {
+    if (!prototxt_path) return fail(nullptr, PE_ERR_INVALID, "null prototxt path");
+    return create_impl(cfg, prototxt_path, out);
+}
+
+static int create_impl(const pe_config* cfg_in, const char* prototxt_path, pe_engine** out) {
+    if (!cfg_in || !out) return fail(nullptr, PE_ERR_INVALID, "null argument");
     *out = nullptr;
+    pe_config cfg_copy = *cfg_in;
+    pe_config* cfg = &cfg_copy;
+    NetDef netdef;
+    NetPlan proto_plan;
+    if (prototxt_path) {
+        std::string perr;
+        if (parse_prototxt_file(prototxt_path, netdef, perr)) return fail(nullptr, PE_ERR_IO, "%s: %s", prototxt_path, perr.c_str());
+        if (build_plan_from_net(netdef, cfg->precision ? 64 : 32, cfg->precision ? 64 : 16, proto_plan, perr))
+            return fail(nullptr, PE_ERR_INVALID, "%s: %s", prototxt_path, perr.c_str());
+        if (cfg->model >= 0 && cfg->model != proto_plan.model)
+            return fail(nullptr, PE_ERR_INVALID, "%s describes the %s model (nms num_parts %d), the configuration asks for model %d", prototxt_path,
+                        proto_plan.model == PE_MODEL_MPI_15 ? "MPI" : "COCO", proto_plan.nms_num_parts, cfg->model);
+        cfg->model = proto_plan.model;
+    }
     if (cfg->model != PE_MODEL_MPI_15 && cfg->model != PE_MODEL_COCO_18) return fail(nullptr, PE_ERR_INVALID, "unknown model %d", cfg->model);
     if (cfg->net_w <= 0 || cfg->net_h <= 0 || cfg->net_w % 8 || cfg->net_h % 8)
         return fail(nullptr, PE_ERR_INVALID, "net resolution %dx%d must be positive multiples of 8", cfg->net_w, cfg->net_h);
@@ -210,7 +269,9 @@ extern "C" int pe_create(const pe_config* cfg, pe_engine** out) {
     memset(&e->post, 0, sizeof e->post);   // PODs: every pointer must be null for pe_destroy on an early failure
     memset(&e->pre, 0, sizeof e->pre);
     e->cfg = *cfg;
-    e->mt = &model_tables(cfg->model);
+    e->mt_own = model_tables(cfg->model);
+    if (prototxt_path) e->mt_own.max_peaks = proto_plan.nms_max_peaks;   // nms_param.max_peaks (NmsLayer::GetMaxPeaks, rtpose.cpp:195)
+    e->mt = &e->mt_own;
     e->planes = cfg->precision;  // 0 fp32, else number of bf16 planes
     if (const char* g = getenv("PE_GRAPH")) e->use_graphs = atoi(g) != 0;
     e->elem = e->planes == 0 ? 4 : 2;
@@ -235,7 +296,7 @@ extern "C" int pe_create(const pe_config* cfg, pe_engine** out) {
         w = pooled(w); h = pooled(h);
     }
     if (e->geo[3].W * 8 != cfg->net_w || e->geo[3].H * 8 != cfg->net_h) { fail(e, PE_ERR_INVALID, "net size not divisible by 8 after pooling"); return bail(PE_ERR_INVALID); }
-    e->plan = build_plan(cfg->model, e->planes ? 64 : 32, e->planes ? 64 : 16);
+    e->plan = prototxt_path ? proto_plan : build_plan(cfg->model, e->planes ? 64 : 32, e->planes ? 64 : 16);
     e->hw.resize(e->plan.convs.size());
     // FLOPs: 2*Cout*Cin*k^2*Hout*Wout per conv and image
     e->flops_per_scale = 0;

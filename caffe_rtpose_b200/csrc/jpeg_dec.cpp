@@ -136,11 +136,11 @@ inline void idct_1d(const int* in, int stride, jlong* o) {
 void idct_islow(const short* coef, const uint16_t* quant, uint8_t* out, int out_stride) {
     int deq[64], ws[64];
     jlong o[8];
-    for (int i = 0; i < 64; i++) deq[i] = (int)coef[i] * (int)quant[i];
+    for (int i = 0; i < 64; i++) deq[i] = (int)((jlong)coef[i] * (jlong)quant[i]);
     for (int c = 0; c < 8; c++) {   // pass 1: columns
         if ((deq[8 + c] | deq[16 + c] | deq[24 + c] | deq[32 + c] | deq[40 + c] | deq[48 + c] | deq[56 + c]) == 0) {
             // libjpeg's shortcut for a column without AC terms; the general formula gives the same value (dc << PASS1_BITS)
-            const int dcv = deq[c] * (1 << PASS1_BITS);
+            const int dcv = (int)((jlong)deq[c] * (1 << PASS1_BITS));   // 64-bit like the general path (corrupt 16-bit DQT x DC overflows int)
             for (int r = 0; r < 8; r++) ws[r * 8 + c] = dcv;
             continue;
         }
@@ -237,7 +237,7 @@ inline bool decode_block(BitReader& br, Comp& c, const HuffTab* dc, const HuffTa
     if (!sp.progressive) {
         int s = huff_decode(br, dc[c.td]);
         if (s > 15) return false;
-        c.pred += s ? extend(br.get(s), s) : 0;
+        c.pred = (int)((unsigned)c.pred + (unsigned)(s ? extend(br.get(s), s) : 0));   // unsigned wrap: no UB on corrupt streams
         blk[0] = (short)c.pred;
         for (int k = 1; k < 64;) {
             const int rs = huff_decode(br, ac[c.ta]);
@@ -255,8 +255,8 @@ inline bool decode_block(BitReader& br, Comp& c, const HuffTab* dc, const HuffTa
         if (sp.Ah == 0) {   // DC first
             const int s = huff_decode(br, dc[c.td]);
             if (s > 15) return false;
-            c.pred += s ? extend(br.get(s), s) : 0;
-            blk[0] = (short)(c.pred * (1 << sp.Al));
+            c.pred = (int)((unsigned)c.pred + (unsigned)(s ? extend(br.get(s), s) : 0));
+            blk[0] = (short)((unsigned)c.pred << sp.Al);
         } else if (br.get(1)) {   // DC refinement
             blk[0] = (short)(blk[0] | (1 << sp.Al));
         }
@@ -406,7 +406,7 @@ extern "C" int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* 
             if (len < 4) return -1;
             restart = rd16(s);
         } else if (m == 0xDA) {                            // SOS: decode one scan into the coefficient arrays
-            if (!have_sof) return -1;
+            if (!have_sof || len < 3) return -1;          // a truncated segment (length field only) has no payload byte to read
             const int ns = s[0];
             if (ns < 1 || ns > (int)comps.size() || len < 6 + 2 * ns) return -1;
             std::vector<Comp*> sc;

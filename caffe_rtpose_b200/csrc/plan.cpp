@@ -7,7 +7,11 @@
 // im2col'ed input so that it is a K=27 1x1 GEMM.
 #include <stdio.h>
 
+#include <algorithm>
+#include <map>
+
 #include "common.h"
+#include "prototxt.h"
 
 namespace pe {
 
@@ -47,131 +51,253 @@ const char* model_part_name(int model, int idx) {
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-NetPlan build_plan(int model, int kp_input, int cpad) {
-    NetPlan p;
-    const ModelTables& mt = model_tables(model);
-    p.model = model;
-    p.c_l1 = 2 * mt.num_limbs;       // PAF branch (L1)
-    p.c_l2 = mt.num_parts + 1;       // part + background branch (L2)
-    p.kp_input = kp_input;
+// ---------------------------------------------------------------------------------------------
+// Execution plan from a network definition (prototxt or built-in).  What Net::Init does for the reference
+// (net.cpp:30-280: blob wiring, shape inference, in-place ReLU) plus the engine's own layout decisions:
+//   * ReLU is fused into the producing conv, Concat is removed: producers write channel slices of a shared buffer
+//     (layout [blobs shared by several concats | the others], slots 8-aligned), consumers get a channel map;
+//   * the concat buffers of successive stages ping-pong between two physical buffers; a blob that feeds several
+//     concats (conv4_4_CPM) is written once and copied once;
+//   * the last Concat (the bottom of ImResize) is never materialised in NHWC: its producers store the planar fp32
+//     stride-8 maps directly.
+// Supported: the deploy-graph family of model/{coco,mpi}/pose_deploy_linevec*.prototxt - stride-1 odd-kernel (<= 7)
+// "same"-padded convolutions, in-place ReLU, 2x2/2 MAX pooling, channel Concat, ImResize(factor 8), Nms, any number
+// of stages.  Anything else is reported as an error (the reference would run it through generic Caffe layers).
+// ---------------------------------------------------------------------------------------------
+int build_plan_from_net(const NetDef& net, int kp_input, int cpad, NetPlan& p, std::string& err) {
+    p = NetPlan();
+    const int NL = (int)net.layers.size();
+    auto fail = [&](const std::string& m) { err = m; return -1; };
+    if (net.inputs.size() != 1) return fail("expected exactly one net input, found " + std::to_string(net.inputs.size()));
+    if (net.input_dims.size() >= 2 && net.input_dims[1] != 3) return fail("the net input must have 3 channels");
+    const std::string input_blob = net.inputs[0];
 
-    auto new_act = [&](int level, int c, const std::string& blob, int blob_c) {
-        ActSpec a; a.level = level; a.C = round_up(c, cpad); a.blob = blob; a.blob_c = blob_c;
+    // ---- special layers and the model (rtpose.cpp:212-229 infers it from the Nms layer's num_parts)
+    int resize_idx = -1, nms_idx = -1;
+    for (int i = 0; i < NL; i++) {
+        if (net.layers[i].type == "ImResize") resize_idx = i;
+        if (net.layers[i].type == "Nms") nms_idx = i;
+    }
+    if (resize_idx < 0 || nms_idx < 0) return fail("the deploy net needs an ImResize and an Nms layer (layer_by_name(\"resize\"/\"nms\"), rtpose.cpp:194-199)");
+    const ProtoLayer& nms = net.layers[nms_idx];
+    const ProtoLayer& rsz = net.layers[resize_idx];
+    if (nms.nms_num_parts == 15) p.model = PE_MODEL_MPI_15;
+    else if (nms.nms_num_parts == 18) p.model = PE_MODEL_COCO_18;
+    else return fail("Unknown number of parts! Couldn't set model (nms num_parts = " + std::to_string(nms.nms_num_parts) + ", rtpose.cpp:228)");
+    if (rsz.resize_factor != 8.f) return fail("ImResize factor " + std::to_string(rsz.resize_factor) + " is not supported (the stride of the net is 8)");
+    if (nms.nms_max_peaks < 1 || nms.nms_max_peaks > 127) return fail("nms max_peaks out of range");
+    if (nms.bottoms.size() != 1 || rsz.tops.size() != 1 || nms.bottoms[0] != rsz.tops[0]) return fail("Nms must consume the ImResize output");
+    const ModelTables& mt = model_tables(p.model);
+    p.c_l1 = 2 * mt.num_limbs; p.c_l2 = mt.num_parts + 1; p.kp_input = kp_input;
+    p.nms_threshold = nms.nms_threshold; p.nms_max_peaks = nms.nms_max_peaks; p.nms_num_parts = nms.nms_num_parts;
+    p.resize_start_scale = rsz.resize_start_scale; p.resize_scale_gap = rsz.resize_scale_gap;
+
+    // ---- producers / consumers / channels / levels
+    std::map<std::string, int> producer, channels, level;
+    std::map<std::string, std::vector<int>> consumers;
+    channels[input_blob] = 3; level[input_blob] = 0;
+    for (int i = 0; i < NL; i++) {
+        const ProtoLayer& l = net.layers[i];
+        if (l.tops.size() != 1) return fail("layer " + l.name + ": exactly one top expected");
+        if (l.bottoms.empty()) return fail("layer " + l.name + ": no bottom");
+        for (const std::string& b : l.bottoms) {
+            if (!channels.count(b)) return fail("layer " + l.name + ": unknown bottom blob " + b);
+            consumers[b].push_back(i);
+        }
+        const std::string& top = l.tops[0];
+        const int lv = level[l.bottoms[0]];
+        if (l.type == "Convolution") {
+            if (l.bottoms.size() != 1) return fail("layer " + l.name + ": one bottom expected");
+            if (l.num_output < 1 || l.kernel < 1 || l.kernel > 7 || l.kernel % 2 == 0 || l.pad != l.kernel / 2 || l.stride != 1)
+                return fail("layer " + l.name + ": only stride-1 'same' convolutions with odd kernel <= 7 are supported (kernel " +
+                            std::to_string(l.kernel) + ", pad " + std::to_string(l.pad) + ", stride " + std::to_string(l.stride) + ")");
+            if (producer.count(top)) return fail("layer " + l.name + ": top " + top + " is produced twice");
+            producer[top] = i; channels[top] = l.num_output; level[top] = lv;
+        } else if (l.type == "ReLU") {
+            if (l.bottoms[0] != top || !producer.count(top) || net.layers[producer[top]].type != "Convolution")
+                return fail("layer " + l.name + ": ReLU must run in place on a convolution output");
+        } else if (l.type == "Pooling") {
+            if (l.pool_method != 0 || l.kernel != 2 || l.stride != 2 || l.pad != 0) return fail("layer " + l.name + ": only 2x2 stride-2 MAX pooling is supported");
+            if (lv >= 3) return fail("layer " + l.name + ": more than three pooling levels");
+            if (producer.count(top)) return fail("layer " + l.name + ": top " + top + " is produced twice");
+            producer[top] = i; channels[top] = channels[l.bottoms[0]]; level[top] = lv + 1;
+        } else if (l.type == "Concat") {
+            if (l.concat_axis != 1) return fail("layer " + l.name + ": only channel concatenation (axis 1) is supported");
+            int c = 0;
+            for (const std::string& b : l.bottoms) {
+                c += channels[b];
+                if (level[b] != lv) return fail("layer " + l.name + ": bottoms of different resolution");
+            }
+            producer[top] = i; channels[top] = c; level[top] = lv;
+        } else if (l.type == "ImResize" || l.type == "Nms") {
+            producer[top] = i; channels[top] = channels[l.bottoms[0]]; level[top] = lv;
+        } else {
+            return fail("layer " + l.name + ": layer type " + l.type + " is not on the pose path and not supported");
+        }
+    }
+    const std::string final_blob = rsz.bottoms[0];
+    if (!producer.count(final_blob) || net.layers[producer[final_blob]].type != "Concat")
+        return fail("the bottom of ImResize must be a Concat (concat_stage7)");
+    const int final_concat = producer[final_blob];
+    if (level[final_blob] != 3) return fail("the net output must be at stride 8 (three pooling levels)");
+    if (channels[final_blob] != mt.num_maps)
+        return fail("the net output has " + std::to_string(channels[final_blob]) + " channels, the " + std::string(p.model == PE_MODEL_MPI_15 ? "MPI" : "COCO") +
+                    " model needs " + std::to_string(mt.num_maps));
+    std::map<std::string, int> final_off;   // blob -> channel offset inside concat_stage7
+    {
+        int off = 0;
+        for (const std::string& b : net.layers[final_concat].bottoms) {
+            if (!producer.count(b) || net.layers[producer[b]].type != "Convolution" || consumers[b].size() != 1)
+                return fail("bottoms of the final Concat must be convolution outputs used nowhere else");
+            final_off[b] = off; off += channels[b];
+        }
+    }
+
+    // ---- concat buffers: slice layout shared by all non-final concats, two physical buffers
+    std::vector<int> concats;
+    for (int i = 0; i < NL; i++) if (net.layers[i].type == "Concat" && i != final_concat) concats.push_back(i);
+    std::map<std::string, int> n_in_concats;
+    for (int ci : concats) for (const std::string& b : net.layers[ci].bottoms) n_in_concats[b]++;
+    struct Slot { int caffe_off, eng_off, c; bool shared; };
+    std::vector<std::vector<Slot>> slots(concats.size());   // per concat, per bottom (concat order)
+    int cc_c = 0;
+    for (size_t j = 0; j < concats.size(); j++) {
+        const ProtoLayer& l = net.layers[concats[j]];
+        if (level[l.tops[0]] != 3) return fail("layer " + l.name + ": Concat is only supported at stride 8");
+        std::vector<Slot>& sl = slots[j];
+        int coff = 0;
+        for (const std::string& b : l.bottoms) {
+            sl.push_back({coff, 0, channels[b], consumers[b].size() > 1});   // read by more than this Concat (conv4_4_CPM: every stage)
+            coff += channels[b];
+        }
+        int eoff = 0;
+        for (int pass = 0; pass < 2; pass++)        // shared blobs first
+            for (Slot& sdef : sl)
+                if (sdef.shared == (pass == 0)) { sdef.eng_off = eoff; eoff += round_up(sdef.c, 8); }
+        const int total = round_up(eoff, cpad);
+        if (j == 0) cc_c = total;
+        else {   // the physical buffers are reused: every concat must have the layout of the first
+            if (sl.size() != slots[0].size() || total != cc_c) return fail("layer " + l.name + ": Concat layouts differ between stages");
+            for (size_t k = 0; k < sl.size(); k++) {
+                if (sl[k].c != slots[0][k].c || sl[k].shared != slots[0][k].shared || sl[k].eng_off != slots[0][k].eng_off)
+                    return fail("layer " + l.name + ": Concat layouts differ between stages");
+                if (sl[k].shared && l.bottoms[k] != net.layers[concats[0]].bottoms[k]) return fail("layer " + l.name + ": shared Concat bottoms differ between stages");
+            }
+        }
+        for (const Slot& sdef : sl) {
+            const std::string& b = l.bottoms[&sdef - &sl[0]];
+            if (!producer.count(b) || net.layers[producer[b]].type != "Convolution") return fail("layer " + l.name + ": Concat bottoms must be convolution outputs");
+        }
+    }
+    const int nbuf = (int)std::min<size_t>(2, concats.size());
+    // reuse is safe when every consumer of concat j is issued before the first producer of concat j+2
+    for (size_t j = 0; j + 2 < concats.size(); j++) {
+        int last_use = 0;
+        for (int c : consumers[net.layers[concats[j]].tops[0]]) last_use = std::max(last_use, c);
+        for (size_t k = 0; k < slots[j + 2].size(); k++)
+            if (!slots[j + 2][k].shared && producer[net.layers[concats[j + 2]].bottoms[k]] < last_use)
+                return fail("the stages overlap in a way the two-buffer concat scheme cannot hold");
+    }
+
+    auto new_act = [&](int lv, int c, const std::string& blob, int blob_c) {
+        ActSpec a; a.level = lv; a.C = round_up(c, cpad); a.blob = blob; a.blob_c = blob_c;
         p.acts.push_back(a);
         if (!blob.empty()) p.blobs.push_back({blob, (int)p.acts.size() - 1, 0, blob_c});
         return (int)p.acts.size() - 1;
-    };
-    auto add_conv = [&](const std::string& name, int in_act, int in_cused, std::vector<int> cin_map, int cin, int cout,
-                        int k, int relu, int level, int out_act, int out_coff, int planar_coff, int im2col) {
-        ConvSpec c;
-        c.name = name; c.cout = cout; c.cin = cin; c.k = k; c.pad = k / 2; c.relu = relu; c.level = level;
-        c.in_act = in_act; c.in_cused = in_cused; c.out_act = out_act; c.out_coff = out_coff;
-        c.planar_coff = planar_coff; c.cin_map = cin_map; c.im2col_input = im2col;
-        c.flops_per_image = 0;
-        p.convs.push_back(c);
-        p.order.push_back({0, (int)p.convs.size() - 1});
-        return (int)p.convs.size() - 1;
     };
     auto ident = [](int n, int padded) {
         std::vector<int> m(padded, -1);
         for (int i = 0; i < n; i++) m[i] = i;
         return m;
     };
+    struct Loc { int act = -1, coff = 0, cused = 0; std::vector<int> cmap; };
+    std::map<std::string, Loc> loc;
 
     // network input, im2col'ed 3x3x3 patches: engine channel (r*3+s)*3+c  <-  original weight index (c, r, s)
     p.input_act = new_act(0, kp_input, "", 0);
     p.acts[p.input_act].C = kp_input;
-    p.blobs.push_back({"image", p.input_act, 12, 3});  // centre tap (r=1,s=1) of the patch = the net input itself
-    int cur = p.input_act, cur_c = 3, level = 0;
-    char nm[64];
-    const int vgg[4][2] = {{64, 2}, {128, 2}, {256, 4}, {512, 2}};
-    for (int b = 0; b < 4; b++) {
-        for (int i = 1; i <= vgg[b][1]; i++) {
-            snprintf(nm, sizeof nm, "conv%d_%d", b + 1, i);
-            const int out = new_act(level, vgg[b][0], nm, vgg[b][0]);
-            if (b == 0 && i == 1) {
-                add_conv(nm, cur, kp_input, std::vector<int>(), 3, 64, 3, 1, level, out, 0, 0, 1);
-            } else {
-                add_conv(nm, cur, p.acts[cur].C, ident(cur_c, p.acts[cur].C), cur_c, vgg[b][0], 3, 1, level, out, 0, 0, 0);
-            }
-            cur = out; cur_c = vgg[b][0];
-        }
-        if (b < 3) {
-            snprintf(nm, sizeof nm, "pool%d_stage1", b + 1);
-            const int out = new_act(level + 1, cur_c, nm, cur_c);
-            p.pools.push_back({nm, cur, out, level});
-            p.order.push_back({1, (int)p.pools.size() - 1});
-            cur = out; level++;
-        }
-    }
-    {
-        const int a43 = new_act(3, 256, "conv4_3_CPM", 256);
-        add_conv("conv4_3_CPM", cur, p.acts[cur].C, ident(512, p.acts[cur].C), 512, 256, 3, 1, 3, a43, 0, 0, 0);
-        cur = a43;
-    }
-    // two concat buffers, ping-ponged by stage: channels [F 128 | L1 slot | L2 slot | pad]
-    const int slot1 = round_up(p.c_l1, 8), slot2 = round_up(p.c_l2, 8);
-    const int off_l1 = 128, off_l2 = 128 + slot1, cc_c = round_up(128 + slot1 + slot2, 64);
-    int cc[2];
-    cc[0] = new_act(3, cc_c, "conv4_4_CPM", 128);
-    cc[1] = new_act(3, cc_c, "", 0);
-    p.acts[cc[0]].C = p.acts[cc[1]].C = cc_c;
-    add_conv("conv4_4_CPM", cur, p.acts[cur].C, ident(256, p.acts[cur].C), 256, 128, 3, 1, 3, cc[0], 0, 0, 0);
-    p.copies.push_back({cc[0], cc[1], 128});
-    p.order.push_back({2, 0});
+    p.blobs.push_back({input_blob, p.input_act, 12, 3});  // centre tap (r=1,s=1) of the patch = the net input itself
+    int cc[2] = {-1, -1};
+    std::map<std::string, std::pair<int, int>> concat_slot;   // blob -> (first concat index j, bottom position k)
+    for (size_t j = 0; j < concats.size(); j++)
+        for (size_t k = 0; k < slots[j].size(); k++)
+            if (!concat_slot.count(net.layers[concats[j]].bottoms[k])) concat_slot[net.layers[concats[j]].bottoms[k]] = {(int)j, (int)k};
 
-    // Caffe concat order of concat_stage{2..6}: [L1 | L2 | F]  (prototxt :731-741)
-    std::vector<int> cc_map(cc_c, -1);
-    for (int i = 0; i < 128; i++) cc_map[i] = p.c_l1 + p.c_l2 + i;
-    for (int i = 0; i < p.c_l1; i++) cc_map[off_l1 + i] = i;
-    for (int i = 0; i < p.c_l2; i++) cc_map[off_l2 + i] = p.c_l1 + i;
-
-    // stage 1: reads F = first 128 channels of cc[0]; its last layers write the L1/L2 slices of cc[0]
-    for (int br = 1; br <= 2; br++) {
-        int in = cc[0], in_cused = 128, in_c = 128;
-        std::vector<int> in_map = ident(128, 128);
-        for (int i = 1; i <= 5; i++) {
-            snprintf(nm, sizeof nm, "conv5_%d_CPM_L%d", i, br);
-            if (i <= 3) {
-                const int out = new_act(3, 128, nm, 128);
-                add_conv(nm, in, in_cused, in_map, in_c, 128, 3, 1, 3, out, 0, 0, 0);
-                in = out; in_cused = p.acts[out].C; in_c = 128; in_map = ident(128, in_cused);
-            } else if (i == 4) {
-                const int out = new_act(3, 512, nm, 512);
-                add_conv(nm, in, in_cused, in_map, in_c, 512, 1, 1, 3, out, 0, 0, 0);
-                in = out; in_cused = p.acts[out].C; in_c = 512; in_map = ident(512, in_cused);
+    for (int i = 0; i < NL; i++) {
+        const ProtoLayer& l = net.layers[i];
+        const std::string& top = l.tops[0];
+        if (l.type == "Convolution") {
+            ConvSpec c;
+            c.name = l.name; c.cout = l.num_output; c.k = l.kernel; c.pad = l.pad; c.level = level[top];
+            c.relu = 0;
+            for (int u : consumers[top]) if (net.layers[u].type == "ReLU") c.relu = 1;
+            c.planar_coff = 0; c.out_coff = 0; c.flops_per_image = 0; c.im2col_input = 0;
+            // input
+            if (l.bottoms[0] == input_blob) {
+                if (l.kernel != 3) return fail("layer " + l.name + ": the first convolution must be 3x3 (it consumes the im2col'ed input)");
+                c.cin = 3; c.in_act = p.input_act; c.in_cused = kp_input; c.im2col_input = 1;
             } else {
-                const int co = br == 1 ? p.c_l1 : p.c_l2;
-                add_conv(nm, in, in_cused, in_map, in_c, co, 1, 0, 3, cc[0], br == 1 ? off_l1 : off_l2, 0, 0);
-                p.blobs.push_back({nm, cc[0], br == 1 ? off_l1 : off_l2, co});
+                const Loc& in = loc[l.bottoms[0]];
+                if (in.act < 0) return fail("layer " + l.name + ": bottom " + l.bottoms[0] + " is not available as a convolution input");
+                if (in.coff != 0) return fail("layer " + l.name + ": bottom " + l.bottoms[0] + " does not start at channel 0 of its buffer");
+                c.cin = channels[l.bottoms[0]]; c.in_act = in.act; c.in_cused = in.cused; c.cin_map = in.cmap;
             }
-        }
-    }
-    // stages 2..6: read cc[(s)&1], write slices of cc[(s+1)&1]; stage 6 writes the final planar maps,
-    // concat_stage7 = [L2 | L1]  (prototxt :2966-2975)
-    for (int s = 2; s <= 6; s++) {
-        const int src = cc[s & 1], dst = cc[(s + 1) & 1];
-        for (int br = 1; br <= 2; br++) {
-            int in = src, in_cused = cc_c, in_c = p.c_l1 + p.c_l2 + 128;
-            std::vector<int> in_map = cc_map;
-            for (int i = 1; i <= 7; i++) {
-                snprintf(nm, sizeof nm, "Mconv%d_stage%d_L%d", i, s, br);
-                if (i <= 6) {
-                    const int out = new_act(3, 128, nm, 128);
-                    add_conv(nm, in, in_cused, in_map, in_c, 128, i <= 5 ? 7 : 1, 1, 3, out, 0, 0, 0);
-                    in = out; in_cused = p.acts[out].C; in_c = 128; in_map = ident(128, in_cused);
-                } else {
-                    const int co = br == 1 ? p.c_l1 : p.c_l2;
-                    if (s < 6) {
-                        add_conv(nm, in, in_cused, in_map, in_c, co, 1, 0, 3, dst, br == 1 ? off_l1 : off_l2, 0, 0);
-                        p.blobs.push_back({nm, dst, br == 1 ? off_l1 : off_l2, co});
-                    } else {
-                        add_conv(nm, in, in_cused, in_map, in_c, co, 1, 0, 3, -1, 0, br == 1 ? p.c_l2 : 0, 0);
-                    }
+            // output
+            if (final_off.count(top)) {
+                if (c.relu) return fail("layer " + l.name + ": a ReLU on the net output is not supported");
+                c.out_act = -1; c.planar_coff = final_off[top];
+            } else if (concat_slot.count(top)) {
+                if (cc[0] < 0) {   // the two ping-pong concat buffers [shared | stage outputs]
+                    for (int b = 0; b < nbuf; b++) { cc[b] = new_act(3, cc_c, "", 0); p.acts[cc[b]].C = cc_c; }
                 }
+                const int j = concat_slot[top].first, k = concat_slot[top].second;
+                const Slot& sdef = slots[j][k];
+                c.out_act = cc[j % nbuf]; c.out_coff = sdef.eng_off;
+                p.blobs.push_back({top, c.out_act, sdef.eng_off, sdef.c});
+                if (sdef.shared || consumers[top].size() > 1) {   // also read directly by convolutions (conv4_4_CPM feeds stage 1)
+                    if (sdef.eng_off != 0) return fail("blob " + top + ": a directly consumed Concat bottom must be first in the buffer");
+                    Loc o; o.act = c.out_act; o.coff = 0; o.cused = round_up(sdef.c, 64); o.cmap = ident(sdef.c, o.cused);
+                    if (o.cused > cc_c) return fail("blob " + top + ": too narrow concat buffer");
+                    loc[top] = o;
+                }
+            } else {
+                c.out_act = new_act(c.level, c.cout, top, c.cout);
+                Loc o; o.act = c.out_act; o.coff = 0; o.cused = p.acts[c.out_act].C; o.cmap = ident(c.cout, o.cused);
+                loc[top] = o;
             }
+            p.convs.push_back(c);
+            p.order.push_back({0, (int)p.convs.size() - 1});
+            if (concat_slot.count(top) && slots[concat_slot[top].first][concat_slot[top].second].shared && nbuf == 2) {
+                p.copies.push_back({cc[0], cc[1], round_up(channels[top], 8)});
+                p.order.push_back({2, (int)p.copies.size() - 1});
+            }
+        } else if (l.type == "Pooling") {
+            const Loc& in = loc[l.bottoms[0]];
+            if (in.act < 0 || in.coff != 0 || p.acts[in.act].level != level[l.bottoms[0]]) return fail("layer " + l.name + ": unsupported pooling input");
+            const int out = new_act(level[top], channels[top], top, channels[top]);
+            if (p.acts[out].C != p.acts[in.act].C) return fail("layer " + l.name + ": channel pitch mismatch");
+            p.pools.push_back({l.name, in.act, out, level[l.bottoms[0]]});
+            p.order.push_back({1, (int)p.pools.size() - 1});
+            Loc o; o.act = out; o.coff = 0; o.cused = p.acts[out].C; o.cmap = ident(channels[top], o.cused);
+            loc[top] = o;
+        } else if (l.type == "Concat" && i != final_concat) {
+            size_t j = 0;
+            while (concats[j] != i) j++;
+            Loc o; o.act = cc[j % nbuf]; o.coff = 0; o.cused = cc_c; o.cmap.assign(cc_c, -1);
+            if (o.act < 0) return fail("layer " + l.name + ": Concat before any of its producers");
+            for (const Slot& sdef : slots[j])
+                for (int q = 0; q < sdef.c; q++) o.cmap[sdef.eng_off + q] = sdef.caffe_off + q;
+            loc[top] = o;
         }
     }
+    if (p.convs.empty() || !p.convs[0].im2col_input) return fail("the first layer must be a convolution on the net input");
+    return 0;
+}
+
+NetPlan build_plan(int model, int kp_input, int cpad) {
+    NetPlan p;
+    std::string err;
+    if (build_plan_from_net(builtin_netdef(model, 6), kp_input, cpad, p, err)) fprintf(stderr, "poseengine: built-in plan: %s\n", err.c_str());
     return p;
 }
 

@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
-    "pe_caffemodel_last_error", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg", "pe_decode_jpeg", "pe_decode_png",
+    "pe_caffemodel_last_error", "pe_create_from_prototxt", "pe_plan_describe", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg", "pe_decode_jpeg", "pe_decode_png",
 ]
 
 
@@ -61,6 +61,8 @@ def lib():
                               "(or `make -C caffe_rtpose_b200`); there is no CPU fallback" % LIB_PATH)
     L = C.CDLL(LIB_PATH)
     L.pe_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+    L.pe_create_from_prototxt.argtypes = [C.POINTER(_Config), C.c_char_p, C.POINTER(C.c_void_p)]
+    L.pe_plan_describe.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int]
     L.pe_destroy.argtypes = [C.c_void_p]
     L.pe_last_error.restype = C.c_char_p
     L.pe_last_error.argtypes = [C.c_void_p]
@@ -218,15 +220,23 @@ class PoseEngine:
     """One GPU worker (the reference's NetCopy + warmup(), rtpose.cpp:133-142, 173-237)."""
 
     def __init__(self, model=COCO_18, net_w=656, net_h=368, disp_w=1280, disp_h=720, num_scales=1, start_scale=1.0,
-                 scale_gap=0.3, device=0, max_batch=1, precision=PREC_BF16X2):
+                 scale_gap=0.3, device=0, max_batch=1, precision=PREC_BF16X2, prototxt=None):
+        """prototxt: path of a deploy prototxt (`new caffe::Net(proto, TEST)`, rtpose.cpp:183); model may then be None
+        and follows the Nms layer's num_parts (rtpose.cpp:212-229).  Without it the built-in graph of `model` is used."""
         L = lib()
-        cfg = _Config(device, model, net_w, net_h, disp_w, disp_h, num_scales, start_scale, scale_gap, max_batch, precision)
+        cfg = _Config(device, -1 if model is None else model, net_w, net_h, disp_w, disp_h, num_scales, start_scale, scale_gap,
+                      max_batch, precision)
         h = C.c_void_p()
-        rc = L.pe_create(C.byref(cfg), C.byref(h))
+        if prototxt is not None:
+            rc = L.pe_create_from_prototxt(C.byref(cfg), os.fsencode(prototxt), C.byref(h))
+        else:
+            rc = L.pe_create(C.byref(cfg), C.byref(h))
         if rc != 0:
             raise PoseEngineError("pe_create failed (%d): %s" % (rc, L.pe_last_error(None).decode()))
         self._h = h
         self.cfg = cfg
+        if model is None:
+            model = {15: MPI_15, 18: COCO_18}[L.pe_nms_get_num_parts(h)]
         self.model = model
         self.num_parts = L.pe_nms_get_num_parts(h)
         self.max_peaks = L.pe_nms_get_max_peaks(h)
@@ -396,6 +406,18 @@ class PoseEngine:
 
     def packed_weights(self):
         return lib().pe_packed_weights_device_ptr(self._h), lib().pe_packed_weights_bytes(self._h)
+
+
+def plan_describe(model=None, prototxt=None):
+    """Text description of the execution plan (host only, no GPU): built-in graph of `model`, or of a prototxt."""
+    L = lib()
+    path = os.fsencode(prototxt) if prototxt is not None else None
+    n = L.pe_plan_describe(-1 if model is None else model, path, None, 0)
+    if n < 0:
+        raise PoseEngineError("pe_plan_describe failed (%d): %s" % (-n, L.pe_last_error(None).decode()))
+    buf = C.create_string_buffer(n + 1)
+    L.pe_plan_describe(-1 if model is None else model, path, buf, n + 1)
+    return buf.value.decode()
 
 
 def write_json(joints, num_parts, frame_scale=1.0):

@@ -264,16 +264,24 @@ struct Global {
     std::atomic<int> produced{0}, finished{0};
     int disp_w = 0, disp_h = 0, net_w = 0, net_h = 0, model = PE_MODEL_COCO_18, num_parts = 18;
     std::vector<std::string> image_list;
+    bool proto_readable = false;   // --caffeproto parsed: engines are created from it
 } global;
 
 // ---------------------------------------------------------------------------------------------- weights
-static int model_from_prototxt(const std::string& path) {   // the reference infers the model from nms num_parts (:212-229)
+// The net is built from --caffeproto like `new Net<float>(proto, TEST)` (rtpose.cpp:183); the model follows the Nms layer's
+// num_parts (:212-229).  -1: file unreadable, -2: not a pose-path graph (message logged).
+static int model_from_prototxt(const std::string& path) {
     std::ifstream f(path);
     if (!f) return -1;
-    std::string tok;
-    while (f >> tok)
-        if (tok == "num_parts:") { int v = 0; f >> v; return v == 15 ? PE_MODEL_MPI_15 : (v == 18 ? PE_MODEL_COCO_18 : -2); }
-    return -2;
+    char buf[64];
+    const int n = pe_plan_describe(-1, path.c_str(), nullptr, 0);
+    if (n < 0) { LOG_ERROR("%s", pe_last_error(nullptr)); return -2; }
+    std::vector<char> text((size_t)n + 1);
+    pe_plan_describe(-1, path.c_str(), text.data(), n + 1);
+    int model = -2;
+    if (sscanf(text.data(), "%63s %d", buf, &model) != 2) return -2;
+    global.proto_readable = true;
+    return model;
 }
 
 static void random_weights(pe_engine* e, const std::string& kind) {
@@ -422,7 +430,8 @@ static bool create_engines(int num_gpu, std::vector<pe_engine*>& engines) {
         c.disp_w = global.disp_w; c.disp_h = global.disp_h; c.num_scales = Fi("num_scales");
         c.start_scale = Fd("start_scale"); c.scale_gap = Fd("scale_gap"); c.max_batch = batch; c.precision = Fi("precision");
         pe_engine* e = nullptr;
-        if (pe_create(&c, &e)) { LOG_ERROR("GPU %d: %s", c.device, pe_last_error(nullptr)); return false; }
+        const int rc = global.proto_readable ? pe_create_from_prototxt(&c, F("caffeproto").c_str(), &e) : pe_create(&c, &e);
+        if (rc) { LOG_ERROR("GPU %d: %s", c.device, pe_last_error(nullptr)); return false; }
         engines.push_back(e);
     }
     if (load_weights(engines[0], Fi("start_device"))) return false;
@@ -618,6 +627,7 @@ int main(int argc, char** argv) {
     if (model < 0 && !F("model").empty()) model = F("model") == "MPI" ? PE_MODEL_MPI_15 : PE_MODEL_COCO_18;
     if (model == -1) { LOG_ERROR("cannot read --caffeproto %s (pass --model COCO|MPI to run without it)", F("caffeproto").c_str()); return 1; }
     if (model == -2) { LOG_ERROR("Unknown number of parts! Couldn't set model"); return 1; }
+    if (global.proto_readable) LOG_INFO("Net built from %s", F("caffeproto").c_str());
     global.model = model;
     {
         std::unique_ptr<ModelDescriptor> md;

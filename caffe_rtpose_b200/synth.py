@@ -24,8 +24,9 @@ _MAPIDX = {
 }
 
 
-def conv_table(model):
-    """[(name, cout, cin, k)] for the 92 convolutions of pose_deploy_linevec.prototxt, in file order."""
+def conv_table(model, stages=6):
+    """[(name, cout, cin, k)] for the convolutions of pose_deploy_linevec.prototxt (92 for the 6-stage files; `stages` = 1, 2, 4
+    gives model/mpi/pose_deploy_linevec_{1,2,4}.prototxt), in file order."""
     nparts = 18 if model == COCO_18 else 15
     c_l1, c_l2 = len(_LIMBS[model]), nparts + 1
     t = []
@@ -48,7 +49,7 @@ def conv_table(model):
             else:
                 t.append((name, c_l1 if br == 1 else c_l2, 512, 1))
     cc = c_l1 + c_l2 + 128
-    for s in range(2, 7):
+    for s in range(2, stages + 1):
         for i in range(1, 8):
             for br in (1, 2):
                 name = "Mconv%d_stage%d_L%d" % (i, s, br)
@@ -63,15 +64,44 @@ def conv_table(model):
     return t
 
 
-def make_weights(model, kind="he", seed=1234):
+def make_weights(model, kind="he", seed=1234, stages=6):
     """dict name -> (w float32 [cout,cin,k,k], b float32 [cout])."""
     rng = np.random.default_rng(seed)
     out = {}
-    for name, co, ci, k in conv_table(model):
+    for name, co, ci, k in conv_table(model, stages):
         std = 0.01 if kind == "caffe" else float(np.sqrt(2.0 / (ci * k * k)))
         w = (rng.standard_normal((co, ci, k, k), dtype=np.float32) * np.float32(std)).astype(np.float32)
         out[name] = (w, np.zeros(co, np.float32))
     return out
+
+
+def netspec_to_prototxt(spec):
+    """Deploy prototxt text from a layer table as tests/golden/netspec_*.json stores it (tools/gen_netspec_fixture.py parsed
+    those tables from the reference's model/*/pose_deploy_linevec*.prototxt): lets the GPU box, which has no /root/reference,
+    feed the engine's prototxt reader the same graphs."""
+    out = ['input: "%s"' % spec["input"]] + ["input_dim: %d" % d for d in spec["input_dim"]]
+    for l in spec["layers"]:
+        out.append("layer {")
+        out.append('  name: "%s"\n  type: "%s"' % (l["name"], l["type"]))
+        out += ['  bottom: "%s"' % b for b in l["bottom"]] + ['  top: "%s"' % t for t in l["top"]]
+        if l["type"] == "Convolution":
+            out.append("  param { lr_mult: 1.0 decay_mult: 1 }\n  param { lr_mult: 2.0 decay_mult: 0 }")
+            out.append("  convolution_param {\n    num_output: %d\n    pad: %d\n    kernel_size: %d" % (l["num_output"], l["pad"], l["kernel_size"]))
+            out.append('    weight_filler { type: "gaussian" std: 0.01 }\n    bias_filler { type: "constant" }\n  }')
+        elif l["type"] == "Pooling":
+            out.append("  pooling_param {\n    pool: %s\n    kernel_size: %d\n    stride: %d\n  }" % (l["pool"], l["kernel_size"], l["stride"]))
+        elif l["type"] == "Concat":
+            out.append("  concat_param { axis: %d }" % l.get("axis", 1))
+        elif l["type"] == "ImResize":
+            out.append("  imresize_param {\n    factor: %g\n    scale_gap: %g\n    start_scale: %g\n    #target_spatial_width: 368\n  }" % (
+                l["factor"], l["scale_gap"], l["start_scale"]))
+        elif l["type"] == "Nms":
+            out.append("  nms_param {\n    threshold: %g" % l["threshold"])
+            if "max_peaks" in l and not l.get("max_peaks_default"):
+                out.append("    max_peaks: %d\n    num_parts: %d" % (l["max_peaks"], l["num_parts"]))
+            out.append("  }")
+        out.append("}")
+    return "\n".join(out) + "\n"
 
 
 def make_frame(idx, h=720, w=1280):

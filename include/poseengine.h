@@ -55,6 +55,15 @@ typedef struct pe_config {
 
 /* new caffe::Net(proto, TEST) + Reshape + warmup()                          rtpose.cpp:173-237 */
 int pe_create(const pe_config* cfg, pe_engine** out);
+/* same, the graph read from a deploy prototxt (--caffeproto, rtpose.cpp:60,183; Net::Init net.cpp:30-280): Convolution /
+ * in-place ReLU / 2x2 MAX Pooling / Concat / ImResize / Nms, any number of CPM stages (model/mpi/pose_deploy_linevec_{1,2,4}
+ * .prototxt); legacy V1 `layers` blocks are upgraded (upgrade_proto.cpp:957).  cfg->model may be -1: the model follows
+ * nms_param.num_parts as in rtpose.cpp:212-229.  nms_param.max_peaks sizes the peak blob (NmsLayer::GetMaxPeaks).
+ * Layer types outside the pose path are PE_ERR_INVALID with the layer named in pe_last_error(NULL). */
+int pe_create_from_prototxt(const pe_config* cfg, const char* prototxt_path, pe_engine** out);
+/* host-only (no GPU): text description of the execution plan of a prototxt (or of the built-in graph of `model` when
+ * prototxt_path is NULL); returns the text length (call with buf NULL to size it) or -PE_ERR_* */
+int pe_plan_describe(int model, const char* prototxt_path, char* buf, int cap);
 void pe_destroy(pe_engine* e);
 /* last error text of this handle (or of the failed pe_create when e == NULL) */
 const char* pe_last_error(const pe_engine* e);

@@ -251,7 +251,9 @@ static void add_concat(OrcNet* n, const std::string& name, const std::vector<std
     n->channels[name] = c;
     n->layers.push_back(l);
 }
-extern "C" OrcNet* orc_net_create(int model) {
+extern "C" OrcNet* orc_net_create(int model) { return orc_net_create_stages(model, 6); }
+// stages = number of CPM stages: 6 = model/{coco,mpi}/pose_deploy_linevec.prototxt, 1 / 2 / 4 = model/mpi/pose_deploy_linevec_{1,2,4}.prototxt
+extern "C" OrcNet* orc_net_create_stages(int model, int stages) {
     OrcNet* n = new OrcNet();
     n->model = model;
     const int cL1 = 2 * orc_model_num_limbs(model), cL2 = orc_model_num_parts(model) + 1;
@@ -287,7 +289,7 @@ extern "C" OrcNet* orc_net_create(int model) {
             p = nm;
         }
     }
-    for (int s = 2; s <= 6; s++) {
+    for (int s = 2; s <= stages; s++) {
         snprintf(nm, 64, "concat_stage%d", s);
         add_concat(n, nm, {p1, p2, "conv4_4_CPM"});
         p1 = p2 = nm;

@@ -57,6 +57,7 @@ const char* orc_model_map_name(int model, int idx);
 /* ---- the deploy graph (pose_deploy_linevec.prototxt) */
 typedef struct OrcNet OrcNet;
 OrcNet* orc_net_create(int model);
+OrcNet* orc_net_create_stages(int model, int stages); /* 1, 2, 4: model/mpi/pose_deploy_linevec_{1,2,4}.prototxt */
 void orc_net_destroy(OrcNet* net);
 int orc_net_num_layers(const OrcNet* net);
 /* type: "Convolution","ReLU","Pooling","Concat","ImResize","Nms" ; returns 0 if idx valid */

@@ -81,6 +81,8 @@ def lib():
         getattr(L, f).restype = C.POINTER(C.c_int)
     L.orc_model_map_name.restype = C.c_char_p
     L.orc_net_create.restype = C.c_void_p
+    L.orc_net_create_stages.restype = C.c_void_p
+    L.orc_net_create_stages.argtypes = [C.c_int, C.c_int]
     L.orc_net_destroy.argtypes = [C.c_void_p]
     L.orc_net_num_layers.argtypes = [C.c_void_p]
     L.orc_net_num_convs.argtypes = [C.c_void_p]
@@ -254,9 +256,9 @@ def json_text(joints, n_parts, frame_scale=1.0):
 class Net:
     """The deploy graph with Caffe CPU arithmetic."""
 
-    def __init__(self, model):
+    def __init__(self, model, stages=6):
         self.model = model
-        self.h = C.c_void_p(lib().orc_net_create(model))
+        self.h = C.c_void_p(lib().orc_net_create_stages(model, stages))
 
     def __del__(self):
         try:

@@ -29,8 +29,24 @@ static std::vector<uint8_t> slurp(const char* p) {
     return d;
 }
 
+// Fixed regression inputs (exact-size heap buffers, so ASAN sees any byte read past the end).
+static void fixed_cases() {
+    // SOS segment whose length field says "no payload" at the very end of the file - the component count
+    // used to be read before the length check (1-byte heap over-read).
+    const uint8_t sos_trunc[] = {0xFF, 0xD8, 0xFF, 0xC0, 0x00, 0x0B, 0x08, 0x00, 0x08, 0x00, 0x08, 0x01, 0x01, 0x11, 0x00, 0xFF, 0xDA, 0x00, 0x02};
+    std::vector<uint8_t> d(sos_trunc, sos_trunc + sizeof sos_trunc);
+    int w = 0, h = 0;
+    std::vector<uint8_t> px(8 * 8 * 3);
+    if (pe_decode_jpeg(d.data(), (long long)d.size(), &w, &h, px.data(), (long long)px.size()) == 0) { printf("truncated SOS accepted\n"); exit(3); }
+    for (size_t cut = 2; cut < d.size(); cut++) {   // every prefix, too
+        std::vector<uint8_t> e(d.begin(), d.begin() + cut);
+        pe_decode_jpeg(e.data(), (long long)e.size(), &w, &h, px.data(), (long long)px.size());
+    }
+}
+
 int main(int argc, char** argv) {
     if (argc < 3) return 2;
+    fixed_cases();
     const int iters = atoi(argv[1]);
     uint64_t s = 987654321;
     auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 33); };

@@ -123,7 +123,10 @@ def test_cli_json_equals_python_path(tmp_path):
     cm = str(tmp_path / "pose.caffemodel")
     engine.write_caffemodel(cm, W, synth.conv_table(model))
     proto = tmp_path / "deploy.prototxt"
-    proto.write_text('layer { name: "nms" type: "Nms" nms_param { threshold: 0.05 max_peaks: 64 num_parts: 18 } }\n')
+    # the deploy prototxt itself (rebuilt from the committed layer table of model/coco/pose_deploy_linevec.prototxt): rtpose.bin
+    # builds the net from it like `new Net<float>(proto, TEST)`
+    import json
+    proto.write_text(synth.netspec_to_prototxt(json.load(open(os.path.join(ROOT, "tests", "golden", "netspec_coco.json")))))
     img_dir = tmp_path / "frames"
     img_dir.mkdir()
     frames = [synth.make_frame(20 + i, disp_h, disp_w) for i in range(5)]

@@ -2,7 +2,7 @@
 """Parse the reference deploy prototxts into compact JSON layer tables.
 
 Run in the build container only (reads /root/reference, which does not exist on
-the GPU box).  Output: tests/golden/netspec_{coco,mpi}.json, which the CPU test
+the GPU box).  Output: tests/golden/netspec_{coco,mpi,mpi_1,mpi_2,mpi_4}.json, which the CPU test
 suite compares with the oracle's and the engine's built-in graph builders
 (reference: model/{coco,mpi}/pose_deploy_linevec.prototxt).
 
@@ -81,16 +81,20 @@ def to_spec(path):
                      start_scale=float(get(ip, "start_scale")))
         npar = get(lay, "nms_param")
         if npar is not None:
-            d.update(threshold=float(get(npar, "threshold")), max_peaks=int(get(npar, "max_peaks")),
-                     num_parts=int(get(npar, "num_parts")))
+            # NmsParameter defaults (caffe.proto:1471-1476): max_peaks 20, num_parts 15
+            d.update(threshold=float(get(npar, "threshold", 0.5)), max_peaks=int(get(npar, "max_peaks", 20)),
+                     num_parts=int(get(npar, "num_parts", 15)), max_peaks_default=get(npar, "max_peaks") is None)
         spec["layers"].append(d)
     return spec
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for model in ("coco", "mpi"):
-        spec = to_spec(os.path.join(REF, model, "pose_deploy_linevec.prototxt"))
+    for model, fname, out in (("coco", "pose_deploy_linevec", "coco"), ("mpi", "pose_deploy_linevec", "mpi"),
+                              ("mpi", "pose_deploy_linevec_1", "mpi_1"), ("mpi", "pose_deploy_linevec_2", "mpi_2"),
+                              ("mpi", "pose_deploy_linevec_4", "mpi_4")):
+        spec = to_spec(os.path.join(REF, model, fname + ".prototxt"))
+        model = out
         with open(os.path.join(OUT, "netspec_%s.json" % model), "w") as f:
             json.dump(spec, f, indent=0, sort_keys=True)
         types = {}
