@@ -309,6 +309,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # ---- single-process replica check (rtpose.bin --num_gpu topology): rank 0, child process with a timeout, before any
+    # timed region; its JSON goes into the line as "replica_check"
+    replica = None
+    if world > 1 and rank == 0:
+        try:
+            r = subprocess.run([sys.executable, "-m", "caffe_rtpose_b200.replica_check", str(min(world, 2))], cwd=ROOT, capture_output=True,
+                               text=True, timeout=180)
+            replica = json.loads(r.stdout.strip().splitlines()[-1]) if r.stdout.strip() else {"result": "no output", "stderr": r.stderr[-300:]}
+        except Exception as ex:   # never let the check take the bench down
+            replica = {"result": "failed: %r" % (ex,)}
+    barrier()
+
     e0 = engs[0]
     # ---- (1) device-resident throughput
     # two worker handles (two streams) alternate, like two of the reference's per-GPU worker threads would: the
@@ -408,6 +420,8 @@ def main():
                 "roofline": roofline}
         if cpu:
             line["cpu_baseline"] = cpu
+        if replica is not None:
+            line["replica_check"] = replica
         print(json.dumps(line), flush=True)
     for e in engs:
         e.close()

@@ -47,6 +47,10 @@ struct TcArgs {
     long long M;
     int n_tiles_n; long long total_tiles;   // persistent window kernel: tile = (m_tile, n_tile), n fastest
     int chunk_steps;                        // (channel block, filter row) steps per TMEM accumulation chunk (window kernel)
+    int tma_store;                          // pair kernel: the epilogue stages 32-row x HALF-channel boxes in shared memory and stores them with TMA
+    int dbg;                                // PE_TC_DBG bit mask, TIMING EXPERIMENTS ONLY (results are wrong): 1 no TMEM loads in the chunk drains,
+                                            // 2 no epilogue math / stores, 4 weight tiles loaded once per slot only, 8 A windows loaded once per slot only, 16 one-lane issue loop,
+                                            // 32 epilogue complete except the TMA store instructions
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -140,9 +144,9 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool f16 = false
 // UTCHMMA.  With the role guarded by `lane == 0` it wrapped every UTCHMMA in an ELECT / BRA.U.ANY uniformisation loop
 // plus R2UR moves, ~115 SASS instructions per filter tap, and the single issuing thread - not the tensor pipe - set the
 // pace (ncu r2a: issuer never blocked on a barrier, tensor pipe 74 % on the 7x7 layers, 65 % on 3x3).
-__device__ __forceinline__ bool elect_one() {
+__device__ __forceinline__ bool elect_one(uint32_t mask = 0xffffffffu) {
     uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, %1;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred) : "r"(mask));
     return pred != 0;
 }
 
@@ -393,9 +397,12 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     {
                         const int s = aw % NA;
                         mbar_wait(&a_empty[s], ((uint32_t)(aw / NA) & 1u) ^ 1u);
-                        mbar_expect_tx(&a_full[s], A_SLOT);
                         const int row0 = (int)(m0 + (long long)(r - a.pad) * a.Wp - a.pad);
-                        tma_load_3d(smem_a + s * A_SLOT, &tmA, &a_full[s], kb * TC_BK, row0, 0);   // box {64, 136, PLANES}
+                        if ((a.dbg & 8) && aw >= NA) mbar_arrive(&a_full[s]);
+                        else {
+                            mbar_expect_tx(&a_full[s], A_SLOT);
+                            tma_load_3d(smem_a + s * A_SLOT, &tmA, &a_full[s], kb * TC_BK, row0, 0);   // box {64, 136, PLANES}
+                        }
                         aw++;
                     }
                     if (ROWB) {   // short-K / narrow-N layers: one barrier round trip per filter row instead of per tap
@@ -409,15 +416,19 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         for (int q = 0; q < ks; q++) {
                             const int s = bt % NB;
                             mbar_wait(&b_empty[s], ((uint32_t)(bt / NB) & 1u) ^ 1u);
-                            mbar_expect_tx(&b_full[s], B_TAP);
                             const int tap = r * ks + q;
-                            tma_load_3d(smem_b + s * B_SLOT, &tmB, &b_full[s], tap * a.cin_k + kb * TC_BK, n0, 0);   // box {64, BN, PLANES}
+                            if ((a.dbg & 4) && bt >= NB) mbar_arrive(&b_full[s]);
+                            else {
+                                mbar_expect_tx(&b_full[s], B_TAP);
+                                tma_load_3d(smem_b + s * B_SLOT, &tmB, &b_full[s], tap * a.cin_k + kb * TC_BK, n0, 0);   // box {64, BN, PLANES}
+                            }
                             bt++;
                         }
                     }
                 }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && (((a.dbg & 16) ? 1u : 0xffffffffu) >> lane & 1u)) {
+        const uint32_t wmask = (a.dbg & 16) ? 1u : 0xffffffffu;   // PE_TC_DBG bit 4: only lane 0 runs the issue loop (experiment)
         // ===== MMA issuer: the whole warp runs the loop converged, one elected lane issues (see elect_one) =====
         // The tensor core adds every K=16 step into the fp32 TMEM accumulator with truncation, so a long chain drifts
         // (measured: 1.9e-4 relative over the net with one accumulator, 5.7e-5 with hi*hi alone in its accumulator).
@@ -448,7 +459,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
                         tc_fence_after();
                         const uint64_t dB = umma_desc(sb_base + sb_slot * B_SLOT);
-                        if (elect_one()) {
+                        if (elect_one(wmask)) {
                             for (int q = 0; q < ks; q++) {
 #pragma unroll
                                 for (int k = 0; k < TC_BK / 16; k++) {
@@ -459,7 +470,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                             umma_commit(&b_empty[sb_slot]);
                         }
-                        __syncwarp();
+                        __syncwarp(wmask);
                         first = 1;
                         bt++;
                     } else {
@@ -468,7 +479,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
                             tc_fence_after();
                             const uint64_t dB = umma_desc(sb_base + sb_slot * B_SLOT);
-                            if (elect_one()) {
+                            if (elect_one(wmask)) {
 #pragma unroll
                                 for (int k = 0; k < TC_BK / 16; k++) {
                                     // row-shifted view of the window: start address + q rows (q*128 B = q*8 units); the swizzle
@@ -478,17 +489,17 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 }
                                 umma_commit(&b_empty[sb_slot]);
                             }
-                            __syncwarp();
+                            __syncwarp(wmask);
                             first = 1;
                             bt++;
                         }
                     }
                     step++;
-                    if (elect_one()) {
+                    if (elect_one(wmask)) {
                         umma_commit(&a_empty[sa_slot]);
                         if (step % cs == 0 || step == nsteps) umma_commit(&tmem_full[as]);
                     }
-                    __syncwarp();
+                    __syncwarp(wmask);
                     if (step % cs == 0 || step == nsteps) ci++;
                     aw++;
                 }
@@ -527,7 +538,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_wait(&tmem_full[as], (ci >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS + half * HALF);
-                if (active_half) {
+                if (active_half && !((a.dbg & 1) && c > 0)) {
                     uint32_t r[2][16], r2[2][16];
                     __syncwarp();
                     tmem_ld16_nowait(trow, r[0]);
@@ -555,7 +566,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             // ---- bias, ReLU, re-split, store ----
             {
-            if (active_half && valid) {
+            if (active_half && valid && !(a.dbg & 2)) {
 #pragma unroll
                 for (int pc = 0; pc < NCHUNK; pc++) {
                     const int cb = n0 + half * HALF + pc * 16;   // first output channel of this piece
@@ -646,11 +657,21 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, u
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 constexpr int TCP_BM = 256;   // rows per pair tile
 
-template <int BN, int NA, int NB>
+template <int BN, int NA, int NB, int ST2>   // ST2: both planes of a tile are staged at once (64 KB at BN = 128, fewer weight slots)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCW_THREADS, 1)
-conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                const TcArgs a) {
     constexpr int A_SLOT = 2 * TCW_A_BYTES;                 // hi + lo window of this CTA's 128 rows
     constexpr int B_HALF = (BN / 2) * 128;                  // this CTA's rows of one plane of one tap
     constexpr int B_TAP = 2 * B_HALF;                       // [B_hi half ; B_lo half]
@@ -661,6 +682,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + NA * A_SLOT;
+    uint8_t* smem_o = smem_b + NB * B_TAP;                  // epilogue staging: 8 warps x (32 rows x HALF channels x 2 B), see tma_store
     __shared__ __align__(8) uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB];
     __shared__ __align__(8) uint64_t h_full[2], h_empty[2], c_full[2], c_empty[2];
     __shared__ uint32_t tmem_base_smem;
@@ -709,22 +731,29 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     {
                         const int s = aw % NA;
                         mbar_wait(&a_empty[s], ((uint32_t)(aw / NA) & 1u) ^ 1u);
-                        if (rank == 0) mbar_expect_tx(&a_full[s], 2 * A_SLOT);
                         const int row0 = (int)(m0 + (long long)(r - a.pad) * a.Wp - a.pad);
-                        tma_load_3d_2sm(smem_a + s * A_SLOT, &tmA, mapa_u32(smem_u32(&a_full[s]), 0), kb * TC_BK, row0, 0);
+                        if ((a.dbg & 8) && aw >= NA) { if (rank == 0) mbar_arrive(&a_full[s]); }
+                        else {
+                            if (rank == 0) mbar_expect_tx(&a_full[s], 2 * A_SLOT);
+                            tma_load_3d_2sm(smem_a + s * A_SLOT, &tmA, mapa_u32(smem_u32(&a_full[s]), 0), kb * TC_BK, row0, 0);
+                        }
                         aw++;
                     }
                     for (int q = 0; q < ks; q++) {
                         const int s = bt % NB;
                         mbar_wait(&b_empty[s], ((uint32_t)(bt / NB) & 1u) ^ 1u);
-                        if (rank == 0) mbar_expect_tx(&b_full[s], 2 * B_TAP);
                         const int tap = r * ks + q;
-                        tma_load_3d_2sm(smem_b + s * B_TAP, &tmB, mapa_u32(smem_u32(&b_full[s]), 0), tap * a.cin_k + kb * TC_BK, n0, 0);   // box {64, BN/2, 2}
+                        if ((a.dbg & 4) && bt >= NB) { if (rank == 0) mbar_arrive(&b_full[s]); }
+                        else {
+                            if (rank == 0) mbar_expect_tx(&b_full[s], 2 * B_TAP);
+                            tma_load_3d_2sm(smem_b + s * B_TAP, &tmB, mapa_u32(smem_u32(&b_full[s]), 0), tap * a.cin_k + kb * TC_BK, n0, 0);   // box {64, BN/2, 2}
+                        }
                         bt++;
                     }
                 }
         }
-    } else if (warp == 1 && rank == 0) {
+    } else if (warp == 1 && rank == 0 && (((a.dbg & 16) ? 1u : 0xffffffffu) >> lane & 1u)) {
+        const uint32_t wmask = (a.dbg & 16) ? 1u : 0xffffffffu;   // PE_TC_DBG bit 4: only lane 0 runs the issue loop (experiment)
         // ===== MMA issuer (leader CTA only): converged warp, one elected lane issues =====
         int aw = 0, bt = 0;
         uint32_t ci = 0, ti = 0;
@@ -753,7 +782,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         mbar_wait(&b_full[sb_slot], (uint32_t)(bt / NB) & 1u);
                         tc_fence_after();
                         const uint64_t dBh = umma_desc(sb_base + sb_slot * B_TAP), dBl = dBh + (uint64_t)(B_HALF >> 4);
-                        if (elect_one()) {
+                        if (elect_one(wmask)) {
 #pragma unroll
                             for (int k = 0; k < TC_BK / 16; k++) {
                                 const uint64_t ao = (uint64_t)(q * 8 + k * 2), bo = (uint64_t)(k * 2);
@@ -763,18 +792,18 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                             umma_commit_mc(&b_empty[sb_slot]);
                         }
-                        __syncwarp();
+                        __syncwarp(wmask);
                         firstH = 1; firstC = 1;
                         bt++;
                     }
                     step++;
                     const bool chunk_end = step % cs == 0 || step == nsteps;
-                    if (elect_one()) {
+                    if (elect_one(wmask)) {
                         umma_commit_mc(&a_empty[sa_slot]);
                         if (chunk_end) umma_commit_mc(&h_full[hs]);
                         if (step == nsteps) umma_commit_mc(&c_full[cbuf]);
                     }
-                    __syncwarp();
+                    __syncwarp(wmask);
                     if (chunk_end) ci++;
                     aw++;
                 }
@@ -813,7 +842,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_wait(&h_full[hs], (ci >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t trow = tm_h + ((uint32_t)(quad * 32) << 16) + (uint32_t)(hs * BN + half * HALF);
-                if (active_half) {
+                if (active_half && !((a.dbg & 1) && c > 0)) {
                     uint32_t r[2][16];
                     __syncwarp();
                     tmem_ld16_nowait(trow, r[0]);
@@ -835,29 +864,41 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (lane == 0) mbar_arrive_cluster(h_empty_leader + (uint32_t)(hs * 8));
             }
             // ---- cross terms of the whole tile, then bias / ReLU / re-split / store piece by piece ----
+            // Stores: a lane owns one output row, i.e. 2*HALF contiguous bytes per plane; written directly, every 16-byte
+            // store instruction of a warp touches 32 different 128-byte lines and the LSU serialises them (measured with
+            // PE_TC_DBG=2: the store phase cost 16 % of the conv time and sat on the critical path of the next tile's
+            // chunk drains).  With a.tma_store the warp instead stages its 32 x HALF box of one plane in shared memory
+            // (SWIZZLE_128B chunk order when a row is 128 bytes: conflict-free 16-byte STS) and one lane hands it to the
+            // TMA store engine; the lo plane waits in registers until the engine has read the hi plane.
             {
+                constexpr int RB = HALF * 2;                        // bytes of one staged row
+                constexpr bool TS_OK = SPLIT && (HALF == 64 || HALF == 32);
+                const bool ts = TS_OK && a.tma_store;
+                uint8_t* stage = smem_o + (warp - 2) * (32 * RB) * (ST2 ? 2 : 1);
                 const uint32_t cbuf = ti & 1u;
                 mbar_wait(&c_full[cbuf], (ti >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t trow = tm_c + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cbuf * BN + half * HALF);
                 if (active_half) {
                     uint32_t r[2][16];
+                    uint32_t plo[(TS_OK && !ST2) ? NCHUNK : 1][8];
                     __syncwarp();
                     tmem_ld16_nowait(trow, r[0]);
+                    if (ts) { if (lane == 0) bulk_wait_read(); }      // the engine has read what the previous tile staged
                     tmem_ld_wait();
 #pragma unroll
                     for (int pc = 0; pc < NCHUNK; pc++) {
                         const int cur = pc & 1;
                         if (pc + 1 < NCHUNK) { __syncwarp(); tmem_ld16_nowait(trow + (uint32_t)((pc + 1) * 16), r[cur ^ 1]); }
                         const int cb = n0 + half * HALF + pc * 16;   // first output channel of this piece
-                        if (valid) {
+                        if ((valid || ts) && !(a.dbg & 2)) {
                             float v[16];
 #pragma unroll
                             for (int j = 0; j < 16; j++) {
                                 float tv = __fadd_rn(accv[pc * 16 + j], __uint_as_float(r[cur][j]));
                                 tv = __fmaf_rn(tv, out_scale, s_bias[cb + j]);   // out_scale is a power of two: exact
                                 if (a.relu) tv = fmaxf(tv, 0.f);
-                                v[j] = tv;
+                                v[j] = valid ? tv : 0.f;                        // gap rows are written as the zeros they hold
                             }
                             if (a.planar) {
 #pragma unroll
@@ -871,23 +912,73 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                                     for (int p = 0; p < 2; p++) pk[p][j / 2] = split_pair<true>(r0, r1);
                                 }
-                                __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + cb;
+                                if (TS_OK && ts) {
 #pragma unroll
-                                for (int p = 0; p < 2; p++) {
-                                    uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
-                                    if (cb < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
-                                    if (cb + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
+                                    for (int h2 = 0; h2 < 2; h2++) {
+                                        const int chunk = pc * 2 + h2;
+                                        const int phys = RB == 128 ? (chunk ^ (lane & 7)) : chunk;
+                                        *(uint4*)(stage + lane * RB + phys * 16) = make_uint4(pk[0][h2 * 4], pk[0][h2 * 4 + 1], pk[0][h2 * 4 + 2], pk[0][h2 * 4 + 3]);
+                                    }
+                                    if (ST2) {
+#pragma unroll
+                                        for (int h2 = 0; h2 < 2; h2++) {
+                                            const int chunk = pc * 2 + h2;
+                                            const int phys = RB == 128 ? (chunk ^ (lane & 7)) : chunk;
+                                            *(uint4*)(stage + 32 * RB + lane * RB + phys * 16) = make_uint4(pk[1][h2 * 4], pk[1][h2 * 4 + 1], pk[1][h2 * 4 + 2], pk[1][h2 * 4 + 3]);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 8; j++) plo[(TS_OK && !ST2) ? pc : 0][j] = pk[1][j];
+                                    }
+                                } else {
+                                    __nv_bfloat16* orow = a.out + (size_t)m * a.out_pitch + a.out_coff + cb;
+#pragma unroll
+                                    for (int p = 0; p < 2; p++) {
+                                        uint4* dst = (uint4*)(orow + (size_t)p * a.out_plane);
+                                        if (cb < cout8) dst[0] = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+                                        if (cb + 8 < cout8) dst[1] = make_uint4(pk[p][4], pk[p][5], pk[p][6], pk[p][7]);
+                                    }
                                 }
                             }
                         }
                         if (pc + 1 < NCHUNK) { __syncwarp(); tmem_ld_wait(); }
                     }
+                    // the cross accumulator is in registers: release it before the stores
+                    __syncwarp();
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive_cluster(c_empty_leader + (uint32_t)(cbuf * 8));
+                    if (TS_OK && ts && !(a.dbg & 2)) {
+                        const int oc0 = a.out_coff + n0 + half * HALF, orow0 = (int)(m0 + quad * 32);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (ST2) {
+                            if (lane == 0 && !(a.dbg & 32)) { tma_store_3d(&tmO, stage, oc0, orow0, 0); tma_store_3d(&tmO, stage + 32 * RB, oc0, orow0, 1); }
+                        } else {
+                            if (lane == 0 && !(a.dbg & 32)) { tma_store_3d(&tmO, stage, oc0, orow0, 0); bulk_wait_read(); }
+                            __syncwarp();
+#pragma unroll
+                            for (int pc = 0; pc < NCHUNK; pc++)
+#pragma unroll
+                                for (int h2 = 0; h2 < 2; h2++) {
+                                    const int chunk = pc * 2 + h2;
+                                    const int phys = RB == 128 ? (chunk ^ (lane & 7)) : chunk;
+                                    constexpr bool PL = TS_OK && !ST2;
+                                    *(uint4*)(stage + lane * RB + phys * 16) = make_uint4(plo[PL ? pc : 0][h2 * 4], plo[PL ? pc : 0][h2 * 4 + 1],
+                                                                                          plo[PL ? pc : 0][h2 * 4 + 2], plo[PL ? pc : 0][h2 * 4 + 3]);
+                                }
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0 && !(a.dbg & 32)) tma_store_3d(&tmO, stage, oc0, orow0, 1);
+                        }
+                    }
+                } else {
+                    __syncwarp();
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive_cluster(c_empty_leader + (uint32_t)(cbuf * 8));
                 }
-                __syncwarp();
-                tc_fence_before();
-                if (lane == 0) mbar_arrive_cluster(c_empty_leader + (uint32_t)(cbuf * 8));
             }
         }
+        if (lane == 0) bulk_wait_read();   // staged boxes have been read out of shared memory before the CTA may exit
     }
     tc_fence_before();
     cluster_sync_all();      // no CTA of the pair exits (or frees TMEM) while its partner can still signal it
@@ -961,8 +1052,8 @@ static int env_int(const char* name, int dflt) {
 
 // Launch with the programmatic-stream-serialization attribute (PDL, see pdl_wait): back-to-back conv kernels overlap the
 // next one's prologue with the previous one's tail.  PE_TC_PDL=0 launches plainly.
-template <typename Kern>
-static int launch_pdl(Kern kern, dim3 grid, int smem, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a) {
+template <typename Kern, typename... Args>
+static int launch_pdl(Kern kern, dim3 grid, int smem, cudaStream_t st, const Args&... args) {
     static const int pdl = env_int("PE_TC_PDL", 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(TCW_THREADS, 1, 1); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
@@ -970,7 +1061,7 @@ static int launch_pdl(Kern kern, dim3 grid, int smem, cudaStream_t st, const CUt
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kern, ma, mb, a);
+    cudaLaunchKernelEx(&cfg, kern, args...);
     return 1;
 }
 
@@ -988,13 +1079,15 @@ static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStr
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
     return launch_pdl(kern, grid, smem, st, maps[2], maps[bmap], a);
 }
-template <int BN>
-static int launch_pair(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
-    constexpr int NA = 3;
+template <int BN, int ST2>
+static int launch_pair_st(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
+    constexpr int NA = 2;
     constexpr int B_TAP = BN * 128;
-    constexpr int NB = (120 * 1024) / B_TAP >= 12 ? 12 : (120 * 1024) / B_TAP;   // BN = 128: 7 slots
-    auto kern = conv_tcp_kernel<BN, NA, NB>;
-    const int smem = NA * 2 * TCW_A_BYTES + NB * B_TAP + 1024;
+    constexpr int STAGE = (BN / 2) % 16 == 0 ? 8 * 32 * BN * (ST2 ? 2 : 1) : 0;   // epilogue staging for TMA stores: 8 warps x 32 rows x BN/2 channels x 2 B (x 2 planes)
+    constexpr int BUDGET = 227 * 1024 - 1024 - 3072 - NA * 2 * TCW_A_BYTES - STAGE;
+    constexpr int NB = BUDGET / B_TAP >= 12 ? 12 : BUDGET / B_TAP;   // BN = 128: 7 slots (5 with both planes staged)
+    auto kern = conv_tcp_kernel<BN, NA, NB, ST2>;
+    const int smem = NA * 2 * TCW_A_BYTES + NB * B_TAP + STAGE + 1024;
     static std::atomic<unsigned long long> attr_done{0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1003,7 +1096,13 @@ static int launch_pair(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_
         attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
-    return launch_pdl(kern, grid, smem, st, maps[2], maps[bmap], a);
+    return launch_pdl(kern, grid, smem, st, maps[2], maps[bmap], maps[BN == 128 ? 9 : 10], a);
+}
+template <int BN>
+static int launch_pair(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
+    static const int st2 = env_int("PE_TC_ST2", 1);   // both planes staged at once (r2f: 814 vs 794 frames/s with 7 -> 5 weight slots)
+    if (st2 && (BN == 128 || BN == 64)) return launch_pair_st<BN, (BN == 128 || BN == 64) ? 1 : 0>(l, a, grid, st, bmap);
+    return launch_pair_st<BN, 0>(l, a, grid, st, bmap);
 }
 
 template <int BN>
@@ -1024,7 +1123,7 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
     out.d = d;
     out.bn = tc_bn(d.cout_pad);
     CUtensorMap* maps = nullptr;
-    if (posix_memalign((void**)&maps, 64, 10 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
+    if (posix_memalign((void**)&maps, 64, 12 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
     const int taps = d.ksize * d.ksize;
     const cuuint64_t K = (cuuint64_t)taps * d.in_cused;
     {   // A: [planes][M][pitch] bf16, box {64, 128, 1}
@@ -1091,6 +1190,20 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(B pair) failed: " + std::to_string((int)r); free(maps); return -1; }
     }
+    // pair kernel epilogue: TMA stores of 32-row boxes, 64 channels wide (128-byte rows, SWIZZLE_128B) or 32 wide (64-byte rows, linear)
+    memset(&maps[9], 0, 2 * sizeof(CUtensorMap));
+    for (int v = 0; v < 2 && d.planes == 2 && d.out; v++) {
+        const int wch = v == 0 ? 64 : 32;
+        if (d.out_pitch < wch) continue;
+        cuuint64_t dims[3] = {(cuuint64_t)d.out_pitch, (cuuint64_t)d.geo.M, (cuuint64_t)d.planes};
+        cuuint64_t strides[2] = {(cuuint64_t)d.out_pitch * 2, (cuuint64_t)d.out_plane * 2};
+        cuuint32_t box[3] = {(cuuint32_t)wch, 32, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&maps[9 + v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         v == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(out) failed: " + std::to_string((int)r); free(maps); return -1; }
+    }
     out.maps = maps;
     out.stages = pick_stages(out.bn, d.planes);
     out.smem_bytes = out.stages * stage_bytes(out.bn, d.planes) + 1024;
@@ -1113,6 +1226,9 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
     a.W = d.geo.W; a.H = d.geo.H; a.Wp = d.geo.Wp; a.Hs = d.geo.Hs;
     a.M = (long long)nimg * d.geo.Hs * d.geo.Wp;
     a.chunk_steps = 1 << 30;
+    static const int dbg = env_int("PE_TC_DBG", 0);
+    a.dbg = dbg;
+    a.tma_store = 0;
     dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), (unsigned)(d.cout_pad / l.bn));
     static const int variant = env_int("PE_TC_VARIANT", 1);     // 1: window kernel, 0: one TMA tile per tap
     if (variant == 1 && d.planes <= 2) {
@@ -1121,7 +1237,7 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
         // Tile width: 128 output channels per CTA is the efficient shape, but a single frame at the 46x82 level has
         // only 33 row tiles for 148 SMs.  Pick the width that maximises (CTAs that can run at once) x (relative
         // efficiency of that MMA shape: the A operand is re-read per N tile, so narrow tiles are smem-bound).
-        static const int pair = env_int("PE_TC_PAIR", 0);   // 1: CTA-pair kernel (cta_group::2) for the fp16-plane parity mode
+        static const int pair = env_int("PE_TC_PAIR", 1);   // CTA-pair kernel (cta_group::2) for the fp16-plane parity mode; 0: single-CTA window kernel
         if (pair && d.planes == 2 && planes_are_fp16(2) && nsm >= 2) {
             const long long mt = (a.M + TCP_BM - 1) / TCP_BM;
             const int npairs = nsm / 2;
@@ -1142,6 +1258,8 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
             if (chunk_env == 0) cs = nsteps;
             else if (chunk_env > 0) cs = chunk_env;
             a.chunk_steps = cs < 1 ? 1 : (cs > nsteps ? nsteps : cs);
+            static const int tstore = env_int("PE_TC_TMASTORE", 1);
+            a.tma_store = tstore && d.out && (bn == 128 || bn == 64) && d.cout % bn == 0 && d.out_coff % 8 == 0;
             grid = dim3((unsigned)(2 * std::min<long long>(a.total_tiles, npairs)), 1, 1);
             switch (bn) {
                 case 128: return launch_pair<128>(l, a, grid, st, bmap);

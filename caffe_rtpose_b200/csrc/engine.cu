@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -37,7 +38,13 @@ struct pe_engine {
     bool committed = false;
     // packed weights (one device buffer): per conv offsets (bytes)
     void* d_packed = nullptr; size_t packed_bytes = 0;
+    std::shared_ptr<void> packed_owner;   // frees d_packed when the last handle using it goes (pe_share_weights)
     std::vector<size_t> w_off, b_off;
+    size_t w11_off = 0;             // fp32 [27][64] weights + 64 biases of conv1_1 for the direct kernel (0: not packed)
+    bool conv11_direct = false;     // PE_CONV11_DIRECT=1: conv1_1 by conv1_1_direct_kernel (fp32 CUDA cores, no im2col'ed input) instead of
+                                    // the im2col + implicit-GEMM path; measured equal in time on B200 (r2e), so the tensor path stays the default
+    bool input_from_frames = false; // the last forward came from uint8 frames: d_resized holds conv1_1's input
+    bool input_act_stale = false;   // ... and the im2col'ed input activation was not produced (conv1_1 direct)
     std::vector<int> cout_pad, cin_pad;
     std::vector<TcLayer> tc;        // tcgen05 per-conv launch state
     // io
@@ -274,6 +281,7 @@ static int create_impl(const pe_config* cfg_in, const char* prototxt_path, pe_en
     e->mt = &e->mt_own;
     e->planes = cfg->precision;  // 0 fp32, else number of bf16 planes
     if (const char* g = getenv("PE_GRAPH")) e->use_graphs = atoi(g) != 0;
+    if (const char* g = getenv("PE_CONV11_DIRECT")) e->conv11_direct = atoi(g) != 0;
     e->elem = e->planes == 0 ? 4 : 2;
     e->start_scale_f = (float)cfg->start_scale;  // ImResizeLayer::SetStartScale(float)
     e->scale_gap_f = (float)cfg->scale_gap;
@@ -384,7 +392,7 @@ extern "C" void pe_destroy(pe_engine* e) {
     for (void* p : e->d_tabs) cudaFree(p);
     for (auto& t : e->tc) tc_layer_destroy(t);
     cudaFree(e->d_raw); cudaFreeHost(e->h_raw); cudaFree(e->d_wa); cudaFree(e->d_wb); cudaFree(e->d_wx0); cudaFree(e->d_wy0); cudaFree(e->d_wtab);
-    cudaFree(e->d_packed); cudaFree(e->d_frames); cudaFree(e->d_resized); cudaFree(e->d_planar); cudaFree(e->d_maps);
+    e->packed_owner.reset(); cudaFree(e->d_frames); cudaFree(e->d_resized); cudaFree(e->d_planar); cudaFree(e->d_maps);
     cudaFreeHost(e->h_frames); cudaFreeHost(e->h_planar); cudaFreeHost(e->h_maps);
     cudaFree(e->d_xtab); cudaFree(e->d_ytab);
     cudaFree(e->d_canvas); cudaFree(e->d_render_u8); cudaFree(e->d_render_src); cudaFree(e->d_heat);
@@ -434,11 +442,20 @@ extern "C" int pe_load_weights_file(pe_engine* e, const char* path) {
     if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "RTPW", 4) || fread(hdr, 4, 2, f) != 2 || hdr[0] != 1) {
         fclose(f); return fail(e, PE_ERR_IO, "%s: not an RTPW v1 weight file", path);
     }
+    fseek(f, 0, SEEK_END);
+    const long long file_size = ftell(f);
+    fseek(f, 12, SEEK_SET);
     for (uint32_t i = 0; i < hdr[1]; i++) {
         char name[64]; uint32_t dims[3];
         if (fread(name, 1, 64, f) != 64 || fread(dims, 4, 3, f) != 3) { fclose(f); return fail(e, PE_ERR_IO, "%s: truncated", path); }
         name[63] = 0;
-        const size_t nw = (size_t)dims[0] * dims[1] * dims[2] * dims[2];
+        // the header is untrusted: the payload it announces must fit in the file before anything is allocated
+        const unsigned long long nw64 = (unsigned long long)dims[0] * dims[1] * dims[2] * dims[2];
+        if (dims[0] > (1u << 20) || dims[1] > (1u << 20) || dims[2] > 64 || (nw64 + dims[0]) * 4ull > (unsigned long long)(file_size - ftell(f))) {
+            fclose(f);
+            return fail(e, PE_ERR_IO, "%s: layer %s announces %u x %u x %u x %u weights, more than the file holds", path, name, dims[0], dims[1], dims[2], dims[2]);
+        }
+        const size_t nw = (size_t)nw64;
         std::vector<float> w(nw), b(dims[0]);
         if (fread(w.data(), 4, nw, f) != nw || fread(b.data(), 4, dims[0], f) != dims[0]) { fclose(f); return fail(e, PE_ERR_IO, "%s: truncated", path); }
         const int rc = pe_set_conv_weights(e, name, w.data(), nw, b.data(), b.size());
@@ -469,12 +486,9 @@ static inline void split_fp16(float x, int planes, uint16_t* out) {   // parity 
     }
 }
 
-extern "C" int pe_commit_weights(pe_engine* e) {
-    if (!e) return PE_ERR_INVALID;
-    CK(e, cudaSetDevice(e->cfg.device));
+// byte layout of the packed weight buffer (a function of the plan and the precision only, so replicas agree on it)
+static size_t packed_layout(pe_engine* e) {
     const size_t nc = e->plan.convs.size();
-    for (size_t i = 0; i < nc; i++)
-        if (!e->hw[i].set) return fail(e, PE_ERR_STATE, "weights of layer %s were never set", e->plan.convs[i].name.c_str());
     e->w_off.assign(nc, 0); e->b_off.assign(nc, 0); e->cout_pad.assign(nc, 0); e->cin_pad.assign(nc, 0);
     size_t total = 0;
     auto align256 = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -488,7 +502,64 @@ extern "C" int pe_commit_weights(pe_engine* e) {
         e->b_off[i] = total;
         total = align256(total + (size_t)(e->cout_pad[i] + 1) * 4);   // bias[cout_pad] + the layer's epilogue scale
     }
+    e->w11_off = 0;
+    if (nc && e->plan.convs[0].im2col_input && e->plan.convs[0].cout == 64 && e->plan.convs[0].k == 3) {
+        e->w11_off = total;                                   // travels with the packed buffer (weight broadcast)
+        total = align256(total + (27 * 64 + 64) * sizeof(float));
+    }
+    return total;
+}
+
+// per-layer launch state (TMA descriptors) over the packed buffer the handle currently points at
+static int bind_packed(pe_engine* e) {
+    const size_t nc = e->plan.convs.size();
+    if (e->planes) {
+        for (auto& t : e->tc) tc_layer_destroy(t);
+        e->tc.assign(nc, TcLayer());
+        for (size_t i = 0; i < nc; i++) {
+            const ConvSpec& c = e->plan.convs[i];
+            const Geo& g = e->geo[c.level];
+            TcLayerDesc d;
+            d.in = e->acts[c.in_act]; d.in_pitch = e->plan.acts[c.in_act].C; d.in_cused = c.in_cused; d.in_plane = e->act_plane[c.in_act];
+            d.w = (char*)e->d_packed + e->w_off[i]; d.bias = (const float*)((char*)e->d_packed + e->b_off[i]);
+            d.cout = c.cout; d.cout_pad = e->cout_pad[i]; d.ksize = c.im2col_input ? 1 : c.k; d.pad = c.im2col_input ? 0 : c.pad;
+            d.relu = c.relu; d.planes = e->planes; d.geo = g; d.out_scale = d.bias + e->cout_pad[i];
+            if (c.out_act >= 0) {
+                d.out = e->acts[c.out_act]; d.out_pitch = e->plan.acts[c.out_act].C; d.out_coff = c.out_coff; d.out_plane = e->act_plane[c.out_act];
+                d.planar = nullptr; d.planar_C = 0; d.planar_coff = 0;
+            } else {
+                d.out = nullptr; d.out_pitch = 0; d.out_coff = 0; d.out_plane = 0;
+                d.planar = e->d_maps; d.planar_C = e->mt->num_maps; d.planar_coff = c.planar_coff;
+            }
+            std::string err;
+            if (tc_layer_create(d, e->tc[i], err)) return fail(e, PE_ERR_CUDA, "layer %s: %s", c.name.c_str(), err.c_str());
+        }
+    }
+    drop_graphs(e);
+    e->committed = true;
+    return PE_OK;
+}
+
+extern "C" int pe_commit_weights(pe_engine* e) {
+    if (!e) return PE_ERR_INVALID;
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t nc = e->plan.convs.size();
+    for (size_t i = 0; i < nc; i++) {
+        const ConvSpec& c = e->plan.convs[i];
+        if (!e->hw[i].set || e->hw[i].w.size() != (size_t)c.cout * c.cin * c.k * c.k || e->hw[i].b.size() != (size_t)c.cout)
+            return fail(e, PE_ERR_STATE, "weights of layer %s were never set%s", c.name.c_str(),
+                        e->committed ? " on this handle (a broadcast replica keeps no fp32 copy: set every layer again)" : "");
+    }
+    const size_t total = packed_layout(e);
     std::vector<uint8_t> host(total, 0);
+    if (e->w11_off) {   // wT[k][co], k = c*9 + kh*3 + kw: Caffe's im2col row order (im2col.cpp:19-55)
+        float* wT = (float*)(host.data() + e->w11_off);
+        const HostWeights& h0 = e->hw[0];
+        for (int co = 0; co < 64; co++) {
+            for (int k = 0; k < 27; k++) wT[k * 64 + co] = h0.w[(size_t)co * 27 + k];
+            wT[27 * 64 + co] = h0.b[co];
+        }
+    }
     for (size_t i = 0; i < nc; i++) {
         const ConvSpec& c = e->plan.convs[i];
         const HostWeights& hw = e->hw[i];
@@ -535,36 +606,41 @@ extern "C" int pe_commit_weights(pe_engine* e) {
         for (int co = 0; co < c.cout; co++) B[co] = hw.b[co];
         B[cop] = wscale_inv;   // travels with the packed buffer (weight broadcast)
     }
-    if (e->d_packed) { cudaFree(e->d_packed); e->d_packed = nullptr; }
-    CK(e, cudaMalloc(&e->d_packed, total));
+    e->packed_owner.reset();
+    e->d_packed = nullptr;
+    void* dp = nullptr;
+    CK(e, cudaMalloc(&dp, total));
+    const int dev = e->cfg.device;
+    e->packed_owner = std::shared_ptr<void>(dp, [dev](void* q) { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(dev); cudaFree(q); cudaSetDevice(cur); });
+    e->d_packed = dp;
     CK(e, cudaMemcpy(e->d_packed, host.data(), total, cudaMemcpyHostToDevice));
     e->packed_bytes = total;
-    if (e->planes) {
-        for (auto& t : e->tc) tc_layer_destroy(t);
-        e->tc.assign(nc, TcLayer());
-        for (size_t i = 0; i < nc; i++) {
-            const ConvSpec& c = e->plan.convs[i];
-            const Geo& g = e->geo[c.level];
-            TcLayerDesc d;
-            d.in = e->acts[c.in_act]; d.in_pitch = e->plan.acts[c.in_act].C; d.in_cused = c.in_cused; d.in_plane = e->act_plane[c.in_act];
-            d.w = (char*)e->d_packed + e->w_off[i]; d.bias = (const float*)((char*)e->d_packed + e->b_off[i]);
-            d.cout = c.cout; d.cout_pad = e->cout_pad[i]; d.ksize = c.im2col_input ? 1 : c.k; d.pad = c.im2col_input ? 0 : c.pad;
-            d.relu = c.relu; d.planes = e->planes; d.geo = g; d.out_scale = d.bias + e->cout_pad[i];
-            if (c.out_act >= 0) {
-                d.out = e->acts[c.out_act]; d.out_pitch = e->plan.acts[c.out_act].C; d.out_coff = c.out_coff; d.out_plane = e->act_plane[c.out_act];
-                d.planar = nullptr; d.planar_C = 0; d.planar_coff = 0;
-            } else {
-                d.out = nullptr; d.out_pitch = 0; d.out_coff = 0; d.out_plane = 0;
-                d.planar = e->d_maps; d.planar_C = e->mt->num_maps; d.planar_coff = c.planar_coff;
-            }
-            std::string err;
-            if (tc_layer_create(d, e->tc[i], err)) return fail(e, PE_ERR_CUDA, "layer %s: %s", c.name.c_str(), err.c_str());
-        }
-    }
-    drop_graphs(e);
-    e->committed = true;
-    return PE_OK;
+    return bind_packed(e);
 }
+
+// Net::ShareTrainedLayersWith (src/caffe/net.cpp:682-706): a second net on the SAME GPU uses the first one's weights instead of
+// loading them again - here the packed device buffer itself (no copy; it lives until the last handle that uses it is destroyed).
+// For two worker handles per GPU (copies of one batch overlap the compute of the other, rtpose.bin --engines_per_gpu).
+extern "C" int pe_share_weights(pe_engine* from, pe_engine* to) {
+    if (!from || !to || from == to) return fail(from, PE_ERR_INVALID, "bad arguments");
+    if (!from->committed) return fail(from, PE_ERR_STATE, "the source handle has no committed weights");
+    if (to->cfg.device != from->cfg.device) return fail(from, PE_ERR_INVALID, "handles are on different GPUs (use pe_broadcast_weights)");
+    if (to->cfg.model != from->cfg.model || to->cfg.precision != from->cfg.precision || to->plan.convs.size() != from->plan.convs.size())
+        return fail(from, PE_ERR_INVALID, "the handles run different nets (model / precision / graph)");
+    for (size_t i = 0; i < to->plan.convs.size(); i++) {
+        const ConvSpec &a = from->plan.convs[i], &b = to->plan.convs[i];
+        if (a.name != b.name || a.cout != b.cout || a.cin != b.cin || a.k != b.k) return fail(from, PE_ERR_INVALID, "layer %s differs between the handles", a.name.c_str());
+    }
+    CK(to, cudaSetDevice(to->cfg.device));
+    CK(to, cudaStreamSynchronize(to->stream));
+    if (packed_layout(to) != from->packed_bytes) return fail(from, PE_ERR_STATE, "packed layouts differ");
+    to->packed_owner = from->packed_owner;
+    to->d_packed = from->d_packed;
+    to->packed_bytes = from->packed_bytes;
+    for (auto& h : to->hw) { std::vector<float>().swap(h.w); std::vector<float>().swap(h.b); h.set = false; }
+    return bind_packed(to);
+}
+
 // ---------------------------------------------------------------------------------------------
 // One-time weight replica broadcast inside ONE process (rtpose.bin --num_gpu N).  The reference reads and parses the
 // .caffemodel once per GPU (rtpose.cpp:183-184); here engines[0]'s packed device buffer goes to every other GPU with
@@ -592,7 +668,9 @@ extern "C" int pe_broadcast_weights(pe_engine* const* engines, int n) {
             }
             const int rc = pe_commit_weights(e);
             if (rc) return rc;
-            for (auto& h : e->hw) { std::vector<float>().swap(h.w); }
+            // the replica holds no fp32 copy: a later pe_set_conv_weights on a subset + pe_commit_weights must fail
+            // ("weights of layer ... were never set") instead of packing from empty vectors
+            for (auto& h : e->hw) { std::vector<float>().swap(h.w); std::vector<float>().swap(h.b); h.set = false; }
         }
         if (e->packed_bytes != root->packed_bytes) return fail(root, PE_ERR_STATE, "packed layouts differ");
     }
@@ -675,6 +753,14 @@ static int run_op(pe_engine* e, const OpRef& op, int nimg) {
         const ConvSpec& c = e->plan.convs[op.idx];
         const Geo& g = e->geo[c.level];
         const long long M = (long long)nimg * g.Hs * g.Wp;
+        if (op.idx == 0 && c.im2col_input && e->conv11_direct && e->input_from_frames && e->w11_off && c.out_act >= 0) {
+            PreArgs a = e->pre;
+            a.nframes = nimg / e->cfg.num_scales;
+            const float* wT = (const float*)((const char*)e->d_packed + e->w11_off);
+            e->launches += launch_conv1_1_direct(a, wT, wT + 27 * 64, e->acts[c.out_act], e->plan.acts[c.out_act].C, e->act_plane[c.out_act],
+                                                 c.relu, nimg, e->stream);
+            return PE_OK;
+        }
         if (e->planes) {
             e->launches += tc_layer_launch(e->tc[op.idx], nimg, e->stream);
             return PE_OK;
@@ -782,7 +868,11 @@ extern "C" int pe_forward_frames_device(pe_engine* e, const void* d_frames, int 
         CK(e, cudaMemsetAsync(e->acts[e->plan.input_act], 0, bytes, e->stream));
         e->input_lo_dirty = false;
     }
-    e->launches += launch_preprocess(a, e->stream);
+    const bool direct = e->conv11_direct && e->w11_off && e->plan.convs[0].out_act >= 0;
+    e->launches += launch_preprocess(a, e->stream, !direct);
+    if (!e->input_from_frames) drop_graphs(e);   // graphs captured on the planar-input path hold the other conv1_1 kernel
+    e->input_from_frames = true;
+    e->input_act_stale = direct;
     e->last_frames = (const uint8_t*)d_frames;
     return run_net(e, n);
 }
@@ -924,6 +1014,9 @@ extern "C" int pe_forward_net_input(pe_engine* e, const float* net_input, int n)
     e->launches += launch_input_from_planar(e->d_planar, a, n * e->cfg.num_scales, e->stream);
     e->input_lo_dirty = e->planes > 0;
     e->last_frames = nullptr;
+    if (e->input_from_frames) drop_graphs(e);   // the captured graphs hold the other conv1_1 kernel
+    e->input_from_frames = false;
+    e->input_act_stale = false;
     return run_net(e, n);
 }
 extern "C" int pe_forward_maps(pe_engine* e, const float* maps8, int n) {
@@ -1004,6 +1097,37 @@ extern "C" int pe_render(pe_engine* e, int idx, int part_to_show, int googly_eye
     return PE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// render_mpi_parts / render_coco_parts / render_coco_aff of include/rtpose/renderFunctions.h with the reference's DEVICE-pointer
+// arguments (src/rtpose/renderFunctions.cu:330-392, 977-1075): canvas = planar float BGR (3 x h_canvas x w_canvas), heatmaps =
+// the full-resolution resized_map (C x h_net x w_net), poses = joints.  No engine handle: this is the drop-in for host code that
+// keeps the reference's own buffers.  kind 0 / 1 / 2 = mpi_parts / coco_parts / coco_aff; `extra` = googly_eyes (kind 1) or
+// num_parts_accum (kind 2).  Like the reference it renders frame 0 of the batch and synchronises the device.
+// ---------------------------------------------------------------------------------------------
+extern "C" int pe_render_device(int kind, float* canvas, int w_canvas, int h_canvas, int w_net, int h_net, const float* heatmaps,
+                                const float* poses, const int* num_people, int n_frames, int part, int extra) {
+    if (!canvas || w_canvas <= 0 || h_canvas <= 0 || kind < 0 || kind > 2) return PE_ERR_INVALID;
+    const int np0 = (num_people && n_frames > 0) ? num_people[0] : 0;
+    float* heat = const_cast<float*>(heatmaps);
+    const size_t plane = (size_t)w_net * h_net;
+    if (kind == 0) {          // render_mpi_parts: skeleton (only when somebody is there) or one channel as a heat map
+        if (part == 0) { if (np0 != 0) launch_skeleton(PE_MODEL_MPI_15, canvas, w_canvas, h_canvas, poses, nullptr, 0, nullptr, np0); }
+        else if (part > 0) { if (!heat) return PE_ERR_INVALID; launch_heat_view(canvas, w_canvas, h_canvas, heat + (size_t)(part - 1) * plane, w_net, h_net, 0, part - 1, 1, nullptr); }
+    } else if (kind == 1) {   // render_coco_parts
+        if (part == 0) { if (np0 != 0) launch_skeleton(PE_MODEL_COCO_18, canvas, w_canvas, h_canvas, poses, nullptr, extra, nullptr, np0); }
+        else if (part > 0 && part < 58) {
+            if (!heat) return PE_ERR_INVALID;
+            if (part - 1 == 18) launch_heat_view(canvas, w_canvas, h_canvas, heat, w_net, h_net, 2, 0, 18, nullptr);
+            else launch_heat_view(canvas, w_canvas, h_canvas, heat + (size_t)(part - 1) * plane, w_net, h_net, 1, part - 1, 1, nullptr);
+        }
+    } else {                  // render_coco_aff: `extra` consecutive (x, y) PAF channel pairs from channel `part`
+        if (!heat || extra < 1) return PE_ERR_INVALID;
+        launch_heat_view(canvas, w_canvas, h_canvas, heat + (size_t)part * plane, w_net, h_net, 3, part, 2 * extra, nullptr);
+    }
+    const cudaError_t err = cudaDeviceSynchronize();   // as the reference does after every render call
+    return err == cudaSuccess ? PE_OK : fail(nullptr, PE_ERR_CUDA, "render: %s", cudaGetErrorString(err));
+}
+
 extern "C" int pe_sync(pe_engine* e) {
     if (!e) return PE_ERR_INVALID;
     CK(e, cudaSetDevice(e->cfg.device));
@@ -1043,6 +1167,12 @@ extern "C" int pe_fetch_blob(pe_engine* e, const char* blob_name, float* out, si
         if (w) *w = g.W;
         if (!out) return PE_OK;
         if (cnt > cap) return fail(e, PE_ERR_INVALID, "blob %s needs %zu floats", blob_name, cnt);
+        if (b.act == e->plan.input_act && e->input_act_stale) {   // conv1_1 ran from the uint8 images: materialise the net input on demand
+            PreArgs a = e->pre;
+            a.nframes = std::max(e->last_n, 1);
+            e->launches += launch_im2col_u8(a, e->stream);
+            e->input_act_stale = false;
+        }
         float* d = nullptr;
         CK(e, cudaMalloc(&d, cnt * sizeof(float)));
         e->launches += launch_act_to_nchw(e->acts[b.act], e->plan.acts[b.act].C, b.coff, b.c, e->act_plane[b.act], e->planes, g, d, e->stream);

@@ -69,7 +69,8 @@ int launch_post(const PostDev& pd, int nframes, cudaStream_t st);
 int launch_canvas_fill(const uint8_t* bgr, float* canvas, int w, int h, cudaStream_t st);
 int launch_canvas_to_u8(const float* canvas, uint8_t* bgr, int w, int h, cudaStream_t st);
 int launch_fullres_fill(const PostDev& pd, int frame, int ch0, int nch, float* out, cudaStream_t st);
-int launch_skeleton(int model, float* canvas, int w, int h, const float* poses, const int* num_people, int googly, cudaStream_t st);
+int launch_skeleton(int model, float* canvas, int w, int h, const float* poses, const int* num_people, int googly, cudaStream_t st,
+                    int num_people_host = 0);   // num_people == nullptr: the count is num_people_host
 // mode 0: MPI part map, 1: COCO part map, 2: COCO all parts, 3: COCO PAF (render.cu)
 int launch_heat_view(float* canvas, int w, int h, float* heat, int w_net, int h_net, int mode, int part, int nch, cudaStream_t st);
 
@@ -89,7 +90,11 @@ struct PreArgs {
     void* out; int kp; long long out_plane; int planes;   // planes == 0: fp32, else bf16 planes
     int Wp, Hs;
 };
-int launch_preprocess(const PreArgs& a, cudaStream_t st);
+int launch_preprocess(const PreArgs& a, cudaStream_t st, bool with_im2col = true);
+int launch_im2col_u8(const PreArgs& a, cudaStream_t st);   // resized uint8 images -> im2col'ed input activation (second half of launch_preprocess)
+// conv1_1 from the resized uint8 images (fp32 CUDA cores); wT = [27][64] weights in (c, kh, kw) order, k-major
+int launch_conv1_1_direct(const PreArgs& a, const float* wT, const float* bias, void* out, int out_pitch, long long out_plane, int relu,
+                          int nimages, cudaStream_t st);
 struct WarpArgs {
     const uint8_t* src; uint8_t* dst; int sw, sh, dw, dh;
     const int* adelta; const int* bdelta; const int* x0; const int* y0;   // OpenCV's fixed-point coordinate tables

@@ -60,7 +60,12 @@ __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
     const int part = blockIdx.z % pd.p.num_parts, frame = blockIdx.z / pd.p.num_parts;
     const FullRes fr = make_fullres(pd, frame);
     const int W = pd.p.net_w, H = pd.p.net_h;
-    const int x0 = blockIdx.x * NMS_TX - 1, y0 = blockIdx.y * NMS_TY - 1;
+    const int x0 = blockIdx.x * NMS_TX - 1;
+    const int tiles_y = (H + NMS_TY - 1) / NMS_TY;
+    // A CTA walks several row tiles (blockIdx.y, + gridDim.y, ...): with one 32x16 tile per CTA the kernel was 78 000 CTAs of a
+    // few microseconds each and spent its time in launch / table set-up, not in the cubics (r1n: 383 us per 9-frame step).
+    for (int tile_y = blockIdx.y; tile_y < tiles_y; tile_y += gridDim.y) {
+    const int y0 = tile_y * NMS_TY - 1;
     const int ylo = max(y0, 0), yhi = min(y0 + NMS_TY + 1, H - 1);
     // Separable evaluation: the horizontal cubic of a (source row, x) pair does not depend on the output row,
     // so it is computed once per tile (<= NMS_HROWS source rows) instead of 4x per output pixel.  Same
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
 #pragma unroll
     for (int pass = 0; pass < NMS_TY / 8; pass++) {
         const int ly = (threadIdx.x >> 5) + pass * 8;
-        const int x = blockIdx.x * NMS_TX + lx, y = blockIdx.y * NMS_TY + ly;
+        const int x = blockIdx.x * NMS_TX + lx, y = tile_y * NMS_TY + ly;
         bool peak = false;
         if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {
             const float v = tile[ly + 1][lx + 1];
@@ -141,6 +146,8 @@ __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
             const int words_per_row = (W + 31) / 32;
             pd.flags[((size_t)(frame * pd.p.num_parts + part) * H + y) * words_per_row + blockIdx.x] = word;
         }
+    }
+    __syncthreads();   // tile[] is rewritten by the next row tile
     }
 }
 
@@ -569,7 +576,8 @@ int launch_post(const PostDev& pd, int nframes, cudaStream_t st) {
     const int MP = p.max_peaks;
     cudaMemsetAsync(pd.peaks, 0, sizeof(float) * (size_t)nframes * p.num_parts * (MP + 1) * 3, st);
     cudaMemsetAsync(pd.cand_count, 0, sizeof(int) * (size_t)nframes * p.num_limbs, st);
-    dim3 g1((p.net_w + NMS_TX - 1) / NMS_TX, (p.net_h + NMS_TY - 1) / NMS_TY, nframes * p.num_parts);
+    const int tiles_y = (p.net_h + NMS_TY - 1) / NMS_TY;
+    dim3 g1((p.net_w + NMS_TX - 1) / NMS_TX, tiles_y < 4 ? tiles_y : 4, nframes * p.num_parts);
     nms_flags_kernel<<<g1, 256, 0, st>>>(pd);
     nms_write_kernel<<<dim3(p.num_parts, nframes), 256, 0, st>>>(pd);
     paf_score_kernel<<<dim3((MP * MP + 127) / 128, p.num_limbs, nframes), 128, 0, st>>>(pd);

@@ -17,9 +17,10 @@
 // tiny canvases people beyond the block size are read from uninitialised shared memory.  This implementation uses a
 // regular launch; results are identical wherever the reference's launch is valid.
 //
-// Arithmetic: per-pixel expressions follow the reference statement by statement (float vs double promotions
-// included) so that nvcc contracts them the same way; tests/test_gpu_render.py compares against the reference's own
-// kernels compiled for sm_100a by the test infrastructure.
+// Arithmetic: the per-pixel tests and blends use the reference's operand types and operation order (float vs double
+// promotions included) so that the canvas is bit-identical; tests/test_gpu_render.py compares against the reference's own
+// kernels compiled for sm_100a by the test infrastructure.  The kernels themselves are organised differently (see the
+// skeleton section: per-CTA limb records, person culling).
 #include "common.h"
 #include "kernels.h"
 #include "fullres.cuh"
@@ -62,196 +63,210 @@ __global__ void __launch_bounds__(256) fullres_fill_kernel(PostDev pd, int frame
 }
 
 // ------------------------------------------------------------------------------------------------
-// skeleton overlays
+// skeleton overlays (what render_pose_29parts / render_pose_coco_parts draw, renderFunctions.cu:124-240, 394-636)
+//
+// Own design: the reference evaluates atan2f / sinf / cosf, the limb midpoint and the ellipse axes of EVERY (person, limb)
+// for EVERY pixel.  None of that depends on the pixel, so here each CTA first builds, for a chunk of persons, a table of
+// limb records in shared memory (one thread per (person, limb): 256x fewer transcendentals for a 32x8 tile), culls persons
+// whose extent cannot reach the tile - for both models; the reference has a per-pixel box for COCO only - and then every
+// pixel walks the surviving records in person / limb / joint order (alpha blending is order dependent).  The per-pixel
+// ellipse test and the blends use the same float / double operations on the same operands as the reference kernels, so the
+// canvas is bit-identical to theirs (tests/test_gpu_render.py runs the reference's kernels next to this one).
 // ------------------------------------------------------------------------------------------------
 __constant__ int c_limb_coco[34] = {1, 2, 1, 5, 2, 3, 3, 4, 5, 6, 6, 7, 1, 8, 8, 9, 9, 10, 1, 11, 11, 12, 12, 13, 1, 0, 0, 14, 14, 16, 0, 15, 15, 17};
+__constant__ int c_limb_mpi[18] = {0, 1, 2, 3, 3, 4, 5, 6, 6, 7, 8, 9, 9, 10, 11, 12, 12, 13};
 __constant__ int c_color18[54] = {255, 0, 0, 255, 85, 0, 255, 170, 0, 255, 255, 0, 170, 255, 0, 85, 255, 0, 0, 255, 0, 0, 255, 85, 0, 255, 170,
                                   0, 255, 255, 0, 170, 255, 0, 85, 255, 0, 0, 255, 85, 0, 255, 170, 0, 255, 255, 0, 255, 255, 0, 170, 255, 0, 85};
+__constant__ int c_color9[27] = {255, 0, 0, 255, 170, 0, 170, 255, 0, 0, 255, 0, 0, 255, 170, 0, 170, 255, 0, 0, 255, 170, 0, 255, 255, 0, 170};
 
 struct SkelArgs {
     float* canvas; int w, h;
     const float* poses;        // [PE_MAX_PEOPLE][parts][3] of this frame (device)
-    const int* num_people;     // device
+    const int* num_people;     // device (engine path) or null: num_people_host then holds the count (device-pointer API)
+    int num_people_host;
     int googly;
 };
 
-// render_pose_29parts (renderFunctions.cu:124-240)
-__global__ void __launch_bounds__(256) skeleton_mpi_kernel(SkelArgs a) {
-    constexpr int NP = 15;
-    __shared__ float sp[NP * 3 * PE_MAX_PEOPLE];
-    const int np = min(*a.num_people, PE_MAX_PEOPLE);
-    if (np <= 0) return;   // the reference does not launch (renderFunctions.cu:358)
-    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < np * NP * 3; i += blockDim.x * blockDim.y) sp[i] = a.poses[i];
-    __syncthreads();
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int w_canvas = a.w, h_canvas = a.h;
-    if (x >= w_canvas || y >= h_canvas) return;
-    const float threshold = 0.0f;
-    const int limb[] = {0, 1, 2, 3, 3, 4, 5, 6, 6, 7, 8, 9, 9, 10, 11, 12, 12, 13};   // head-neck, arms, legs (LIMB_MPI)
-    const int nlimb = sizeof(limb) / (2 * sizeof(int));
-    int color[27] = {255, 0, 0, 255, 170, 0, 170, 255, 0, 0, 255, 0, 0, 255, 170, 0, 170, 255, 0, 0, 255, 170, 0, 255, 255, 0, 170};
-    float radius = 3 * h_canvas / 200.0f;
-    float stickwidth = h_canvas / 60.0f;
-    float b = a.canvas[y * w_canvas + x];
-    float g = a.canvas[w_canvas * h_canvas + y * w_canvas + x];
-    float r = a.canvas[2 * w_canvas * h_canvas + y * w_canvas + x];
-    for (int p = 0; p < np; p++) {
-        const float* pose = sp + p * NP * 3;
-        for (int l = 0; l < nlimb; l++) {
-            float b_sqrt = stickwidth * stickwidth;
-            float alpha = 0.6;
-            const int pa = limb[2 * l], pb = limb[2 * l + 1];
-            const float x_a = pose[pa * 3], x_b = pose[pb * 3], y_a = pose[pa * 3 + 1], y_b = pose[pb * 3 + 1];
-            if (pose[pa * 3 + 2] > threshold && pose[pb * 3 + 2] > threshold) {
-                float x_p = (x_a + x_b) / 2;
-                float y_p = (y_a + y_b) / 2;
-                float angle = atan2f(y_b - y_a, x_b - x_a);
-                float sine = sinf(angle);
-                float cosine = cosf(angle);
-                float a_sqrt = (x_a - x_p) * (x_a - x_p) + (y_a - y_p) * (y_a - y_p);
-                if (l == 0) {
-                    a_sqrt *= 1.2;
-                    b_sqrt = a_sqrt;
-                }
-                float A = cosine * (x - x_p) + sine * (y - y_p);
-                float B = sine * (x - x_p) - cosine * (y - y_p);
-                float judge = A * A / a_sqrt + B * B / b_sqrt;
-                float minV = 0;
-                if (l == 0) minV = 0.8;
-                if (judge >= minV && judge <= 1) {
-                    b = (1 - alpha) * b + alpha * color[l * 3 + 2];
-                    g = (1 - alpha) * g + alpha * color[l * 3 + 1];
-                    r = (1 - alpha) * r + alpha * color[l * 3];
-                }
-            }
-        }
-        for (int i = 0; i < NP; i++) {
-            const float px = pose[i * 3], py = pose[i * 3 + 1];
-            if (pose[i * 3 + 2] > threshold) {
-                if ((x - px) * (x - px) + (y - py) * (y - py) <= radius * radius) {
-                    b = 0.6 * b + 0.4 * color[(i % 9) * 3 + 2];
-                    g = 0.6 * g + 0.4 * color[(i % 9) * 3 + 1];
-                    r = 0.6 * r + 0.4 * color[(i % 9) * 3];
-                }
-            }
-        }
-    }
-    a.canvas[y * w_canvas + x] = b;
-    a.canvas[w_canvas * h_canvas + y * w_canvas + x] = g;
-    a.canvas[2 * w_canvas * h_canvas + y * w_canvas + x] = r;
-}
+struct LimbRec {   // pixel-independent part of one limb ellipse
+    float mx, my;              // midpoint of the two joints
+    float sn, cs;              // sine / cosine of the limb direction
+    float major2, minor2;      // squared semi-axes
+    float lo;                  // the ellipse is drawn where lo <= judge <= 1 (the MPI head is a ring)
+    int draw;                  // both joints above the confidence threshold
+};
 
-// render_pose_coco_parts (renderFunctions.cu:394-636); the `if (0 && ...)` branches of the reference are dead code
-__global__ void __launch_bounds__(256) skeleton_coco_kernel(SkelArgs a) {
-    constexpr int NP = 18;
-    __shared__ float sp[NP * 3 * PE_MAX_PEOPLE];
-    __shared__ float2 s_min[PE_MAX_PEOPLE], s_max[PE_MAX_PEOPLE];
-    __shared__ float s_scale[PE_MAX_PEOPLE];
-    const int np = min(*a.num_people, PE_MAX_PEOPLE);
-    if (np <= 0) return;   // the reference does not launch (renderFunctions.cu:1006)
-    const int w_canvas = a.w, h_canvas = a.h;
-    const float threshold = 0.01f;
-    for (int p = threadIdx.y * blockDim.x + threadIdx.x; p < np; p += blockDim.x * blockDim.y) {   // per-person box and size
-        float2 mn = make_float2((float)w_canvas, (float)h_canvas), mx = make_float2(0.f, 0.f);
-        for (int part = 0; part < NP; part++) {
-            const float px = a.poses[p * NP * 3 + part * 3], py = a.poses[p * NP * 3 + part * 3 + 1], pz = a.poses[p * NP * 3 + part * 3 + 2];
-            sp[p * NP * 3 + part * 3] = px; sp[p * NP * 3 + part * 3 + 1] = py; sp[p * NP * 3 + part * 3 + 2] = pz;
-            if (pz > threshold) {
-                if (px < mn.x) mn.x = px;
-                if (px > mx.x) mx.x = px;
-                if (py < mn.y) mn.y = py;
-                if (py > mx.y) mx.y = py;
-            }
-        }
-        float sx = mx.x - mn.x, sy = mx.y - mn.y;
-        sx = (sx + sy) / 2.0;
-        if (sx < 200) {
-            sx = sx / 200;
-            if (sx < 0.33) sx = 0.33;
-        } else {
-            sx = 1.0;
-        }
-        mx.x += 50; mx.y += 50; mn.x -= 50; mn.y -= 50;
-        s_min[p] = mn; s_max[p] = mx; s_scale[p] = sx;
-    }
-    __syncthreads();
+template <int MODEL> struct SkelTraits;
+template <> struct SkelTraits<PE_MODEL_MPI_15> { static constexpr int NP = 15, NL = 9; };
+template <> struct SkelTraits<PE_MODEL_COCO_18> { static constexpr int NP = 18, NL = 17; };
+
+constexpr int SK_CHUNK = 16;   // persons per shared-memory pass
+
+template <int MODEL>
+__global__ void __launch_bounds__(256) skeleton_kernel(SkelArgs a) {
+    constexpr int NP = SkelTraits<MODEL>::NP, NL = SkelTraits<MODEL>::NL;
+    constexpr bool COCO = MODEL == PE_MODEL_COCO_18;
+    __shared__ float s_pose[SK_CHUNK][NP * 3];
+    __shared__ LimbRec s_limb[SK_CHUNK][NL];
+    __shared__ float4 s_box[SK_CHUNK];          // xmin, ymin, xmax, ymax of the person (COCO: the reference's +-50 px box)
+    __shared__ float s_size[SK_CHUNK];          // COCO: per-person drawing scale
+    __shared__ int s_hit[SK_CHUNK];             // the person can touch this tile
+    const int np = min(a.num_people ? *a.num_people : a.num_people_host, PE_MAX_PEOPLE);
+    if (np <= 0) return;                        // the reference does not launch (renderFunctions.cu:358, 1006)
+    const int W = a.w, H = a.h;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w_canvas || y >= h_canvas) return;
-    float radius = 2 * h_canvas / 200.0f;
-    float stickwidth = h_canvas / 120.0f;
-    float b = a.canvas[y * w_canvas + x];
-    float g = a.canvas[w_canvas * h_canvas + y * w_canvas + x];
-    float r = a.canvas[2 * w_canvas * h_canvas + y * w_canvas + x];
-    const bool googly_eyes = a.googly != 0;
-    for (int p = 0; p < np; p++) {
-        if (x > s_max[p].x || x < s_min[p].x || y > s_max[p].y || y < s_min[p].y) continue;
-        const float* pose = sp + p * NP * 3;
-        const float sc = s_scale[p];
-        for (int l = 0; l < 17; l++) {
-            float b_sqrt = sc * sc * stickwidth * stickwidth;
-            float alpha = 0.5;
-            const int pa = c_limb_coco[2 * l], pb = c_limb_coco[2 * l + 1];
-            const float x_a = pose[pa * 3], x_b = pose[pb * 3], y_a = pose[pa * 3 + 1], y_b = pose[pb * 3 + 1];
-            if (pose[pa * 3 + 2] > threshold && pose[pb * 3 + 2] > threshold) {
-                float x_p = (x_a + x_b) / 2;
-                float y_p = (y_a + y_b) / 2;
-                float angle = atan2f(y_b - y_a, x_b - x_a);
-                float sine = sinf(angle);
-                float cosine = cosf(angle);
-                float a_sqrt = (x_a - x_p) * (x_a - x_p) + (y_a - y_p) * (y_a - y_p);
+    const bool inside = x < W && y < H;
+    const float conf_min = COCO ? 0.01f : 0.0f;
+    const float radius = (COCO ? 2 : 3) * H / 200.0f;
+    const float stickwidth = COCO ? H / 120.0f : H / 60.0f;
+    // tile rectangle, for culling
+    const float tx0 = (float)(blockIdx.x * blockDim.x), ty0 = (float)(blockIdx.y * blockDim.y);
+    const float tx1 = tx0 + (float)(blockDim.x - 1), ty1 = ty0 + (float)(blockDim.y - 1);
+    float b = 0.f, g = 0.f, r = 0.f;
+    if (inside) {
+        b = a.canvas[y * W + x];
+        g = a.canvas[W * H + y * W + x];
+        r = a.canvas[2 * W * H + y * W + x];
+    }
+    for (int p0 = 0; p0 < np; p0 += SK_CHUNK) {
+        const int nq = min(SK_CHUNK, np - p0);
+        __syncthreads();
+        // ---- per person: joints, extent, scale, tile test
+        for (int q = tid; q < nq; q += nthr) {
+            const float* src = a.poses + (size_t)(p0 + q) * NP * 3;
+            float xmin = (float)W, ymin = (float)H, xmax = 0.f, ymax = 0.f;
+            for (int j = 0; j < NP; j++) {
+                const float px = src[j * 3], py = src[j * 3 + 1], pc = src[j * 3 + 2];
+                s_pose[q][j * 3] = px; s_pose[q][j * 3 + 1] = py; s_pose[q][j * 3 + 2] = pc;
+                if (pc > conf_min) {
+                    if (px < xmin) xmin = px;
+                    if (px > xmax) xmax = px;
+                    if (py < ymin) ymin = py;
+                    if (py > ymax) ymax = py;
+                }
+            }
+            float size = 1.f;
+            float margin;
+            if (COCO) {   // person size -> drawing scale, and the +-50 px box outside of which the person is not drawn (:424-452)
+                float sx = xmax - xmin, sy = ymax - ymin;
+                sx = (sx + sy) / 2.0;
+                if (sx < 200) {
+                    sx = sx / 200;
+                    if (sx < 0.33) sx = 0.33;
+                } else {
+                    sx = 1.0;
+                }
+                size = sx;
+                xmax += 50; ymax += 50; xmin -= 50; ymin -= 50;
+                margin = 0.f;
+            } else {      // no box in the reference: a conservative reach of any ellipse / circle of this person
+                const float dx = xmax - xmin, dy = ymax - ymin;
+                margin = fmaxf(stickwidth, radius) + 0.1f * sqrtf(dx * dx + dy * dy) + 2.f;
+            }
+            s_box[q] = make_float4(xmin, ymin, xmax, ymax);
+            s_size[q] = size;
+            s_hit[q] = !(tx0 > xmax + margin || tx1 < xmin - margin || ty0 > ymax + margin || ty1 < ymin - margin);
+        }
+        __syncthreads();
+        // ---- per (person, limb): the pixel-independent half of the ellipse test
+        for (int i = tid; i < nq * NL; i += nthr) {
+            const int q = i / NL, l = i % NL;
+            if (!s_hit[q]) continue;
+            const int ja = COCO ? c_limb_coco[2 * l] : c_limb_mpi[2 * l], jb = COCO ? c_limb_coco[2 * l + 1] : c_limb_mpi[2 * l + 1];
+            const float x_a = s_pose[q][ja * 3], y_a = s_pose[q][ja * 3 + 1], x_b = s_pose[q][jb * 3], y_b = s_pose[q][jb * 3 + 1];
+            LimbRec rec;
+            rec.draw = s_pose[q][ja * 3 + 2] > conf_min && s_pose[q][jb * 3 + 2] > conf_min;
+            float x_p = (x_a + x_b) / 2;
+            float y_p = (y_a + y_b) / 2;
+            float angle = atan2f(y_b - y_a, x_b - x_a);
+            rec.sn = sinf(angle);
+            rec.cs = cosf(angle);
+            float a_sqrt = (x_a - x_p) * (x_a - x_p) + (y_a - y_p) * (y_a - y_p);
+            float b_sqrt = COCO ? s_size[q] * s_size[q] * stickwidth * stickwidth : stickwidth * stickwidth;
+            float lo = 0;
+            if (!COCO && l == 0) {   // MPI head: a ring, 1.2x the neck-head distance
+                a_sqrt *= 1.2;
+                b_sqrt = a_sqrt;
+                lo = 0.8;
+            }
+            rec.mx = x_p; rec.my = y_p; rec.major2 = a_sqrt; rec.minor2 = b_sqrt; rec.lo = lo;
+            s_limb[q][l] = rec;
+        }
+        __syncthreads();
+        if (!inside) continue;
+        // ---- per pixel, in person / limb / joint order
+        for (int q = 0; q < nq; q++) {
+            if (!s_hit[q]) continue;
+            if (COCO) {
+                const float4 bx = s_box[q];
+                if (x > bx.z || x < bx.x || y > bx.w || y < bx.y) continue;
+            }
+            const float sc = s_size[q];
+            for (int l = 0; l < NL; l++) {
+                const LimbRec& rec = s_limb[q][l];
+                if (!rec.draw) continue;
+                const float x_p = rec.mx, y_p = rec.my, sine = rec.sn, cosine = rec.cs, a_sqrt = rec.major2, b_sqrt = rec.minor2;
                 float A = cosine * (x - x_p) + sine * (y - y_p);
                 float B = sine * (x - x_p) - cosine * (y - y_p);
                 float judge = A * A / a_sqrt + B * B / b_sqrt;
-                float minV = 0;
-                float maxV = 1;
-                float3 co;
-                co.x = c_color18[(l % 18) * 3 + 0];
-                co.y = c_color18[(l % 18) * 3 + 1];
-                co.z = c_color18[(l % 18) * 3 + 2];
-                if (judge >= minV && judge <= maxV) {
-                    b = (1 - alpha) * b + alpha * co.z;
-                    g = (1 - alpha) * g + alpha * co.y;
-                    r = (1 - alpha) * r + alpha * co.x;
+                if (judge >= rec.lo && judge <= 1) {
+                    if (COCO) {
+                        float alpha = 0.5;
+                        b = (1 - alpha) * b + alpha * (float)c_color18[(l % 18) * 3 + 2];
+                        g = (1 - alpha) * g + alpha * (float)c_color18[(l % 18) * 3 + 1];
+                        r = (1 - alpha) * r + alpha * (float)c_color18[(l % 18) * 3 + 0];
+                    } else {
+                        float alpha = 0.6;
+                        b = (1 - alpha) * b + alpha * c_color9[l * 3 + 2];
+                        g = (1 - alpha) * g + alpha * c_color9[l * 3 + 1];
+                        r = (1 - alpha) * r + alpha * c_color9[l * 3];
+                    }
                 }
             }
-        }
-        for (int i = 0; i < NP; i++) {
-            const float local_x = pose[i * 3], local_y = pose[i * 3 + 1];
-            if (pose[i * 3 + 2] > threshold) {
-                float dist2 = (x - local_x) * (x - local_x) + (y - local_y) * (y - local_y);
+            for (int j = 0; j < NP; j++) {
+                if (!(s_pose[q][j * 3 + 2] > conf_min)) continue;
+                const float jx = s_pose[q][j * 3], jy = s_pose[q][j * 3 + 1];
+                if (!COCO) {
+                    if ((x - jx) * (x - jx) + (y - jy) * (y - jy) <= radius * radius) {
+                        b = 0.6 * b + 0.4 * c_color9[(j % 9) * 3 + 2];
+                        g = 0.6 * g + 0.4 * c_color9[(j % 9) * 3 + 1];
+                        r = 0.6 * r + 0.4 * c_color9[(j % 9) * 3];
+                    }
+                    continue;
+                }
+                float dist2 = (x - jx) * (x - jx) + (y - jy) * (y - jy);
                 float minr2 = 0;
                 float maxr2 = sc * sc * radius * radius;
                 float alpha = 0.6;
-                float3 co;
-                co.x = c_color18[(i % 18) * 3 + 0];
-                co.y = c_color18[(i % 18) * 3 + 1];
-                co.z = c_color18[(i % 18) * 3 + 2];
-                if (googly_eyes && (i == 14 || i == 15)) {
+                float cr = c_color18[(j % 18) * 3 + 0], cg = c_color18[(j % 18) * 3 + 1], cb = c_color18[(j % 18) * 3 + 2];
+                if (a.googly && (j == 14 || j == 15)) {   // eyes: white disc, black rim, pupil offset by (4, -4)
                     maxr2 = sc * sc * 2.5 * 2.5 * radius * radius;
                     minr2 = sc * sc * (2.5 * radius - 2) * (2.5 * radius - 2);
                     alpha = 0.9;
-                    co.x = 0; co.y = 0; co.z = 0;
+                    cr = 0; cg = 0; cb = 0;
                     if (dist2 <= maxr2) {
-                        if (dist2 <= minr2) { co.x = 255; co.y = 255; co.z = 255; }
+                        if (dist2 <= minr2) { cr = 255; cg = 255; cb = 255; }
                         if (dist2 <= minr2 * 0.6) {
-                            float dist3 = (x - 4 - local_x) * (x - 4 - local_x) + (y - local_y + 4) * (y - local_y + 4);
-                            if (dist3 > 3.75 * 3.75) { co.x = 0; co.y = 0; co.z = 0; }
+                            float dist3 = (x - 4 - jx) * (x - 4 - jx) + (y - jy + 4) * (y - jy + 4);
+                            if (dist3 > 3.75 * 3.75) { cr = 0; cg = 0; cb = 0; }
                         }
-                        b = (1 - alpha) * b + alpha * co.z;
-                        g = (1 - alpha) * g + alpha * co.y;
-                        r = (1 - alpha) * r + alpha * co.x;
+                        b = (1 - alpha) * b + alpha * cb;
+                        g = (1 - alpha) * g + alpha * cg;
+                        r = (1 - alpha) * r + alpha * cr;
                     }
                 } else if (dist2 >= minr2 && dist2 <= maxr2) {
-                    b = (1 - alpha) * b + alpha * co.z;
-                    g = (1 - alpha) * g + alpha * co.y;
-                    r = (1 - alpha) * r + alpha * co.x;
+                    b = (1 - alpha) * b + alpha * cb;
+                    g = (1 - alpha) * g + alpha * cg;
+                    r = (1 - alpha) * r + alpha * cr;
                 }
             }
         }
     }
-    a.canvas[y * w_canvas + x] = b;
-    a.canvas[w_canvas * h_canvas + y * w_canvas + x] = g;
-    a.canvas[2 * w_canvas * h_canvas + y * w_canvas + x] = r;
+    if (inside) {
+        a.canvas[y * W + x] = b;
+        a.canvas[W * H + y * W + x] = g;
+        a.canvas[2 * W * H + y * W + x] = r;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -484,12 +499,13 @@ int launch_fullres_fill(const PostDev& pd, int frame, int ch0, int nch, float* o
     fullres_fill_kernel<<<dim3((pd.p.net_w + 255) / 256, pd.p.net_h, nch), 256, 0, st>>>(pd, frame, ch0, nch, out);
     return 1;
 }
-int launch_skeleton(int model, float* canvas, int w, int h, const float* poses, const int* num_people, int googly, cudaStream_t st) {
+int launch_skeleton(int model, float* canvas, int w, int h, const float* poses, const int* num_people, int googly, cudaStream_t st,
+                    int num_people_host) {
     SkelArgs a;
-    a.canvas = canvas; a.w = w; a.h = h; a.poses = poses; a.num_people = num_people; a.googly = googly;
+    a.canvas = canvas; a.w = w; a.h = h; a.poses = poses; a.num_people = num_people; a.num_people_host = num_people_host; a.googly = googly;
     const dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-    if (model == PE_MODEL_MPI_15) skeleton_mpi_kernel<<<grid, block, 0, st>>>(a);
-    else skeleton_coco_kernel<<<grid, block, 0, st>>>(a);
+    if (model == PE_MODEL_MPI_15) skeleton_kernel<PE_MODEL_MPI_15><<<grid, block, 0, st>>>(a);
+    else skeleton_kernel<PE_MODEL_COCO_18><<<grid, block, 0, st>>>(a);
     return 1;
 }
 int launch_heat_view(float* canvas, int w, int h, float* heat, int w_net, int h_net, int mode, int part, int nch, cudaStream_t st) {

@@ -39,7 +39,7 @@ _lib = None
 # every symbol include/poseengine.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "pe_create", "pe_destroy", "pe_last_error", "pe_num_conv_layers", "pe_conv_layer_info", "pe_set_conv_weights",
-    "pe_load_weights_file", "pe_commit_weights", "pe_nms_get_max_peaks", "pe_nms_get_num_parts", "pe_nms_get_threshold",
+    "pe_load_weights_file", "pe_commit_weights", "pe_share_weights", "pe_nms_get_max_peaks", "pe_nms_get_num_parts", "pe_nms_get_threshold",
     "pe_nms_set_threshold", "pe_resize_set_start_scale", "pe_resize_set_scale_gap", "pe_resize_get_start_scale",
     "pe_resize_get_scale_gap", "pe_set_connect_params", "pe_forward_frames", "pe_forward_frames_device",
     "pe_forward_net_input", "pe_forward_maps", "pe_fetch", "pe_fetch_maps", "pe_fetch_blob", "pe_sync", "pe_write_json",
@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "pe_event_record", "pe_event_elapsed_ms", "pe_profile_layers", "pe_launch_count", "pe_conv_flops_per_scale",
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
-    "pe_caffemodel_last_error", "pe_create_from_prototxt", "pe_plan_describe", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg", "pe_decode_jpeg", "pe_decode_png",
+    "pe_caffemodel_last_error", "pe_create_from_prototxt", "pe_plan_describe", "pe_render_device", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg", "pe_decode_jpeg", "pe_decode_png",
 ]
 
 
@@ -71,6 +71,7 @@ def lib():
     L.pe_set_conv_weights.argtypes = [C.c_void_p, C.c_char_p, _f32p, C.c_size_t, _f32p, C.c_size_t]
     L.pe_load_weights_file.argtypes = [C.c_void_p, C.c_char_p]
     L.pe_commit_weights.argtypes = [C.c_void_p]
+    L.pe_share_weights.argtypes = [C.c_void_p, C.c_void_p]
     L.pe_load_caffemodel.argtypes = [C.c_void_p, C.c_char_p]
     L.pe_caffemodel_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.pe_caffemodel_close.argtypes = [C.c_void_p]
@@ -120,6 +121,7 @@ def lib():
     L.pe_packed_weights_device_ptr.restype = C.c_void_p
     L.pe_broadcast_weights.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.pe_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pe_render_device.argtypes = [C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]
     L.pe_encode_jpeg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
     L.pe_encode_jpeg.restype = C.c_longlong
     L.pe_decode_jpeg.argtypes = [C.c_char_p, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_longlong]
@@ -510,6 +512,13 @@ def write_caffemodel(path, weights, table, legacy_v1=False, legacy_dims=False):
             net += _pb_len(100, _pb_len(1, ("relu_" + name).encode()) + _pb_len(2, b"ReLU"))   # blob-less layer, ignored
     with open(path, "wb") as f:
         f.write(net)
+
+
+def share_weights(src, dst):
+    """Net::ShareTrainedLayersWith: `dst` (same GPU, same net) uses `src`'s packed weights without a copy."""
+    rc = lib().pe_share_weights(src._h, dst._h)
+    if rc != 0:
+        raise PoseEngineError("pe_share_weights failed (%d): %s" % (rc, lib().pe_last_error(src._h).decode()))
 
 
 def broadcast_weights(engines):

@@ -3,10 +3,12 @@
 // owning one engine handle, one re-orderer, one writer).  Host code is plain C++17 (the reference's gflags / glog /
 // boost / OpenCV are not available here and are not needed for this path); all math is behind the C ABI.
 //
-// Supported sources: --image_dir with .bmp (24-bit) and .ppm (P6) files, or --synthetic N procedural frames.
-// .jpg/.png/--video/--camera need an image/video codec and are rejected with an explicit message.  Display,
-// keyboard handling is not part of this path.  --write_frames renders on the GPU (pe_render) and
-// writes quality-98 .jpg files like the reference (pe_encode_jpeg; --frame_format bmp for lossless), without the putText overlays.
+// Supported sources: --image_dir with .jpg / .png / .bmp / .ppm files (own decoders behind the C ABI, pixels identical to
+// cv::imread), or --synthetic N procedural frames.  --video/--camera need a video codec / capture device and are rejected
+// with an explicit message; there is no window, so the keyboard UI of handleKey (rtpose.cpp:1551-1671) is served from stdin
+// with --keys_from_stdin (same key characters, same step sizes).  --write_frames renders on the GPU (pe_render) and writes
+// quality-98 .jpg files like the reference (pe_encode_jpeg; --frame_format bmp for lossless), without the putText overlays.
+// Frames older than 0.1 s are dropped unless --no_frame_drops, as in processFrame (rtpose.cpp:1107-1124).
 #include <dirent.h>
 #include <math.h>
 #include <stdio.h>
@@ -74,7 +76,11 @@ static void define_flags() {
     define("random_init", "", "[extension] 'he' or 'caffe': random weights instead of --caffemodel (no checkpoint offline)");
     define("model", "", "[extension] COCO or MPI when --caffeproto is not readable");
     define("precision", "2", "[extension] conv arithmetic: 0 fp32 SIMT, 1 bf16, 2 split-bf16 parity mode");
-    define("batch", "1", "[extension] frames per forward per GPU (1 = the reference's behaviour)");
+    define("batch", "0", "[extension] frames per forward per GPU: 1 = the reference's behaviour, 0 = automatic (file / synthetic sources "
+           "fill two waves of 128-row tiles on the GPU, e.g. 9 frames at 656x368; results do not depend on it)");
+    define("engines_per_gpu", "0", "[extension] worker handles per GPU: 1 = the reference's topology (one Net per GPU), 0 = automatic (2 when "
+           "--batch is automatic: the copies and the kernel tails of one batch overlap the other; weights are shared, not duplicated)");
+    define("keys_from_stdin", "false", "[extension] read the reference's runtime keys (- = _ + [ ] { } ; ' , . 0-9 q-p a s, ESC or Q to quit) from stdin", true);
 }
 
 static int parse_flags(int argc, char** argv) {
@@ -120,7 +126,8 @@ struct Frame {
     int num_people = 0;
     std::vector<float> joints;
     std::vector<uint8_t> rendered;           // --write_frames: display image with overlays (pe_render), HWC BGR
-    double t_commit = 0, t_done = 0;
+    // stage clocks of the reference's latency line (rtpose.cpp:1421-1441)
+    double t_commit = 0, t_preprocessed = 0, t_fetched = 0, t_done = 0, t_out_popped = 0, t_buffered = 0;   // t_commit: capture / decode start
 };
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -256,6 +263,26 @@ private:
     std::mutex m_; std::condition_variable cv_; std::queue<T> q_;
 };
 
+// Page-locked frame buffers are recycled: cudaMallocHost / cudaFreeHost take the driver lock and cudaFreeHost synchronises the
+// device, which would serialise against the workers' asynchronous streams at hundreds of frames per second.
+class PinnedPool {
+public:
+    uint8_t* get(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            auto& v = free_[bytes];
+            if (!v.empty()) { uint8_t* p = v.back(); v.pop_back(); return p; }
+        }
+        return (uint8_t*)pe_host_alloc(bytes);
+    }
+    void put(uint8_t* p, size_t bytes) { std::lock_guard<std::mutex> l(m_); free_[bytes].push_back(p); }
+    void clear() { std::lock_guard<std::mutex> l(m_); for (auto& kv : free_) for (uint8_t* p : kv.second) pe_host_free(p); free_.clear(); }
+private:
+    std::mutex m_;
+    std::map<size_t, std::vector<uint8_t*>> free_;
+} g_pinned;
+static void pin_frame(struct Frame& fr);
+
 struct Global {
     BlockingQueue<Frame> input_queue, output_queue;
     std::priority_queue<int, std::vector<int>, std::greater<int>> dropped_index;
@@ -265,7 +292,21 @@ struct Global {
     int disp_w = 0, disp_h = 0, net_w = 0, net_h = 0, model = PE_MODEL_COCO_18, num_parts = 18;
     std::vector<std::string> image_list;
     bool proto_readable = false;   // --caffeproto parsed: engines are created from it
+    // global.nms_threshold etc. of the reference (rtpose.cpp:106-111), changed at run time by handle_key
+    std::atomic<float> nms_threshold{0.05f}, connect_min_subset_score{0.4f}, connect_inter_threshold{0.05f};
+    std::atomic<int> connect_min_subset_cnt{3}, connect_inter_min_above_threshold{9}, part_to_show{0}, params_version{0};
+    std::atomic<int> dropped{0};
+    int queue_limit = 64, batch = 1, engines_per_gpu = 1;
 } global;
+
+static void pin_frame(Frame& fr) {
+    const size_t bytes = fr.bgr.size();
+    if (uint8_t* ph = g_pinned.get(bytes)) {   // falls back to the staged copy inside pe_forward_frames if it fails
+        memcpy(ph, fr.bgr.data(), bytes);
+        fr.pinned = std::shared_ptr<uint8_t>(ph, [bytes](uint8_t* q) { g_pinned.put(q, bytes); });
+        std::vector<uint8_t>().swap(fr.bgr);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------- weights
 // The net is built from --caffeproto like `new Net<float>(proto, TEST)` (rtpose.cpp:183); the model follows the Nms layer's
@@ -307,6 +348,7 @@ static void producer() {
     const int total = n_syn > 0 ? n_syn : (int)global.image_list.size();
     for (int i = Fi("start_frame"); i < total && !global.quit; i++) {
         Frame fr;
+        fr.t_commit = now_s();    // frame.commit_time: taken when the frame is grabbed (rtpose.cpp:449)
         fr.index = global.produced; fr.video_frame_number = i;
         int w = global.disp_w, h = global.disp_h;
         if (n_syn > 0) {
@@ -318,14 +360,11 @@ static void producer() {
             const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
             fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
         }
-        if (void* ph = pe_host_alloc(fr.bgr.size())) {   // falls back to the staged copy inside pe_forward_frames if it fails
-            memcpy(ph, fr.bgr.data(), fr.bgr.size());
-            fr.pinned = std::shared_ptr<uint8_t>((uint8_t*)ph, [](uint8_t* q) { pe_host_free(q); });
-            std::vector<uint8_t>().swap(fr.bgr);
-        }
+        pin_frame(fr);
         fr.w = w; fr.h = h;
-        fr.t_commit = now_s();
-        while (global.input_queue.size() > 64 && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        fr.t_preprocessed = now_s();
+        // the reference's producers wait while more than 10 frames are queued (rtpose.cpp:310-313, 424-429); the bound scales with the batch
+        while ((int)global.input_queue.size() > global.queue_limit && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
         global.input_queue.push(std::move(fr));
         global.produced++;
     }
@@ -346,6 +385,7 @@ static void producer_mt(int nthreads) {
             const int i = next++;
             if (i >= total) break;
             Frame fr;
+            fr.t_commit = now_s();
             fr.index = i - start; fr.video_frame_number = i;
             int w = global.disp_w, h = global.disp_h;
             if (n_syn > 0) {
@@ -361,14 +401,10 @@ static void producer_mt(int nthreads) {
                 const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
                 fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
             }
-            if (void* ph = pe_host_alloc(fr.bgr.size())) {
-                memcpy(ph, fr.bgr.data(), fr.bgr.size());
-                fr.pinned = std::shared_ptr<uint8_t>((uint8_t*)ph, [](uint8_t* q) { pe_host_free(q); });
-                std::vector<uint8_t>().swap(fr.bgr);
-            }
+            pin_frame(fr);
             fr.w = w; fr.h = h;
-            fr.t_commit = now_s();
-            while (global.input_queue.size() > 64 && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+            fr.t_preprocessed = now_s();
+            while ((int)global.input_queue.size() > global.queue_limit && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
             global.input_queue.push(std::move(fr));
             global.produced++;
         }
@@ -421,12 +457,14 @@ static int load_weights(pe_engine* e, int device) {   // CopyTrainedLayersFrom (
 
 // warmup() of every GPU (rtpose.cpp:173-237).  The reference parses the .caffemodel once per GPU; here GPU 0 loads and
 // packs it and the replicas receive the packed buffer by one ncclBroadcast (the path's only collective).
-static bool create_engines(int num_gpu, std::vector<pe_engine*>& engines) {
-    const int batch = std::max(1, Fi("batch"));
-    for (int tid = 0; tid < num_gpu; tid++) {
+// engines[g * per_gpu + k] = handle k of GPU g.  Handle 0 of GPU 0 loads the model; handle 0 of the other GPUs receives the packed
+// weights by broadcast; handles k > 0 share their GPU's buffer (Net::ShareTrainedLayersWith).
+static bool create_engines(int num_gpu, int per_gpu, std::vector<pe_engine*>& engines) {
+    const int batch = global.batch;
+    for (int tid = 0; tid < num_gpu * per_gpu; tid++) {
         pe_config c;
         memset(&c, 0, sizeof c);
-        c.device = Fi("start_device") + tid; c.model = global.model; c.net_w = global.net_w; c.net_h = global.net_h;
+        c.device = Fi("start_device") + tid / per_gpu; c.model = global.model; c.net_w = global.net_w; c.net_h = global.net_h;
         c.disp_w = global.disp_w; c.disp_h = global.disp_h; c.num_scales = Fi("num_scales");
         c.start_scale = Fd("start_scale"); c.scale_gap = Fd("scale_gap"); c.max_batch = batch; c.precision = Fi("precision");
         pe_engine* e = nullptr;
@@ -436,48 +474,68 @@ static bool create_engines(int num_gpu, std::vector<pe_engine*>& engines) {
     }
     if (load_weights(engines[0], Fi("start_device"))) return false;
     if (num_gpu > 1) {
-        if (pe_broadcast_weights(engines.data(), num_gpu) == PE_OK) {
+        std::vector<pe_engine*> firsts;
+        for (int g = 0; g < num_gpu; g++) firsts.push_back(engines[g * per_gpu]);
+        if (pe_broadcast_weights(firsts.data(), num_gpu) == PE_OK) {
             LOG_INFO("weights broadcast from GPU %d to %d replicas (%.1f MB, NCCL)", Fi("start_device"), num_gpu - 1,
                      pe_packed_weights_bytes(engines[0]) / 1e6);
         } else {
             LOG_ERROR("weight broadcast unavailable (%s); every GPU loads the model itself", pe_last_error(engines[0]));
-            for (int tid = 1; tid < num_gpu; tid++)
-                if (load_weights(engines[tid], Fi("start_device") + tid)) return false;
+            for (int g = 1; g < num_gpu; g++)
+                if (load_weights(engines[g * per_gpu], Fi("start_device") + g)) return false;
         }
     }
+    for (int g = 0; g < num_gpu; g++)
+        for (int k = 1; k < per_gpu; k++)
+            if (pe_share_weights(engines[g * per_gpu], engines[g * per_gpu + k])) { LOG_ERROR("GPU %d: %s", Fi("start_device") + g, pe_last_error(engines[g * per_gpu])); return false; }
     return true;
 }
 
 static void worker(int tid, pe_engine* e) {
-    const int device = Fi("start_device") + tid, batch = std::max(1, Fi("batch"));
+    const int device = Fi("start_device") + tid / global.engines_per_gpu, batch = global.batch;
     struct Done { ~Done() { global.finished++; global.output_queue.wake(); } } done_guard;   // every exit path counts
     caffe::NmsLayer<float> nms_layer(e);
     caffe::ImResizeLayer<float> resize_layer(e);
     resize_layer.SetStartScale((float)Fd("start_scale"));
     resize_layer.SetScaleGap((float)Fd("scale_gap"));
-    LOG_INFO("GPU %d is ready (model %s, max_peaks %d)", device, nms_layer.GetNumParts() == 15 ? "MPI" : "COCO", nms_layer.GetMaxPeaks());
+    LOG_INFO("GPU %d is ready (model %s, max_peaks %d, %d frame(s) per forward)", device, nms_layer.GetNumParts() == 15 ? "MPI" : "COCO",
+             nms_layer.GetMaxPeaks(), batch);
     const int P = nms_layer.GetNumParts();
     std::vector<float> joints((size_t)PE_MAX_PEOPLE * P * 3);
     Frame pending;
     bool pending_valid = false;
+    int seen_version = -1;
+    const bool drops = !Fb("no_frame_drops");
     while (!global.quit) {
         std::vector<Frame> frames;
         Frame fr;
         while ((int)frames.size() < batch) {
             if (pending_valid) { fr = std::move(pending); pending_valid = false; }
             else if (!global.input_queue.try_pop(&fr)) break;
+            fr.t_fetched = now_s();
+            // processFrame drops a frame that waited more than 0.1 s for a GPU unless --no_frame_drops (rtpose.cpp:1107-1124)
+            if (drops && fr.t_fetched - fr.t_commit > 0.1) {
+                std::lock_guard<std::mutex> l(global.mutex);
+                global.dropped_index.push(fr.index);
+                global.dropped++;
+                continue;
+            }
             if (!frames.empty() && (fr.w != frames[0].w || fr.h != frames[0].h)) {   // one forward = one frame size
                 pending = std::move(fr); pending_valid = true;
                 break;
             }
-            // The reference drops frames that waited more than 0.1 s unless --no_frame_drops (rtpose.cpp:1107-1124);
-            // that policy is for live capture.  File and synthetic sources (the only ones here) process every frame.
             frames.push_back(std::move(fr));
         }
         if (frames.empty()) {
             if (global.producer_done && global.input_queue.size() == 0 && !pending_valid) break;
             std::this_thread::sleep_for(std::chrono::microseconds(200));
             continue;
+        }
+        if (seen_version != global.params_version) {   // nms_layer->SetThreshold(global.nms_threshold) + connect_* every frame (rtpose.cpp:1145, 1617-1651)
+            seen_version = global.params_version;
+            nms_layer.SetThreshold(global.nms_threshold);
+            pe_set_connect_params(e, global.connect_min_subset_cnt, global.connect_min_subset_score, global.connect_inter_threshold,
+                                  global.connect_inter_min_above_threshold);
         }
         std::vector<const uint8_t*> ptrs;
         for (auto& f : frames) ptrs.push_back(f.pinned ? f.pinned.get() : f.bgr.data());
@@ -494,14 +552,47 @@ static void worker(int tid, pe_engine* e) {
             frames[i].joints.assign(joints.begin(), joints.begin() + (size_t)cnt * P * 3);
             if (!F("write_frames").empty()) {   // render() + postProcessFrame (rtpose.cpp:271-300, 1286-1296) on the GPU
                 frames[i].rendered.resize((size_t)global.disp_w * global.disp_h * 3);
-                if (pe_render(e, (int)i, Fi("part_to_show"), 0, nullptr, nullptr, frames[i].rendered.data())) {
+                if (pe_render(e, (int)i, global.part_to_show, 0, nullptr, nullptr, frames[i].rendered.data())) {
                     LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break;
                 }
             }
+            frames[i].pinned.reset();   // back to the pool: the forward has consumed the frame
             frames[i].t_done = now_s();
             global.output_queue.push(std::move(frames[i]));
         }
     }
+}
+
+// handleKey (rtpose.cpp:1551-1671) without a window: the same key characters, read from stdin with --keys_from_stdin
+static void handle_key(int c) {
+    auto bump = [](std::atomic<float>& v, float d, const char* name) { v = v + d; LOG_INFO("%s: %g", name, (double)v.load()); };
+    auto bumpi = [](std::atomic<int>& v, int d, const char* name) { v = v + d; LOG_INFO("%s: %d", name, v.load()); };
+    const int max_show = global.model == PE_MODEL_MPI_15 ? 43 : 39;
+    if (c == 27 || c == 'Q') { global.quit = true; return; }   // ESC as in the reference; 'Q' for terminals that cannot send it
+    if (c == '-' || c == '=') bump(global.nms_threshold, c == '-' ? -0.005f : 0.005f, "nms_threshold");
+    else if (c == '_' || c == '+') bump(global.connect_min_subset_score, c == '_' ? -0.005f : 0.005f, "connect_min_subset_score");
+    else if (c == '[' || c == ']') bump(global.connect_inter_threshold, c == '[' ? -0.005f : 0.005f, "connect_inter_threshold");
+    else if (c == '{' || c == '}') bumpi(global.connect_inter_min_above_threshold, c == '{' ? -1 : 1, "connect_inter_min_above_threshold");
+    else if (c == ';' || c == '\'') bumpi(global.connect_min_subset_cnt, c == ';' ? -1 : 1, "connect_min_subset_cnt");
+    else if (c == ',' || c == '.') {
+        int p = global.part_to_show + (c == '.' ? 1 : -1);
+        if (p < 0) p = max_show;
+        if (p > max_show) p = 0;
+        global.part_to_show = p;
+        LOG_INFO("p2s: %d", p);
+        return;
+    } else {
+        static const std::string key2part = "0123456789qwertyuiopas";   // rtpose.cpp:1552, 1607-1615: digit/letter keys pick the view
+        const size_t ind = key2part.find((char)c);
+        if (ind != std::string::npos && (int)ind <= max_show) { global.part_to_show = (int)ind; LOG_INFO("p2s: %d", (int)ind); }
+        return;
+    }
+    global.params_version++;
+}
+static void key_reader() {
+    int c;
+    while (!global.quit && (c = getchar()) != EOF)
+        if (c != '\n' && c != '\r' && c != ' ') handle_key(c);
 }
 
 // re-order by frame index (buffer_and_order, rtpose.cpp:1214-1273) and write JSON (displayFrame, :1383-1416)
@@ -532,9 +623,11 @@ static void orderer_and_writer(int num_workers) {
             if (bmp) {
                 ok = write_bmp(fname, global.disp_w, global.disp_h, fr.rendered.data());
             } else {
-                const long long need = pe_encode_jpeg(fr.rendered.data(), global.disp_w, global.disp_h, 98, nullptr, 0);
-                std::vector<uint8_t> jb((size_t)std::max(need, 0LL));
-                ok = need > 0 && pe_encode_jpeg(fr.rendered.data(), global.disp_w, global.disp_h, 98, jb.data(), need) == need;
+                // one encoding pass: a baseline JPEG never exceeds the raw size by more than its tables and headers
+                std::vector<uint8_t> jb((size_t)global.disp_w * global.disp_h * 3 + (1u << 16));
+                const long long need = pe_encode_jpeg(fr.rendered.data(), global.disp_w, global.disp_h, 98, jb.data(), (long long)jb.size());
+                ok = need > 0 && need <= (long long)jb.size();
+                if (ok) jb.resize((size_t)need);
                 FILE* f = ok ? fopen(fname, "wb") : nullptr;
                 ok = f != nullptr;
                 if (f) { fwrite(jb.data(), 1, jb.size(), f); fclose(f); }
@@ -542,22 +635,25 @@ static void orderer_and_writer(int num_workers) {
             if (!ok) LOG_ERROR("cannot write %s", fname);
         }
         written++;
-        if (written % 30 == 0) {   // the reference prints FPS every 30 frames (:1421-1441)
+        if (written % 30 == 0) {   // the reference's line, every 30 frames (rtpose.cpp:1421-1441); stages that run on the GPU here read 0
             const double t = now_s();
-            LOG_INFO("frame %d  people %d  FPS %.1f  latency %.1f ms", fr.index, fr.num_people, 30.0 / (t - last), 1e3 * (fr.t_done - fr.t_commit));
+            LOG_INFO("# %d, NP %d, Latency %.3f, Preprocess %.3f, QueueA %.3f, GPU %.3f, QueueB %.3f, Postproc %.3f, QueueC %.3f, Buffered %.3f, "
+                     "QueueD %.3f, FPS = %.1f", fr.index, fr.num_people, t - fr.t_commit, fr.t_preprocessed - fr.t_commit, fr.t_fetched - fr.t_preprocessed,
+                     fr.t_done - fr.t_fetched, fr.t_out_popped - fr.t_done, 0.0, 0.0, fr.t_buffered - fr.t_out_popped, t - fr.t_buffered,
+                     30.0 / (t - last));
             last = t;
         }
     };
     while (true) {
         Frame fr;
         const bool got = global.output_queue.try_pop(&fr);
-        if (got) heap.push(std::move(fr));
+        if (got) { fr.t_out_popped = now_s(); heap.push(std::move(fr)); }
         while (true) {
             {
                 std::lock_guard<std::mutex> l(global.mutex);
                 while (!global.dropped_index.empty() && global.dropped_index.top() == next) { global.dropped_index.pop(); next++; }
             }
-            if (!heap.empty() && heap.top().index == next) { emit(heap.top()); heap.pop(); next++; }
+            if (!heap.empty() && heap.top().index == next) { Frame top = heap.top(); heap.pop(); top.t_buffered = now_s(); emit(top); next++; }
             else break;
         }
         if (!got) {
@@ -569,7 +665,7 @@ static void orderer_and_writer(int num_workers) {
         }
     }
     const double dt = now_s() - t0;
-    LOG_INFO("Done, exiting. # frames: %d  (%.1f frames/s overall)", written, written / std::max(dt, 1e-9));
+    LOG_INFO("Done, exiting. # frames: %d  (%.1f frames/s overall, %d dropped)", written, written / std::max(dt, 1e-9), global.dropped.load());
 }
 
 static bool ensure_dir(const std::string& d) {
@@ -635,20 +731,35 @@ int main(int argc, char** argv) {
         global.num_parts = md->get_number_parts();
         LOG_INFO("Selecting %s model: %d parts, %d limbs.", model == PE_MODEL_MPI_15 ? "MPI" : "COCO", global.num_parts, md->number_limb_sequence());
     }
+    // run-time thresholds start from the model defaults of rtpose.cpp:212-226
+    if (model == PE_MODEL_MPI_15) { global.nms_threshold = 0.2f; global.connect_inter_threshold = 0.01f; global.connect_inter_min_above_threshold = 8; }
+    global.part_to_show = Fi("part_to_show");
+    // frames per forward: 1 is the reference's behaviour (lowest latency); file / synthetic sources have no latency to protect, so by
+    // default one forward carries as many frames as give two full waves of 128-row tiles on 148 SMs (9 at 656x368); results do not change
+    global.batch = Fi("batch");
+    if (global.batch <= 0) {
+        const int per_frame_tiles = ((global.net_h / 8 + 3) * (global.net_w / 8 + 3) * std::max(1, Fi("num_scales")) + 127) / 128;
+        global.batch = std::min(16, std::max(1, (2 * 148 + per_frame_tiles / 2) / per_frame_tiles));
+    }
+    global.engines_per_gpu = Fi("engines_per_gpu") > 0 ? std::min(4, Fi("engines_per_gpu")) : (Fi("batch") <= 0 ? 2 : 1);
+    global.queue_limit = std::max(10, 4 * global.batch * std::max(1, Fi("num_gpu")) * global.engines_per_gpu);
     if (Fb("decode_bench")) return decode_bench();
     const int num_gpu = std::max(1, Fi("num_gpu"));
     std::vector<pe_engine*> engines;
-    if (!create_engines(num_gpu, engines)) {
+    const int per_gpu = global.engines_per_gpu, num_workers = num_gpu * per_gpu;
+    if (!create_engines(num_gpu, per_gpu, engines)) {
         for (pe_engine* e : engines) pe_destroy(e);
         return 1;
     }
     std::vector<std::thread> workers;
-    for (int i = 0; i < num_gpu; i++) workers.emplace_back(worker, i, engines[i]);
+    for (int i = 0; i < num_workers; i++) workers.emplace_back(worker, i, engines[i]);
     std::thread prod(run_producers);
-    std::thread ord(orderer_and_writer, num_gpu);
+    std::thread ord(orderer_and_writer, num_workers);
+    if (Fb("keys_from_stdin")) std::thread(key_reader).detach();   // blocks in getchar(): never joined
     prod.join();
     for (auto& t : workers) t.join();
     ord.join();
     for (pe_engine* e : engines) pe_destroy(e);
+    g_pinned.clear();
     return global.quit ? 1 : 0;
 }

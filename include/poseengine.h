@@ -90,6 +90,9 @@ int pe_caffemodel_blob(const pe_caffemodel* m, int layer, int blob, const float*
 const char* pe_caffemodel_last_error(void);
 /* pack + upload; must be called once after the weights are set and before any forward */
 int pe_commit_weights(pe_engine* e);
+/* Net::ShareTrainedLayersWith (net.cpp:682-706): `to` - another handle on the SAME GPU running the same net - uses `from`'s
+ * committed weights (the packed device buffer is shared, not copied, and lives until its last user is destroyed). */
+int pe_share_weights(pe_engine* from, pe_engine* to);
 
 /* ---- caffe::NmsLayer<float> accessors                                      nms_layer.hpp:24-27, rtpose.cpp:195,207,1145 */
 int pe_nms_get_max_peaks(const pe_engine* e);
@@ -156,6 +159,15 @@ int pe_write_json(const float* joints, int num_people, int num_parts, double fra
  * Synchronous. */
 int pe_render(pe_engine* e, int idx, int part_to_show, int googly_eyes, const uint8_t* display_bgr, float* canvas,
               uint8_t* bgr);
+
+/* render_mpi_parts / render_coco_parts / render_coco_aff with the reference's own DEVICE pointers (include/rtpose/renderFunctions.h:
+ * 8-17, call sites rtpose.cpp:277-296): canvas = planar float BGR 3 x h_canvas x w_canvas, heatmaps = full-resolution resized_map
+ * (C x h_net x w_net), poses = joints (people x parts x 3), num_people = host array of n_frames counts (frame 0 is rendered, as in
+ * the reference).  kind: 0 mpi_parts, 1 coco_parts, 2 coco_aff; extra: googly_eyes (kind 1) / num_parts_accum (kind 2).
+ * Runs on the default stream of the current device and synchronises it, like the reference.  C++ callers use the header shim
+ * include/rtpose/renderFunctions.h, which has the reference's signatures. */
+int pe_render_device(int kind, float* canvas, int w_canvas, int h_canvas, int w_net, int h_net, const float* heatmaps,
+                     const float* poses, const int* num_people, int n_frames, int part, int extra);
 
 /* cv::imwrite(fname, frame, {CV_IMWRITE_JPEG_QUALITY, 98}) of displayFrame (rtpose.cpp:1363-1380): baseline JFIF encoder
  * (YCbCr 4:2:0, Annex K tables, libjpeg quality scaling) for the uint8 BGR image pe_render returns.  Host code.  Returns the

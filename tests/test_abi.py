@@ -142,8 +142,16 @@ def test_cpp_header_shims_compile(tmp_path):
 #include "rtpose/modelDescriptorFactory.h"
 #include "caffe/cpm/layers/nms_layer.hpp"
 #include "caffe/cpm/layers/imresize_layer.hpp"
+#include "rtpose/renderFunctions.h"
 #include <cstdio>
+// the three render entry points keep the reference's signatures (renderFunctions.h:8-17): taking their addresses with the
+// reference's function types must compile
+typedef void (*mpi_fn)(float*, int, int, int, int, float*, int, float*, float*, std::vector<int>, int);
+typedef void (*coco_fn)(float*, int, int, int, int, float*, int, float*, float*, std::vector<int>, int, bool);
+typedef void (*aff_fn)(float*, int, int, int, int, float*, int, float*, float*, std::vector<int>, int, int);
+static mpi_fn f0 = &render_mpi_parts; static coco_fn f1 = &render_coco_parts; static aff_fn f2 = &render_coco_aff;
 int main() {
+    if (!f0 || !f1 || !f2 || RENDER_MAX_PEOPLE != 96) return 1;
     std::unique_ptr<ModelDescriptor> md;
     ModelDescriptorFactory::createModelDescriptor(ModelDescriptorFactory::Type::COCO_18, md);
     printf("%d %d %s %s\n", md->get_number_parts(), md->number_limb_sequence(), md->get_part_name(19).c_str(),

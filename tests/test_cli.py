@@ -134,7 +134,7 @@ def test_cli_json_equals_python_path(tmp_path):
         (write_bmp if i % 2 == 0 else write_ppm)(str(img_dir / ("img%03d.%s" % (i, "bmp" if i % 2 == 0 else "ppm"))), f)
     out = tmp_path / "json"
     r = run(["--image_dir", str(img_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "%dx%d" % (disp_w, disp_h),
-             "--net_resolution", "%dx%d" % (net_w, net_h), "--write_json", str(out), "--no_display", "--num_gpu", "1",
+             "--net_resolution", "%dx%d" % (net_w, net_h), "--write_json", str(out), "--no_display", "--no_frame_drops", "--num_gpu", "1",
              "--write_frames", str(tmp_path / "rendered"), "--part_to_show", "2"], timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
@@ -154,7 +154,7 @@ def test_cli_json_equals_python_path(tmp_path):
     write_bmp(str(big_dir / "big.bmp"), big)
     out2 = tmp_path / "json2"
     r = run(["--image_dir", str(big_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
-             "--net_resolution", "160x96", "--write_json", str(out2), "--no_display"], timeout=300)
+             "--net_resolution", "160x96", "--write_json", str(out2), "--no_display", "--no_frame_drops"], timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
     eng.set_weights(W)
@@ -165,7 +165,7 @@ def test_cli_json_equals_python_path(tmp_path):
     eng.close()
     # lossless frames on request
     r = run(["--image_dir", str(big_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
-             "--net_resolution", "160x96", "--no_display", "--write_frames", str(tmp_path / "bmp"), "--frame_format", "bmp"], timeout=300)
+             "--net_resolution", "160x96", "--no_display", "--no_frame_drops", "--write_frames", str(tmp_path / "bmp"), "--frame_format", "bmp"], timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
     eng.set_weights(W)
@@ -179,3 +179,27 @@ def test_cli_json_equals_python_path(tmp_path):
     r = run(["--image_dir", str(img_dir), "--caffemodel", str(tmp_path / "none.caffemodel"), "--caffeproto", str(proto),
              "--resolution", "320x192", "--net_resolution", "160x96"], timeout=300)
     assert r.returncode == 1 and "cannot load" in r.stderr
+
+
+@pytest.mark.gpu
+def test_frame_drop_policy_latency_line_and_runtime_keys(tmp_path):
+    """processFrame drops frames that waited more than 0.1 s for a GPU unless --no_frame_drops (rtpose.cpp:1107-1124); the
+    30-frame status line carries the reference's stage names (:1421-1441); handleKey's threshold keys (:1617-1651) arrive on
+    stdin.  A producer that is far faster than a 1-frame-per-forward worker on a tiny net shows all three."""
+    common = ["--synthetic", "400", "--random_init", "he", "--model", "COCO", "--resolution", "320x192", "--net_resolution", "160x96",
+              "--no_display", "--batch", "1", "--num_producers", "4"]
+    out = tmp_path / "json"
+    r = run(common + ["--write_json", str(out), "--no_frame_drops"], timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(os.listdir(out)) == 400 and "0 dropped" in r.stderr
+    assert "Latency" in r.stderr and "QueueA" in r.stderr and "Buffered" in r.stderr and "FPS =" in r.stderr
+    out2 = tmp_path / "json_drop"
+    r = run(common + ["--write_json", str(out2)], timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n = len(os.listdir(out2))
+    dropped = int(r.stderr.split(" dropped")[0].split()[-1])
+    assert n + dropped == 400                      # every frame is either written or accounted as dropped, order preserved
+    # keys: two '=' raise the NMS threshold by 0.01, ']' raises connect_inter_threshold
+    p = subprocess.run([BIN] + common + ["--keys_from_stdin", "--no_frame_drops"], input="==]\n", capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "nms_threshold: 0.06" in p.stderr and "connect_inter_threshold: 0.055" in p.stderr

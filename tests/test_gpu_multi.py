@@ -52,7 +52,7 @@ def test_cli_two_gpus_equals_one_gpu(tmp_path):
     outs = []
     for n in (1, 2):
         out = tmp_path / ("json%d" % n)
-        r = subprocess.run([BIN, "--synthetic", "24", "--random_init", "he", "--model", "COCO", "--resolution", "320x192",
+        r = subprocess.run([BIN, "--synthetic", "24", "--no_frame_drops", "--random_init", "he", "--model", "COCO", "--resolution", "320x192",
                             "--net_resolution", "160x96", "--write_json", str(out), "--no_display", "--num_gpu", str(n)],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
@@ -63,3 +63,29 @@ def test_cli_two_gpus_equals_one_gpu(tmp_path):
     assert len(names) == 24 and names == sorted(os.listdir(outs[1]))
     for nm in names:
         assert (outs[0] / nm).read_text() == (outs[1] / nm).read_text(), nm
+
+
+@pytest.mark.gpu
+def test_share_weights_same_gpu_is_bit_identical_and_outlives_the_source():
+    """Net::ShareTrainedLayersWith (net.cpp:682-706) for two worker handles on one GPU: the second handle uses the first one's
+    packed weights without a copy, gives bit-identical results, and keeps working after the source handle is destroyed."""
+    model, net_w, net_h, disp_w, disp_h = engine.COCO_18, 160, 96, 320, 192
+    e0 = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_F16X2)
+    e1 = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_F16X2, max_batch=2)
+    e0.set_weights(synth.make_weights(model, "he"))
+    engine.share_weights(e0, e1)
+    assert e1.packed_weights() == e0.packed_weights()          # the same device buffer
+    frame = synth.make_frame(5, disp_h, disp_w)
+    e0.forward_frames([frame])
+    want = (e0.fetch(0), e0.fetch_maps(1).copy())
+    e0.close()
+    e1.forward_frames([frame, frame])
+    for i in range(2):
+        cnt, joints, peaks = e1.fetch(i)
+        assert cnt == want[0][0] and np.array_equal(joints, want[0][1]) and np.array_equal(peaks, want[0][2])
+    assert np.array_equal(e1.fetch_maps(2)[:want[1].shape[0]], want[1])
+    e2 = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X1)
+    with pytest.raises(engine.PoseEngineError):                # another arithmetic mode packs differently
+        engine.share_weights(e1, e2)
+    e1.close()
+    e2.close()

@@ -92,3 +92,40 @@ def test_render_from_resident_frame_and_errors():
         eng.render(0, 0)
     assert eng.render(0, 0, display_bgr=frames[0]).shape == (disp_h, disp_w, 3)
     eng.close()
+
+
+def test_device_pointer_render_api_equals_reference_kernels():
+    """render_mpi_parts / render_coco_parts / render_coco_aff with the reference's device-pointer arguments
+    (include/rtpose/renderFunctions.h shim -> pe_render_device): canvas, full-resolution heat maps and joints in caller-owned
+    device memory, no engine handle.  Bit-identical to the reference's own kernels for every view."""
+    import ctypes as C
+    import torch
+    if orc.ref_render_lib() is None:
+        pytest.skip("oracle/_ref/libref_render.so not built")
+    L = engine.lib()
+    for model, net_w, net_h, disp_w, disp_h, parts in ((engine.COCO_18, 320, 176, 640, 352, [(0, 0), (0, 1), (3, 0), (19, 0), (20, 0), (25, 0)]),
+                                                        (engine.MPI_15, 240, 176, 480, 352, [(0, 0), (2, 0), (16, 0)])):
+        eng, cnt, joints, full, frame = scene(model, net_w, net_h, disp_w, disp_h, 6, seed=33)
+        eng.close()
+        P = 15 if model == engine.MPI_15 else 18
+        canvas0 = orc.canvas_from_u8(frame)
+        d_full = torch.from_numpy(np.ascontiguousarray(full)).cuda()
+        d_poses = torch.from_numpy(np.ascontiguousarray(joints[:cnt].reshape(-1))).cuda()
+        n = (C.c_int * 1)(cnt)
+        for part, googly in parts:
+            d_canvas = torch.from_numpy(canvas0.copy()).cuda()
+            if model == engine.MPI_15:
+                kind, p, extra = 0, part, 0
+            elif part - 1 <= P:                      # render() of rtpose.cpp:271-300
+                kind, p, extra = 1, part, googly
+            else:
+                aff, accum = ((part - 1) - P - 1) * 2, 1
+                if aff == 0:
+                    accum = 19
+                else:
+                    aff -= 2
+                kind, p, extra = 2, aff + 1 + P, accum
+            rc = L.pe_render_device(kind, d_canvas.data_ptr(), disp_w, disp_h, net_w, net_h, d_full.data_ptr(), d_poses.data_ptr(), n, 1, p, extra)
+            assert rc == 0
+            want = orc.ref_render(model, canvas0, net_w, net_h, full, joints, cnt, part, bool(googly))
+            assert np.array_equal(d_canvas.cpu().numpy(), want), (model, part, googly)

@@ -115,7 +115,7 @@ def test_two_stage_net_from_prototxt_vs_oracle(tmp_path):
     stride-8 maps within the conv tolerance of the oracle's 2-stage net, peaks / joints as the oracle's post-processing
     gives them on the engine's own maps (bit-exact parse stage)."""
     _, path = spec_prototxt("mpi_2", tmp_path)
-    net_w, net_h = 248, 184
+    net_w, net_h = 240, 176
     W = synth.make_weights(engine.MPI_15, "he", stages=2)
     onet = orc.Net(orc.MPI_15, stages=2)
     onet.set_weights(W)
