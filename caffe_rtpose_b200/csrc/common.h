@@ -50,6 +50,7 @@ struct ConvSpec {
     int out_act, out_coff;     // output activation (or -1: final planar maps) and channel offset
     int planar_coff;           // channel offset in concat_stage7 when out_act == -1
     std::vector<int> cin_map;  // engine input channel -> original cin index (-1: zero pad)
+    std::vector<int> cin_prod; // engine input channel -> index of the conv that produced it (-1: zero pad / the net input)
     int im2col_input;          // conv1_1: the input activation already holds the 3x3x3 patch (K=27)
     double flops_per_image;
 };

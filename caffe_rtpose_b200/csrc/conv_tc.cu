@@ -47,6 +47,7 @@ struct TcArgs {
     long long M;
     int n_tiles_n; long long total_tiles;   // persistent window kernel: tile = (m_tile, n_tile), n fastest
     int chunk_steps;                        // (channel block, filter row) steps per TMEM accumulation chunk (window kernel)
+    unsigned* range;                        // [0]: running max |stored value| of this layer as float bits (atomicMax; values are >= 0), or null
     int tma_store;                          // pair kernel: the epilogue stages 32-row x HALF-channel boxes in shared memory and stores them with TMA
     int dbg;                                // PE_TC_DBG bit mask, TIMING EXPERIMENTS ONLY (results are wrong): 1 no TMEM loads in the chunk drains,
                                             // 2 no epilogue math / stores, 4 weight tiles loaded once per slot only, 8 A windows loaded once per slot only, 16 one-lane issue loop,
@@ -163,6 +164,16 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
 
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// Range tracking of the 16-bit planes: every epilogue warp folds the largest |value| it stores into one word per layer.  The
+// host reads it to calibrate per-layer power-of-two activation scales (engine.cu, pe_calibrate) and to report values that
+// left the fp16 range instead of letting inf / flushed zeros poison the following layers silently.
+__device__ __forceinline__ void range_publish(unsigned* range, float m) {
+    if (!range) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(range, __float_as_uint(m));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -516,6 +527,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int cout8 = (a.cout + 7) & ~7;
         const float out_scale = __ldg(a.out_scale);
         uint32_t ci = 0;
+        float range_max = 0.f;   // largest |value| this warp stores (range tracking of the fp16 planes, see TcArgs::range)
         const int nsteps = a.kblocks_per_tap * ks;
         const int nchunks = (nsteps + a.chunk_steps - 1) / a.chunk_steps;
         for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -576,6 +588,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         float tv = __fmaf_rn(accv[pc * 16 + j], out_scale, s_bias[cb + j]);   // out_scale is a power of two: exact
                         if (a.relu) tv = fmaxf(tv, 0.f);
                         v[j] = tv;
+                        if (cb + j < a.cout) range_max = fmaxf(range_max, fabsf(tv));
                     }
                     if (a.planar) {
 #pragma unroll
@@ -601,6 +614,7 @@ conv_tcw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             }
         }
+        range_publish(a.range, range_max);
     }
     __syncthreads();
     if (warp == 1) {
@@ -821,6 +835,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const float out_scale = __ldg(a.out_scale);
         const uint32_t h_empty_leader = mapa_u32(smem_u32(&h_empty[0]), 0), c_empty_leader = mapa_u32(smem_u32(&c_empty[0]), 0);
         uint32_t ci = 0, ti = 0;
+        float range_max = 0.f;
         const int nsteps = a.kblocks_per_tap * ks;
         const int nchunks = (nsteps + a.chunk_steps - 1) / a.chunk_steps;
         for (long long t = tile0; t < total_tiles; t += tile_stride, ti++) {
@@ -899,6 +914,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 tv = __fmaf_rn(tv, out_scale, s_bias[cb + j]);   // out_scale is a power of two: exact
                                 if (a.relu) tv = fmaxf(tv, 0.f);
                                 v[j] = valid ? tv : 0.f;                        // gap rows are written as the zeros they hold
+                                if (cb + j < a.cout) range_max = fmaxf(range_max, fabsf(v[j]));
                             }
                             if (a.planar) {
 #pragma unroll
@@ -979,6 +995,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
         if (lane == 0) bulk_wait_read();   // staged boxes have been read out of shared memory before the CTA may exit
+        range_publish(a.range, range_max);
     }
     tc_fence_before();
     cluster_sync_all();      // no CTA of the pair exits (or frees TMEM) while its partner can still signal it
@@ -1221,7 +1238,7 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
     a.bias = d.bias;
     a.out = (__nv_bfloat16*)d.out; a.out_pitch = d.out_pitch; a.out_coff = d.out_coff; a.out_plane = d.out_plane;
     a.planar = d.planar; a.planar_C = d.planar_C; a.planar_coff = d.planar_coff;
-    a.cout = d.cout; a.relu = d.relu; a.out_scale = d.out_scale;
+    a.cout = d.cout; a.relu = d.relu; a.out_scale = d.out_scale; a.range = d.range;
     a.ksize = d.ksize; a.pad = d.pad; a.kblocks_per_tap = d.in_cused / TC_BK; a.cin_k = d.in_cused;
     a.W = d.geo.W; a.H = d.geo.H; a.Wp = d.geo.Wp; a.Hs = d.geo.Hs;
     a.M = (long long)nimg * d.geo.Hs * d.geo.Wp;

@@ -12,6 +12,7 @@ struct TcLayerDesc {
     const float* bias;
     int cout, cout_pad, ksize, pad, relu, planes;
     const float* out_scale = nullptr;                             // device: epilogue factor 2^-k (weights packed with 2^k)
+    unsigned* range = nullptr;                                    // device: running max |stored value| (float bits), or null
     Geo geo;                                                      // geo.N = max images
     void* out; int out_pitch, out_coff; long long out_plane;      // bf16 planes, or
     float* planar; int planar_C, planar_coff;                     // final fp32 maps (N, planar_C, H, W)

@@ -39,8 +39,15 @@ struct pe_engine {
     // packed weights (one device buffer): per conv offsets (bytes)
     void* d_packed = nullptr; size_t packed_bytes = 0;
     std::shared_ptr<void> packed_owner;   // frees d_packed when the last handle using it goes (pe_share_weights)
+    // fp16-plane range management (parity mode): per-conv-output power-of-two scale s (stored value = true value * s), the true
+    // biases / weight-scale inverses the packed epilogue fields derive from, and the kernels' running max |stored value| per conv
+    std::vector<float> conv_scale, wsi;   // per conv: scale of its stored output; inverse of the power of two folded into its weights
+    std::vector<std::vector<float>> bias_true;
+    unsigned* d_range = nullptr;
+    bool calibrated = false, check_range = false;
     std::vector<size_t> w_off, b_off;
     size_t w11_off = 0;             // fp32 [27][64] weights + 64 biases of conv1_1 for the direct kernel (0: not packed)
+    float w11_scale = 1.f;          // activation scale currently folded into that copy
     bool conv11_direct = false;     // PE_CONV11_DIRECT=1: conv1_1 by conv1_1_direct_kernel (fp32 CUDA cores, no im2col'ed input) instead of
                                     // the im2col + implicit-GEMM path; measured equal in time on B200 (r2e), so the tensor path stays the default
     bool input_from_frames = false; // the last forward came from uint8 frames: d_resized holds conv1_1's input
@@ -282,6 +289,7 @@ static int create_impl(const pe_config* cfg_in, const char* prototxt_path, pe_en
     e->planes = cfg->precision;  // 0 fp32, else number of bf16 planes
     if (const char* g = getenv("PE_GRAPH")) e->use_graphs = atoi(g) != 0;
     if (const char* g = getenv("PE_CONV11_DIRECT")) e->conv11_direct = atoi(g) != 0;
+    if (const char* g = getenv("PE_CHECK_RANGE")) e->check_range = atoi(g) != 0;
     e->elem = e->planes == 0 ? 4 : 2;
     e->start_scale_f = (float)cfg->start_scale;  // ImResizeLayer::SetStartScale(float)
     e->scale_gap_f = (float)cfg->scale_gap;
@@ -392,7 +400,7 @@ extern "C" void pe_destroy(pe_engine* e) {
     for (void* p : e->d_tabs) cudaFree(p);
     for (auto& t : e->tc) tc_layer_destroy(t);
     cudaFree(e->d_raw); cudaFreeHost(e->h_raw); cudaFree(e->d_wa); cudaFree(e->d_wb); cudaFree(e->d_wx0); cudaFree(e->d_wy0); cudaFree(e->d_wtab);
-    e->packed_owner.reset(); cudaFree(e->d_frames); cudaFree(e->d_resized); cudaFree(e->d_planar); cudaFree(e->d_maps);
+    e->packed_owner.reset(); cudaFree(e->d_range); cudaFree(e->d_frames); cudaFree(e->d_resized); cudaFree(e->d_planar); cudaFree(e->d_maps);
     cudaFreeHost(e->h_frames); cudaFreeHost(e->h_planar); cudaFreeHost(e->h_maps);
     cudaFree(e->d_xtab); cudaFree(e->d_ytab);
     cudaFree(e->d_canvas); cudaFree(e->d_render_u8); cudaFree(e->d_render_src); cudaFree(e->d_heat);
@@ -510,9 +518,84 @@ static size_t packed_layout(pe_engine* e) {
     return total;
 }
 
+// Range scales.  Every conv output is stored as  true value * s  with s = conv_scale[producer] (a power of two; pools and copies
+// pass values through unchanged).  A consumer whose input channels come from producers with DIFFERENT scales (a Concat: conv4_4_CPM
+// next to the previous stage's L1 / L2 outputs) folds the ratios into its weights: packed w[ci] = w[ci] * s_ref / s(ci) * 2^k, so that
+//   acc = 2^k * s_ref * sum_ci w[ci] * a[ci]     and     stored = acc * out_scale + bias,  out_scale = s_out / (2^k * s_ref),
+// bias = true bias * s_out - all factors powers of two, hence exact, and ReLU commutes with them: range scaling is free at run time.
+static float input_ref_scale(const pe_engine* e, const ConvSpec& c) {
+    for (int pc : c.cin_prod) if (pc >= 0) return e->conv_scale[pc];
+    return 1.f;   // the net input
+}
+static void fill_epilogue_fields(const pe_engine* e, int i, float* B) {
+    const ConvSpec& c = e->plan.convs[i];
+    const float s_ref = input_ref_scale(e, c);
+    const float s_out = c.out_act >= 0 ? e->conv_scale[i] : 1.f;   // the planar stride-8 maps are true values
+    for (int co = 0; co < c.cout; co++) B[co] = e->bias_true[i][co] * s_out;
+    B[e->cout_pad[i]] = e->wsi[i] * s_out / s_ref;
+}
+
+// Weights of conv i into `dst` (the layer's region of the packed buffer, host copy): fp32 [K][cout_pad] for the SIMT mode, else
+// P 16-bit planes [P][cout_pad][K] (K-major rows: the tcgen05 B operand) of w * 2^k, the per-channel range ratios folded in.
+// Sets e->wsi[i] = 2^-k.
+static void pack_conv_weights(pe_engine* e, int i, uint8_t* dst) {
+    const ConvSpec& c = e->plan.convs[i];
+    const HostWeights& hw = e->hw[i];
+    const int taps = c.im2col_input ? 1 : c.k * c.k, cp = e->cin_pad[i], cop = e->cout_pad[i];
+    const size_t K = (size_t)taps * cp;
+    const float s_ref = input_ref_scale(e, c);
+    std::vector<float> chan(cp, 1.f);   // s_ref / s(ci) per engine input channel
+    for (int ec = 0; ec < cp && ec < (int)c.cin_prod.size(); ec++)
+        if (c.cin_prod[ec] >= 0) chan[ec] = s_ref / e->conv_scale[c.cin_prod[ec]];
+    auto src = [&](int co, int kk) -> float {  // engine K index -> Caffe weight (co, ci, r, s)
+        if (c.im2col_input) {
+            if (kk >= 27) return 0.f;
+            const int tap = kk / 3, ci = kk % 3;
+            return hw.w[((size_t)co * 3 + ci) * 9 + tap];
+        }
+        const int tap = kk / cp, ec = kk % cp;
+        const int ci = ec < (int)c.cin_map.size() ? c.cin_map[ec] : -1;
+        if (ci < 0) return 0.f;
+        return hw.w[((size_t)co * c.cin + ci) * c.k * c.k + tap] * chan[ec];
+    };
+    memset(dst, 0, K * cop * e->elem * (e->planes ? e->planes : 1));
+    float wscale_inv = 1.f;
+    if (e->planes == 0) {  // fp32 [K][cout_pad]
+        float* W = (float*)dst;
+        for (size_t kk = 0; kk < K; kk++)
+            for (int co = 0; co < c.cout; co++) W[kk * cop + co] = src(co, (int)kk);
+    } else {
+        uint16_t* W = (uint16_t*)dst;
+        const size_t plane = (size_t)cop * K;
+        // fp16 planes: scale the layer by 2^k so that max|w| lands in [2^13, 2^14) - small weights would otherwise
+        // put their lo plane into fp16 subnormals.  Exact (power of two); the epilogue multiplies by 2^-k.
+        float wscale = 1.f;
+        if (planes_are_fp16(e->planes)) {
+            float mx = 0.f;
+            for (int co = 0; co < c.cout; co++)
+                for (size_t kk = 0; kk < K; kk++) mx = fmaxf(mx, fabsf(src(co, (int)kk)));
+            int ex = 0;
+            if (mx > 0.f && mx < 3e38f) { frexpf(mx, &ex); wscale = ldexpf(1.f, std::max(-100, std::min(100, 14 - ex))); }
+        }
+        wscale_inv = 1.f / wscale;
+        for (int co = 0; co < c.cout; co++)
+            for (size_t kk = 0; kk < K; kk++) {
+                uint16_t h[3];
+                if (planes_are_fp16(e->planes)) split_fp16(src(co, (int)kk) * wscale, e->planes, h);
+                else split_bf16(src(co, (int)kk), e->planes, h);
+                for (int p = 0; p < e->planes; p++) W[p * plane + (size_t)co * K + kk] = h[p];
+            }
+    }
+    e->wsi[i] = wscale_inv;
+}
+
 // per-layer launch state (TMA descriptors) over the packed buffer the handle currently points at
 static int bind_packed(pe_engine* e) {
     const size_t nc = e->plan.convs.size();
+    if (planes_are_fp16(e->planes) && !e->d_range) {
+        CK(e, cudaMalloc(&e->d_range, nc * sizeof(unsigned)));
+        CK(e, cudaMemset(e->d_range, 0, nc * sizeof(unsigned)));
+    }
     if (e->planes) {
         for (auto& t : e->tc) tc_layer_destroy(t);
         e->tc.assign(nc, TcLayer());
@@ -524,6 +607,7 @@ static int bind_packed(pe_engine* e) {
             d.w = (char*)e->d_packed + e->w_off[i]; d.bias = (const float*)((char*)e->d_packed + e->b_off[i]);
             d.cout = c.cout; d.cout_pad = e->cout_pad[i]; d.ksize = c.im2col_input ? 1 : c.k; d.pad = c.im2col_input ? 0 : c.pad;
             d.relu = c.relu; d.planes = e->planes; d.geo = g; d.out_scale = d.bias + e->cout_pad[i];
+            d.range = (planes_are_fp16(e->planes) && e->d_range) ? e->d_range + i : nullptr;
             if (c.out_act >= 0) {
                 d.out = e->acts[c.out_act]; d.out_pitch = e->plan.acts[c.out_act].C; d.out_coff = c.out_coff; d.out_plane = e->act_plane[c.out_act];
                 d.planar = nullptr; d.planar_C = 0; d.planar_coff = 0;
@@ -551,6 +635,10 @@ extern "C" int pe_commit_weights(pe_engine* e) {
                         e->committed ? " on this handle (a broadcast replica keeps no fp32 copy: set every layer again)" : "");
     }
     const size_t total = packed_layout(e);
+    e->bias_true.assign(nc, std::vector<float>());
+    e->w11_scale = 1.f; e->calibrated = false;
+    e->wsi.assign(nc, 1.f);
+    e->conv_scale.assign(nc, 1.f);
     std::vector<uint8_t> host(total, 0);
     if (e->w11_off) {   // wT[k][co], k = c*9 + kh*3 + kw: Caffe's im2col row order (im2col.cpp:19-55)
         float* wT = (float*)(host.data() + e->w11_off);
@@ -561,50 +649,9 @@ extern "C" int pe_commit_weights(pe_engine* e) {
         }
     }
     for (size_t i = 0; i < nc; i++) {
-        const ConvSpec& c = e->plan.convs[i];
-        const HostWeights& hw = e->hw[i];
-        const int taps = c.im2col_input ? 1 : c.k * c.k, cp = e->cin_pad[i], cop = e->cout_pad[i];
-        const size_t K = (size_t)taps * cp;
-        float wscale_inv = 1.f;
-        auto src = [&](int co, int kk) -> float {  // engine K index -> Caffe weight (co, ci, r, s)
-            if (c.im2col_input) {
-                if (kk >= 27) return 0.f;
-                const int tap = kk / 3, ci = kk % 3;
-                return hw.w[((size_t)co * 3 + ci) * 9 + tap];
-            }
-            const int tap = kk / cp, ec = kk % cp;
-            const int ci = ec < (int)c.cin_map.size() ? c.cin_map[ec] : -1;
-            if (ci < 0) return 0.f;
-            return hw.w[((size_t)co * c.cin + ci) * c.k * c.k + tap];
-        };
-        if (e->planes == 0) {  // fp32 [K][cout_pad]
-            float* W = (float*)(host.data() + e->w_off[i]);
-            for (size_t kk = 0; kk < K; kk++)
-                for (int co = 0; co < c.cout; co++) W[kk * cop + co] = src(co, (int)kk);
-        } else {               // bf16 planes [P][cout_pad][K]  (K-major rows: the tcgen05 B operand)
-            uint16_t* W = (uint16_t*)(host.data() + e->w_off[i]);
-            const size_t plane = (size_t)cop * K;
-            // fp16 planes: scale the layer by 2^k so that max|w| lands in [2^13, 2^14) - small weights would otherwise
-            // put their lo plane into fp16 subnormals.  Exact (power of two); the epilogue multiplies by 2^-k.
-            float wscale = 1.f;
-            if (planes_are_fp16(e->planes)) {
-                float mx = 0.f;
-                for (float v : hw.w) mx = fmaxf(mx, fabsf(v));
-                int ex = 0;
-                if (mx > 0.f && mx < 3e38f) { frexpf(mx, &ex); wscale = ldexpf(1.f, std::max(-30, std::min(30, 14 - ex))); }
-            }
-            wscale_inv = 1.f / wscale;
-            for (int co = 0; co < c.cout; co++)
-                for (size_t kk = 0; kk < K; kk++) {
-                    uint16_t h[3];
-                    if (planes_are_fp16(e->planes)) split_fp16(src(co, (int)kk) * wscale, e->planes, h);
-                    else split_bf16(src(co, (int)kk), e->planes, h);
-                    for (int p = 0; p < e->planes; p++) W[p * plane + (size_t)co * K + kk] = h[p];
-                }
-        }
-        float* B = (float*)(host.data() + e->b_off[i]);
-        for (int co = 0; co < c.cout; co++) B[co] = hw.b[co];
-        B[cop] = wscale_inv;   // travels with the packed buffer (weight broadcast)
+        pack_conv_weights(e, (int)i, host.data() + e->w_off[i]);
+        e->bias_true[i] = e->hw[i].b;
+        fill_epilogue_fields(e, (int)i, (float*)(host.data() + e->b_off[i]));   // travels with the packed buffer (weight broadcast)
     }
     e->packed_owner.reset();
     e->d_packed = nullptr;
@@ -638,6 +685,7 @@ extern "C" int pe_share_weights(pe_engine* from, pe_engine* to) {
     to->d_packed = from->d_packed;
     to->packed_bytes = from->packed_bytes;
     for (auto& h : to->hw) { std::vector<float>().swap(h.w); std::vector<float>().swap(h.b); h.set = false; }
+    to->conv_scale = from->conv_scale; to->calibrated = from->calibrated; to->bias_true.clear();
     return bind_packed(to);
 }
 
@@ -1001,6 +1049,132 @@ extern "C" int pe_forward_camera_frames(pe_engine* e, const uint8_t* const* fram
     return pe_forward_frames_device(e, e->d_frames, n);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Range calibration of the fp16-plane parity mode.  The planes hold value * s with a per-activation power-of-two s; without
+// calibration s = 1, which suits nets whose activations are O(1e-2 .. 1e3) (the trained pose models).  A net outside that range -
+// the prototxt's own gaussian(0.01) filler shrinks every layer until the maps are ~3e-11 - would flush to zero (or overflow to inf)
+// silently.  pe_calibrate runs ONE forward layer by layer: each conv first runs with s_out = 1 while the epilogue records the
+// largest |output| (fp32, before the fp16 split), s_out is set to bring that maximum into [32, 64) (1000x headroom to 65504), the
+// epilogue fields are rewritten (fill_epilogue_fields) and the layer runs again.  Pools and copies pass stored values through; a layer
+// whose input channels carry different scales (the Concat of conv4_4_CPM with the previous stage's outputs) gets the ratios folded
+// into its re-packed weights (pack_conv_weights).  Afterwards the kernels keep recording the maxima: pe_range_status reports a
+// layer that left the range (PE_ERR_RANGE), and with PE_CHECK_RANGE=1 every pe_fetch does.
+// ---------------------------------------------------------------------------------------------
+static int upload_fields(pe_engine* e, int i) {
+    std::vector<float> B((size_t)e->cout_pad[i] + 1, 0.f);
+    fill_epilogue_fields(e, i, B.data());
+    CK(e, cudaMemcpyAsync((char*)e->d_packed + e->b_off[i], B.data(), B.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    return PE_OK;
+}
+
+static int upload_weights(pe_engine* e, int i) {   // re-pack layer i with the current input scales (host fp32 copy needed)
+    const ConvSpec& c = e->plan.convs[i];
+    const size_t K = (size_t)(c.im2col_input ? 1 : c.k * c.k) * e->cin_pad[i];
+    std::vector<uint8_t> buf(K * e->cout_pad[i] * e->elem * (e->planes ? e->planes : 1));
+    pack_conv_weights(e, i, buf.data());
+    CK(e, cudaMemcpyAsync((char*)e->d_packed + e->w_off[i], buf.data(), buf.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return PE_OK;
+}
+
+extern "C" int pe_calibrate(pe_engine* e, const uint8_t* const* frames, int n) {
+    int rc = check_n(e, n); if (rc) return rc;
+    if (!frames) return fail(e, PE_ERR_INVALID, "null frames");
+    if (!e->committed) return fail(e, PE_ERR_STATE, "pe_commit_weights has not been called");
+    if (!planes_are_fp16(e->planes)) return PE_OK;   // fp32 / bf16 modes have fp32's exponent range
+    const size_t nc = e->plan.convs.size();
+    if (e->bias_true.size() != nc || e->bias_true[0].empty() || e->hw[0].w.empty())
+        return fail(e, PE_ERR_STATE, "this handle received its weights by broadcast / sharing: calibrate the source handle before replicating");
+    CK(e, cudaSetDevice(e->cfg.device));
+    drop_graphs(e);
+    // frames -> device -> net input (the im2col path: conv1_1 is calibrated like every other layer)
+    const size_t fb = (size_t)e->cfg.disp_w * e->cfg.disp_h * 3;
+    CK(e, cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < n; i++) { if (!frames[i]) return fail(e, PE_ERR_INVALID, "null frame %d", i); memcpy(e->h_frames + i * fb, frames[i], fb); }
+    CK(e, cudaMemcpyAsync(e->d_frames, e->h_frames, fb * n, cudaMemcpyHostToDevice, e->stream));
+    PreArgs a = e->pre;
+    a.frames = e->d_frames; a.nframes = n;
+    const bool direct_was = e->conv11_direct;
+    e->conv11_direct = false;
+    e->launches += launch_preprocess(a, e->stream, true);
+    e->input_from_frames = true; e->input_act_stale = false; e->last_frames = e->d_frames;
+    const int nimg = n * e->cfg.num_scales;
+    auto restore = [&](int code) { e->conv11_direct = direct_was; return code; };
+    for (const OpRef& op : e->plan.order) {
+        if (op.type != 0) { if ((rc = run_op(e, op, nimg))) return restore(rc); continue; }
+        const int i = op.idx;
+        const ConvSpec& c = e->plan.convs[i];
+        // the producers of this layer's input are final: fold their scales into the weights if they are not all equal to what is packed
+        bool mixed = false;
+        const float s_ref = input_ref_scale(e, c);
+        for (int pc : c.cin_prod) if (pc >= 0 && e->conv_scale[pc] != s_ref) mixed = true;
+        if (mixed || e->calibrated) { if ((rc = upload_weights(e, i))) return restore(rc); }
+        if (c.out_act >= 0) {
+            e->conv_scale[i] = 1.f;               // measure the true output range: fp32 epilogue values, before the fp16 split
+            if ((rc = upload_fields(e, i))) return restore(rc);
+            CK(e, cudaMemsetAsync(e->d_range + i, 0, sizeof(unsigned), e->stream));
+            if ((rc = run_op(e, op, nimg))) return restore(rc);
+            unsigned bits = 0;
+            CK(e, cudaMemcpyAsync(&bits, e->d_range + i, sizeof bits, cudaMemcpyDeviceToHost, e->stream));
+            CK(e, cudaStreamSynchronize(e->stream));
+            float m; memcpy(&m, &bits, 4);
+            if (m > 0.f && m < 3e38f) { int ex = 0; frexpf(m, &ex); e->conv_scale[i] = ldexpf(1.f, std::max(-100, std::min(100, 6 - ex))); }   // m * s in [32, 64)
+        }
+        if ((rc = upload_fields(e, i))) return restore(rc);
+        if ((rc = run_op(e, op, nimg))) return restore(rc);
+    }
+    e->conv11_direct = direct_was;
+    if (e->w11_off) {   // the direct conv1_1 kernel has its own fp32 copy of the layer: fold the output scale into it
+        const float s_out = e->conv_scale[0];
+        std::vector<float> w(27 * 64 + 64);
+        CK(e, cudaMemcpy(w.data(), (char*)e->d_packed + e->w11_off, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        const float rel = s_out / e->w11_scale;
+        for (float& v : w) v *= rel;
+        CK(e, cudaMemcpy((char*)e->d_packed + e->w11_off, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+        e->w11_scale = s_out;
+    }
+    CK(e, cudaMemsetAsync(e->d_range, 0, nc * sizeof(unsigned), e->stream));
+    e->calibrated = true;
+    return run_post_and_return(e, n);
+}
+
+// Largest |stored value| / 65504 over the conv layers since the last call (PE_ERR_RANGE when a layer reached the fp16 limit, or when
+// a layer's maximum fell below 2^-10 - its lo plane then lives in fp16 subnormals and parity is lost); *layer64 names the worst one.
+extern "C" int pe_range_status(pe_engine* e, float* worst_ratio, char* layer64) {
+    if (!e) return PE_ERR_INVALID;
+    if (worst_ratio) *worst_ratio = 0.f;
+    if (layer64) layer64[0] = 0;
+    if (!e->d_range) return PE_OK;
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    const size_t nc = e->plan.convs.size();
+    std::vector<unsigned> bits(nc);
+    CK(e, cudaMemcpy(bits.data(), e->d_range, nc * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CK(e, cudaMemset(e->d_range, 0, nc * sizeof(unsigned)));
+    float worst = 0.f, smallest = 3e38f;
+    int iw = -1, is = -1;
+    for (size_t i = 0; i < nc; i++) {
+        if (e->plan.convs[i].out_act < 0) continue;   // fp32 maps
+        float m; memcpy(&m, &bits[i], 4);
+        if (bits[i] == 0) continue;                   // layer did not run since the last call
+        if (!(m <= 3e38f) || m / 65504.f > worst) { worst = (m <= 3e38f) ? m / 65504.f : 2.f; iw = (int)i; }
+        if (m < smallest) { smallest = m; is = (int)i; }
+    }
+    if (worst_ratio) *worst_ratio = worst;
+    if (worst >= 1.f) {
+        if (layer64) snprintf(layer64, 64, "%s", e->plan.convs[iw].name.c_str());
+        return fail(e, PE_ERR_RANGE, "layer %s produced values outside the fp16 range of the parity mode (max |v| = %.3g x scale): run pe_calibrate",
+                    e->plan.convs[iw].name.c_str(), worst * 65504.f);
+    }
+    if (is >= 0 && smallest < 9.765625e-4f) {
+        if (layer64) snprintf(layer64, 64, "%s", e->plan.convs[is].name.c_str());
+        return fail(e, PE_ERR_RANGE, "layer %s: largest stored value %.3g is below 2^-10, the fp16 planes lose precision: run pe_calibrate",
+                    e->plan.convs[is].name.c_str(), smallest);
+    }
+    if (layer64 && iw >= 0) snprintf(layer64, 64, "%s", e->plan.convs[iw].name.c_str());
+    return PE_OK;
+}
+
 extern "C" int pe_forward_net_input(pe_engine* e, const float* net_input, int n) {
     int rc = check_n(e, n); if (rc) return rc;
     if (!net_input) return fail(e, PE_ERR_INVALID, "null input");
@@ -1138,6 +1312,7 @@ extern "C" int pe_fetch(pe_engine* e, int idx, float* joints, int* num_people, f
     if (!e) return PE_ERR_INVALID;
     if (idx < 0 || idx >= e->last_n) return fail(e, PE_ERR_INVALID, "frame index %d outside the last forward (n=%d)", idx, e->last_n);
     int rc = pe_sync(e); if (rc) return rc;
+    if (e->check_range && idx == 0) { rc = pe_range_status(e, nullptr, nullptr); if (rc) return rc; }   // PE_CHECK_RANGE=1: range problems are errors
     const int P = e->mt->num_parts, MP = e->mt->max_peaks;
     if (num_people) *num_people = e->h_num_people[idx];
     if (joints) memcpy(joints, e->h_joints + (size_t)idx * PE_MAX_PEOPLE * P * 3, sizeof(float) * PE_MAX_PEOPLE * P * 3);

@@ -210,8 +210,9 @@ int build_plan_from_net(const NetDef& net, int kp_input, int cpad, NetPlan& p, s
         for (int i = 0; i < n; i++) m[i] = i;
         return m;
     };
-    struct Loc { int act = -1, coff = 0, cused = 0; std::vector<int> cmap; };
+    struct Loc { int act = -1, coff = 0, cused = 0; std::vector<int> cmap, prod; };   // prod: producing conv per engine channel
     std::map<std::string, Loc> loc;
+    std::map<std::string, int> conv_index;   // blob -> index in p.convs of its producer
 
     // network input, im2col'ed 3x3x3 patches: engine channel (r*3+s)*3+c  <-  original weight index (c, r, s)
     p.input_act = new_act(0, kp_input, "", 0);
@@ -240,7 +241,7 @@ int build_plan_from_net(const NetDef& net, int kp_input, int cpad, NetPlan& p, s
                 const Loc& in = loc[l.bottoms[0]];
                 if (in.act < 0) return fail("layer " + l.name + ": bottom " + l.bottoms[0] + " is not available as a convolution input");
                 if (in.coff != 0) return fail("layer " + l.name + ": bottom " + l.bottoms[0] + " does not start at channel 0 of its buffer");
-                c.cin = channels[l.bottoms[0]]; c.in_act = in.act; c.in_cused = in.cused; c.cin_map = in.cmap;
+                c.cin = channels[l.bottoms[0]]; c.in_act = in.act; c.in_cused = in.cused; c.cin_map = in.cmap; c.cin_prod = in.prod;
             }
             // output
             if (final_off.count(top)) {
@@ -257,14 +258,19 @@ int build_plan_from_net(const NetDef& net, int kp_input, int cpad, NetPlan& p, s
                 if (sdef.shared || consumers[top].size() > 1) {   // also read directly by convolutions (conv4_4_CPM feeds stage 1)
                     if (sdef.eng_off != 0) return fail("blob " + top + ": a directly consumed Concat bottom must be first in the buffer");
                     Loc o; o.act = c.out_act; o.coff = 0; o.cused = round_up(sdef.c, 64); o.cmap = ident(sdef.c, o.cused);
+                    o.prod.assign(o.cused, -1);
+                    for (int q = 0; q < sdef.c; q++) o.prod[q] = (int)p.convs.size();
                     if (o.cused > cc_c) return fail("blob " + top + ": too narrow concat buffer");
                     loc[top] = o;
                 }
             } else {
                 c.out_act = new_act(c.level, c.cout, top, c.cout);
                 Loc o; o.act = c.out_act; o.coff = 0; o.cused = p.acts[c.out_act].C; o.cmap = ident(c.cout, o.cused);
+                o.prod.assign(o.cused, -1);
+                for (int q = 0; q < c.cout; q++) o.prod[q] = (int)p.convs.size();
                 loc[top] = o;
             }
+            conv_index[top] = (int)p.convs.size();
             p.convs.push_back(c);
             p.order.push_back({0, (int)p.convs.size() - 1});
             if (concat_slot.count(top) && slots[concat_slot[top].first][concat_slot[top].second].shared && nbuf == 2) {
@@ -279,14 +285,19 @@ int build_plan_from_net(const NetDef& net, int kp_input, int cpad, NetPlan& p, s
             p.pools.push_back({l.name, in.act, out, level[l.bottoms[0]]});
             p.order.push_back({1, (int)p.pools.size() - 1});
             Loc o; o.act = out; o.coff = 0; o.cused = p.acts[out].C; o.cmap = ident(channels[top], o.cused);
+            o.prod = in.prod;   // max pooling passes the producer (and its scale) through
             loc[top] = o;
         } else if (l.type == "Concat" && i != final_concat) {
             size_t j = 0;
             while (concats[j] != i) j++;
             Loc o; o.act = cc[j % nbuf]; o.coff = 0; o.cused = cc_c; o.cmap.assign(cc_c, -1);
             if (o.act < 0) return fail("layer " + l.name + ": Concat before any of its producers");
-            for (const Slot& sdef : slots[j])
-                for (int q = 0; q < sdef.c; q++) o.cmap[sdef.eng_off + q] = sdef.caffe_off + q;
+            o.prod.assign(cc_c, -1);
+            for (size_t k = 0; k < slots[j].size(); k++) {
+                const Slot& sdef = slots[j][k];
+                const int pc = conv_index[l.bottoms[k]];
+                for (int q = 0; q < sdef.c; q++) { o.cmap[sdef.eng_off + q] = sdef.caffe_off + q; o.prod[sdef.eng_off + q] = pc; }
+            }
             loc[top] = o;
         }
     }

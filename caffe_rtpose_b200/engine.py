@@ -39,7 +39,7 @@ _lib = None
 # every symbol include/poseengine.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "pe_create", "pe_destroy", "pe_last_error", "pe_num_conv_layers", "pe_conv_layer_info", "pe_set_conv_weights",
-    "pe_load_weights_file", "pe_commit_weights", "pe_share_weights", "pe_nms_get_max_peaks", "pe_nms_get_num_parts", "pe_nms_get_threshold",
+    "pe_load_weights_file", "pe_commit_weights", "pe_share_weights", "pe_calibrate", "pe_range_status", "pe_nms_get_max_peaks", "pe_nms_get_num_parts", "pe_nms_get_threshold",
     "pe_nms_set_threshold", "pe_resize_set_start_scale", "pe_resize_set_scale_gap", "pe_resize_get_start_scale",
     "pe_resize_get_scale_gap", "pe_set_connect_params", "pe_forward_frames", "pe_forward_frames_device",
     "pe_forward_net_input", "pe_forward_maps", "pe_fetch", "pe_fetch_maps", "pe_fetch_blob", "pe_sync", "pe_write_json",
@@ -72,6 +72,8 @@ def lib():
     L.pe_load_weights_file.argtypes = [C.c_void_p, C.c_char_p]
     L.pe_commit_weights.argtypes = [C.c_void_p]
     L.pe_share_weights.argtypes = [C.c_void_p, C.c_void_p]
+    L.pe_calibrate.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
+    L.pe_range_status.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_char_p]
     L.pe_load_caffemodel.argtypes = [C.c_void_p, C.c_char_p]
     L.pe_caffemodel_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.pe_caffemodel_close.argtypes = [C.c_void_p]
@@ -351,6 +353,19 @@ class PoseEngine:
         n = maps8.shape[0] // self.cfg.num_scales
         assert maps8.shape == (n * self.cfg.num_scales, self.num_maps, self.cfg.net_h // 8, self.cfg.net_w // 8), maps8.shape
         self._ck(lib().pe_forward_maps(self._h, maps8, n))
+
+    def calibrate(self, frames):
+        """pe_calibrate: per-layer power-of-two activation scales of the parity mode from one forward on `frames`."""
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        arr = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+        self._ck(lib().pe_calibrate(self._h, arr, len(frames)))
+
+    def range_status(self):
+        """(rc, worst |stored value| / 65504, layer name); rc != 0 (PE_ERR_RANGE = 5) when a layer left the fp16 range."""
+        worst = C.c_float()
+        name = C.create_string_buffer(64)
+        rc = lib().pe_range_status(self._h, C.byref(worst), name)
+        return rc, worst.value, name.value.decode()
 
     def sync(self):
         self._ck(lib().pe_sync(self._h))

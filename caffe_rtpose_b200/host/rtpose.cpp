@@ -80,6 +80,8 @@ static void define_flags() {
            "fill two waves of 128-row tiles on the GPU, e.g. 9 frames at 656x368; results do not depend on it)");
     define("engines_per_gpu", "0", "[extension] worker handles per GPU: 1 = the reference's topology (one Net per GPU), 0 = automatic (2 when "
            "--batch is automatic: the copies and the kernel tails of one batch overlap the other; weights are shared, not duplicated)");
+    define("calibrate_range", "true", "[extension] parity mode: derive per-layer power-of-two activation scales from one synthetic frame at start-up "
+           "(pe_calibrate), so that a model of any magnitude keeps fp32-level results", true);
     define("keys_from_stdin", "false", "[extension] read the reference's runtime keys (- = _ + [ ] { } ; ' , . 0-9 q-p a s, ESC or Q to quit) from stdin", true);
 }
 
@@ -473,6 +475,12 @@ static bool create_engines(int num_gpu, int per_gpu, std::vector<pe_engine*>& en
         engines.push_back(e);
     }
     if (load_weights(engines[0], Fi("start_device"))) return false;
+    if (Fb("calibrate_range") && Fi("precision") == 2) {   // before the weights are replicated: the scales travel inside the packed buffer
+        std::vector<uint8_t> probe;
+        synthetic_frame(0, global.disp_w, global.disp_h, probe);
+        const uint8_t* ptr = probe.data();
+        if (pe_calibrate(engines[0], &ptr, 1)) { LOG_ERROR("GPU %d: range calibration failed: %s", Fi("start_device"), pe_last_error(engines[0])); return false; }
+    }
     if (num_gpu > 1) {
         std::vector<pe_engine*> firsts;
         for (int g = 0; g < num_gpu; g++) firsts.push_back(engines[g * per_gpu]);

@@ -22,6 +22,7 @@ extern "C" {
 #define PE_ERR_CUDA 2      /* CUDA runtime / driver failure (message in pe_last_error) */
 #define PE_ERR_STATE 3     /* call out of order (e.g. forward before weights) */
 #define PE_ERR_IO 4        /* file could not be read / parsed */
+#define PE_ERR_RANGE 5     /* parity mode: a layer's values left the range of the fp16 planes (see pe_calibrate) */
 
 #define PE_MODEL_MPI_15 0  /* ModelDescriptorFactory::Type::MPI_15  (modelDescriptorFactory.h:16-19) */
 #define PE_MODEL_COCO_18 1 /* ModelDescriptorFactory::Type::COCO_18 */
@@ -90,6 +91,17 @@ int pe_caffemodel_blob(const pe_caffemodel* m, int layer, int blob, const float*
 const char* pe_caffemodel_last_error(void);
 /* pack + upload; must be called once after the weights are set and before any forward */
 int pe_commit_weights(pe_engine* e);
+/* Range management of the parity mode (PE_PREC_F16X2).  Its activation planes are fp16 x power-of-two scale per layer; the default
+ * scale 1 suits the trained pose models.  pe_calibrate runs one forward on the given HOST frames layer by layer, measures every
+ * layer's largest |output| in fp32 and sets the scales so that the stored maxima sit in [32, 64) - after that a net of any
+ * magnitude (e.g. the prototxt's gaussian(0.01) filler, whose maps are ~3e-11) keeps fp32-level parity.  Exact: scales are powers
+ * of two folded into the epilogue's bias / factor.  Call it on the handle that owns the weights, before pe_broadcast_weights /
+ * pe_share_weights (the scales travel inside the packed buffer).  Results of the calibration forward are fetchable as usual.
+ * pe_range_status: since the previous call, largest |stored value| / 65504 over all layers; PE_ERR_RANGE (and pe_last_error names
+ * the layer) if a layer reached the fp16 limit or shrank below 2^-10.  With the environment variable PE_CHECK_RANGE=1 every
+ * pe_fetch(idx 0) performs this check, so range problems are errors instead of silent inf / zeros. */
+int pe_calibrate(pe_engine* e, const uint8_t* const* frames, int n);
+int pe_range_status(pe_engine* e, float* worst_ratio, char* layer64);
 /* Net::ShareTrainedLayersWith (net.cpp:682-706): `to` - another handle on the SAME GPU running the same net - uses `from`'s
  * committed weights (the packed device buffer is shared, not copied, and lives until its last user is destroyed). */
 int pe_share_weights(pe_engine* from, pe_engine* to);

@@ -98,6 +98,25 @@ def test_caffemodel_wire_reader(tmp_path, v1, legacy_dims):
         engine.read_caffemodel(str(bad))
 
 
+@pytest.mark.parametrize("fname,v1", [("caffemodel_v2.caffemodel", False), ("caffemodel_v1.caffemodel", True)])
+def test_caffemodel_written_by_google_protobuf(fname, v1):
+    """Files NOT produced by this repo's writer: tools/gen_caffemodel_fixture.py serialised them with Google's protobuf runtime from
+    descriptors restating caffe.proto - `layer` + BlobShape + packed data + skipped fields (bottom/top/param/phase/convolution_param,
+    diff arrays, blob-less layers), and legacy `layers` + num/channels/height/width + UNPACKED floats + blobs_lr/weight_decay."""
+    gold = os.path.join(ROOT, "tests", "golden")
+    want = np.load(os.path.join(gold, "caffemodel_fixture.npz"))
+    layers = engine.read_caffemodel(os.path.join(gold, fname))
+    conv = [l for l in layers if l[2]]
+    assert [l[0] for l in conv] == ["conv1_1", "conv5_5_CPM_L2", "Mconv7_stage6_L1"]
+    assert len(layers) == (3 if v1 else 6)                       # V2 file also holds three blob-less ReLU layers
+    for name, typ, blobs in conv:
+        assert typ == ("V1:4" if v1 else "Convolution")
+        w, b = want[name + "_w"], want[name + "_b"]
+        assert len(blobs) == 2
+        assert np.array_equal(blobs[0][0], w.ravel()) and blobs[0][1] == w.shape
+        assert np.array_equal(blobs[1][0], b) and blobs[1][1] == ((1, 1, 1, len(b)) if v1 else (len(b),))
+
+
 def test_header_is_plain_c_and_links(tmp_path):
     """include/poseengine.h must be consumable from C (the ABI a cgo/JNI/ctypes/C++ caller binds) and every call
     used by the reference-side stub of INTEGRATION.md must link against libposeengine.so."""

@@ -134,7 +134,7 @@ def test_cli_json_equals_python_path(tmp_path):
         (write_bmp if i % 2 == 0 else write_ppm)(str(img_dir / ("img%03d.%s" % (i, "bmp" if i % 2 == 0 else "ppm"))), f)
     out = tmp_path / "json"
     r = run(["--image_dir", str(img_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "%dx%d" % (disp_w, disp_h),
-             "--net_resolution", "%dx%d" % (net_w, net_h), "--write_json", str(out), "--no_display", "--no_frame_drops", "--num_gpu", "1",
+             "--net_resolution", "%dx%d" % (net_w, net_h), "--write_json", str(out), "--no_display", "--no_frame_drops", "--nocalibrate_range", "--num_gpu", "1",
              "--write_frames", str(tmp_path / "rendered"), "--part_to_show", "2"], timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
@@ -154,7 +154,7 @@ def test_cli_json_equals_python_path(tmp_path):
     write_bmp(str(big_dir / "big.bmp"), big)
     out2 = tmp_path / "json2"
     r = run(["--image_dir", str(big_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
-             "--net_resolution", "160x96", "--write_json", str(out2), "--no_display", "--no_frame_drops"], timeout=300)
+             "--net_resolution", "160x96", "--write_json", str(out2), "--no_display", "--no_frame_drops", "--nocalibrate_range"], timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
     eng.set_weights(W)
@@ -165,7 +165,7 @@ def test_cli_json_equals_python_path(tmp_path):
     eng.close()
     # lossless frames on request
     r = run(["--image_dir", str(big_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
-             "--net_resolution", "160x96", "--no_display", "--no_frame_drops", "--write_frames", str(tmp_path / "bmp"), "--frame_format", "bmp"], timeout=300)
+             "--net_resolution", "160x96", "--no_display", "--no_frame_drops", "--nocalibrate_range", "--write_frames", str(tmp_path / "bmp"), "--frame_format", "bmp"], timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
     eng.set_weights(W)

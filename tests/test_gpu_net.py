@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 # bf16x2: operands carry 16 significand bits and the tensor core accumulates in truncated fp32: ~2e-4.
 # bf16x1 is the non-parity "fast" mode and only sanity-checked.
 # measured on B200 (tools/gpu_diag.py): SIMT 5e-6, parity mode 8e-6 (160x96) / 1.1e-5 (656x368), bf16x3 4e-4, bf16x1 2e-2
-TOL = {engine.PREC_FP32_SIMT: 5e-5, engine.PREC_BF16X2: 1e-4, engine.PREC_BF16X3: 1e-3, engine.PREC_BF16X1: 6e-2}
+# (the parity-mode bound is 3x the measured value, so that a regression to the un-chunked accumulation, 7e-5, fails)
+TOL = {engine.PREC_FP32_SIMT: 5e-5, engine.PREC_BF16X2: 3e-5, engine.PREC_BF16X3: 1e-3, engine.PREC_BF16X1: 6e-2}
 
 
 def rel(a, b):
@@ -213,4 +214,42 @@ def test_camera_frames_warp_affine_bit_exact(sh, sw):
         disp, os_ = orc.display_image(f, disp_w, disp_h)
         assert s == os_
         assert np.array_equal(img[i:i + 1], orc.preprocess(disp, net_h, net_w, 1, 1.0, 0.3))
+    eng.close()
+
+
+def test_load_caffemodel_serialised_by_google_protobuf(small, tmp_path):
+    """Net::CopyTrainedLayersFrom on a complete .caffemodel that this repo's writer never touched: Google's protobuf runtime
+    serialises all 92 layers (descriptors of tools/gen_caffemodel_fixture.py, V2 `layer` blocks with the fields a Caffe snapshot
+    carries); the loaded net must equal the one fed through pe_set_conv_weights bit for bit."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("gen_cm", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                         "tools", "gen_caffemodel_fixture.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    s = small
+    Net = gen.build("caffe_full", True)
+    net = Net()
+    net.name = "COCO_pose_deploy"
+    for name, co, ci, k in synth.conv_table(s["model"]):
+        l = net.layer.add()
+        l.name, l.type, l.phase = name, "Convolution", 1
+        l.bottom.append("b"); l.top.append(name)
+        l.convolution_param.num_output = co
+        w, b = s["W"][name]
+        for arr in (w, b):
+            blob = l.blobs.add()
+            blob.shape.dim.extend(arr.shape)
+            blob.data.extend(arr.ravel().tolist())
+        r = net.layer.add()
+        r.name, r.type = "relu_" + name, "ReLU"
+    p = str(tmp_path / "pb.caffemodel")
+    open(p, "wb").write(net.SerializeToString())
+    eng = engine.PoseEngine(s["model"], s["net_w"], s["net_h"], 320, 192, precision=engine.PREC_BF16X2)
+    eng.load_caffemodel(p)
+    eng.forward_frames(s["frames"][:1])
+    maps = eng.fetch_maps(1)
+    eng.set_weights(s["W"])
+    eng.forward_frames(s["frames"][:1])
+    assert np.array_equal(maps, eng.fetch_maps(1))
     eng.close()

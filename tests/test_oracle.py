@@ -8,7 +8,7 @@
   * convolution            vs a naive direct loop at 1e-4 (the bar of test_convolution_layer.cpp:231-265)
   * INTER_AREA             == committed cv2 fixtures (tests/golden/area_cv2.npz)               bit-exact
   * stage-level goldens    == tests/golden/parse_*.npz (peaks, joints, subset, JSON)          bit-exact
-ImResize/NMS are pinned against the reference's own CUDA kernels in tests/test_gpu_reference.py.
+ImResize/NMS are pinned against the reference's own CUDA kernels in tests/test_gpu_post.py (test_reference_cuda_kernels_equal_oracle).
 """
 import json
 import os
