@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 # one the driver runs); the others are extra lines for BASELINE.md section 5 (`--workload C3` ...).
 #            model   net_w net_h disp_w disp_h S  start gap  frames/step  distinct frames   description
 WORKLOADS = {
-    "C1": ("MPI_15", 496, 368, 640, 480, 1, 1.0, 0.3, 12, 96, "C1: MPI 496x368, 1 scale, synthetic 640x480 stream, W-he random-init weights"),
+    "C1": ("MPI_15", 496, 368, 640, 480, 1, 1.0, 0.3, 11, 99, "C1: MPI 496x368, 1 scale, synthetic 640x480 stream, W-he random-init weights"),
     "C2": ("COCO_18", 656, 368, 1280, 720, 1, 1.0, 0.3, 9, 72, "C2: COCO 656x368, 1 scale, synthetic 720p stream, W-he random-init weights"),
     "C3": ("COCO_18", 656, 368, 1280, 720, 3, 1.0, 0.15, 3, 72, "C3: COCO 656x368, 3 scales (1.0/0.85/0.70), synthetic 720p stream, W-he random-init weights"),
     "C5": ("COCO_18", 992, 736, 1920, 1080, 4, 1.0, 0.15, 1, 24, "C5 per GPU: COCO 992x736, 4 scales (gap 0.15), synthetic 1080p stream, W-he random-init weights"),

@@ -1232,7 +1232,7 @@ void tc_layer_destroy(TcLayer& l) {
     l.maps = nullptr;
 }
 
-int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
+int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st, int share) {
     const TcLayerDesc& d = l.d;
     TcArgs a;
     a.bias = d.bias;
@@ -1258,11 +1258,12 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st) {
         if (pair && d.planes == 2 && planes_are_fp16(2) && nsm >= 2) {
             const long long mt = (a.M + TCP_BM - 1) / TCP_BM;
             const int npairs = nsm / 2;
+            const int npairs_eff = std::max(1, npairs / (share < 1 ? 1 : share));   // pairs this layer can count on next to its sibling branch
             int bn = l.bn, bmap = 6;
             if (l.bn == 128) {   // same trade-off as below, in units of CTA pairs
-                const double s128 = (double)std::min<long long>(mt * (d.cout_pad / 128), npairs) * 1.00;
-                const double s64 = (double)std::min<long long>(mt * (d.cout_pad / 64), npairs) * 0.80;
-                const double s32 = (double)std::min<long long>(mt * (d.cout_pad / 32), npairs) * 0.55;
+                const double s128 = (double)std::min<long long>(mt * (d.cout_pad / 128), npairs_eff) * 1.00;
+                const double s64 = (double)std::min<long long>(mt * (d.cout_pad / 64), npairs_eff) * 0.80;
+                const double s32 = (double)std::min<long long>(mt * (d.cout_pad / 32), npairs_eff) * 0.55;
                 if (s64 > s128 && s64 >= s32) { bn = 64; bmap = 7; }
                 else if (s32 > s128 && s32 > s64) { bn = 32; bmap = 8; }
             }

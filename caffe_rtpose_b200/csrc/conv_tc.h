@@ -26,6 +26,8 @@ struct TcLayer {
 int tc_cout_pad(int cout);   // N-tile granularity used for a layer with `cout` outputs
 int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err);
 void tc_layer_destroy(TcLayer& l);
-int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st);   // returns kernels launched
+// share: number of independent layers expected to run concurrently (2 when the L1 / L2 branches run on two streams): the tile
+// width is then chosen for 1/share of the GPU.  Returns kernels launched.
+int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st, int share = 1);
 
 }  // namespace pe

@@ -18,6 +18,11 @@
 #include "conv_tc.h"
 #include "prototxt.h"
 
+// NVTX ranges (header-only nvtx3: resolved at run time, no-ops without a profiler attached) around the phases of a forward, so that
+// nsys / ncu timelines read like the reference's stage names
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } };
+
 using namespace pe;
 
 static thread_local std::string g_create_error;
@@ -56,6 +61,14 @@ struct pe_engine {
     std::vector<TcLayer> tc;        // tcgen05 per-conv launch state
     // io
     cudaStream_t stream = nullptr;
+    // Second lane: the L2 branch of every stage runs on its own stream next to the L1 branch (they only meet at the stage
+    // boundaries), so the tail of one layer overlaps the head of an independent one and a single frame fills more SMs.
+    cudaStream_t stream2 = nullptr;
+    bool two_lanes = false;
+    std::vector<int> op_lane;                    // per plan.order entry
+    std::vector<std::vector<int>> op_waits;      // convs on the OTHER lane whose completion this op needs
+    std::vector<cudaEvent_t> conv_done;          // per conv: recorded after its launch when another lane waits for it
+    int last_lane1_conv = -1;
     cudaEvent_t ev[16] = {};
     uint8_t* d_frames = nullptr; uint8_t* d_resized = nullptr;
     uint8_t* h_frames = nullptr;    // pinned staging
@@ -88,6 +101,7 @@ struct pe_engine {
 };
 
 static void drop_graphs(pe_engine* e);
+static int setup_lanes(pe_engine* e);
 
 static int fail(pe_engine* e, int code, const char* fmt, ...) {
     char buf[1024];
@@ -314,6 +328,7 @@ static int create_impl(const pe_config* cfg_in, const char* prototxt_path, pe_en
     if (e->geo[3].W * 8 != cfg->net_w || e->geo[3].H * 8 != cfg->net_h) { fail(e, PE_ERR_INVALID, "net size not divisible by 8 after pooling"); return bail(PE_ERR_INVALID); }
     e->plan = prototxt_path ? proto_plan : build_plan(cfg->model, e->planes ? 64 : 32, e->planes ? 64 : 16);
     e->hw.resize(e->plan.convs.size());
+    if (e->planes && setup_lanes(e)) return bail(PE_ERR_CUDA);
     // FLOPs: 2*Cout*Cin*k^2*Hout*Wout per conv and image
     e->flops_per_scale = 0;
     for (auto& c : e->plan.convs) {
@@ -408,6 +423,8 @@ extern "C" void pe_destroy(pe_engine* e) {
     cudaFree(pd.flags); cudaFree(pd.peaks); cudaFree(pd.cands); cudaFree(pd.cand_count); cudaFree(pd.conns);
     cudaFree(pd.conn_count); cudaFree(pd.subset); cudaFree(pd.subset_rows); cudaFree(pd.joints); cudaFree(pd.num_people);
     cudaFreeHost(e->h_joints); cudaFreeHost(e->h_num_people); cudaFreeHost(e->h_peaks);
+    for (cudaEvent_t ev : e->conv_done) if (ev) cudaEventDestroy(ev);
+    if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
     for (int i = 0; i < 16; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -796,7 +813,8 @@ extern "C" int pe_set_connect_params(pe_engine* e, int min_cnt, float min_score,
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-static int run_op(pe_engine* e, const OpRef& op, int nimg) {
+static int run_op(pe_engine* e, const OpRef& op, int nimg, cudaStream_t st = nullptr, int share = 1) {
+    if (!st) st = e->stream;
     if (op.type == 0) {
         const ConvSpec& c = e->plan.convs[op.idx];
         const Geo& g = e->geo[c.level];
@@ -806,11 +824,11 @@ static int run_op(pe_engine* e, const OpRef& op, int nimg) {
             a.nframes = nimg / e->cfg.num_scales;
             const float* wT = (const float*)((const char*)e->d_packed + e->w11_off);
             e->launches += launch_conv1_1_direct(a, wT, wT + 27 * 64, e->acts[c.out_act], e->plan.acts[c.out_act].C, e->act_plane[c.out_act],
-                                                 c.relu, nimg, e->stream);
+                                                 c.relu, nimg, st);
             return PE_OK;
         }
         if (e->planes) {
-            e->launches += tc_layer_launch(e->tc[op.idx], nimg, e->stream);
+            e->launches += tc_layer_launch(e->tc[op.idx], nimg, st, share);
             return PE_OK;
         }
         ConvArgs a;
@@ -822,7 +840,7 @@ static int run_op(pe_engine* e, const OpRef& op, int nimg) {
         a.cin_pad = e->cin_pad[op.idx]; a.cout = c.cout; a.cout_pad = e->cout_pad[op.idx];
         a.ksize = c.im2col_input ? 1 : c.k; a.pad = c.im2col_input ? 0 : c.pad; a.relu = c.relu;
         a.W = g.W; a.H = g.H; a.Wp = g.Wp; a.Hs = g.Hs; a.N = nimg; a.M = M;
-        e->launches += launch_conv_simt(a, e->stream);
+        e->launches += launch_conv_simt(a, st);
     } else if (op.type == 1) {
         const PoolSpec& p = e->plan.pools[op.idx];
         const Geo& gi = e->geo[p.level_in]; const Geo& go = e->geo[p.level_in + 1];
@@ -830,14 +848,14 @@ static int run_op(pe_engine* e, const OpRef& op, int nimg) {
         a.in = e->acts[p.in_act]; a.out = e->acts[p.out_act]; a.C = e->plan.acts[p.in_act].C;
         a.in_plane = e->act_plane[p.in_act]; a.out_plane = e->act_plane[p.out_act]; a.planes = e->planes;
         a.Wi = gi.W; a.Hi = gi.H; a.Wpi = gi.Wp; a.Hsi = gi.Hs; a.Wo = go.W; a.Ho = go.H; a.Wpo = go.Wp; a.Hso = go.Hs; a.N = nimg;
-        e->launches += launch_pool(a, e->stream);
+        e->launches += launch_pool(a, st);
     } else {
         const CopySpec& c = e->plan.copies[op.idx];
         const Geo& g = e->geo[3];
         CopyArgs a;
         a.src = e->acts[c.src_act]; a.dst = e->acts[c.dst_act]; a.pitch = e->plan.acts[c.src_act].C; a.channels = c.channels;
         a.elem_bytes = e->elem; a.M = (long long)nimg * g.Hs * g.Wp; a.plane = e->act_plane[c.src_act]; a.planes = e->planes;
-        e->launches += launch_copy_channels(a, e->stream);
+        e->launches += launch_copy_channels(a, st);
     }
     return PE_OK;
 }
@@ -855,9 +873,62 @@ static int run_post_and_return(pe_engine* e, int n) {
 }
 
 static int run_net_eager(pe_engine* e, int n) {
+    NvtxRange r("pe: conv stack + parse");
     const int nimg = n * e->cfg.num_scales;
-    for (const OpRef& op : e->plan.order) { const int rc = run_op(e, op, nimg); if (rc) return rc; }
+    if (!e->two_lanes) {
+        for (const OpRef& op : e->plan.order) { const int rc = run_op(e, op, nimg); if (rc) return rc; }
+        return run_post_and_return(e, n);
+    }
+    // two lanes: an op waits for the convs of the other lane it reads from (events), everything else is stream order
+    for (size_t k = 0; k < e->plan.order.size(); k++) {
+        const OpRef& op = e->plan.order[k];
+        cudaStream_t st = e->op_lane[k] ? e->stream2 : e->stream;
+        for (int pc : e->op_waits[k]) CK(e, cudaStreamWaitEvent(st, e->conv_done[pc], 0));
+        const int rc = run_op(e, op, nimg, st, 2);
+        if (rc) return rc;
+        if (op.type == 0 && e->conv_done[op.idx]) CK(e, cudaEventRecord(e->conv_done[op.idx], st));
+    }
+    if (e->last_lane1_conv >= 0) CK(e, cudaStreamWaitEvent(e->stream, e->conv_done[e->last_lane1_conv], 0));   // join before the parse stage
     return run_post_and_return(e, n);
+}
+
+// Lane assignment and cross-lane dependencies of the plan (branch *_L2 -> lane 1).  Enabled when every lane-1 op is a conv whose
+// inputs come from convs (through pools / copies / concat slices) - true for the pose_deploy_linevec family.
+static int setup_lanes(pe_engine* e) {
+    const NetPlan& p = e->plan;
+    const size_t nc = p.convs.size();
+    e->op_lane.assign(p.order.size(), 0);
+    e->op_waits.assign(p.order.size(), std::vector<int>());
+    e->conv_done.assign(nc, nullptr);
+    e->last_lane1_conv = -1;
+    e->two_lanes = false;
+    if (const char* g = getenv("PE_TWO_LANES")) { if (atoi(g) == 0) return PE_OK; }
+    std::vector<int> conv_lane(nc, 0);
+    int n1 = 0;
+    for (size_t i = 0; i < nc; i++) {
+        const std::string& nm = p.convs[i].name;
+        if (nm.size() > 3 && nm.compare(nm.size() - 3, 3, "_L2") == 0) { conv_lane[i] = 1; n1++; }
+    }
+    if (!n1) return PE_OK;
+    std::vector<char> need_event(nc, 0);
+    for (size_t k = 0; k < p.order.size(); k++) {
+        const OpRef& op = p.order[k];
+        if (op.type != 0) continue;                         // pools and the F copy stay on lane 0 (the trunk)
+        const int lane = conv_lane[op.idx];
+        e->op_lane[k] = lane;
+        if (lane) e->last_lane1_conv = op.idx;
+        std::vector<int>& w = e->op_waits[k];
+        for (int pc : p.convs[op.idx].cin_prod)
+            if (pc >= 0 && conv_lane[pc] != lane && std::find(w.begin(), w.end(), pc) == w.end()) { w.push_back(pc); need_event[pc] = 1; }
+    }
+    // (The copy of the shared blob into the second concat buffer follows its producer on lane 0; the first lane-1 reader of that
+    // buffer also waits for a lane-0 conv of the previous stage, which is behind the copy in stream order.)
+    if (e->last_lane1_conv >= 0) need_event[e->last_lane1_conv] = 1;
+    CK(e, cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    for (size_t i = 0; i < nc; i++)
+        if (need_event[i]) CK(e, cudaEventCreateWithFlags(&e->conv_done[i], cudaEventDisableTiming));
+    e->two_lanes = true;
+    return PE_OK;
 }
 
 static int run_net(pe_engine* e, int n) {
@@ -907,6 +978,7 @@ static int check_n(pe_engine* e, int n) {
 }
 
 extern "C" int pe_forward_frames_device(pe_engine* e, const void* d_frames, int n) {
+    NvtxRange r("pe_forward_frames_device");
     int rc = check_n(e, n); if (rc) return rc;
     CK(e, cudaSetDevice(e->cfg.device));
     PreArgs a = e->pre;
@@ -925,6 +997,7 @@ extern "C" int pe_forward_frames_device(pe_engine* e, const void* d_frames, int 
     return run_net(e, n);
 }
 extern "C" int pe_forward_frames(pe_engine* e, const uint8_t* const* frames, int n) {
+    NvtxRange r("pe_forward_frames (H2D)");
     int rc = check_n(e, n); if (rc) return rc;
     if (!frames) return fail(e, PE_ERR_INVALID, "null frames");
     CK(e, cudaSetDevice(e->cfg.device));
@@ -1309,6 +1382,7 @@ extern "C" int pe_sync(pe_engine* e) {
     return PE_OK;
 }
 extern "C" int pe_fetch(pe_engine* e, int idx, float* joints, int* num_people, float* peaks) {
+    NvtxRange r("pe_fetch (sync + D2H results)");
     if (!e) return PE_ERR_INVALID;
     if (idx < 0 || idx >= e->last_n) return fail(e, PE_ERR_INVALID, "frame index %d outside the last forward (n=%d)", idx, e->last_n);
     int rc = pe_sync(e); if (rc) return rc;

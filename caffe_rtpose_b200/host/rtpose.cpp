@@ -745,9 +745,9 @@ int main(int argc, char** argv) {
     // frames per forward: 1 is the reference's behaviour (lowest latency); file / synthetic sources have no latency to protect, so by
     // default one forward carries as many frames as give two full waves of 128-row tiles on 148 SMs (9 at 656x368); results do not change
     global.batch = Fi("batch");
-    if (global.batch <= 0) {
-        const int per_frame_tiles = ((global.net_h / 8 + 3) * (global.net_w / 8 + 3) * std::max(1, Fi("num_scales")) + 127) / 128;
-        global.batch = std::min(16, std::max(1, (2 * 148 + per_frame_tiles / 2) / per_frame_tiles));
+    if (global.batch <= 0) {   // largest batch whose 256-row pair tiles still fit two waves of the 74 CTA pairs (one tile more costs a third wave)
+        const long long rows = (long long)(global.net_h / 8 + 3) * (global.net_w / 8 + 3) * std::max(1, Fi("num_scales"));
+        global.batch = (int)std::min<long long>(16, std::max<long long>(1, (2LL * 74 * 256) / rows));
     }
     global.engines_per_gpu = Fi("engines_per_gpu") > 0 ? std::min(4, Fi("engines_per_gpu")) : (Fi("batch") <= 0 ? 2 : 1);
     global.queue_limit = std::max(10, 4 * global.batch * std::max(1, Fi("num_gpu")) * global.engines_per_gpu);
