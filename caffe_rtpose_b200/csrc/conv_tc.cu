@@ -650,8 +650,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Arrive on a barrier of the pair's leader.  RELAXED: what the arrival publishes is "my tcgen05.ld of this TMEM buffer has completed"
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order that), no global or shared data.  With .release.cluster the compiler
+// emitted MEMBAR.ALL.GPU + ERRBAR in front of every arrive - 17 % of the epilogue warps' stall samples (ncu r2k) on the path that
+// frees the accumulator for the MMA warp.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
     asm volatile(
@@ -678,6 +682,10 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 16-byte store to a shared-memory address (explicit state space: through a pointer rebuilt from an integer the compiler emits generic ST.E)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int TCP_BM = 256;   // rows per pair tile
@@ -890,6 +898,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 constexpr bool TS_OK = SPLIT && (HALF == 64 || HALF == 32);
                 const bool ts = TS_OK && a.tma_store;
                 uint8_t* stage = smem_o + (warp - 2) * (32 * RB) * (ST2 ? 2 : 1);
+                const uint32_t stage_s = smem_u32(stage);
                 const uint32_t cbuf = ti & 1u;
                 mbar_wait(&c_full[cbuf], (ti >> 1) & 1u);
                 tc_fence_after();
@@ -933,14 +942,14 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                     for (int h2 = 0; h2 < 2; h2++) {
                                         const int chunk = pc * 2 + h2;
                                         const int phys = RB == 128 ? (chunk ^ (lane & 7)) : chunk;
-                                        *(uint4*)(stage + lane * RB + phys * 16) = make_uint4(pk[0][h2 * 4], pk[0][h2 * 4 + 1], pk[0][h2 * 4 + 2], pk[0][h2 * 4 + 3]);
+                                        sts128(stage_s + lane * RB + phys * 16, pk[0][h2 * 4], pk[0][h2 * 4 + 1], pk[0][h2 * 4 + 2], pk[0][h2 * 4 + 3]);
                                     }
                                     if (ST2) {
 #pragma unroll
                                         for (int h2 = 0; h2 < 2; h2++) {
                                             const int chunk = pc * 2 + h2;
                                             const int phys = RB == 128 ? (chunk ^ (lane & 7)) : chunk;
-                                            *(uint4*)(stage + 32 * RB + lane * RB + phys * 16) = make_uint4(pk[1][h2 * 4], pk[1][h2 * 4 + 1], pk[1][h2 * 4 + 2], pk[1][h2 * 4 + 3]);
+                                            sts128(stage_s + 32 * RB + lane * RB + phys * 16, pk[1][h2 * 4], pk[1][h2 * 4 + 1], pk[1][h2 * 4 + 2], pk[1][h2 * 4 + 3]);
                                         }
                                     } else {
 #pragma unroll
@@ -979,8 +988,8 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                     const int chunk = pc * 2 + h2;
                                     const int phys = RB == 128 ? (chunk ^ (lane & 7)) : chunk;
                                     constexpr bool PL = TS_OK && !ST2;
-                                    *(uint4*)(stage + lane * RB + phys * 16) = make_uint4(plo[PL ? pc : 0][h2 * 4], plo[PL ? pc : 0][h2 * 4 + 1],
-                                                                                          plo[PL ? pc : 0][h2 * 4 + 2], plo[PL ? pc : 0][h2 * 4 + 3]);
+                                    sts128(stage_s + lane * RB + phys * 16, plo[PL ? pc : 0][h2 * 4], plo[PL ? pc : 0][h2 * 4 + 1], plo[PL ? pc : 0][h2 * 4 + 2],
+                                           plo[PL ? pc : 0][h2 * 4 + 3]);
                                 }
                             fence_async_smem();
                             __syncwarp();

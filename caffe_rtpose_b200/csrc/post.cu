@@ -47,13 +47,14 @@ __global__ void axis_table_kernel(AxisTap* tab, int t, int ori, int num_scales, 
 
 // ------------------------------------------------------------------------------------------------
 // Kernel 1: resize + nms_register_kernel (nms_layer.cu:14-46) fused.
-// One CTA = one 32x8 full-resolution tile of one (frame, part); values incl. the 1-pixel halo are
+// One CTA pass = one 32 x NMS_TY full-resolution tile of one (frame, part); values incl. the 1-pixel halo are
 // produced in shared memory, the strict 8-neighbour test runs from there, and each warp row becomes
 // one 32-bit word of the peak bitmask (warp ballot) - raster order is preserved by construction.
 // ------------------------------------------------------------------------------------------------
 #define NMS_TX 32
-#define NMS_TY 16
-#define NMS_HROWS 8
+#define NMS_TY 64     // rows per tile: 66 x 34 vertical cubics per CTA pass (9 per thread) between block barriers; at 16 rows the kernel was
+                      // barrier / latency bound (353 us per 9-frame step for ~60 us of arithmetic, ncu r2k)
+#define NMS_HROWS 14  // source rows a 66-row window can touch at stride 8 (66 / 8 + 4 taps, rounded up), else the non-separable path runs
 __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
     __shared__ float tile[NMS_TY + 2][NMS_TX + 2];
     __shared__ float hrow[NMS_HROWS][NMS_TX + 2];
@@ -577,7 +578,7 @@ int launch_post(const PostDev& pd, int nframes, cudaStream_t st) {
     cudaMemsetAsync(pd.peaks, 0, sizeof(float) * (size_t)nframes * p.num_parts * (MP + 1) * 3, st);
     cudaMemsetAsync(pd.cand_count, 0, sizeof(int) * (size_t)nframes * p.num_limbs, st);
     const int tiles_y = (p.net_h + NMS_TY - 1) / NMS_TY;
-    dim3 g1((p.net_w + NMS_TX - 1) / NMS_TX, tiles_y < 4 ? tiles_y : 4, nframes * p.num_parts);
+    dim3 g1((p.net_w + NMS_TX - 1) / NMS_TX, tiles_y < 8 ? tiles_y : 8, nframes * p.num_parts);
     nms_flags_kernel<<<g1, 256, 0, st>>>(pd);
     nms_write_kernel<<<dim3(p.num_parts, nframes), 256, 0, st>>>(pd);
     paf_score_kernel<<<dim3((MP * MP + 127) / 128, p.num_limbs, nframes), 128, 0, st>>>(pd);

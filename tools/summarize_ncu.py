@@ -55,5 +55,27 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst, batch="9", precision="2", workload="C2"):
+    """per-launch dram bytes / duration / tensor-pipe % of the conv launches of ONE step (ncu --metrics ... -k regex:conv_tc) ->
+    profiles/conv_traffic.json, the file bench.py reads `roofline.traffic` from."""
+    import json
+    rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("==")) if len(r) > 14 and r[0].isdigit()]
+    per = collections.OrderedDict()
+    for r in rows:
+        per.setdefault(int(r[0]), {"kernel": re.sub(r"\(.*", "", r[4]).replace("void ", "")})[r[12]] = float(r[14].replace(",", ""))
+    n = len(per)
+    rd = sum(v.get("dram__bytes_read.sum", 0) for v in per.values())
+    wr = sum(v.get("dram__bytes_write.sum", 0) for v in per.values())
+    t = sum(v.get("gpu__time_duration.sum", 0) for v in per.values())
+    tp = sum(v.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0) * v.get("gpu__time_duration.sum", 0) for v in per.values()) / max(t, 1)
+    out = {"source": "%s (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active... "
+                     "-k regex:conv_tc, the %d conv launches of one forward of %s frames, PE_GRAPH=0 PE_TWO_LANES=0)" % (src, n, batch),
+           "batch": int(batch), "precision": int(precision), "workload": workload, "launches": n, "dram_read_bytes_per_step": rd,
+           "dram_write_bytes_per_step": wr, "traffic_bytes_per_launch": (rd + wr) / max(n, 1), "tensor_pipe_pct_time_weighted": round(tp, 1),
+           "gpu_time_us_sum_under_ncu": round(t / 1e3, 2)}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
