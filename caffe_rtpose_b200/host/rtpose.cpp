@@ -247,6 +247,49 @@ static void synthetic_frame(int idx, int w, int h, std::vector<uint8_t>& bgr) {
             }
 }
 
+// ---------------------------------------------------------------------------------------------- text overlays
+// displayFrame's cv::putText lines (rtpose.cpp:1317-1353): "%4.1f fps" (or "%4.2f s/gpu" with --write_frames) at (25, 35), the
+// people count at the top right with a black shadow, the name of the shown part at (W - 175, 55); switched off by --no_text.
+// cv::putText draws OpenCV's Hershey strokes (third-party font data); this is a 5x7 bitmap font of our own, scaled to the same
+// cap height, so the overlays carry the same information at the same places but are not pixel-identical to OpenCV's.
+static const unsigned char kFont5x7[][5] = {   // columns, LSB = top row; ASCII 32..122 subset, missing glyphs are blank
+    {0x00,0x00,0x00,0x00,0x00},{0x00,0x00,0x5F,0x00,0x00},{0x00,0x07,0x00,0x07,0x00},{0x14,0x7F,0x14,0x7F,0x14},{0x24,0x2A,0x7F,0x2A,0x12},
+    {0x23,0x13,0x08,0x64,0x62},{0x36,0x49,0x55,0x22,0x50},{0x00,0x05,0x03,0x00,0x00},{0x00,0x1C,0x22,0x41,0x00},{0x00,0x41,0x22,0x1C,0x00},
+    {0x14,0x08,0x3E,0x08,0x14},{0x08,0x08,0x3E,0x08,0x08},{0x00,0x50,0x30,0x00,0x00},{0x08,0x08,0x08,0x08,0x08},{0x00,0x60,0x60,0x00,0x00},
+    {0x20,0x10,0x08,0x04,0x02},{0x3E,0x51,0x49,0x45,0x3E},{0x00,0x42,0x7F,0x40,0x00},{0x42,0x61,0x51,0x49,0x46},{0x21,0x41,0x45,0x4B,0x31},
+    {0x18,0x14,0x12,0x7F,0x10},{0x27,0x45,0x45,0x45,0x39},{0x3C,0x4A,0x49,0x49,0x30},{0x01,0x71,0x09,0x05,0x03},{0x36,0x49,0x49,0x49,0x36},
+    {0x06,0x49,0x49,0x29,0x1E},{0x00,0x36,0x36,0x00,0x00},{0x00,0x56,0x36,0x00,0x00},{0x08,0x14,0x22,0x41,0x00},{0x14,0x14,0x14,0x14,0x14},
+    {0x00,0x41,0x22,0x14,0x08},{0x02,0x01,0x51,0x09,0x06},{0x32,0x49,0x79,0x41,0x3E},{0x7E,0x11,0x11,0x11,0x7E},{0x7F,0x49,0x49,0x49,0x36},
+    {0x3E,0x41,0x41,0x41,0x22},{0x7F,0x41,0x41,0x22,0x1C},{0x7F,0x49,0x49,0x49,0x41},{0x7F,0x09,0x09,0x09,0x01},{0x3E,0x41,0x49,0x49,0x7A},
+    {0x7F,0x08,0x08,0x08,0x7F},{0x00,0x41,0x7F,0x41,0x00},{0x20,0x40,0x41,0x3F,0x01},{0x7F,0x08,0x14,0x22,0x41},{0x7F,0x40,0x40,0x40,0x40},
+    {0x7F,0x02,0x0C,0x02,0x7F},{0x7F,0x04,0x08,0x10,0x7F},{0x3E,0x41,0x41,0x41,0x3E},{0x7F,0x09,0x09,0x09,0x06},{0x3E,0x41,0x51,0x21,0x5E},
+    {0x7F,0x09,0x19,0x29,0x46},{0x46,0x49,0x49,0x49,0x31},{0x01,0x01,0x7F,0x01,0x01},{0x3F,0x40,0x40,0x40,0x3F},{0x1F,0x20,0x40,0x20,0x1F},
+    {0x3F,0x40,0x38,0x40,0x3F},{0x63,0x14,0x08,0x14,0x63},{0x07,0x08,0x70,0x08,0x07},{0x61,0x51,0x49,0x45,0x43},{0x00,0x7F,0x41,0x41,0x00},
+    {0x02,0x04,0x08,0x10,0x20},{0x00,0x41,0x41,0x7F,0x00},{0x04,0x02,0x01,0x02,0x04},{0x40,0x40,0x40,0x40,0x40},{0x00,0x01,0x02,0x04,0x00},
+    {0x20,0x54,0x54,0x54,0x78},{0x7F,0x48,0x44,0x44,0x38},{0x38,0x44,0x44,0x44,0x20},{0x38,0x44,0x44,0x48,0x7F},{0x38,0x54,0x54,0x54,0x18},
+    {0x08,0x7E,0x09,0x01,0x02},{0x0C,0x52,0x52,0x52,0x3E},{0x7F,0x08,0x04,0x04,0x78},{0x00,0x44,0x7D,0x40,0x00},{0x20,0x40,0x44,0x3D,0x00},
+    {0x7F,0x10,0x28,0x44,0x00},{0x00,0x41,0x7F,0x40,0x00},{0x7C,0x04,0x18,0x04,0x78},{0x7C,0x08,0x04,0x04,0x78},{0x38,0x44,0x44,0x44,0x38},
+    {0x7C,0x14,0x14,0x14,0x08},{0x08,0x14,0x14,0x18,0x7C},{0x7C,0x08,0x04,0x04,0x08},{0x48,0x54,0x54,0x54,0x20},{0x04,0x3F,0x44,0x40,0x20},
+    {0x3C,0x40,0x40,0x20,0x7C},{0x1C,0x20,0x40,0x20,0x1C},{0x3C,0x40,0x30,0x40,0x3C},{0x44,0x28,0x10,0x28,0x44},{0x0C,0x50,0x50,0x50,0x3C},
+    {0x44,0x64,0x54,0x4C,0x44}};
+// (x, y) = left end of the baseline, like cv::putText; font_scale as OpenCV's (0.75 -> 16-pixel caps); colour BGR
+static void put_text(uint8_t* bgr, int W, int H, const char* text, int x, int y, double font_scale, const int color[3], int thickness) {
+    const int cell = std::max(1, (int)lrint(font_scale * 22.0 / 7.0));   // Hershey simplex caps are 22 units high at scale 1
+    for (const char* p = text; *p; p++, x += 6 * cell) {
+        const int ch = (unsigned char)*p;
+        if (ch < 32 || ch > 122) continue;
+        const unsigned char* g = kFont5x7[ch - 32];
+        for (int cx = 0; cx < 5; cx++)
+            for (int cy = 0; cy < 7; cy++) {
+                if (!((g[cx] >> cy) & 1)) continue;
+                const int px0 = x + cx * cell, py0 = y - (7 - cy) * cell, ext = cell + thickness - 1;
+                for (int yy = py0; yy < py0 + ext; yy++)
+                    for (int xx = px0; xx < px0 + ext; xx++)
+                        if (xx >= 0 && xx < W && yy >= 0 && yy < H) { uint8_t* d = bgr + ((size_t)yy * W + xx) * 3; d[0] = (uint8_t)color[0]; d[1] = (uint8_t)color[1]; d[2] = (uint8_t)color[2]; }
+            }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- queue
 template <typename T>
 class BlockingQueue {   // the subset of caffe::BlockingQueue the demo uses (push / try_pop / pop / size), std-only
@@ -609,7 +652,7 @@ static void orderer_and_writer(int num_workers) {
     std::priority_queue<Frame, std::vector<Frame>, decltype(cmp)> heap(cmp);
     int next = 0, written = 0;
     const double t0 = now_s();
-    double last = t0;
+    double last = t0, fps_now = 0;   // FPS of the last 30 frames, as displayFrame keeps it
     const std::string out = F("write_json");
     auto emit = [&](const Frame& fr) {
         if (!out.empty()) {
@@ -621,6 +664,30 @@ static void orderer_and_writer(int num_workers) {
             pe_write_json(fr.joints.data(), fr.num_people, global.num_parts, fr.scale, buf.data(), need + 1);
             FILE* f = fopen(fname, "wb");
             if (f) { fwrite(buf.data(), 1, (size_t)need, f); fclose(f); }
+        }
+        if (!F("write_frames").empty() && !fr.rendered.empty() && !Fb("no_text")) {   // displayFrame :1317-1353
+            Frame& mfr = const_cast<Frame&>(fr);
+            char tmp[256];
+            const int c_fps[3] = {255, 150, 150}, c_black[3] = {0, 0, 0}, c_cnt[3] = {150, 150, 255}, c_white[3] = {255, 255, 255};
+            snprintf(tmp, sizeof tmp, "%4.2f s/gpu", fps_now > 0 ? std::max(1, Fi("num_gpu")) * 1.0 / fps_now : 0.0);
+            put_text(mfr.rendered.data(), global.disp_w, global.disp_h, tmp, 25, 35, 0.75, c_fps, 1);
+            snprintf(tmp, sizeof tmp, "%4d", fr.num_people);
+            put_text(mfr.rendered.data(), global.disp_w, global.disp_h, tmp, global.disp_w - 100 + 2, 35 + 2, 0.75, c_black, 2);
+            put_text(mfr.rendered.data(), global.disp_w, global.disp_h, tmp, global.disp_w - 100, 35, 0.75, c_cnt, 2);
+            const int p2s = global.part_to_show;
+            if (p2s != 0) {
+                if (p2s - 1 <= global.num_parts) snprintf(tmp, sizeof tmp, "%10s", pe_model_part_name(global.model, p2s - 1));
+                else {
+                    int aff = ((p2s - 1) - global.num_parts - 1) * 2;
+                    if (aff == 0) snprintf(tmp, sizeof tmp, "%10s", "PAFs");
+                    else {
+                        aff = aff - 2 + 1 + global.num_parts;
+                        std::string uv = pe_model_part_name(global.model, aff);
+                        snprintf(tmp, sizeof tmp, "%10s", uv.substr(0, uv.find("(")).c_str());
+                    }
+                }
+                put_text(mfr.rendered.data(), global.disp_w, global.disp_h, tmp, global.disp_w - 175 + 1, 55 + 1, 0.5, c_white, 1);
+            }
         }
         if (!F("write_frames").empty() && !fr.rendered.empty()) {   // displayFrame :1363-1380 (cv::imwrite, JPEG quality 98)
             const bool bmp = F("frame_format") == "bmp";
@@ -649,6 +716,7 @@ static void orderer_and_writer(int num_workers) {
                      "QueueD %.3f, FPS = %.1f", fr.index, fr.num_people, t - fr.t_commit, fr.t_preprocessed - fr.t_commit, fr.t_fetched - fr.t_preprocessed,
                      fr.t_done - fr.t_fetched, fr.t_out_popped - fr.t_done, 0.0, 0.0, fr.t_buffered - fr.t_out_popped, t - fr.t_buffered,
                      30.0 / (t - last));
+            fps_now = 30.0 / (t - last);
             last = t;
         }
     };

@@ -135,7 +135,7 @@ def test_cli_json_equals_python_path(tmp_path):
     out = tmp_path / "json"
     r = run(["--image_dir", str(img_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "%dx%d" % (disp_w, disp_h),
              "--net_resolution", "%dx%d" % (net_w, net_h), "--write_json", str(out), "--no_display", "--no_frame_drops", "--nocalibrate_range", "--num_gpu", "1",
-             "--write_frames", str(tmp_path / "rendered"), "--part_to_show", "2"], timeout=300)
+             "--write_frames", str(tmp_path / "rendered"), "--part_to_show", "2", "--no_text"], timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
     eng.set_weights(W)
@@ -165,13 +165,20 @@ def test_cli_json_equals_python_path(tmp_path):
     eng.close()
     # lossless frames on request
     r = run(["--image_dir", str(big_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
-             "--net_resolution", "160x96", "--no_display", "--no_frame_drops", "--nocalibrate_range", "--write_frames", str(tmp_path / "bmp"), "--frame_format", "bmp"], timeout=300)
+             "--net_resolution", "160x96", "--no_display", "--no_frame_drops", "--nocalibrate_range", "--write_frames", str(tmp_path / "bmp"), "--frame_format", "bmp", "--no_text"], timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
     eng.set_weights(W)
     eng.forward_camera_frames([big])
-    assert np.array_equal(read_bmp(str(tmp_path / "bmp" / "big.bmp")), eng.render(0, 0))
+    plain = read_bmp(str(tmp_path / "bmp" / "big.bmp"))
+    assert np.array_equal(plain, eng.render(0, 0))
     eng.close()
+    # without --no_text the fps / people-count overlays of displayFrame (rtpose.cpp:1317-1353) are drawn: only the top band changes
+    r = run(["--image_dir", str(big_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
+             "--net_resolution", "160x96", "--no_display", "--no_frame_drops", "--nocalibrate_range", "--write_frames", str(tmp_path / "txt"), "--frame_format", "bmp"], timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    texted = read_bmp(str(tmp_path / "txt" / "big.bmp"))
+    assert np.array_equal(texted[60:], plain[60:]) and (texted[:60] != plain[:60]).any()
     # --resolution -1x-1 takes the size from the first image (rtpose.cpp:1683-1686); missing model file is an error
     r = run(["--image_dir", str(img_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "-1x-1",
              "--net_resolution", "%dx%d" % (net_w, net_h), "--no_display"], timeout=300)
