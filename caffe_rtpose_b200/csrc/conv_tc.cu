@@ -10,17 +10,18 @@
 //     pixels (common.h), so the A tile of one (tap, 64-channel block) is ONE 2-D TMA box {64 ch x 128 rows}
 //     at a shifted row coordinate; zero padding = TMA out-of-bounds fill + never-written gap rows.
 //   * TMA (cp.async.bulk.tensor.3d, SWIZZLE_128B) stages A and B tiles into shared memory, completion on
-//     mbarriers; a STAGES-deep ring overlaps loads with MMAs.
-//   * One elected thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32), M=128, N=BN,
-//     K=16 per instruction, accumulator in TMEM (BN columns x 128 lanes, fp32).
+//     mbarriers; rings of slots overlap loads with MMAs.  The k taps of one filter row share one 136-row A window.
+//   * One elected lane issues tcgen05.mma.kind::f16 (K=16 per instruction), accumulators in TMEM, fp32.
 //   * Split precision: activations and weights are stored as P 16-bit "planes" whose sum is the fp32 value
 //     (hi / lo); the kernel issues the cross products hi*hi, hi*lo, lo*hi on the tensor core.  P=1 plain bf16,
 //     P=2 = parity mode on fp16 planes (kernels.h), ~1e-5 over the whole net.
-//   * Epilogue warps read TMEM with tcgen05.ld (32 lanes x 16 columns), add bias, ReLU, re-split into
-//     planes and store NHWC bf16 (channel-slice stores implement Concat), or - for the last stage - store
-//     the planar fp32 concat_stage7 blob directly (coalesced along x).
-//   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-//     (each owns the TMEM lane quadrant warp_id % 4).
+//   * Epilogue warps read TMEM with tcgen05.ld, sum the accumulation chunks in registers (round to nearest), add bias,
+//     ReLU, re-split into planes and store NHWC planes (channel-slice stores implement Concat; TMA stores from a
+//     swizzled staging tile in the pair kernel), or - for the last stage - the planar fp32 concat_stage7 blob.
+// Three kernels, newest first:
+//   conv_tcp_kernel  CTA pairs (cta_group::2, M = 256), the product kernel of the parity mode          (round 2)
+//   conv_tcw_kernel  one CTA per 128-row tile, persistent, window trick, N-concatenated split precision  (round 1)
+//   conv_tc_kernel   one TMA tile per tap, non-persistent; baseline kept for A/B and the 3-plane mode
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -690,14 +691,21 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 constexpr int TCP_BM = 256;   // rows per pair tile
 
-template <int BN, int NA, int NB, int ST2>   // ST2: both planes of a tile are staged at once (64 KB at BN = 128, fewer weight slots)
+// ST2: both planes of a tile are staged at once (64 KB at BN = 128, fewer weight slots).
+// ALT (BN = 64, short tiles: conv1_1 / conv1_2): the two epilogue warp groups take alternate tiles, each with its own pair of
+// hi*hi accumulators (4 + 2 accumulators = 384 TMEM columns), instead of half the columns of every tile.
+template <int BN, int NA, int NB, int ST2, int ALT_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCW_THREADS, 1)
 conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                 const TcArgs a) {
     constexpr int A_SLOT = 2 * TCW_A_BYTES;                 // hi + lo window of this CTA's 128 rows
     constexpr int B_HALF = (BN / 2) * 128;                  // this CTA's rows of one plane of one tap
     constexpr int B_TAP = 2 * B_HALF;                       // [B_hi half ; B_lo half]
-    constexpr int TMEM_COLS = 4 * BN <= 32 ? 32 : (4 * BN <= 64 ? 64 : (4 * BN <= 128 ? 128 : (4 * BN <= 256 ? 256 : 512)));
+    constexpr bool ALT = ALT_ != 0;
+    static_assert(!ALT || BN == 64, "alternating epilogue groups: 64-wide tiles only");
+    constexpr int NH = ALT ? 4 : 2;                         // hi*hi accumulators
+    constexpr int TCOLS = (NH + 2) * BN;
+    constexpr int TMEM_COLS = TCOLS <= 32 ? 32 : (TCOLS <= 64 ? 64 : (TCOLS <= 128 ? 128 : (TCOLS <= 256 ? 256 : 512)));
     constexpr uint32_t IDESC = umma_idesc(TCP_BM, BN, true);
 
     extern __shared__ uint8_t smem_raw[];
@@ -706,7 +714,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* smem_b = smem + NA * A_SLOT;
     uint8_t* smem_o = smem_b + NB * B_TAP;                  // epilogue staging: 8 warps x (32 rows x HALF channels x 2 B), see tma_store
     __shared__ __align__(8) uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB];
-    __shared__ __align__(8) uint64_t h_full[2], h_empty[2], c_full[2], c_empty[2];
+    __shared__ __align__(8) uint64_t h_full[NH], h_empty[NH], c_full[2], c_empty[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_bias[512];
 
@@ -721,7 +729,9 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], 16); mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 16); }
+        // h_empty / c_empty collect the epilogue warps of BOTH CTAs that work on a tile: 16, or 8 when the warp groups alternate tiles (ALT)
+        for (int s = 0; s < NH; s++) { mbar_init(&h_full[s], 1); mbar_init(&h_empty[s], ALT ? 8 : 16); }
+        for (int s = 0; s < 2; s++) { mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], ALT ? 8 : 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -740,7 +750,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = tmem_base_smem;
     pdl_launch_dependents();
     pdl_wait();
-    const uint32_t tm_h = tmem_base, tm_c = tmem_base + 2 * BN;
+    const uint32_t tm_h = tmem_base, tm_c = tmem_base + NH * BN;
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer (both CTAs): own A window, own half of every weight tile; bytes land on the leader's barriers =====
@@ -780,6 +790,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int aw = 0, bt = 0;
         uint32_t ci = 0, ti = 0;
         const int nsteps = a.kblocks_per_tap * ks, cs = a.chunk_steps;
+        const uint32_t nchunks = (uint32_t)((nsteps + cs - 1) / cs);
         const uint32_t sa_base = smem_u32(smem_a), sb_base = smem_u32(smem_b);
         for (long long t = tile0; t < total_tiles; t += tile_stride, ti++) {
             const uint32_t cbuf = ti & 1u;
@@ -791,8 +802,11 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int kb = 0; kb < a.kblocks_per_tap; kb++)
                 for (int r = 0; r < ks; r++) {
                     if (step % cs == 0) {
-                        hs = (int)(ci & 1u);
-                        mbar_wait(&h_empty[hs], ((ci >> 1) & 1u) ^ 1u);
+                        // accumulator and its use count: two that all tiles share, or (ALT) two per warp group (= tile parity)
+                        const uint32_t c = (uint32_t)(step / cs);
+                        const uint32_t use = ALT ? (ti >> 1) * ((nchunks + 1u - (c & 1u)) >> 1) + (c >> 1) : (ci >> 1);
+                        hs = ALT ? (int)((ti & 1u) * 2u + (c & 1u)) : (int)(ci & 1u);
+                        mbar_wait(&h_empty[hs], (use & 1u) ^ 1u);
                         accH = tm_h + (uint32_t)(hs * BN);
                         firstH = 0;
                     }
@@ -832,12 +846,16 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else if (warp >= 2) {
         // ===== epilogue (both CTAs): 8 warps; warp w owns TMEM lanes 32*(w%4).. (this CTA's rows) and column half (w-2)/4 =====
-        constexpr bool SPLIT = (BN / 2) % 16 == 0;
+        // ALT (BN = 64: conv1_1 / conv1_2, 8500 short tiles each): the two warp groups take ALTERNATE tiles instead of half the columns
+        // of every tile.  A 64-wide tile's MMAs last 0.2 - 2 us but its epilogue (drain, convert, stage, store) ~3 us of latency, so
+        // with all 8 warps on one tile the kernel ran at the epilogue's latency; two tiles in flight double the rate.
+        constexpr bool SPLIT = !ALT && (BN / 2) % 16 == 0;
         constexpr int HALF = SPLIT ? BN / 2 : BN;
         constexpr int NCHUNK = HALF / 16;
         const int quad = warp & 3;
-        const int half = SPLIT ? (warp - 2) / 4 : 0;
-        const bool active_half = SPLIT || (warp - 2) / 4 == 0;
+        const int group = (warp - 2) / 4;
+        const int half = SPLIT ? group : 0;
+        const bool active_half = SPLIT || ALT || group == 0;
         const int per_img = a.Hs * a.Wp;
         const int cout8 = (a.cout + 7) & ~7;
         const float out_scale = __ldg(a.out_scale);
@@ -847,6 +865,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int nsteps = a.kblocks_per_tap * ks;
         const int nchunks = (nsteps + a.chunk_steps - 1) / a.chunk_steps;
         for (long long t = tile0; t < total_tiles; t += tile_stride, ti++) {
+            if (ALT && (int)(ti & 1u) != group) continue;     // the other group's tile
             const long long m0 = (t / n_tiles_n) * TCP_BM + (long long)rank * TC_BM;
             const int n0 = (int)(t % n_tiles_n) * BN;
             const long long m = m0 + quad * 32 + lane;
@@ -861,8 +880,9 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             float accv[HALF];
             // ---- hi*hi chunks, summed in registers with round-to-nearest ----
             for (int c = 0; c < nchunks; c++, ci++) {
-                const int hs = (int)(ci & 1u);
-                mbar_wait(&h_full[hs], (ci >> 1) & 1u);
+                const uint32_t use = ALT ? (ti >> 1) * (uint32_t)((nchunks + 1 - (c & 1)) >> 1) + (uint32_t)(c >> 1) : (ci >> 1);
+                const int hs = ALT ? group * 2 + (c & 1) : (int)(ci & 1u);
+                mbar_wait(&h_full[hs], use & 1u);
                 tc_fence_after();
                 const uint32_t trow = tm_h + ((uint32_t)(quad * 32) << 16) + (uint32_t)(hs * BN + half * HALF);
                 if (active_half && !((a.dbg & 1) && c > 0)) {
@@ -895,7 +915,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // TMA store engine; the lo plane waits in registers until the engine has read the hi plane.
             {
                 constexpr int RB = HALF * 2;                        // bytes of one staged row
-                constexpr bool TS_OK = SPLIT && (HALF == 64 || HALF == 32);
+                constexpr bool TS_OK = (SPLIT || ALT) && (HALF == 64 || HALF == 32);
                 const bool ts = TS_OK && a.tma_store;
                 uint8_t* stage = smem_o + (warp - 2) * (32 * RB) * (ST2 ? 2 : 1);
                 const uint32_t stage_s = smem_u32(stage);
@@ -1105,14 +1125,15 @@ static int launch_win_inst(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStr
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
     return launch_pdl(kern, grid, smem, st, maps[2], maps[bmap], a);
 }
-template <int BN, int ST2>
+template <int BN, int ST2, int ALT>
 static int launch_pair_st(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
     constexpr int NA = 2;
     constexpr int B_TAP = BN * 128;
-    constexpr int STAGE = (BN / 2) % 16 == 0 ? 8 * 32 * BN * (ST2 ? 2 : 1) : 0;   // epilogue staging for TMA stores: 8 warps x 32 rows x BN/2 channels x 2 B (x 2 planes)
+    // epilogue staging for TMA stores: 8 warps x 32 rows x (BN/2 channels, or all 64 when the warp groups alternate tiles) x 2 B (x 2 planes)
+    constexpr int STAGE = (BN / 2) % 16 == 0 ? 8 * 32 * BN * (ALT ? 2 : 1) * (ST2 ? 2 : 1) : 0;
     constexpr int BUDGET = 227 * 1024 - 1024 - 3072 - NA * 2 * TCW_A_BYTES - STAGE;
     constexpr int NB = BUDGET / B_TAP >= 12 ? 12 : BUDGET / B_TAP;   // BN = 128: 7 slots (5 with both planes staged)
-    auto kern = conv_tcp_kernel<BN, NA, NB, ST2>;
+    auto kern = conv_tcp_kernel<BN, NA, NB, ST2, ALT>;
     const int smem = NA * 2 * TCW_A_BYTES + NB * B_TAP + STAGE + 1024;
     static std::atomic<unsigned long long> attr_done{0};
     int dev = 0;
@@ -1122,13 +1143,19 @@ static int launch_pair_st(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStre
         attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
-    return launch_pdl(kern, grid, smem, st, maps[2], maps[bmap], maps[BN == 128 ? 9 : 10], a);
+    return launch_pdl(kern, grid, smem, st, maps[2], maps[bmap], maps[(BN == 128 || ALT) ? 9 : 10], a);   // 64-channel boxes (ALT: one warp stores all 64 columns of its rows)
 }
 template <int BN>
 static int launch_pair(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
     static const int st2 = env_int("PE_TC_ST2", 1);   // both planes staged at once (r2f: 814 vs 794 frames/s with 7 -> 5 weight slots)
-    if (st2 && (BN == 128 || BN == 64)) return launch_pair_st<BN, (BN == 128 || BN == 64) ? 1 : 0>(l, a, grid, st, bmap);
-    return launch_pair_st<BN, 0>(l, a, grid, st, bmap);
+    // alternating epilogue groups for 64-wide tiles with few accumulation chunks (conv1_1, conv1_2): their epilogue latency, not the MMAs, set the pace
+    static const int alt = env_int("PE_TC_ALT", 1);
+    if (BN == 64 && alt) {
+        const int nsteps = a.kblocks_per_tap * a.ksize;
+        if ((nsteps + a.chunk_steps - 1) / a.chunk_steps <= 4) return launch_pair_st<BN, 1, BN == 64 ? 1 : 0>(l, a, grid, st, bmap);
+    }
+    if (st2 && (BN == 128 || BN == 64)) return launch_pair_st<BN, (BN == 128 || BN == 64) ? 1 : 0, 0>(l, a, grid, st, bmap);
+    return launch_pair_st<BN, 0, 0>(l, a, grid, st, bmap);
 }
 
 template <int BN>
