@@ -262,6 +262,94 @@ def test_jpeg_decoder_equals_cv_imread_bit_for_bit():
         engine.decode_jpeg(enc.tobytes()[:40])
 
 
+def _decode_route(data, fast):
+    """(return code, pixels) of pe_decode_jpeg on one of its two routes (PE_JPEG_FAST is read per call)."""
+    os.environ["PE_JPEG_FAST"] = "1" if fast else "0"
+    try:
+        try:
+            return 0, engine.decode_jpeg(data)
+        except engine.PoseEngineError as ex:
+            return 1, str(ex)
+    finally:
+        del os.environ["PE_JPEG_FAST"]
+
+
+def test_jpeg_fast_route_equals_general_route_also_on_corrupt_streams():
+    """The sequential fast route of jpeg_dec.cpp (8-byte refills, combined code+value lookahead, AVX2 islow IDCT with its range
+    guard, fused row-wise output) is only allowed to be faster: same pixels and same verdict as the general route on valid
+    files of every sampling / restart / Huffman flavour and on byte-mutated and truncated streams (where the 32-bit IDCT guard
+    and the stop rules of the entropy decoder matter)."""
+    import cv2
+    from caffe_rtpose_b200 import synth
+
+    rng = np.random.default_rng(7)
+    streams = []
+    for h, w in [(96, 160), (37, 53), (16, 16), (9, 250)]:
+        img = synth.make_frame(5, h, w)
+        flat = np.full((h, w, 3), 255, np.uint8)
+        flat[::2] = 0                                   # extreme contrast: large coefficients
+        for pic in (img, flat, rng.integers(0, 256, (h, w, 3), dtype=np.uint8)):
+            for q in (100, 90, 30, 3):
+                for name, params in _jpeg_variants(cv2, q):
+                    if "progressive" not in name:
+                        streams.append(cv2.imencode(".jpg", pic, params)[1].tobytes())
+            streams.append(cv2.imencode(".jpg", pic[:, :, 1], [cv2.IMWRITE_JPEG_QUALITY, 85])[1].tobytes())
+            streams.append(bytes(engine.encode_jpeg(pic, 98)))
+    n_ok = n_bad = 0
+    for data in streams:
+        rc_f, px_f = _decode_route(data, True)
+        rc_g, px_g = _decode_route(data, False)
+        assert rc_f == rc_g == 0 and np.array_equal(px_f, px_g)
+    for data in streams[::3]:
+        sos = data.index(b"\xff\xda")
+        for trial in range(12):
+            buf = bytearray(data)
+            kind = trial % 4
+            if kind == 0:      # flip bytes inside the entropy-coded data
+                for _ in range(int(rng.integers(1, 4))):
+                    buf[int(rng.integers(sos + 12, len(buf) - 2))] = int(rng.integers(0, 256))
+            elif kind == 1:    # flip bytes in the tables / headers
+                buf[int(rng.integers(4, sos))] = int(rng.integers(0, 256))
+            elif kind == 2:    # truncate
+                buf = buf[:int(rng.integers(sos, len(buf)))]
+            else:              # inflate a quantiser entry and a few data bytes: drives blocks past the 32-bit IDCT guard
+                dqt = data.index(b"\xff\xdb")
+                buf[dqt + 5 + int(rng.integers(0, 8))] = 255
+                buf[int(rng.integers(sos + 12, len(buf) - 2))] = int(rng.integers(0, 256))
+            rc_f, px_f = _decode_route(bytes(buf), True)
+            rc_g, px_g = _decode_route(bytes(buf), False)
+            assert rc_f == rc_g, (trial, rc_f, rc_g)
+            if rc_f == 0:
+                assert np.array_equal(px_f, px_g), trial
+                n_ok += 1
+            else:
+                n_bad += 1
+    assert n_ok > 100 and n_bad > 5   # the mutations are neither all harmless nor all fatal
+
+
+def test_jpeg_idct_scalar_fallback_equals_avx2_form(tmp_path):
+    """The AVX2 IDCT hands a block to the 64-bit scalar form when a value leaves the 32-bit-safe range.  A build whose bound is
+    64 (almost every block falls back) must produce the library's pixels."""
+    import ctypes as C
+
+    import cv2
+    from caffe_rtpose_b200 import synth
+
+    so = str(tmp_path / "libjpegdec_b64.so")
+    src = os.path.join(ROOT, "caffe_rtpose_b200", "csrc", "jpeg_dec.cpp")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DPE_IDCT32_BOUND=64", "-I", os.path.join(ROOT, "include"), src, "-o", so],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    alt = C.CDLL(so)
+    alt.pe_decode_jpeg.argtypes = [C.c_char_p, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_longlong]
+    for h, w, q in [(120, 200, 95), (64, 64, 40), (33, 70, 100)]:
+        data = cv2.imencode(".jpg", synth.make_frame(2, h, w), [cv2.IMWRITE_JPEG_QUALITY, q])[1].tobytes()
+        ww, hh = C.c_int(), C.c_int()
+        out = np.zeros((h, w, 3), np.uint8)
+        assert alt.pe_decode_jpeg(data, len(data), C.byref(ww), C.byref(hh), out.ctypes.data, out.size) == 0
+        assert np.array_equal(out, engine.decode_jpeg(data))
+
+
 def _png_chunk(tag, body):
     import struct
     import zlib
