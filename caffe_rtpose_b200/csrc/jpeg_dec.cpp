@@ -684,7 +684,10 @@ static int decode_impl(const uint8_t* data, long long size, int* w, int* h, uint
             if (fast_done) return decode_impl(data, size, w, h, bgr, cap, false);   // more scans after a complete one: the general route decides
             // interleaved: MCUs of h x v blocks per component over the padded grid; single component: its real blocks
             const int units_x = ns > 1 ? mcux : sc[0]->nbw, units_y = ns > 1 ? mcuy : sc[0]->nbh;
-            if (allow_fast && !progressive && !any_scan && ns == (int)comps.size()) {
+            bool distinct = true;   // a (corrupt) scan that names a component twice accumulates coefficients: general route only
+            for (int i = 0; i < ns; i++)
+                for (int j = i + 1; j < ns; j++) distinct = distinct && sc[i] != sc[j];
+            if (allow_fast && !progressive && !any_scan && distinct && ns == (int)comps.size()) {
                 // ---- fast route: one interleaved sequential scan, every block transformed as it leaves the entropy decoder
                 for (auto& c : comps) c.plane.resize((size_t)c.pw * c.ph);
                 FastBits fb;

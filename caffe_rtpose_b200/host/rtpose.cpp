@@ -21,6 +21,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <fstream>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -49,7 +50,8 @@ static void define_flags() {
     define("part_to_show", "0", "Part to show from the start.");
     define("write_frames", "", "Write frames with format prefix%06d.jpg");
     define("probe_image", "", "[extension] decode this image file, print WxH and an FNV-1a hash of the BGR pixels, exit (no GPU)");
-    define("num_producers", "1", "[extension] decoder threads for --image_dir / --synthetic (the reference has one)");
+    define("num_producers", "0", "[extension] decoder threads for --image_dir / --synthetic: 1 = the reference's single producer, 0 = automatic "
+           "(with automatic --batch: 10 per GPU, at most 48 and the host's cores minus the worker threads - one B200 consumes ~800 frames/s, a thread decodes ~100)");
     define("decode_bench", "false", "[extension] run only the producer stage (decode + queue), print frames/s, exit (no GPU)", true);
     define("frame_format", "jpg", "[extension] jpg (quality 98, as the reference) or bmp (lossless) for --write_frames");
     define("no_frame_drops", "false", "Dont drop frames.", true);
@@ -191,7 +193,10 @@ static std::string lower_ext(const std::string& p) {
 }
 
 // cv::imread (rtpose.cpp:302-391): the decoder is chosen by the file's signature, not its name
-static bool read_image(const std::string& path, int& w, int& h, std::vector<uint8_t>& bgr) {
+// dst_alloc (optional): where the pixels of a .jpg / .png should go (a page-locked buffer of the given size, or nullptr); when it
+// delivers one, the decoder writes there directly, *dst is set and bgr stays empty - no staging copy of 2.7 MB per 720p frame
+static bool read_image(const std::string& path, int& w, int& h, std::vector<uint8_t>& bgr, const std::function<uint8_t*(size_t)>* dst_alloc = nullptr,
+                       uint8_t** dst = nullptr) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) return false;
     uint8_t magic[8] = {0};
@@ -212,7 +217,13 @@ static bool read_image(const std::string& path, int& w, int& h, std::vector<uint
     auto dec = jpg ? pe_decode_jpeg : pe_decode_png;
     int rc = dec(data.data(), n, &w, &h, nullptr, 0);
     if (rc == 0 && (long long)w * h > (1LL << 28)) { LOG_ERROR("%s: %dx%d is larger than this build accepts", path.c_str(), w, h); return false; }
-    if (rc == 0) { bgr.resize((size_t)w * h * 3); rc = dec(data.data(), n, &w, &h, bgr.data(), (long long)bgr.size()); }
+    if (rc == 0) {
+        const size_t bytes = (size_t)w * h * 3;
+        uint8_t* out = dst_alloc ? (*dst_alloc)(bytes) : nullptr;
+        if (out) *dst = out;
+        else { bgr.resize(bytes); out = bgr.data(); }
+        rc = dec(data.data(), n, &w, &h, out, (long long)bytes);
+    }
     if (rc == -2) LOG_ERROR("%s: JPEG variant not handled (arithmetic-coded / lossless / 12-bit / CMYK / unusual chroma sampling)", path.c_str());
     return rc == 0;
 }
@@ -344,7 +355,22 @@ struct Global {
     int queue_limit = 64, batch = 1, engines_per_gpu = 1;
 } global;
 
+// --image_dir frame: .jpg / .png decode straight into a page-locked buffer of the pool; other formats (and an exhausted pool) go
+// through fr.bgr and pin_frame
+static bool read_frame_image(const std::string& path, int& w, int& h, Frame& fr) {
+    size_t got_bytes = 0;
+    const std::function<uint8_t*(size_t)> alloc = [&](size_t bytes) { got_bytes = bytes; return g_pinned.get(bytes); };
+    uint8_t* ph = nullptr;
+    const bool ok = read_image(path, w, h, fr.bgr, &alloc, &ph);
+    if (ph) {
+        const size_t bytes = got_bytes;
+        fr.pinned = std::shared_ptr<uint8_t>(ph, [bytes](uint8_t* q) { g_pinned.put(q, bytes); });   // returned to the pool also when decoding failed
+    }
+    return ok;
+}
+
 static void pin_frame(Frame& fr) {
+    if (fr.pinned) return;   // decoded in place
     const size_t bytes = fr.bgr.size();
     if (uint8_t* ph = g_pinned.get(bytes)) {   // falls back to the staged copy inside pe_forward_frames if it fails
         memcpy(ph, fr.bgr.data(), bytes);
@@ -400,7 +426,7 @@ static void producer() {
             synthetic_frame(i, w, h, fr.bgr);
         } else {
             const std::string& p = global.image_list[i];
-            const bool ok = read_image(p, w, h, fr.bgr);
+            const bool ok = read_frame_image(p, w, h, fr);
             if (!ok) { LOG_ERROR("cannot decode %s (supported: .jpg, .png, 24-bit .bmp, P6 .ppm)", p.c_str()); continue; }
             const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
             fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
@@ -437,7 +463,7 @@ static void producer_mt(int nthreads) {
                 synthetic_frame(i, w, h, fr.bgr);
             } else {
                 const std::string& p = global.image_list[i];
-                if (!read_image(p, w, h, fr.bgr)) {
+                if (!read_frame_image(p, w, h, fr)) {
                     LOG_ERROR("cannot decode %s (supported: .jpg, .png, 24-bit .bmp, P6 .ppm)", p.c_str());
                     std::lock_guard<std::mutex> l(global.mutex);
                     global.dropped_index.push(fr.index);
@@ -460,8 +486,15 @@ static void producer_mt(int nthreads) {
     global.producer_done = true;
     global.input_queue.wake();
 }
+static int num_producers() {
+    if (Fi("num_producers") > 0) return Fi("num_producers");
+    if (Fi("batch") > 0) return 1;   // an explicit batch (1 = the reference's behaviour) keeps the reference's single producer
+    const int cores = (int)std::thread::hardware_concurrency();
+    const int gpus = std::max(1, Fi("num_gpu"));
+    return std::max(1, std::min(std::min(48, 10 * gpus), cores - 2 * gpus - 2));
+}
 static void run_producers() {
-    const int n = Fi("num_producers");
+    const int n = num_producers();
     if (n > 1) producer_mt(n); else producer();
 }
 
@@ -484,7 +517,7 @@ static int decode_bench() {
     bool contiguous = true;   // every index once, gaps only where a file was dropped
     for (size_t i = 1; i < order.size(); i++) contiguous = contiguous && order[i] != order[i - 1];
     printf("decoded %d frames (%.1f MB) with %d producer(s) in %.3f s: %.1f frames/s, dropped %d, indices_unique %d\n", (int)frames,
-           bytes / 1e6, std::max(1, Fi("num_producers")), dt, frames / std::max(dt, 1e-9), (int)global.dropped_index.size(), contiguous ? 1 : 0);
+           bytes / 1e6, num_producers(), dt, frames / std::max(dt, 1e-9), (int)global.dropped_index.size(), contiguous ? 1 : 0);
     return 0;
 }
 
