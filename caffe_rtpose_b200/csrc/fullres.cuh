@@ -23,6 +23,28 @@ __device__ __forceinline__ float cubic_ref(float v0, float v1, float v2, float v
     return __double2float_rn(acc);
 }
 
+// cubic_ref split into the part that depends only on the four taps and the part that depends on the fraction d: full-resolution
+// neighbours along one axis share their taps (8 outputs per source interval at stride 8), so a thread that walks along the axis
+// evaluates cubic_prep once per interval and cubic_eval per output - the same operations on the same operands in the same order
+// as cubic_ref (bit-identical), with 3 instead of 8 float<->double conversions and ~12 instead of ~30 arithmetic instructions per output.
+struct CubicTaps { float a, c; double b, v1; };
+__device__ __forceinline__ CubicTaps cubic_prep(float v0, float v1, float v2, float v3) {
+    CubicTaps t;
+    const float h = __fmul_rn(0.5f, v0);
+    t.a = __fmaf_rn(v3, 0.5f, __fmaf_rn(v2, -1.5f, __fmaf_rn(v1, 1.5f, -h)));
+    t.b = __fma_rn((double)v3, -0.5, __fma_rn((double)v2, 2.0, (double)__fmaf_rn(v1, -2.5f, v0)));
+    t.c = __fmaf_rn(v2, 0.5f, -h);
+    t.v1 = (double)v1;
+    return t;
+}
+__device__ __forceinline__ float cubic_eval(const CubicTaps& t, float d, double dd) {   // dd == (double)d
+    const float t1 = __fmul_rn(__fmul_rn(__fmul_rn(t.a, d), d), d);
+    double acc = __fma_rn(dd, __dmul_rn(dd, t.b), (double)t1);
+    acc = __dadd_rn(acc, (double)__fmul_rn(d, t.c));
+    acc = __dadd_rn(acc, t.v1);
+    return __double2float_rn(acc);
+}
+
 struct FullRes {
     const float* maps;     // this frame: [S][C][h8][w8]
     const AxisTap* xt;     // [S][net_w]

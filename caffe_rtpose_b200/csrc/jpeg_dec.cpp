@@ -21,6 +21,7 @@
 // unusual (second scan, failure, no AVX2) re-runs the general route, whose result is the definition.  PE_JPEG_FAST=0 disables
 // the fast route (tests compare the two).
 // Host code, no GPU.
+#include "jpeg_tables.h"
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -667,6 +668,21 @@ static int decode_impl(const uint8_t* data, long long size, int* w, int* h, uint
                     c->q_latched = true;
                 }
                 sc.push_back(c);
+            }
+            if (!any_scan) {
+                // Motion-JPEG frames (AVI 'MJPG', cameras) usually leave the DHT segment out when the tables are the Annex K ones:
+                // like libjpeg(-turbo)'s jinit_huff_decoder -> std_huff_tables, slots 0 (luminance) and 1 (chrominance) that are
+                // still undefined when decoding starts get the standard tables; a later DHT replaces them as usual.
+                auto load_std = [](HuffTab& t, const uint8_t* bits, const uint8_t* vals, int nvals) {
+                    if (t.set) return;
+                    for (int l = 1; l <= 16; l++) t.bits[l] = bits[l - 1];
+                    memcpy(t.vals, vals, (size_t)nvals);
+                    t.build();
+                };
+                load_std(dc[0], pe_jpeg::kDcLumBits, pe_jpeg::kDcVal, 12);
+                load_std(dc[1], pe_jpeg::kDcChrBits, pe_jpeg::kDcVal, 12);
+                load_std(ac[0], pe_jpeg::kAcLumBits, pe_jpeg::kAcLumVal, 162);
+                load_std(ac[1], pe_jpeg::kAcChrBits, pe_jpeg::kAcChrVal, 162);
             }
             ScanParams sp;
             sp.Ss = s[1 + 2 * ns]; sp.Se = s[2 + 2 * ns]; sp.Ah = s[3 + 2 * ns] >> 4; sp.Al = s[3 + 2 * ns] & 15;

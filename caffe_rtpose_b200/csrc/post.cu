@@ -52,76 +52,120 @@ __global__ void axis_table_kernel(AxisTap* tab, int t, int ori, int num_scales, 
 // one 32-bit word of the peak bitmask (warp ballot) - raster order is preserved by construction.
 // ------------------------------------------------------------------------------------------------
 #define NMS_TX 32
-#define NMS_TY 64     // rows per tile: 66 x 34 vertical cubics per CTA pass (9 per thread) between block barriers; at 16 rows the kernel was
-                      // barrier / latency bound (353 us per 9-frame step for ~60 us of arithmetic, ncu r2k)
-#define NMS_HROWS 14  // source rows a 66-row window can touch at stride 8 (66 / 8 + 4 taps, rounded up), else the non-separable path runs
-__global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
-    __shared__ float tile[NMS_TY + 2][NMS_TX + 2];
-    __shared__ float hrow[NMS_HROWS][NMS_TX + 2];
+#define NMS_TY 46        // rows per tile pass (368 = 8 x 46, 736 = 16 x 46)
+#define NMS_HROWS 12     // source rows a 48-row window can touch at stride 8 (48 / 8 + 4 taps, rounded up), else the non-separable path runs
+#define NMS_THREADS 128  // 128 threads, <= 88 registers, < 10 KB shared memory: a CTA fits next to a resident conv CTA of another handle
+constexpr int NMS_COLS = NMS_TX + 2;                              // tile columns incl. the halo
+constexpr int NMS_ROWS = NMS_TY + 2;
+constexpr int NMS_NSEG = NMS_THREADS / NMS_COLS;                  // column threads per tile column (3)
+constexpr int NMS_SEG = (NMS_ROWS + NMS_NSEG - 1) / NMS_NSEG;     // consecutive rows one thread walks down (17)
+constexpr int NMS_XCH = 4;                                        // consecutive columns one thread of the horizontal pass produces
+constexpr int NMS_NXCH = (NMS_COLS + NMS_XCH - 1) / NMS_XCH;
+// ncu r2p: the previous version (one vertical cubic_ref per thread and pixel, flat-index divisions, five tap loads) issued 161 warp
+// instructions per cubic at 80 % issue utilisation for ~30 of arithmetic.  Here a thread walks DOWN one tile column: the four taps
+// of a vertical cubic change every 8 rows at stride 8, so cubic_prep runs once per source interval and cubic_eval (3 conversions,
+// 4 fp64 + 4 fp32 operations) per pixel, row fractions come from a per-tile table, sums over the scales stay in registers.
+__global__ void __launch_bounds__(NMS_THREADS) nms_flags_kernel(PostDev pd) {
+    __shared__ float tile[NMS_ROWS][NMS_COLS];
+    __shared__ float hrow[NMS_HROWS][NMS_COLS];
+    __shared__ double s_ydd[NMS_ROWS];
+    __shared__ float s_yd[NMS_ROWS];
+    __shared__ uint32_t s_yi[NMS_ROWS];      // the four source rows of a tile row relative to the window's first, one byte each
     const int part = blockIdx.z % pd.p.num_parts, frame = blockIdx.z / pd.p.num_parts;
     const FullRes fr = make_fullres(pd, frame);
     const int W = pd.p.net_w, H = pd.p.net_h;
     const int x0 = blockIdx.x * NMS_TX - 1;
     const int tiles_y = (H + NMS_TY - 1) / NMS_TY;
-    // A CTA walks several row tiles (blockIdx.y, + gridDim.y, ...): with one 32x16 tile per CTA the kernel was 78 000 CTAs of a
-    // few microseconds each and spent its time in launch / table set-up, not in the cubics (r1n: 383 us per 9-frame step).
+    const int ctx = threadIdx.x % NMS_COLS, cseg = threadIdx.x / NMS_COLS;       // vertical pass: my column and row segment
+    const bool cactive = cseg < NMS_NSEG && x0 + ctx >= 0 && x0 + ctx < W;
+    // A CTA walks several row tiles (blockIdx.y, + gridDim.y, ...)
     for (int tile_y = blockIdx.y; tile_y < tiles_y; tile_y += gridDim.y) {
     const int y0 = tile_y * NMS_TY - 1;
     const int ylo = max(y0, 0), yhi = min(y0 + NMS_TY + 1, H - 1);
     // Separable evaluation: the horizontal cubic of a (source row, x) pair does not depend on the output row,
     // so it is computed once per tile (<= NMS_HROWS source rows) instead of 4x per output pixel.  Same
     // operations on the same operands as fullres_at -> bit-identical values.
-    constexpr int NOUT = (NMS_TY + 2) * (NMS_TX + 2);
-    constexpr int NQ = (NOUT + 255) / 256;
-    float acc[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; q++) acc[q] = 0.f;
     bool separable = true;
     for (int n = 0; n < fr.S; n++) {
         const int rlo = fr.yt[n * H + ylo].i0, rhi = fr.yt[n * H + yhi].i3;
         if (rhi - rlo + 1 > NMS_HROWS) separable = false;
     }
     if (separable) {
+        float acc[NMS_SEG];
+#pragma unroll
+        for (int j = 0; j < NMS_SEG; j++) acc[j] = 0.f;
         const size_t plane = (size_t)fr.h8 * fr.w8;
         for (int n = 0; n < fr.S; n++) {
             const int rlo = fr.yt[n * H + ylo].i0, rhi = fr.yt[n * H + yhi].i3;
             const int nrows = rhi - rlo + 1;
             const float* s = fr.maps + ((size_t)n * fr.C + part) * plane;
-            __syncthreads();
-            for (int it = threadIdx.x; it < nrows * (NMS_TX + 2); it += 256) {
-                const int r = it / (NMS_TX + 2), tx = it % (NMS_TX + 2);
-                const int x = x0 + tx;
-                float v = 0.f;
-                if (x >= 0 && x < W) {
-                    const AxisTap ax = fr.xt[n * W + x];
-                    const float* row = s + (size_t)(rlo + r) * fr.w8;
-                    v = cubic_ref(__ldg(row + ax.i0), __ldg(row + ax.i1), __ldg(row + ax.i2), __ldg(row + ax.i3), ax.d);
+            __syncthreads();                                   // the previous scale's tables and rows have been consumed
+            for (int i = threadIdx.x; i < NMS_ROWS; i += NMS_THREADS) {
+                const int y = y0 + i;
+                uint32_t pk = 0xffffffffu;                     // row outside the image
+                if (y >= 0 && y < H) {
+                    const AxisTap ay = fr.yt[n * H + y];
+                    pk = (uint32_t)(ay.i0 - rlo) | (uint32_t)(ay.i1 - rlo) << 8 | (uint32_t)(ay.i2 - rlo) << 16 | (uint32_t)(ay.i3 - rlo) << 24;
+                    s_yd[i] = ay.d;
+                    s_ydd[i] = (double)ay.d;
                 }
-                hrow[r][tx] = v;
+                s_yi[i] = pk;
+            }
+            // horizontal pass: one thread per (source row, run of NMS_XCH columns); the taps change every 8 columns
+            for (int it = threadIdx.x; it < nrows * NMS_NXCH; it += NMS_THREADS) {
+                const int r = it / NMS_NXCH, c0 = (it % NMS_NXCH) * NMS_XCH;
+                const float* row = s + (size_t)(rlo + r) * fr.w8;
+                int p0 = -1, p1 = -1, p2 = -1, p3 = -1;
+                CubicTaps ct = {0.f, 0.f, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < NMS_XCH; k++) {
+                    const int tx = c0 + k, x = x0 + tx;
+                    if (tx < NMS_COLS) {
+                        float v = 0.f;
+                        if (x >= 0 && x < W) {
+                            const AxisTap ax = fr.xt[n * W + x];
+                            if (ax.i0 != p0 || ax.i1 != p1 || ax.i2 != p2 || ax.i3 != p3) {
+                                p0 = ax.i0; p1 = ax.i1; p2 = ax.i2; p3 = ax.i3;
+                                ct = cubic_prep(__ldg(row + p0), __ldg(row + p1), __ldg(row + p2), __ldg(row + p3));
+                            }
+                            v = cubic_eval(ct, ax.d, (double)ax.d);
+                        }
+                        hrow[r][tx] = v;
+                    }
+                }
             }
             __syncthreads();
+            // vertical pass: down my column, taps re-prepared when the source interval changes
+            if (cactive) {
+                uint32_t cur = 0xfffffffeu;
+                CubicTaps ct = {0.f, 0.f, 0.0, 0.0};
 #pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                const int i = threadIdx.x + q * 256;
-                if (i < NOUT) {
-                    const int ty = i / (NMS_TX + 2), tx = i % (NMS_TX + 2);
-                    const int x = x0 + tx, y = y0 + ty;
-                    if (x >= 0 && x < W && y >= 0 && y < H) {
-                        const AxisTap ay = fr.yt[n * H + y];
-                        acc[q] = __fadd_rn(acc[q], cubic_ref(hrow[ay.i0 - rlo][tx], hrow[ay.i1 - rlo][tx], hrow[ay.i2 - rlo][tx],
-                                                             hrow[ay.i3 - rlo][tx], ay.d));
+                for (int j = 0; j < NMS_SEG; j++) {
+                    const int ty = cseg * NMS_SEG + j;
+                    if (ty < NMS_ROWS) {
+                        const uint32_t pk = s_yi[ty];
+                        if (pk != 0xffffffffu) {
+                            if (pk != cur) {
+                                cur = pk;
+                                ct = cubic_prep(hrow[pk & 255u][ctx], hrow[(pk >> 8) & 255u][ctx], hrow[(pk >> 16) & 255u][ctx], hrow[pk >> 24][ctx]);
+                            }
+                            acc[j] = __fadd_rn(acc[j], cubic_eval(ct, s_yd[ty], s_ydd[ty]));
+                        }
                     }
                 }
             }
         }
+        if (cseg < NMS_NSEG) {
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            const int i = threadIdx.x + q * 256;
-            if (i < NOUT) tile[i / (NMS_TX + 2)][i % (NMS_TX + 2)] = __fdiv_rn(acc[q], fr.inv_div);
+            for (int j = 0; j < NMS_SEG; j++) {
+                const int ty = cseg * NMS_SEG + j;
+                if (ty < NMS_ROWS) tile[ty][ctx] = fr.S == 1 ? acc[j] : __fdiv_rn(acc[j], fr.inv_div);   // x / 1.0f == x; outside the image: 0
+            }
         }
     } else {
-        for (int i = threadIdx.x; i < NOUT; i += 256) {
-            const int ty = i / (NMS_TX + 2), tx = i % (NMS_TX + 2);
+        constexpr int NOUT = NMS_ROWS * NMS_COLS;
+        for (int i = threadIdx.x; i < NOUT; i += NMS_THREADS) {
+            const int ty = i / NMS_COLS, tx = i % NMS_COLS;
             const int x = x0 + tx, y = y0 + ty;
             float v = 0.f;
             if (x >= 0 && x < W && y >= 0 && y < H) v = fullres_at(fr, part, y, x);
@@ -129,23 +173,26 @@ __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
         }
     }
     __syncthreads();
-    const int lx = threadIdx.x & 31;
-#pragma unroll
-    for (int pass = 0; pass < NMS_TY / 8; pass++) {
-        const int ly = (threadIdx.x >> 5) + pass * 8;
-        const int x = blockIdx.x * NMS_TX + lx, y = tile_y * NMS_TY + ly;
-        bool peak = false;
-        if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {
-            const float v = tile[ly + 1][lx + 1];
-            if (v > pd.p.nms_threshold) {
-                peak = v > tile[ly][lx + 1] && v > tile[ly + 2][lx + 1] && v > tile[ly + 1][lx] && v > tile[ly + 1][lx + 2] &&
-                       v > tile[ly][lx] && v > tile[ly + 2][lx] && v > tile[ly + 2][lx + 2] && v > tile[ly][lx + 2];
-            }
-        }
-        const unsigned word = __ballot_sync(0xffffffffu, peak);
-        if (lx == 0 && y < H) {
-            const int words_per_row = (W + 31) / 32;
-            pd.flags[((size_t)(frame * pd.p.num_parts + part) * H + y) * words_per_row + blockIdx.x] = word;
+    // strict 8-neighbour test: a warp walks down its rows with the 3 x 3 window sliding through registers (3 shared-memory loads
+    // per pixel instead of 9), lane = column, one ballot = one 32-bit word of the bitmask
+    {
+        constexpr int NW = NMS_THREADS / 32, RPW = (NMS_TY + NW - 1) / NW;
+        const int lx = threadIdx.x & 31, r0 = (threadIdx.x >> 5) * RPW, r1 = min(r0 + RPW, NMS_TY);
+        const int x = blockIdx.x * NMS_TX + lx;
+        const bool x_in = x > 0 && x < W - 1;
+        const int words_per_row = (W + 31) / 32;
+        unsigned* frow = pd.flags + ((size_t)(frame * pd.p.num_parts + part) * H) * words_per_row + blockIdx.x;
+        const float thr = pd.p.nms_threshold;
+        float a0 = tile[r0][lx], a1 = tile[r0][lx + 1], a2 = tile[r0][lx + 2];
+        float b0 = tile[r0 + 1][lx], b1 = tile[r0 + 1][lx + 1], b2 = tile[r0 + 1][lx + 2];
+        for (int ly = r0; ly < r1; ly++) {
+            const float c0 = tile[ly + 2][lx], c1 = tile[ly + 2][lx + 1], c2 = tile[ly + 2][lx + 2];
+            const int y = tile_y * NMS_TY + ly;
+            const bool peak = x_in && y > 0 && y < H - 1 && b1 > thr && b1 > a1 && b1 > c1 && b1 > b0 && b1 > b2 && b1 > a0 && b1 > c0 &&
+                              b1 > c2 && b1 > a2;
+            const unsigned word = __ballot_sync(0xffffffffu, peak);
+            if (lx == 0 && y < H) frow[(size_t)y * words_per_row] = word;
+            a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
         }
     }
     __syncthreads();   // tile[] is rewritten by the next row tile
@@ -158,7 +205,7 @@ __global__ void __launch_bounds__(256) nms_flags_kernel(PostDev pd) {
 // rank; the first max_peaks get the 7x7 score-weighted centroid (window values re-evaluated on the fly,
 // including the reference's width-for-height bound that aliases into the next channel's first rows).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) nms_write_kernel(PostDev pd) {
+__global__ void __launch_bounds__(256, 6) nms_write_kernel(PostDev pd) {
     __shared__ int s_scan[256];
     __shared__ int s_pos[128];       // flat y*W+x of the first max_peaks peaks
     __shared__ float s_win[4][49];
@@ -393,7 +440,7 @@ __global__ void __launch_bounds__(512) limb_greedy_kernel(PostDev pd) {
 // the reference: num_parts index slots (flat index of the peak's score in the peaks blob, 0 = empty),
 // then [num_parts+1] = score (double), [num_parts+2] = count.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) assemble_kernel(PostDev pd) {
+__global__ void __launch_bounds__(256, 6) assemble_kernel(PostDev pd) {
     __shared__ int s_rows;
     __shared__ int s_conn_of_slot[130];   // peak slot of part A (1..max_peaks) -> connection index of this limb
     __shared__ int s_found[130];
@@ -579,7 +626,7 @@ int launch_post(const PostDev& pd, int nframes, cudaStream_t st) {
     cudaMemsetAsync(pd.cand_count, 0, sizeof(int) * (size_t)nframes * p.num_limbs, st);
     const int tiles_y = (p.net_h + NMS_TY - 1) / NMS_TY;
     dim3 g1((p.net_w + NMS_TX - 1) / NMS_TX, tiles_y < 8 ? tiles_y : 8, nframes * p.num_parts);
-    nms_flags_kernel<<<g1, 256, 0, st>>>(pd);
+    nms_flags_kernel<<<g1, NMS_THREADS, 0, st>>>(pd);
     nms_write_kernel<<<dim3(p.num_parts, nframes), 256, 0, st>>>(pd);
     paf_score_kernel<<<dim3((MP * MP + 127) / 128, p.num_limbs, nframes), 128, 0, st>>>(pd);
     limb_greedy_kernel<<<dim3(p.num_limbs, nframes), 512, sizeof(unsigned long long) * pd.sort_stride, st>>>(pd);

@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libposeengine.so")
+# PE_LIB: another build of the same library (A/B measurements of two builds on one box, tools/ab_lib.sh); never a different implementation
+LIB_PATH = os.environ.get("PE_LIB") or os.path.join(HERE, "libposeengine.so")
 
 MPI_15, COCO_18 = 0, 1
 PREC_FP32_SIMT, PREC_BF16X1, PREC_BF16X2, PREC_BF16X3 = 0, 1, 2, 3
@@ -48,6 +49,7 @@ ABI_SYMBOLS = [
     "pe_packed_weights_bytes", "pe_packed_weights_device_ptr", "pe_load_caffemodel", "pe_caffemodel_open",
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
     "pe_caffemodel_last_error", "pe_create_from_prototxt", "pe_plan_describe", "pe_render_device", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg", "pe_decode_jpeg", "pe_decode_png",
+    "pe_video_open", "pe_video_close", "pe_video_info", "pe_video_read", "pe_video_last_error",
 ]
 
 
@@ -128,6 +130,12 @@ def lib():
     L.pe_encode_jpeg.restype = C.c_longlong
     L.pe_decode_jpeg.argtypes = [C.c_char_p, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_longlong]
     L.pe_decode_png.argtypes = L.pe_decode_jpeg.argtypes
+    L.pe_video_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.pe_video_close.argtypes = [C.c_void_p]
+    L.pe_video_close.restype = None
+    L.pe_video_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p]
+    L.pe_video_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
+    L.pe_video_last_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -567,6 +575,67 @@ def decode_jpeg(data):
     if rc != 0:
         raise PoseEngineError("pe_decode_jpeg failed (%d)" % rc)
     return out
+
+
+class VideoCapture:
+    """cv::VideoCapture as getFrameFromCam uses it for --video (rtpose.cpp:394-411, 433-446, 525-545): open / isOpened / get(FPS,
+    FRAME_COUNT, FRAME_WIDTH, FRAME_HEIGHT, POS_FRAMES) / set(POS_FRAMES) / read, over pe_video_* (Motion-JPEG and uncompressed AVI)."""
+    CAP_PROP_POS_FRAMES, CAP_PROP_FRAME_WIDTH, CAP_PROP_FRAME_HEIGHT, CAP_PROP_FPS, CAP_PROP_FRAME_COUNT = 1, 3, 4, 5, 7
+
+    def __init__(self, path=None):
+        self._h = None
+        self.error = ""
+        if path is not None:
+            self.open(path)
+
+    def open(self, path):
+        self.release()
+        h = C.c_void_p()
+        if lib().pe_video_open(os.fsencode(path), C.byref(h)) != 0:
+            self.error = lib().pe_video_last_error().decode()
+            return False
+        self._h = h
+        w, hh, n, fps, cc = C.c_int(), C.c_int(), C.c_int(), C.c_double(), C.create_string_buffer(5)
+        lib().pe_video_info(h, C.byref(w), C.byref(hh), C.byref(fps), C.byref(n), cc)
+        self.width, self.height, self.frame_count, self.fps, self.fourcc, self.pos = w.value, hh.value, n.value, fps.value, cc.value.decode(), 0
+        return True
+
+    def isOpened(self):
+        return self._h is not None
+
+    def get(self, prop):
+        if self._h is None:
+            return 0.0
+        return float({self.CAP_PROP_POS_FRAMES: self.pos, self.CAP_PROP_FRAME_WIDTH: self.width, self.CAP_PROP_FRAME_HEIGHT: self.height,
+                      self.CAP_PROP_FPS: self.fps, self.CAP_PROP_FRAME_COUNT: self.frame_count}.get(prop, 0))
+
+    def set(self, prop, value):
+        if self._h is None or prop != self.CAP_PROP_POS_FRAMES:
+            return False
+        self.pos = max(0, min(int(value), self.frame_count))
+        return True
+
+    def read(self):
+        """(True, uint8 BGR HWC frame) and the position advances, or (False, None) at the end / on a broken frame."""
+        if self._h is None or self.pos >= self.frame_count:
+            return False, None
+        out = np.empty((self.height, self.width, 3), np.uint8)
+        if lib().pe_video_read(self._h, self.pos, out.ctypes.data, out.size) != 0:
+            self.error = lib().pe_video_last_error().decode()
+            return False, None
+        self.pos += 1
+        return True, out
+
+    def release(self):
+        if self._h is not None:
+            lib().pe_video_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 def decode_png(data):

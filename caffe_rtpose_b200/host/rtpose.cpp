@@ -4,7 +4,8 @@
 // boost / OpenCV are not available here and are not needed for this path); all math is behind the C ABI.
 //
 // Supported sources: --image_dir with .jpg / .png / .bmp / .ppm files (own decoders behind the C ABI, pixels identical to
-// cv::imread), or --synthetic N procedural frames.  --video/--camera need a video codec / capture device and are rejected
+// cv::imread), --video with Motion-JPEG / uncompressed .avi files (csrc/video.cpp), or --synthetic N procedural frames.  Other video
+// codecs and --camera need a codec library / capture device and are rejected
 // with an explicit message; there is no window, so the keyboard UI of handleKey (rtpose.cpp:1551-1671) is served from stdin
 // with --keys_from_stdin (same key characters, same step sizes).  --write_frames renders on the GPU (pe_render) and writes
 // quality-98 .jpg files like the reference (pe_encode_jpeg; --frame_format bmp for lossless), without the putText overlays.
@@ -58,6 +59,9 @@ static void define_flags() {
     define("write_json", "", "Write joint data with json format as prefix%06d.json");
     define("camera", "0", "The camera index for VideoCapture.");
     define("video", "", "Use a video file instead of the camera.");
+    define("video_realtime", "true", "[extension] --video: true = the reference's pacing (frames are committed at the file's frame rate, "
+           "rtpose.cpp:446-462) and its single producer; false = decode as fast as the GPUs consume (offline processing, combine with "
+           "--no_frame_drops)", true);
     define("image_dir", "", "Process a directory of images.");
     define("start_frame", "0", "Skip to frame # of video");
     define("caffemodel", "model/coco/pose_iter_440000.caffemodel", "Caffe model.");
@@ -347,6 +351,9 @@ struct Global {
     std::atomic<int> produced{0}, finished{0};
     int disp_w = 0, disp_h = 0, net_w = 0, net_h = 0, model = PE_MODEL_COCO_18, num_parts = 18;
     std::vector<std::string> image_list;
+    pe_video* video = nullptr;     // --video (cv::VideoCapture of getFrameFromCam)
+    int video_frames = 0, video_w = 0, video_h = 0;
+    double video_fps = 0;
     bool proto_readable = false;   // --caffeproto parsed: engines are created from it
     // global.nms_threshold etc. of the reference (rtpose.cpp:106-111), changed at run time by handle_key
     std::atomic<float> nms_threshold{0.05f}, connect_min_subset_score{0.4f}, connect_inter_threshold{0.05f};
@@ -414,25 +421,63 @@ static void random_weights(pe_engine* e, const std::string& kind) {
 }
 
 // ---------------------------------------------------------------------------------------------- threads
+static int source_frame_count() {
+    if (Fi("synthetic") > 0) return Fi("synthetic");
+    if (global.video) return global.video_frames;
+    return (int)global.image_list.size();
+}
+// frame i of the source (synthetic / --video / --image_dir) into fr; false: could not be decoded (message logged)
+static bool fetch_source_frame(int i, Frame& fr) {
+    int w = global.disp_w, h = global.disp_h;
+    if (Fi("synthetic") > 0) {
+        synthetic_frame(i, w, h, fr.bgr);
+    } else if (global.video) {   // cap >> image_uchar_orig (rtpose.cpp:431): decoded straight into a page-locked buffer
+        w = global.video_w; h = global.video_h;
+        const size_t bytes = (size_t)w * h * 3;
+        uint8_t* ph = g_pinned.get(bytes);
+        uint8_t* dst = ph;
+        if (ph) fr.pinned = std::shared_ptr<uint8_t>(ph, [bytes](uint8_t* q) { g_pinned.put(q, bytes); });
+        else { fr.bgr.resize(bytes); dst = fr.bgr.data(); }
+        if (pe_video_read(global.video, i, dst, (long long)bytes)) { LOG_ERROR("%s", pe_video_last_error()); return false; }
+    } else {
+        const std::string& p = global.image_list[i];
+        if (!read_frame_image(p, w, h, fr)) { LOG_ERROR("cannot decode %s (supported: .jpg, .png, 24-bit .bmp, P6 .ppm)", p.c_str()); return false; }
+        const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
+        fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
+    }
+    pin_frame(fr);
+    fr.w = w; fr.h = h;
+    return true;
+}
+
 static void producer() {
-    const int n_syn = Fi("synthetic");
-    const int total = n_syn > 0 ? n_syn : (int)global.image_list.size();
-    for (int i = Fi("start_frame"); i < total && !global.quit; i++) {
+    const int total = source_frame_count();
+    // --video: frames are committed at the file's frame rate (rtpose.cpp:446-462) and the file loops at its end unless results are
+    // being written (:525-545; the reference exits only with --write_frames, here also with --write_json: a looping writer would
+    // overwrite its own files)
+    const bool paced = global.video && Fb("video_realtime");
+    const bool loop = global.video && F("write_frames").empty() && F("write_json").empty() && !Fb("decode_bench");
+    const double frame_time = global.video_fps > 0 ? 1.0 / global.video_fps : 0;
+    double last_frame_time = -1;
+    for (int i = Fi("start_frame"); !global.quit; i++) {
+        if (i >= total) {
+            if (!loop || total <= 0) break;
+            LOG_INFO("Looping video after %d frames", total);
+            i = 0;
+        }
         Frame fr;
         fr.t_commit = now_s();    // frame.commit_time: taken when the frame is grabbed (rtpose.cpp:449)
         fr.index = global.produced; fr.video_frame_number = i;
-        int w = global.disp_w, h = global.disp_h;
-        if (n_syn > 0) {
-            synthetic_frame(i, w, h, fr.bgr);
-        } else {
-            const std::string& p = global.image_list[i];
-            const bool ok = read_frame_image(p, w, h, fr);
-            if (!ok) { LOG_ERROR("cannot decode %s (supported: .jpg, .png, 24-bit .bmp, P6 .ppm)", p.c_str()); continue; }
-            const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
-            fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
+        if (!fetch_source_frame(i, fr)) {
+            if (global.video) break;   // a broken frame ends a video (cap >> returns an empty Mat)
+            continue;
         }
-        pin_frame(fr);
-        fr.w = w; fr.h = h;
+        if (paced) {
+            const double interval = now_s() - last_frame_time;
+            if (last_frame_time >= 0 && interval < frame_time) std::this_thread::sleep_for(std::chrono::duration<double>(frame_time - interval));
+            last_frame_time = now_s();
+            fr.t_commit = last_frame_time;
+        }
         fr.t_preprocessed = now_s();
         // the reference's producers wait while more than 10 frames are queued (rtpose.cpp:310-313, 424-429); the bound scales with the batch
         while ((int)global.input_queue.size() > global.queue_limit && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
@@ -445,11 +490,10 @@ static void producer() {
 
 // [extension] --num_producers N > 1.  The reference decodes on ONE thread (getFrameFromDir, rtpose.cpp:302-391); a 720p JPEG
 // takes ~12 ms here, i.e. ~80 frames/s per thread against ~740 frames/s that one GPU consumes, so the producer stage is
-// what scales with threads.  N threads take file indices from a shared counter; order is restored downstream by the
-// re-orderer through Frame::index, and a file that fails to decode becomes a dropped index (as dropped frames do).
+// what scales with threads.  N threads take frame indices from a shared counter; order is restored downstream by the
+// re-orderer through Frame::index, and a frame that fails to decode becomes a dropped index (as dropped frames do).
 static void producer_mt(int nthreads) {
-    const int n_syn = Fi("synthetic");
-    const int total = n_syn > 0 ? n_syn : (int)global.image_list.size(), start = Fi("start_frame");
+    const int total = source_frame_count(), start = Fi("start_frame");
     std::atomic<int> next{start};
     auto body = [&]() {
         while (!global.quit) {
@@ -458,22 +502,11 @@ static void producer_mt(int nthreads) {
             Frame fr;
             fr.t_commit = now_s();
             fr.index = i - start; fr.video_frame_number = i;
-            int w = global.disp_w, h = global.disp_h;
-            if (n_syn > 0) {
-                synthetic_frame(i, w, h, fr.bgr);
-            } else {
-                const std::string& p = global.image_list[i];
-                if (!read_frame_image(p, w, h, fr)) {
-                    LOG_ERROR("cannot decode %s (supported: .jpg, .png, 24-bit .bmp, P6 .ppm)", p.c_str());
-                    std::lock_guard<std::mutex> l(global.mutex);
-                    global.dropped_index.push(fr.index);
-                    continue;
-                }
-                const size_t slash = p.find_last_of('/'), dot = p.find_last_of('.');
-                fr.stem = p.substr(slash == std::string::npos ? 0 : slash + 1, dot - (slash == std::string::npos ? 0 : slash + 1));
+            if (!fetch_source_frame(i, fr)) {
+                std::lock_guard<std::mutex> l(global.mutex);
+                global.dropped_index.push(fr.index);
+                continue;
             }
-            pin_frame(fr);
-            fr.w = w; fr.h = h;
             fr.t_preprocessed = now_s();
             while ((int)global.input_queue.size() > global.queue_limit && !global.quit) std::this_thread::sleep_for(std::chrono::milliseconds(1));
             global.input_queue.push(std::move(fr));
@@ -489,6 +522,7 @@ static void producer_mt(int nthreads) {
 static int num_producers() {
     if (Fi("num_producers") > 0) return Fi("num_producers");
     if (Fi("batch") > 0) return 1;   // an explicit batch (1 = the reference's behaviour) keeps the reference's single producer
+    if (global.video && (Fb("video_realtime") || (F("write_frames").empty() && F("write_json").empty()))) return 1;   // pacing / looping: one reader, like cap >>
     const int cores = (int)std::thread::hardware_concurrency();
     const int gpus = std::max(1, Fi("num_gpu"));
     return std::max(1, std::min(std::min(48, 10 * gpus), cores - 2 * gpus - 2));
@@ -795,8 +829,9 @@ int main(int argc, char** argv) {
         printf("%dx%d %016llx\n", w, h, (unsigned long long)hash);
         return 0;
     }
-    if (!F("video").empty() || (F("image_dir").empty() && Fi("synthetic") <= 0)) {
-        LOG_ERROR("camera/video capture needs a video codec that this build does not have; use --image_dir (.bmp/.ppm) or --synthetic N");
+    if (F("video").empty() && F("image_dir").empty() && Fi("synthetic") <= 0) {
+        LOG_ERROR("Couldn't open camera %d: camera capture needs a capture device and driver interface this build does not have; use --video "
+                  "(Motion-JPEG / uncompressed .avi), --image_dir or --synthetic N", Fi("camera"));
         return 1;
     }
     if (F("frame_format") != "jpg" && F("frame_format") != "bmp") { LOG_ERROR("--frame_format must be jpg or bmp"); return 1; }
@@ -821,6 +856,13 @@ int main(int argc, char** argv) {
             if (!read_image(p, global.disp_w, global.disp_h, tmp)) return 1;
             LOG_INFO("Setting display resolution from first image: %dx%d", global.disp_w, global.disp_h);
         }
+    }
+    if (!F("video").empty() && F("image_dir").empty() && Fi("synthetic") <= 0) {   // cap.open(FLAGS_video) (rtpose.cpp:406, 1677-1682)
+        if (pe_video_open(F("video").c_str(), &global.video)) { LOG_ERROR("Couldn't open video file %s: %s", F("video").c_str(), pe_video_last_error()); return 1; }
+        char cc[5];
+        pe_video_info(global.video, &global.video_w, &global.video_h, &global.video_fps, &global.video_frames, cc);
+        LOG_INFO("Video %s: %dx%d, %d frames, %.3f fps, %s", F("video").c_str(), global.video_w, global.video_h, global.video_frames, global.video_fps, cc);
+        if (global.disp_w == -1) { global.disp_w = global.video_w; global.disp_h = global.video_h; }
     }
     if (global.disp_w <= 0 || global.disp_h <= 0) { LOG_ERROR("Invalid resolution without video/images: %dx%d", global.disp_w, global.disp_h); return 1; }
     LOG_INFO("Display resolution: %dx%d", global.disp_w, global.disp_h);
@@ -870,5 +912,6 @@ int main(int argc, char** argv) {
     ord.join();
     for (pe_engine* e : engines) pe_destroy(e);
     g_pinned.clear();
+    pe_video_close(global.video);
     return global.quit ? 1 : 0;
 }

@@ -196,6 +196,18 @@ int pe_decode_jpeg(const uint8_t* data, long long size, int* w, int* h, uint8_t*
  * bit depths, converted as cv::imread(IMREAD_COLOR) does (8-bit BGR, alpha dropped, 16-bit -> high byte). */
 int pe_decode_png(const uint8_t* data, long long size, int* w, int* h, uint8_t* bgr, long long cap);
 
+/* cv::VideoCapture of getFrameFromCam for --video (rtpose.cpp:394-411 open / CV_CAP_PROP_FPS / CV_CAP_PROP_POS_FRAMES, :433-446,
+ * :525-545 CV_CAP_PROP_FRAME_COUNT, :1677-1682 frame size): RIFF AVI / OpenDML files whose video stream is Motion-JPEG (frames go
+ * through pe_decode_jpeg) or uncompressed 24/32-bit DIB.  Other containers / inter-frame codecs: PE_ERR_INVALID, the FourCC in
+ * pe_video_last_error() (thread-local).  Frames are addressed by index, pe_video_read is thread-safe on one handle; pixels are
+ * uint8 BGR HWC of the video's own size (pe_forward_camera_frames scales them to the display size like the reference's warpAffine). */
+typedef struct pe_video pe_video;
+int pe_video_open(const char* path, pe_video** out);
+void pe_video_close(pe_video* v);
+int pe_video_info(const pe_video* v, int* w, int* h, double* fps, int* frame_count, char fourcc[5]);
+int pe_video_read(const pe_video* v, int index, uint8_t* bgr, long long cap);
+const char* pe_video_last_error(void);
+
 /* ---- model descriptor tables (modelDescriptorFactory.cpp:6-28,30-55) */
 int pe_model_num_parts(int model);
 int pe_model_num_limbs(int model);

@@ -3,6 +3,7 @@ declares, fails loudly without a GPU (no CPU fallback), and its host-only entry 
 descriptor tables) match the oracle and the reference's own modelDescriptorFactory.cpp."""
 import ctypes as C
 import os
+import struct
 import re
 import subprocess
 
@@ -500,3 +501,136 @@ def test_parsers_survive_corrupt_files(tmp_path):
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
     acc, rej = [int(v) for v in r.stdout.split()[1::2]]
     assert acc > 500 and rej > 500   # the mutations are neither all harmless nor all fatal
+
+
+def _riff_chunk(tag, body):
+    return tag + struct.pack("<I", len(body)) + body + (b"\0" if len(body) & 1 else b"")
+
+
+def _write_avi(path, frames, fourcc, fps=(25, 1), bits=24, height_sign=1, chunk_tag=b"00dc", extra_movi=b"", in_rec=False):
+    """Minimal AVI 1.0 writer for the tests (the RIFF structure AVI files share): hdrl(avih, strl(strh, strf)) + movi."""
+    import struct as st
+    w, h = frames and frames[0][1] or (16, 16)
+    payloads = [f[0] for f in frames]
+    avih = st.pack("<IIIIIIIIIIIIII", 1000000 * fps[1] // fps[0], 0, 0, 0x10, len(payloads), 0, 1, 0, w, h, 0, 0, 0, 0)
+    strh = b"vids" + fourcc + st.pack("<IHHIIIIIIIIHHHH", 0, 0, 0, 0, fps[1], fps[0], 0, len(payloads), 0, 0xFFFFFFFF, 0, 0, 0, w, h)
+    strf = st.pack("<IiiHH4sIiiII", 40, w, h * height_sign, 1, bits, fourcc if fourcc not in (b"DIB ", b"\0\0\0\0") else b"\0\0\0\0", 0, 0, 0, 0, 0)
+    aud_strh = b"auds" + b"\0" * 44          # a second (audio) stream must not disturb the frame index
+    hdrl = b"hdrl" + _riff_chunk(b"avih", avih) + _riff_chunk(b"LIST", b"strl" + _riff_chunk(b"strh", strh) + _riff_chunk(b"strf", strf)) + \
+        _riff_chunk(b"LIST", b"strl" + _riff_chunk(b"strh", aud_strh) + _riff_chunk(b"strf", b"\0" * 16))
+    chunks = b"".join(_riff_chunk(chunk_tag, p) + _riff_chunk(b"01wb", b"\1\2\3") for p in payloads)
+    if in_rec:
+        chunks = _riff_chunk(b"LIST", b"rec " + chunks)
+    movi = b"movi" + chunks + extra_movi
+    body = b"AVI " + _riff_chunk(b"LIST", hdrl) + _riff_chunk(b"JUNK", b"\0" * 13) + _riff_chunk(b"LIST", movi) + _riff_chunk(b"idx1", b"\0" * 16)
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + st.pack("<I", len(body)) + body)
+
+
+def test_video_reader_equals_opencv(tmp_path):
+    """--video (cv::VideoCapture, rtpose.cpp:394-411): AVI files written by OpenCV itself (its FFmpeg and its built-in MJPEG writer)
+    read back frame for frame - count, size, fps as cv2.VideoCapture reports them, pixels bit-identical to OpenCV's own MJPEG reader
+    (imdecode = libjpeg arithmetic) - plus seeking, the end of the file and the error paths."""
+    import cv2
+    frames = [synth.make_frame(i, 120, 176) for i in range(6)]
+    for api in (cv2.CAP_OPENCV_MJPEG, cv2.CAP_FFMPEG):
+        path = str(tmp_path / ("v%d.avi" % api))
+        wr = cv2.VideoWriter(path, api, cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (176, 120))
+        if not wr.isOpened():
+            continue
+        for f in frames:
+            wr.write(f)
+        wr.release()
+        ref = cv2.VideoCapture(path, cv2.CAP_OPENCV_MJPEG)
+        cap = engine.VideoCapture(path)
+        assert cap.isOpened(), cap.error
+        assert cap.fourcc == "MJPG" and (cap.width, cap.height) == (176, 120)
+        assert cap.get(cap.CAP_PROP_FRAME_COUNT) == ref.get(cv2.CAP_PROP_FRAME_COUNT) == len(frames)
+        assert abs(cap.get(cap.CAP_PROP_FPS) - ref.get(cv2.CAP_PROP_FPS)) < 1e-9
+        for i in range(len(frames)):
+            ok, got = cap.read()
+            rok, want = ref.read()
+            assert ok and rok and np.array_equal(got, want), (api, i)
+            assert int(np.argmin([np.abs(got.astype(int) - f.astype(int)).mean() for f in frames])) == i   # and it is the frame that was written
+        assert cap.read() == (False, None) and cap.get(cap.CAP_PROP_POS_FRAMES) == len(frames)
+        cap.set(cap.CAP_PROP_POS_FRAMES, 3)                                       # FLAGS_start_frame / looping (rtpose.cpp:409-411, 541-543)
+        ref.set(cv2.CAP_PROP_POS_FRAMES, 3)
+        assert np.array_equal(cap.read()[1], ref.read()[1])
+        cap.release()
+    # error paths: missing file, not an AVI, an inter-frame codec
+    cap = engine.VideoCapture(str(tmp_path / "missing.avi"))
+    assert not cap.isOpened() and "Couldn't open video file" in cap.error
+    (tmp_path / "x.mp4").write_bytes(b"\0\0\0\x18ftypmp42" + b"\0" * 64)
+    cap = engine.VideoCapture(str(tmp_path / "x.mp4"))
+    assert not cap.isOpened() and "not a RIFF AVI" in cap.error
+    _write_avi(str(tmp_path / "h264.avi"), [(b"\0\0\0\1abc", (176, 120))], b"H264")
+    cap = engine.VideoCapture(str(tmp_path / "h264.avi"))
+    assert not cap.isOpened() and "H264" in cap.error
+
+
+def test_video_reader_avi_structure_variants(tmp_path):
+    """Hand-built AVI files: uncompressed DIB frames (bottom-up and top-down, 24 and 32 bit, rows padded to 4 bytes), 'rec ' lists,
+    a second stream, JUNK chunks, odd-sized chunks, dropped (empty) frames, Motion-JPEG frames without DHT, a truncated file."""
+    import cv2
+    rng = np.random.default_rng(5)
+    w, h = 13, 7                                   # 39 bytes per row -> padded to 40
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(4)]
+
+    def dib(img, bits, top_down):
+        px = img if bits == 24 else np.concatenate([img, np.full((h, w, 1), 255, np.uint8)], axis=2)
+        stride = (w * bits // 8 + 3) & ~3
+        rows = [px[y].tobytes().ljust(stride, b"\0") for y in (range(h) if top_down else range(h - 1, -1, -1))]
+        return b"".join(rows)
+
+    for bits in (24, 32):
+        for top_down in (False, True):
+            for in_rec in (False, True):
+                path = str(tmp_path / ("dib%d_%d_%d.avi" % (bits, top_down, in_rec)))
+                payloads = [(dib(im, bits, top_down), (w, h)) for im in imgs]
+                payloads.insert(2, (b"", (w, h)))   # dropped frame: repeats frame 1
+                _write_avi(path, payloads, b"DIB ", fps=(30000, 1001), bits=bits, height_sign=-1 if top_down else 1, chunk_tag=b"00db", in_rec=in_rec)
+                cap = engine.VideoCapture(path)
+                assert cap.isOpened(), cap.error
+                assert (cap.width, cap.height, cap.frame_count, cap.fourcc) == (w, h, 5, "DIB ") and abs(cap.fps - 30000 / 1001) < 1e-9
+                want = [imgs[0], imgs[1], imgs[1], imgs[2], imgs[3]]
+                for i in range(5):
+                    ok, got = cap.read()
+                    assert ok and np.array_equal(got, want[i]), (bits, top_down, in_rec, i)
+    # the uncompressed file OpenCV's FFmpeg writer produces (fourcc 0) reads back identically
+    path = str(tmp_path / "raw.avi")
+    wr = cv2.VideoWriter(path, cv2.CAP_FFMPEG, 0, 10.0, (w + 3, h + 1))
+    if wr.isOpened():
+        big = [rng.integers(0, 256, (h + 1, w + 3, 3), dtype=np.uint8) for _ in range(3)]
+        for f in big:
+            wr.write(f)
+        wr.release()
+        cap = engine.VideoCapture(path)
+        if cap.isOpened():                           # FFmpeg may pick a pixel format other than bgr24; then the reader must refuse
+            for f in big:
+                assert np.array_equal(cap.read()[1], f)
+    # Motion-JPEG frames without Huffman tables (what cameras and many capture tools write): the Annex K tables apply
+    img = synth.make_frame(3, 64, 96)
+    ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
+    data = enc.tobytes()
+    out, i = bytearray(data[:2]), 2
+    while i < len(data):                             # drop the DHT segments; quality-90 baseline files use the standard tables
+        assert data[i] == 0xFF
+        m, ln = data[i + 1], struct.unpack(">H", data[i + 2:i + 4])[0]
+        if m == 0xDA:
+            out += data[i:]
+            break
+        if m != 0xC4:
+            out += data[i:i + 2 + ln]
+        i += 2 + ln
+    assert len(out) < len(data) - 400
+    assert np.array_equal(engine.decode_jpeg(bytes(out)), cv2.imdecode(enc, cv2.IMREAD_COLOR))
+    path = str(tmp_path / "nodht.avi")
+    _write_avi(path, [(bytes(out), (96, 64))] * 3, b"MJPG")
+    cap = engine.VideoCapture(path)
+    assert cap.isOpened() and np.array_equal(cap.read()[1], cv2.imdecode(enc, cv2.IMREAD_COLOR))
+    # a recording that was cut off: the complete frames stay readable
+    whole = open(path, "rb").read()
+    cut = str(tmp_path / "cut.avi")
+    open(cut, "wb").write(whole[:len(whole) - len(out) - 40])
+    cap = engine.VideoCapture(cut)
+    assert cap.isOpened() and cap.frame_count == 2 and cap.read()[0] and cap.read()[0] and not cap.read()[0]

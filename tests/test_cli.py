@@ -33,8 +33,10 @@ def test_flag_surface_matches_reference():
 
 def test_flag_errors():
     assert run(["--bogus", "1"]).returncode == 1
-    r = run([])  # no camera/video support without a codec: explicit message, not a hang
-    assert r.returncode == 1 and "codec" in r.stderr
+    r = run([])  # no camera capture in this build: explicit message, not a hang
+    assert r.returncode == 1 and "Couldn't open camera 0" in r.stderr
+    r = run(["--video", "/nonexistent/clip.avi", "--model", "COCO"])   # CHECK(cap.open(FLAGS_video)) (rtpose.cpp:406)
+    assert r.returncode == 1 and "Couldn't open video file /nonexistent/clip.avi" in r.stderr
     r = run(["--synthetic", "2", "--resolution", "abc", "--model", "COCO"])
     assert r.returncode == 1 and "resolution format" in r.stderr
     r = run(["--synthetic", "2", "--model", "COCO", "--frame_format", "png"])
@@ -109,6 +111,37 @@ def test_multi_producer_decode_stage_without_gpu(tmp_path):
         assert ("dropped 1" in out) == (n > 1)   # the single-thread path skips the file without consuming an index
 
 
+def write_mjpeg_avi(path, frames, fps=25.0):
+    import cv2
+    h, w, _ = frames[0].shape
+    wr = cv2.VideoWriter(path, cv2.CAP_OPENCV_MJPEG, cv2.VideoWriter_fourcc(*"MJPG"), fps, (w, h))
+    assert wr.isOpened()
+    for f in frames:
+        wr.write(f)
+    wr.release()
+
+
+def test_video_source_decode_stage_without_gpu(tmp_path):
+    """--video (rtpose.cpp:394-411): a Motion-JPEG .avi goes through the producer stage; --resolution -1x-1 takes the video's size
+    (:1677-1682); --video_realtime false lets several decoder threads read one file; the reference's pacing holds the file's frame
+    rate; --start_frame skips."""
+    path = str(tmp_path / "clip.avi")
+    write_mjpeg_avi(path, [synth.make_frame(i, 90, 160) for i in range(10)], fps=50.0)
+    for n in (1, 3):
+        r = run(["--video", path, "--decode_bench", "--novideo_realtime", "--num_producers", str(n), "--model", "COCO", "--resolution", "-1x-1",
+                 "--write_json", str(tmp_path / "j")])
+        assert r.returncode == 0, r.stderr
+        assert "Video %s: 160x90, 10 frames, 50.000 fps, MJPG" % path in r.stderr and "Display resolution: 160x90" in r.stderr
+        out = r.stdout.strip().splitlines()[-1]
+        assert out.startswith("decoded 10 frames") and "indices_unique 1" in out and ("with %d producer" % n) in out, out
+    r = run(["--video", path, "--decode_bench", "--model", "COCO", "--resolution", "160x90", "--start_frame", "4"])   # paced: 6 frames at 50 fps
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.strip().splitlines()[-1]
+    assert out.startswith("decoded 6 frames") and "with 1 producer" in out
+    secs = float(out.split(" in ")[1].split(" s")[0])
+    assert 0.09 < secs < 1.0, out          # 5 frame intervals of 20 ms
+
+
 def write_ppm(path, bgr):
     h, w, _ = bgr.shape
     with open(path, "wb") as f:
@@ -162,6 +195,25 @@ def test_cli_json_equals_python_path(tmp_path):
     cnt, joints, _ = eng.fetch(0)
     assert abs(sc - 320 / 480.0) < 1e-12
     assert (out2 / "big.json").read_text() == eng.json(joints, sc)
+    eng.close()
+    # --video: the frames of a Motion-JPEG .avi (other size than --resolution: GPU warpAffine) give the JSON files the same pixels give
+    # through the Python path; files are named after the video frame number (rtpose.cpp:1399-1402)
+    clip = str(tmp_path / "clip.avi")
+    vframes = [synth.make_frame(40 + i, 270, 480) for i in range(4)]
+    write_mjpeg_avi(clip, vframes)
+    out3 = tmp_path / "json3"
+    r = run(["--video", clip, "--novideo_realtime", "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
+             "--net_resolution", "160x96", "--write_json", str(out3), "--no_display", "--no_frame_drops", "--nocalibrate_range"], timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    cap = engine.VideoCapture(clip)
+    eng = engine.PoseEngine(model, net_w, net_h, disp_w, disp_h, precision=engine.PREC_BF16X2)
+    eng.set_weights(W)
+    for i in range(4):
+        ok, fr = cap.read()
+        assert ok
+        sc = eng.forward_camera_frames([fr])
+        cnt, joints, _ = eng.fetch(0)
+        assert (out3 / ("frame%06d.json" % i)).read_text() == eng.json(joints, sc)
     eng.close()
     # lossless frames on request
     r = run(["--image_dir", str(big_dir), "--caffemodel", cm, "--caffeproto", str(proto), "--resolution", "320x192",
