@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="frames per forward per GPU (default: per workload; C2: 9 x 4165 rows = 1.98 waves of 128-row tiles on 148 SMs)")
     ap.add_argument("--precision", type=int, default=2, help="0 fp32 SIMT, 1 bf16, 2 f16x2 split (parity mode), 3 bf16x3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--handles", type=int, default=int(os.environ.get("PE_BENCH_HANDLES", "2")),
+                    help="engine handles (worker streams) per GPU that alternate over the steps, as rtpose.bin --engines_per_gpu")
     return ap.parse_args()
 
 
@@ -252,10 +254,11 @@ def main():
     B = args.batch or wl.batch
     n_frames = max(wl.n_frames // B, 2) * B
 
-    # ---- engines: two handles per GPU (as the reference runs one Net per worker thread) so that the H2D of
+    NH = max(1, min(4, args.handles))
+    # ---- engines: NH (default two) handles per GPU (as the reference runs one Net per worker thread) so that the H2D of
     # one batch overlaps the compute of the other in the end-to-end loop
     engs = [engine.PoseEngine(model, wl.net_w, wl.net_h, wl.disp_w, wl.disp_h, num_scales=wl.S, start_scale=wl.start, scale_gap=wl.gap,
-                              device=local_rank, max_batch=B, precision=args.precision) for _ in range(2)]
+                              device=local_rank, max_batch=B, precision=args.precision) for _ in range(NH)]
     table = synth.conv_table(model)
     if rank == 0:
         W = synth.make_weights(model, "he")
@@ -326,15 +329,15 @@ def main():
     # two worker handles (two streams) alternate, like two of the reference's per-GPU worker threads would: the
     # small-grid parse kernels of one batch overlap the conv stack of the next.  Timed with torch CUDA events on
     # the null stream bracketing both engine streams (device-wide sync on both sides).
-    for i in range(max(args.warmup, 4)):   # >= 2 forwards per handle: the 2nd captures its CUDA graph
-        engs[i % 2].forward_frames_device(batch_dev(i), B)
+    for i in range(max(args.warmup, 2 * NH)):   # >= 2 forwards per handle: the 2nd captures its CUDA graph
+        engs[i % NH].forward_frames_device(batch_dev(i), B)
     barrier()
     launches0 = sum(e.launch_count() for e in engs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     ev0.record()
     for i in range(args.steps):
-        engs[i % 2].forward_frames_device(batch_dev(args.warmup + i), B)
+        engs[i % NH].forward_frames_device(batch_dev(args.warmup + i), B)
     for e in engs:
         e.sync()
     ev1.record()
@@ -345,7 +348,7 @@ def main():
     value = world * B * args.steps / (ms_dev * 1e-3)
 
     # ---- (2) end to end through the public call: host frames in, joints out, every step
-    for i in range(2):
+    for i in range(NH):
         engs[i].forward_frames(batch_host(i))
     for e in engs:
         e.fetch(0)
@@ -354,14 +357,14 @@ def main():
     t0 = time.perf_counter()
     got = 0
     for i in range(args.steps):
-        e = engs[i % 2]
-        if i >= 2:
+        e = engs[i % NH]
+        if i >= NH:
             for k in range(B):
-                n, joints, _ = e.fetch(k)   # results of step i-2 (sync on that handle's stream only)
+                n, joints, _ = e.fetch(k)   # results of step i-NH (sync on that handle's stream only)
             got += 1
         e.forward_frames(batch_host(i))
-    for j in range(min(2, args.steps)):
-        e = engs[(args.steps - 1 - j) % 2]
+    for j in range(min(NH, args.steps) - 1, -1, -1):   # drain in submission order
+        e = engs[(args.steps - 1 - j) % NH]
         for k in range(B):
             e.fetch(k)
         got += 1
@@ -412,12 +415,12 @@ def main():
                 "vs_baseline": None, "dtype": {0: "f32", 1: "bf16", 2: "f16x2 (2 fp16 planes, 3 tcgen05 MMAs per MAC, fp32 accumulate)", 3: "bf16x3 (split, fp32 accumulate)"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": wl.desc,
-                           "frames_per_step_per_gpu": B, "precision_mode": args.precision, "sharding": "frames round-robin, one rank per GPU",
+                           "frames_per_step_per_gpu": B, "handles_per_gpu": NH, "precision_mode": args.precision, "sharding": "frames round-robin, one rank per GPU",
                            "l2": "%d distinct frames (%d MB) cycled > 126 MB L2; activations of one step >> L2" % (n_frames, n_frames * frame_bytes // 1000000),
                            "collective": "init broadcast of packed weights only (NCCL)" if world > 1 else "none"},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": d2h,
-                        "how": "pe_forward_frames (pinned host frames) + pe_fetch every step, two handles per GPU, wall clock max over ranks"},
+                        "how": "pe_forward_frames (pinned host frames) + pe_fetch every step, %d handles per GPU, wall clock max over ranks" % NH},
                 "gpu_launches": int(launches),
                 "roofline": roofline}
         if cpu:

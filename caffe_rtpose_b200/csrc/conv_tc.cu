@@ -49,6 +49,8 @@ struct TcArgs {
     int n_tiles_n; long long total_tiles;   // persistent window kernel: tile = (m_tile, n_tile), n fastest
     int chunk_steps;                        // (channel block, filter row) steps per TMEM accumulation chunk (window kernel)
     unsigned* range;                        // [0]: running max |stored value| of this layer as float bits (atomicMax; values are >= 0), or null
+    int a_hi_only;                          // pair kernel: the lo plane of the input is identically zero (conv1_1 on uint8 frames: k/256 - 0.5 is exact in
+                                            // fp16): only the hi window is loaded and the A_lo x B_hi product is not issued - same result bit for bit
     int tma_store;                          // pair kernel: the epilogue stages 32-row x HALF-channel boxes in shared memory and stores them with TMA
     int dbg;                                // PE_TC_DBG bit mask, TIMING EXPERIMENTS ONLY (results are wrong): 1 no TMEM loads in the chunk drains,
                                             // 2 no epilogue math / stores, 4 weight tiles loaded once per slot only, 8 A windows loaded once per slot only, 16 one-lane issue loop,
@@ -766,7 +768,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const int row0 = (int)(m0 + (long long)(r - a.pad) * a.Wp - a.pad);
                         if ((a.dbg & 8) && aw >= NA) { if (rank == 0) mbar_arrive(&a_full[s]); }
                         else {
-                            if (rank == 0) mbar_expect_tx(&a_full[s], 2 * A_SLOT);
+                            if (rank == 0) mbar_expect_tx(&a_full[s], a.a_hi_only ? 2 * TCW_A_BYTES : 2 * A_SLOT);   // tmA's box holds one plane then
                             tma_load_3d_2sm(smem_a + s * A_SLOT, &tmA, mapa_u32(smem_u32(&a_full[s]), 0), kb * TC_BK, row0, 0);
                         }
                         aw++;
@@ -824,7 +826,7 @@ conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 const uint64_t ao = (uint64_t)(q * 8 + k * 2), bo = (uint64_t)(k * 2);
                                 umma_f16_2sm(accH, dA0 + ao, dBh + bo, IDESC, k ? 1u : firstH);
                                 umma_f16_2sm(accC, dA0 + ao, dBl + bo, IDESC, k ? 1u : firstC);
-                                umma_f16_2sm(accC, dA1 + ao, dBh + bo, IDESC, 1u);
+                                if (!a.a_hi_only) umma_f16_2sm(accC, dA1 + ao, dBh + bo, IDESC, 1u);
                             }
                             umma_commit_mc(&b_empty[sb_slot]);
                         }
@@ -1143,7 +1145,7 @@ static int launch_pair_st(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStre
         attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const CUtensorMap* maps = (const CUtensorMap*)l.maps;
-    return launch_pdl(kern, grid, smem, st, maps[2], maps[bmap], maps[(BN == 128 || ALT) ? 9 : 10], a);   // 64-channel boxes (ALT: one warp stores all 64 columns of its rows)
+    return launch_pdl(kern, grid, smem, st, maps[a.a_hi_only ? 11 : 2], maps[bmap], maps[(BN == 128 || ALT) ? 9 : 10], a);   // 64-channel boxes (ALT: one warp stores all 64 columns of its rows)
 }
 template <int BN>
 static int launch_pair(const TcLayer& l, const TcArgs& a, dim3 grid, cudaStream_t st, int bmap) {
@@ -1176,7 +1178,7 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
     out.d = d;
     out.bn = tc_bn(d.cout_pad);
     CUtensorMap* maps = nullptr;
-    if (posix_memalign((void**)&maps, 64, 12 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
+    if (posix_memalign((void**)&maps, 64, 13 * sizeof(CUtensorMap))) { err = "alloc"; return -1; }
     const int taps = d.ksize * d.ksize;
     const cuuint64_t K = (cuuint64_t)taps * d.in_cused;
     {   // A: [planes][M][pitch] bf16, box {64, 128, 1}
@@ -1198,6 +1200,16 @@ int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err) {
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(A window) failed: " + std::to_string((int)r); free(maps); return -1; }
+    }
+    {   // A window, hi plane only (TcArgs::a_hi_only): box {64, 136, 1}
+        cuuint64_t dims[3] = {(cuuint64_t)d.in_cused, (cuuint64_t)d.geo.M, (cuuint64_t)d.planes};
+        cuuint64_t strides[2] = {(cuuint64_t)d.in_pitch * 2, (cuuint64_t)d.in_plane * 2};
+        cuuint32_t box[3] = {TC_BK, TCW_ROWS, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&maps[11], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d.in, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(A window, one plane) failed: " + std::to_string((int)r); free(maps); return -1; }
     }
     {   // B: [planes][cout_pad][K] bf16, box {64, BN, 1}
         cuuint64_t dims[3] = {K, (cuuint64_t)d.cout_pad, (cuuint64_t)d.planes};
@@ -1268,7 +1280,7 @@ void tc_layer_destroy(TcLayer& l) {
     l.maps = nullptr;
 }
 
-int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st, int share) {
+int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st, int share, int a_hi_only) {
     const TcLayerDesc& d = l.d;
     TcArgs a;
     a.bias = d.bias;
@@ -1282,6 +1294,8 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st, int share) {
     static const int dbg = env_int("PE_TC_DBG", 0);
     a.dbg = dbg;
     a.tma_store = 0;
+    static const int hi_only_env = env_int("PE_TC_HIONLY", 1);   // 0: always load both input planes (A/B measurement)
+    a.a_hi_only = 0;
     dim3 grid((unsigned)((a.M + TC_BM - 1) / TC_BM), (unsigned)(d.cout_pad / l.bn));
     static const int variant = env_int("PE_TC_VARIANT", 1);     // 1: window kernel, 0: one TMA tile per tap
     if (variant == 1 && d.planes <= 2) {
@@ -1305,6 +1319,7 @@ int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st, int share) {
             }
             a.n_tiles_n = d.cout_pad / bn;
             a.total_tiles = mt * a.n_tiles_n;
+            a.a_hi_only = a_hi_only && hi_only_env;
             const int nsteps = a.kblocks_per_tap * a.ksize;
             static const int chunk_env = env_int("PE_TC_CHUNK", -1);
             static const int chunk_mul = env_int("PE_TC_CHUNK_MUL", 1);

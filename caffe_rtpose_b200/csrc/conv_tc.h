@@ -27,7 +27,8 @@ int tc_cout_pad(int cout);   // N-tile granularity used for a layer with `cout` 
 int tc_layer_create(const TcLayerDesc& d, TcLayer& out, std::string& err);
 void tc_layer_destroy(TcLayer& l);
 // share: number of independent layers expected to run concurrently (2 when the L1 / L2 branches run on two streams): the tile
-// width is then chosen for 1/share of the GPU.  Returns kernels launched.
-int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st, int share = 1);
+// width is then chosen for 1/share of the GPU.  a_hi_only: the caller guarantees that the input's lo plane is identically zero (parity
+// mode, conv1_1 fed from uint8 frames); the pair kernel then skips that plane.  Returns kernels launched.
+int tc_layer_launch(const TcLayer& l, int nimg, cudaStream_t st, int share = 1, int a_hi_only = 0);
 
 }  // namespace pe

@@ -828,7 +828,9 @@ static int run_op(pe_engine* e, const OpRef& op, int nimg, cudaStream_t st = nul
             return PE_OK;
         }
         if (e->planes) {
-            e->launches += tc_layer_launch(e->tc[op.idx], nimg, st, share);
+            // conv1_1 on uint8 frames: (k/256 - 0.5) x 2^s is exact in one fp16 plane, the im2col kernel leaves the lo plane zero
+            const int hi_only = op.idx == 0 && c.im2col_input && e->input_from_frames && !e->input_lo_dirty;
+            e->launches += tc_layer_launch(e->tc[op.idx], nimg, st, share, hi_only);
             return PE_OK;
         }
         ConvArgs a;

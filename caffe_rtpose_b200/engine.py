@@ -130,12 +130,13 @@ def lib():
     L.pe_encode_jpeg.restype = C.c_longlong
     L.pe_decode_jpeg.argtypes = [C.c_char_p, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_longlong]
     L.pe_decode_png.argtypes = L.pe_decode_jpeg.argtypes
-    L.pe_video_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
-    L.pe_video_close.argtypes = [C.c_void_p]
-    L.pe_video_close.restype = None
-    L.pe_video_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p]
-    L.pe_video_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
-    L.pe_video_last_error.restype = C.c_char_p
+    if hasattr(L, "pe_video_open") or "PE_LIB" not in os.environ:   # an older A/B build (PE_LIB) may predate the video reader
+        L.pe_video_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.pe_video_close.argtypes = [C.c_void_p]
+        L.pe_video_close.restype = None
+        L.pe_video_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p]
+        L.pe_video_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
+        L.pe_video_last_error.restype = C.c_char_p
     _lib = L
     return L
 
