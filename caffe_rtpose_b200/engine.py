@@ -50,6 +50,7 @@ ABI_SYMBOLS = [
     "pe_caffemodel_close", "pe_caffemodel_num_layers", "pe_caffemodel_layer", "pe_caffemodel_blob",
     "pe_caffemodel_last_error", "pe_create_from_prototxt", "pe_plan_describe", "pe_render_device", "pe_host_alloc", "pe_host_free", "pe_forward_camera_frames", "pe_broadcast_weights", "pe_render", "pe_encode_jpeg", "pe_decode_jpeg", "pe_decode_png",
     "pe_video_open", "pe_video_close", "pe_video_info", "pe_video_read", "pe_video_last_error",
+    "pe_camera_open", "pe_camera_close", "pe_camera_info", "pe_camera_grab", "pe_camera_last_error", "pe_yuyv_to_bgr",
 ]
 
 
@@ -137,6 +138,12 @@ def lib():
         L.pe_video_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p]
         L.pe_video_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
         L.pe_video_last_error.restype = C.c_char_p
+    if hasattr(L, "pe_camera_open") or "PE_LIB" not in os.environ:
+        L.pe_camera_open.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.pe_camera_close.argtypes = [C.c_void_p]
+        L.pe_camera_close.restype = None
+        L.pe_camera_last_error.restype = C.c_char_p
+        L.pe_yuyv_to_bgr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p]
     _lib = L
     return L
 
@@ -637,6 +644,16 @@ class VideoCapture:
             self.release()
         except Exception:
             pass
+
+
+def yuyv_to_bgr(yuyv):
+    """cv::cvtColor(COLOR_YUV2BGR_YUYV) of an (h, w, 2) uint8 YUYV image - the conversion of camera frames (pe_camera_grab)."""
+    yuyv = np.ascontiguousarray(yuyv, np.uint8)
+    h, w, _ = yuyv.shape
+    out = np.empty((h, w, 3), np.uint8)
+    if lib().pe_yuyv_to_bgr(yuyv.ctypes.data, w, h, 2 * w, out.ctypes.data) != 0:
+        raise PoseEngineError("pe_yuyv_to_bgr: bad arguments (odd width?)")
+    return out
 
 
 def decode_png(data):

@@ -4,8 +4,8 @@
 // boost / OpenCV are not available here and are not needed for this path); all math is behind the C ABI.
 //
 // Supported sources: --image_dir with .jpg / .png / .bmp / .ppm files (own decoders behind the C ABI, pixels identical to
-// cv::imread), --video with Motion-JPEG / uncompressed .avi files (csrc/video.cpp), or --synthetic N procedural frames.  Other video
-// codecs and --camera need a codec library / capture device and are rejected
+// cv::imread), --video with Motion-JPEG / uncompressed .avi files (csrc/video.cpp), the camera (--camera N: Video4Linux2 capture,
+// csrc/camera.cpp), or --synthetic N procedural frames.  Other video codecs need a codec library and are rejected
 // with an explicit message; there is no window, so the keyboard UI of handleKey (rtpose.cpp:1551-1671) is served from stdin
 // with --keys_from_stdin (same key characters, same step sizes).  --write_frames renders on the GPU (pe_render) and writes
 // quality-98 .jpg files like the reference (pe_encode_jpeg; --frame_format bmp for lossless), without the putText overlays.
@@ -354,6 +354,8 @@ struct Global {
     pe_video* video = nullptr;     // --video (cv::VideoCapture of getFrameFromCam)
     int video_frames = 0, video_w = 0, video_h = 0;
     double video_fps = 0;
+    pe_camera* camera = nullptr;   // cap.open(FLAGS_camera) when no --video / --image_dir / --synthetic is given
+    int camera_w = 0, camera_h = 0;
     bool proto_readable = false;   // --caffeproto parsed: engines are created from it
     // global.nms_threshold etc. of the reference (rtpose.cpp:106-111), changed at run time by handle_key
     std::atomic<float> nms_threshold{0.05f}, connect_min_subset_score{0.4f}, connect_inter_threshold{0.05f};
@@ -424,6 +426,7 @@ static void random_weights(pe_engine* e, const std::string& kind) {
 static int source_frame_count() {
     if (Fi("synthetic") > 0) return Fi("synthetic");
     if (global.video) return global.video_frames;
+    if (global.camera) return 0x7fffffff;   // until ESC / a capture error
     return (int)global.image_list.size();
 }
 // frame i of the source (synthetic / --video / --image_dir) into fr; false: could not be decoded (message logged)
@@ -431,6 +434,14 @@ static bool fetch_source_frame(int i, Frame& fr) {
     int w = global.disp_w, h = global.disp_h;
     if (Fi("synthetic") > 0) {
         synthetic_frame(i, w, h, fr.bgr);
+    } else if (global.camera) {   // cap >> image_uchar_orig from the capture device
+        w = global.camera_w; h = global.camera_h;
+        const size_t bytes = (size_t)w * h * 3;
+        uint8_t* ph = g_pinned.get(bytes);
+        uint8_t* dst = ph;
+        if (ph) fr.pinned = std::shared_ptr<uint8_t>(ph, [bytes](uint8_t* q) { g_pinned.put(q, bytes); });
+        else { fr.bgr.resize(bytes); dst = fr.bgr.data(); }
+        if (pe_camera_grab(global.camera, dst, (long long)bytes, 0)) { LOG_ERROR("%s", pe_camera_last_error()); return false; }
     } else if (global.video) {   // cap >> image_uchar_orig (rtpose.cpp:431): decoded straight into a page-locked buffer
         w = global.video_w; h = global.video_h;
         const size_t bytes = (size_t)w * h * 3;
@@ -469,9 +480,10 @@ static void producer() {
         fr.t_commit = now_s();    // frame.commit_time: taken when the frame is grabbed (rtpose.cpp:449)
         fr.index = global.produced; fr.video_frame_number = i;
         if (!fetch_source_frame(i, fr)) {
-            if (global.video) break;   // a broken frame ends a video (cap >> returns an empty Mat)
+            if (global.video || global.camera) break;   // a broken frame ends a video / the capture (cap >> returns an empty Mat)
             continue;
         }
+        if (global.camera) fr.t_commit = now_s();    // the frame was taken while the call blocked
         if (paced) {
             const double interval = now_s() - last_frame_time;
             if (last_frame_time >= 0 && interval < frame_time) std::this_thread::sleep_for(std::chrono::duration<double>(frame_time - interval));
@@ -522,6 +534,7 @@ static void producer_mt(int nthreads) {
 static int num_producers() {
     if (Fi("num_producers") > 0) return Fi("num_producers");
     if (Fi("batch") > 0) return 1;   // an explicit batch (1 = the reference's behaviour) keeps the reference's single producer
+    if (global.camera) return 1;
     if (global.video && (Fb("video_realtime") || (F("write_frames").empty() && F("write_json").empty()))) return 1;   // pacing / looping: one reader, like cap >>
     const int cores = (int)std::thread::hardware_concurrency();
     const int gpus = std::max(1, Fi("num_gpu"));
@@ -829,10 +842,19 @@ int main(int argc, char** argv) {
         printf("%dx%d %016llx\n", w, h, (unsigned long long)hash);
         return 0;
     }
-    if (F("video").empty() && F("image_dir").empty() && Fi("synthetic") <= 0) {
-        LOG_ERROR("Couldn't open camera %d: camera capture needs a capture device and driver interface this build does not have; use --video "
-                  "(Motion-JPEG / uncompressed .avi), --image_dir or --synthetic N", Fi("camera"));
-        return 1;
+    if (F("video").empty() && F("image_dir").empty() && Fi("synthetic") <= 0) {   // the camera (rtpose.cpp:401-405, 1694-1695)
+        int cw = 0, ch = 0;
+        if (sscanf(F("camera_resolution").c_str(), "%dx%d", &cw, &ch) != 2) {
+            LOG_ERROR("Error, camera resolution format (%s) invalid, should be e.g., 1280x720", F("camera_resolution").c_str());
+            return 1;
+        }
+        if (pe_camera_open(Fi("camera"), cw, ch, &global.camera)) {
+            LOG_ERROR("%s; other sources: --video (Motion-JPEG / uncompressed .avi), --image_dir, --synthetic N", pe_camera_last_error());
+            return 1;
+        }
+        char cc[5];
+        pe_camera_info(global.camera, &global.camera_w, &global.camera_h, cc);
+        LOG_INFO("Camera %d: %dx%d %s", Fi("camera"), global.camera_w, global.camera_h, cc);
     }
     if (F("frame_format") != "jpg" && F("frame_format") != "bmp") { LOG_ERROR("--frame_format must be jpg or bmp"); return 1; }
     if (sscanf(F("resolution").c_str(), "%dx%d", &global.disp_w, &global.disp_h) != 2) { LOG_ERROR("Error, resolution format (%s) invalid, should be e.g., 960x540", F("resolution").c_str()); return 1; }
@@ -913,5 +935,6 @@ int main(int argc, char** argv) {
     for (pe_engine* e : engines) pe_destroy(e);
     g_pinned.clear();
     pe_video_close(global.video);
+    pe_camera_close(global.camera);
     return global.quit ? 1 : 0;
 }

@@ -208,6 +208,20 @@ int pe_video_info(const pe_video* v, int* w, int* h, double* fps, int* frame_cou
 int pe_video_read(const pe_video* v, int index, uint8_t* bgr, long long cap);
 const char* pe_video_last_error(void);
 
+/* cv::VideoCapture on a camera index (rtpose.cpp:401-405 cap.open(FLAGS_camera) + CV_CAP_PROP_FRAME_WIDTH/HEIGHT from
+ * --camera_resolution, :431 cap >> image): Video4Linux2 streaming capture from /dev/video<index>, Motion-JPEG (pe_decode_jpeg) or YUYV
+ * frames.  pe_camera_grab blocks for the next frame (timeout_ms <= 0: 5 s) and returns it as uint8 BGR HWC of the size
+ * pe_camera_info reports (the driver may grant another size than asked for).  Errors: PE_ERR_IO / PE_ERR_INVALID, text in
+ * pe_camera_last_error() (thread-local; "Couldn't open camera N ..." as the reference's CHECK).
+ * pe_yuyv_to_bgr: cv::cvtColor(COLOR_YUV2BGR_YUYV), the conversion OpenCV's V4L2 back end applies to YUYV frames. */
+typedef struct pe_camera pe_camera;
+int pe_camera_open(int index, int want_w, int want_h, pe_camera** out);
+void pe_camera_close(pe_camera* c);
+int pe_camera_info(const pe_camera* c, int* w, int* h, char fourcc[5]);
+int pe_camera_grab(pe_camera* c, uint8_t* bgr, long long cap, int timeout_ms);
+const char* pe_camera_last_error(void);
+int pe_yuyv_to_bgr(const uint8_t* yuyv, int w, int h, long long stride, uint8_t* bgr);
+
 /* ---- model descriptor tables (modelDescriptorFactory.cpp:6-28,30-55) */
 int pe_model_num_parts(int model);
 int pe_model_num_limbs(int model);

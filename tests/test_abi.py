@@ -634,3 +634,21 @@ def test_video_reader_avi_structure_variants(tmp_path):
     open(cut, "wb").write(whole[:len(whole) - len(out) - 40])
     cap = engine.VideoCapture(cut)
     assert cap.isOpened() and cap.frame_count == 2 and cap.read()[0] and cap.read()[0] and not cap.read()[0]
+
+
+def test_camera_conversion_equals_opencv_and_open_fails_loudly():
+    """Camera frames (rtpose.cpp:401-405, 431): YUYV -> BGR with cv::cvtColor(COLOR_YUV2BGR_YUYV)'s arithmetic (what OpenCV's V4L2
+    back end applies), bit for bit incl. the saturating corners; opening a device that does not exist reports the reference's message."""
+    import cv2
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (36, 50, 2), dtype=np.uint8)
+    img[0, :8] = [[0, 0], [255, 255], [16, 128], [235, 128], [0, 255], [255, 0], [81, 90], [81, 240]]
+    assert np.array_equal(engine.yuyv_to_bgr(img), cv2.cvtColor(img, cv2.COLOR_YUV2BGR_YUYV))
+    grid = np.stack(np.meshgrid(np.arange(0, 256, 5), np.arange(0, 256, 3), indexing="ij"), -1).astype(np.uint8)   # (Y, U|V) sweep
+    grid = grid[:, :grid.shape[1] // 2 * 2]
+    assert np.array_equal(engine.yuyv_to_bgr(grid), cv2.cvtColor(np.ascontiguousarray(grid), cv2.COLOR_YUV2BGR_YUYV))
+    with pytest.raises(engine.PoseEngineError):
+        engine.yuyv_to_bgr(np.zeros((4, 5, 2), np.uint8))          # odd width
+    h = C.c_void_p()
+    assert engine.lib().pe_camera_open(63, 1280, 720, C.byref(h)) != 0 and not h.value
+    assert b"Couldn't open camera 63 (/dev/video63" in engine.lib().pe_camera_last_error()

@@ -33,8 +33,10 @@ def test_flag_surface_matches_reference():
 
 def test_flag_errors():
     assert run(["--bogus", "1"]).returncode == 1
-    r = run([])  # no camera capture in this build: explicit message, not a hang
-    assert r.returncode == 1 and "Couldn't open camera 0" in r.stderr
+    r = run(["--camera", "7"])  # CHECK(cap.open(FLAGS_camera)) (rtpose.cpp:402): no capture device here -> the message, not a hang
+    assert r.returncode == 1 and "Couldn't open camera 7 (/dev/video7" in r.stderr
+    r = run(["--camera_resolution", "wide"])
+    assert r.returncode == 1 and "camera resolution format (wide) invalid" in r.stderr
     r = run(["--video", "/nonexistent/clip.avi", "--model", "COCO"])   # CHECK(cap.open(FLAGS_video)) (rtpose.cpp:406)
     assert r.returncode == 1 and "Couldn't open video file /nonexistent/clip.avi" in r.stderr
     r = run(["--synthetic", "2", "--resolution", "abc", "--model", "COCO"])
