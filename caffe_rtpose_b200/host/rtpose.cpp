@@ -361,6 +361,9 @@ struct Global {
     std::atomic<float> nms_threshold{0.05f}, connect_min_subset_score{0.4f}, connect_inter_threshold{0.05f};
     std::atomic<int> connect_min_subset_cnt{3}, connect_inter_min_above_threshold{9}, part_to_show{0}, params_version{0};
     std::atomic<int> dropped{0};
+    // global.uistate (rtpose.cpp:96-104): googly eyes, video pause / seek, driven by handle_key
+    std::atomic<bool> googly_eyes{false}, video_paused{false};
+    std::atomic<int> seek_delta{0};
     int queue_limit = 64, batch = 1, engines_per_gpu = 1;
 } global;
 
@@ -471,6 +474,11 @@ static void producer() {
     const double frame_time = global.video_fps > 0 ? 1.0 / global.video_fps : 0;
     double last_frame_time = -1;
     for (int i = Fi("start_frame"); !global.quit; i++) {
+        if (global.video) {   // uistate.seek_to_frame / is_video_paused (rtpose.cpp:434-446): a paused video keeps delivering its current frame
+            const int d = global.seek_delta.exchange(0);
+            if (d) { i = std::max(0, std::min(total - 1, i + d)); LOG_INFO("Seek to frame %d", i); }
+            else if (global.video_paused && i > Fi("start_frame")) i--;
+        }
         if (i >= total) {
             if (!loop || total <= 0) break;
             LOG_INFO("Looping video after %d frames", total);
@@ -683,7 +691,7 @@ static void worker(int tid, pe_engine* e) {
             frames[i].joints.assign(joints.begin(), joints.begin() + (size_t)cnt * P * 3);
             if (!F("write_frames").empty()) {   // render() + postProcessFrame (rtpose.cpp:271-300, 1286-1296) on the GPU
                 frames[i].rendered.resize((size_t)global.disp_w * global.disp_h * 3);
-                if (pe_render(e, (int)i, global.part_to_show, 0, nullptr, nullptr, frames[i].rendered.data())) {
+                if (pe_render(e, (int)i, global.part_to_show, global.googly_eyes ? 1 : 0, nullptr, nullptr, frames[i].rendered.data())) {
                     LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break;
                 }
             }
@@ -700,6 +708,15 @@ static void handle_key(int c) {
     auto bumpi = [](std::atomic<int>& v, int d, const char* name) { v = v + d; LOG_INFO("%s: %d", name, v.load()); };
     const int max_show = global.model == PE_MODEL_MPI_15 ? 43 : 39;
     if (c == 27 || c == 'Q') { global.quit = true; return; }   // ESC as in the reference; 'Q' for terminals that cannot send it
+    if (c == 'g') { global.googly_eyes = !global.googly_eyes; LOG_INFO("googly eyes: %d", (int)global.googly_eyes.load()); return; }   // rtpose.cpp:1568-1570
+    if (c == 'l' || c == 'k' || c == 'L' || c == 'K' || c == ' ') {   // rudimentary seeking in video (:1572-1593): 30 frames, 2 with shift; space pauses
+        if (global.video && c != ' ') {
+            const int d = (c == 'L' || c == 'K') ? 2 : 30;
+            global.seek_delta += (c == 'l' || c == 'L') ? d : -d;
+        }
+        if (c == ' ') { global.video_paused = !global.video_paused; LOG_INFO("paused: %d", (int)global.video_paused.load()); }
+        return;
+    }
     if (c == '-' || c == '=') bump(global.nms_threshold, c == '-' ? -0.005f : 0.005f, "nms_threshold");
     else if (c == '_' || c == '+') bump(global.connect_min_subset_score, c == '_' ? -0.005f : 0.005f, "connect_min_subset_score");
     else if (c == '[' || c == ']') bump(global.connect_inter_threshold, c == '[' ? -0.005f : 0.005f, "connect_inter_threshold");
@@ -723,7 +740,7 @@ static void handle_key(int c) {
 static void key_reader() {
     int c;
     while (!global.quit && (c = getchar()) != EOF)
-        if (c != '\n' && c != '\r' && c != ' ') handle_key(c);
+        if (c != '\n' && c != '\r') handle_key(c);
 }
 
 // re-order by frame index (buffer_and_order, rtpose.cpp:1214-1273) and write JSON (displayFrame, :1383-1416)
@@ -916,6 +933,7 @@ int main(int argc, char** argv) {
     }
     global.engines_per_gpu = Fi("engines_per_gpu") > 0 ? std::min(4, Fi("engines_per_gpu")) : (Fi("batch") <= 0 ? 2 : 1);
     global.queue_limit = std::max(10, 4 * global.batch * std::max(1, Fi("num_gpu")) * global.engines_per_gpu);
+    if (Fb("keys_from_stdin")) std::thread(key_reader).detach();   // blocks in getchar(): never joined
     if (Fb("decode_bench")) return decode_bench();
     const int num_gpu = std::max(1, Fi("num_gpu"));
     std::vector<pe_engine*> engines;
@@ -928,7 +946,6 @@ int main(int argc, char** argv) {
     for (int i = 0; i < num_workers; i++) workers.emplace_back(worker, i, engines[i]);
     std::thread prod(run_producers);
     std::thread ord(orderer_and_writer, num_workers);
-    if (Fb("keys_from_stdin")) std::thread(key_reader).detach();   // blocks in getchar(): never joined
     prod.join();
     for (auto& t : workers) t.join();
     ord.join();

@@ -142,6 +142,14 @@ def test_video_source_decode_stage_without_gpu(tmp_path):
     assert out.startswith("decoded 6 frames") and "with 1 producer" in out
     secs = float(out.split(" in ")[1].split(" s")[0])
     assert 0.09 < secs < 1.0, out          # 5 frame intervals of 20 ms
+    # handleKey's video keys (rtpose.cpp:1572-1593) from stdin: 'l' jumps 30 frames ahead, so a 120-frame clip ends ~30 frames early
+    long_clip = str(tmp_path / "long.avi")
+    write_mjpeg_avi(long_clip, [synth.make_frame(i % 3, 48, 64) for i in range(120)], fps=200.0)
+    p = subprocess.run([BIN, "--video", long_clip, "--decode_bench", "--model", "COCO", "--resolution", "64x48", "--keys_from_stdin"],
+                       input="l", capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    n = int(p.stdout.strip().splitlines()[-1].split()[1])
+    assert "Seek to frame" in p.stderr and 85 <= n <= 95, (n, p.stderr[-300:])
 
 
 def write_ppm(path, bgr):
