@@ -136,7 +136,9 @@ extern "C" int pe_video_open(const char* path, pe_video** out) {
         return fail(PE_ERR_INVALID, std::string(path) + ": not a RIFF AVI file (the containers read here: AVI / OpenDML with Motion-JPEG or "
                                         "uncompressed frames; other containers need a video library this build does not have)");
     int n_streams = 0;
-    if (!v->walk(0, v->file_size, 0, false, n_streams)) return fail(PE_ERR_IO, std::string(path) + ": read error while indexing");
+    bool walked = false;
+    try { walked = v->walk(0, v->file_size, 0, false, n_streams); } catch (...) { walked = false; }   // no exception crosses the C ABI
+    if (!walked) return fail(PE_ERR_IO, std::string(path) + ": read error while indexing");
     if (v->stream < 0 || v->w <= 0 || v->h <= 0 || v->w > 32768 || v->h > 32768) return fail(PE_ERR_INVALID, std::string(path) + ": no video stream");
     char cc[5] = {0, 0, 0, 0, 0};
     memcpy(cc, v->compression, 4);
@@ -182,7 +184,8 @@ extern "C" int pe_video_read(const pe_video* v, int index, uint8_t* bgr, long lo
     while (index > 0 && v->frames[index].size == 0) index--;
     const FrameRef fr = v->frames[index];
     if (fr.size == 0) { memset(bgr, 0, (size_t)v->w * v->h * 3); return PE_OK; }
-    std::vector<uint8_t> buf(fr.size);
+    std::vector<uint8_t> buf;
+    try { buf.resize(fr.size); } catch (...) { g_video_error = v->path + ": out of memory for a frame"; return PE_ERR_IO; }
     if (!v->read_at(fr.off, buf.data(), fr.size)) { g_video_error = v->path + ": read error"; return PE_ERR_IO; }
     if (v->mjpeg) {
         int jw = 0, jh = 0;

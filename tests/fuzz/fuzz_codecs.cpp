@@ -1,6 +1,6 @@
-// Mutation fuzzer for the parsers that read untrusted files: pe_decode_jpeg, pe_decode_png, the .caffemodel reader.
+// Mutation fuzzer for the parsers that read untrusted files: pe_decode_jpeg, pe_decode_png, the .caffemodel reader, the AVI reader.
 // Built with -fsanitize=address,undefined by tests/test_abi.py::test_parsers_survive_corrupt_files; any finding aborts.
-// usage: fuzz_codecs <iterations> <file>...   (.jpg / .png by signature, anything else is treated as a .caffemodel)
+// usage: fuzz_codecs <iterations> <file>...   (.jpg / .png / .avi by signature, anything else is treated as a .caffemodel)
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
     for (int a = 2; a < argc; a++) {
         const std::vector<uint8_t> base = slurp(argv[a]);
         if (base.size() < 16) return 2;
-        const bool jpg = base[0] == 0xFF && base[1] == 0xD8, png = base[1] == 'P' && base[2] == 'N';
+        const bool jpg = base[0] == 0xFF && base[1] == 0xD8, png = base[1] == 'P' && base[2] == 'N', avi = !memcmp(base.data(), "RIFF", 4);
         for (int it = 0; it < iters; it++) {
             std::vector<uint8_t> d = base;
             const int nm = 1 + rnd() % 6;
@@ -75,6 +75,24 @@ int main(int argc, char** argv) {
                     rc = dec(d.data(), (long long)d.size(), &w, &h, px.data(), (long long)px.size());
                 }
                 (rc == 0 ? ok : rejected)++;
+            } else if (avi) {
+                FILE* f = fopen(tmp.c_str(), "wb");
+                if (!f) return 2;
+                fwrite(d.data(), 1, d.size(), f);
+                fclose(f);
+                pe_video* v = nullptr;
+                if (pe_video_open(tmp.c_str(), &v) != 0) { rejected++; continue; }
+                int w = 0, h = 0, n = 0;
+                double fps = 0;
+                char cc[5];
+                pe_video_info(v, &w, &h, &fps, &n, cc);
+                bool all = true;
+                if ((long long)w * h <= 4000000) {
+                    std::vector<uint8_t> px((size_t)w * h * 3);   // exact size: a row written past the frame is an ASAN finding
+                    for (int i = 0; i < n && i < 64; i++) all = (pe_video_read(v, i, px.data(), (long long)px.size()) == 0) && all;
+                }
+                (all ? ok : rejected)++;
+                pe_video_close(v);
             } else {
                 FILE* f = fopen(tmp.c_str(), "wb");
                 if (!f) return 2;

@@ -473,7 +473,7 @@ def test_png_decoder_equals_cv_imread():
 
 
 def test_parsers_survive_corrupt_files(tmp_path):
-    """The three parsers that read untrusted files (JPEG, PNG, .caffemodel) under AddressSanitizer + UBSan on thousands of
+    """The parsers that read untrusted files (JPEG, PNG, .caffemodel, AVI) under AddressSanitizer + UBSan on thousands of
     mutated files: they must accept or reject, never read out of bounds / overflow / crash."""
     import cv2
     from caffe_rtpose_b200 import synth
@@ -490,12 +490,18 @@ def test_parsers_survive_corrupt_files(tmp_path):
          "conv1_2": (rng.standard_normal((5, 4, 1, 1)).astype(np.float32), np.ones(5, np.float32))}
     engine.write_caffemodel(str(tmp_path / "m.caffemodel"), W, [("conv1_1", 4, 3, 3), ("conv1_2", 5, 4, 1)])
     files.append(str(tmp_path / "m.caffemodel"))
+    # AVI reader: a Motion-JPEG file and an uncompressed one (tiny frames keep the mutated headers' claims decodable)
+    small = cv2.imencode(".jpg", img[:24, :32], [cv2.IMWRITE_JPEG_QUALITY, 75])[1].tobytes()
+    _write_avi(str(tmp_path / "v.avi"), [(small, (32, 24))] * 3, b"MJPG")
+    dib = b"".join(bytes(img[y, :9].tobytes()).ljust(28, b"\0") for y in range(6, -1, -1))
+    _write_avi(str(tmp_path / "w.avi"), [(dib, (9, 7))] * 3, b"DIB ", chunk_tag=b"00db", in_rec=True)
+    files += [str(tmp_path / "v.avi"), str(tmp_path / "w.avi")]
     src = os.path.join(ROOT, "caffe_rtpose_b200", "csrc")
     exe = str(tmp_path / "fuzz_codecs")
     r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
                         "-I", os.path.join(ROOT, "include"), "-I", src, "-I", "/usr/local/cuda/include",
                         os.path.join(ROOT, "tests", "fuzz", "fuzz_codecs.cpp"), os.path.join(src, "jpeg_dec.cpp"), os.path.join(src, "png_dec.cpp"),
-                        os.path.join(src, "caffemodel.cpp"), "-o", exe], capture_output=True, text=True, timeout=300)
+                        os.path.join(src, "caffemodel.cpp"), os.path.join(src, "video.cpp"), "-o", exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([exe, "1500"] + files, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
