@@ -202,7 +202,7 @@ def run_reference(args, rank, world):
                                        % (args.steps, wl.disp_w, wl.disp_h, wl.net_w, wl.net_h, wl.S, best_n, cores)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def parity_note(wl, eng, frame, ref):
@@ -225,8 +225,33 @@ def parity_note(wl, eng, frame, ref):
     return note
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON line: everything else that libraries write to file descriptor 1 while the bench runs
+    (NCCL prints "NCCL version ..." there at the first communicator, whatever NCCL_DEBUG says) is routed to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+        return
+    sys.stdout.flush()
+    while data:
+        data = data[os.write(_JSON_FD, data):]
+
+
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -427,7 +452,7 @@ def main():
             line["cpu_baseline"] = cpu
         if replica is not None:
             line["replica_check"] = replica
-        print(json.dumps(line), flush=True)
+        emit(line)
     for e in engs:
         e.close()
     if dist is not None:
