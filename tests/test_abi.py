@@ -634,6 +634,16 @@ def test_video_reader_avi_structure_variants(tmp_path):
     _write_avi(path, [(bytes(out), (96, 64))] * 3, b"MJPG")
     cap = engine.VideoCapture(path)
     assert cap.isOpened() and np.array_equal(cap.read()[1], cv2.imdecode(enc, cv2.IMREAD_COLOR))
+    # OpenDML: frames continue in 'AVIX' extension RIFFs after the first one (files > 1 GB); foreign RIFFs in between are skipped
+    import struct as st
+    first = open(path, "rb").read()
+    more = b"AVIX" + _riff_chunk(b"LIST", b"movi" + _riff_chunk(b"00dc", bytes(out)) + _riff_chunk(b"01wb", b"\0\0") + _riff_chunk(b"00dc", bytes(out)))
+    odml = str(tmp_path / "odml.avi")
+    open(odml, "wb").write(first + b"RIFF" + st.pack("<I", 12) + b"WAVEfmt \0\0\0\0" + b"RIFF" + st.pack("<I", len(more)) + more)
+    cap = engine.VideoCapture(odml)
+    assert cap.isOpened() and cap.frame_count == 5
+    cap.set(cap.CAP_PROP_POS_FRAMES, 4)
+    assert np.array_equal(cap.read()[1], cv2.imdecode(enc, cv2.IMREAD_COLOR))
     # a recording that was cut off: the complete frames stay readable
     whole = open(path, "rb").read()
     cut = str(tmp_path / "cut.avi")
