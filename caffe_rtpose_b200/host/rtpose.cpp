@@ -8,7 +8,8 @@
 // csrc/camera.cpp), or --synthetic N procedural frames.  Other video codecs need a codec library and are rejected
 // with an explicit message; there is no window, so the keyboard UI of handleKey (rtpose.cpp:1551-1671) is served from stdin
 // with --keys_from_stdin (same key characters, same step sizes).  --write_frames renders on the GPU (pe_render) and writes
-// quality-98 .jpg files like the reference (pe_encode_jpeg; --frame_format bmp for lossless), without the putText overlays.
+// quality-98 .jpg files like the reference (pe_encode_jpeg; --frame_format bmp for lossless) with displayFrame's text overlays
+// (own bitmap font, --no_text turns them off).
 // Frames older than 0.1 s are dropped unless --no_frame_drops, as in processFrame (rtpose.cpp:1107-1124).
 #include <dirent.h>
 #include <math.h>
@@ -347,7 +348,7 @@ struct Global {
     BlockingQueue<Frame> input_queue, output_queue;
     std::priority_queue<int, std::vector<int>, std::greater<int>> dropped_index;
     std::mutex mutex;
-    std::atomic<bool> producer_done{false}, quit{false};
+    std::atomic<bool> producer_done{false}, quit{false}, failed{false};   // quit: stop all threads (ESC or an error); failed: it was an error
     std::atomic<int> produced{0}, finished{0};
     int disp_w = 0, disp_h = 0, net_w = 0, net_h = 0, model = PE_MODEL_COCO_18, num_parts = 18;
     std::vector<std::string> image_list;
@@ -683,16 +684,16 @@ static void worker(int tid, pe_engine* e) {
         if (frames[0].w == global.disp_w && frames[0].h == global.disp_h) frc = pe_forward_frames(e, ptrs.data(), (int)ptrs.size());
         else frc = pe_forward_camera_frames(e, ptrs.data(), (int)ptrs.size(), frames[0].w, frames[0].h, &scale);   // warpAffine on the GPU
         for (auto& f : frames) f.scale = scale;
-        if (frc) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break; }
+        if (frc) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.failed = global.quit = true; break; }
         for (size_t i = 0; i < frames.size(); i++) {
             int cnt = 0;
-            if (pe_fetch(e, (int)i, joints.data(), &cnt, nullptr)) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break; }
+            if (pe_fetch(e, (int)i, joints.data(), &cnt, nullptr)) { LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.failed = global.quit = true; break; }
             frames[i].num_people = cnt;
             frames[i].joints.assign(joints.begin(), joints.begin() + (size_t)cnt * P * 3);
             if (!F("write_frames").empty()) {   // render() + postProcessFrame (rtpose.cpp:271-300, 1286-1296) on the GPU
                 frames[i].rendered.resize((size_t)global.disp_w * global.disp_h * 3);
                 if (pe_render(e, (int)i, global.part_to_show, global.googly_eyes ? 1 : 0, nullptr, nullptr, frames[i].rendered.data())) {
-                    LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.quit = true; break;
+                    LOG_ERROR("GPU %d: %s", device, pe_last_error(e)); global.failed = global.quit = true; break;
                 }
             }
             frames[i].pinned.reset();   // back to the pool: the forward has consumed the frame
@@ -953,5 +954,5 @@ int main(int argc, char** argv) {
     g_pinned.clear();
     pe_video_close(global.video);
     pe_camera_close(global.camera);
-    return global.quit ? 1 : 0;
+    return global.failed ? 1 : 0;   // ESC ends the run with 0 like the reference (rtpose.cpp:1564, 1775-1779)
 }
