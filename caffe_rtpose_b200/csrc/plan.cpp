@@ -50,6 +50,7 @@ const char* model_part_name(int model, int idx) {
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static const int kMaxChannels = 16384;   // a user's prototxt is untrusted input: channel counts stay far inside int arithmetic (the pose nets use <= 512)
 
 // ---------------------------------------------------------------------------------------------
 // Execution plan from a network definition (prototxt or built-in).  What Net::Init does for the reference
@@ -111,6 +112,7 @@ int build_plan_from_net(const NetDef& net, int kp_input, int cpad, NetPlan& p, s
             if (l.num_output < 1 || l.kernel < 1 || l.kernel > 7 || l.kernel % 2 == 0 || l.pad != l.kernel / 2 || l.stride != 1)
                 return fail("layer " + l.name + ": only stride-1 'same' convolutions with odd kernel <= 7 are supported (kernel " +
                             std::to_string(l.kernel) + ", pad " + std::to_string(l.pad) + ", stride " + std::to_string(l.stride) + ")");
+            if (l.num_output > kMaxChannels) return fail("layer " + l.name + ": num_output " + std::to_string(l.num_output) + " is larger than this engine plans for (" + std::to_string(kMaxChannels) + ")");
             if (producer.count(top)) return fail("layer " + l.name + ": top " + top + " is produced twice");
             producer[top] = i; channels[top] = l.num_output; level[top] = lv;
         } else if (l.type == "ReLU") {
@@ -127,6 +129,7 @@ int build_plan_from_net(const NetDef& net, int kp_input, int cpad, NetPlan& p, s
             for (const std::string& b : l.bottoms) {
                 c += channels[b];
                 if (level[b] != lv) return fail("layer " + l.name + ": bottoms of different resolution");
+                if (c > kMaxChannels) return fail("layer " + l.name + ": more than " + std::to_string(kMaxChannels) + " channels");
             }
             producer[top] = i; channels[top] = c; level[top] = lv;
         } else if (l.type == "ImResize" || l.type == "Nms") {

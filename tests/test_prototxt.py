@@ -102,11 +102,30 @@ def test_prototxt_syntax_and_errors(tmp_path):
                      (text.replace('type: "ReLU"', 'type: "Sigmoid"', 1), "Sigmoid"),
                      (text.replace("num_output: 64", "num_output: x64", 1), "integer"),
                      (text[:text.index("layer {", len(text) // 2) + 9], "unbalanced|end of file"),
+                     (text.replace("num_output: 64", "num_output: 2147483647", 1), "num_output 2147483647 is larger"),   # found by the fuzzer below
                      (text.replace('bottom: "conv1_1"', 'bottom: "nope"', 1), "unknown bottom")):
         with pytest.raises(engine.PoseEngineError, match=msg):
             plan_of(bad)
     with pytest.raises(engine.PoseEngineError, match="cannot open"):
         engine.plan_describe(prototxt=str(tmp_path / "missing.prototxt"))
+
+
+def test_prototxt_reader_survives_corrupt_files(tmp_path):
+    """--caffeproto is a user file: the reader and the plan builder under ASAN + UBSan on mutated deploy files (bytes, cut-offs, dropped
+    and repeated blocks, extreme numbers, renamed blobs) - every outcome is a plan or an error message, never a crash."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "caffe_rtpose_b200", "csrc")
+    files = [spec_prototxt(n, tmp_path)[1] for n in ("coco", "mpi_2")]
+    exe = str(tmp_path / "fuzz_prototxt")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-I", os.path.join(root, "include"),
+                        "-I", src, "-I", "/usr/local/cuda/include", os.path.join(root, "tests", "fuzz", "fuzz_prototxt.cpp"), os.path.join(src, "prototxt.cpp"),
+                        os.path.join(src, "plan.cpp"), "-o", exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, "1200"] + files, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
+    parsed, planned, rejected = [int(v) for v in r.stdout.split()[1::2]]
+    assert parsed > 200 and planned > 100 and rejected > 200   # the mutations are neither all harmless nor all fatal
 
 
 @pytest.mark.gpu
