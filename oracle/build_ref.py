@@ -8,6 +8,10 @@ the resulting shared objects are kept under oracle/_ref/ (git-ignored, travels t
   libref_host.so  g++   src/rtpose/modelDescriptor{,Factory}.cpp (unmodified)
                         examples/rtpose/rtpose.cpp:144-152, 549-751, 808-1076 (ColumnCompare,
                         connectLimbs, connectLimbsCOCO)  src/caffe/util/im2col.cpp:8-56 (im2col_cpu)
+                        second translation unit: rtpose.cpp:239-269 (process_and_pad_image), :474-479 (display scale),
+                        :509-511 (per-scale target size), :1395-1414 (JSON writer);
+                        src/caffe/layers/pooling_layer.cpp:90-105, 151-186 (pooled size, MAX loop),
+                        src/caffe/layers/relu_layer.cpp:15-18
   libref_cpm.so   nvcc  src/caffe/cpm/layers/imresize_layer.cu:8-18,97-155
                         src/caffe/cpm/layers/nms_layer.cu:13-113
                         (sm_100a; default -fmad, as the reference Makefile:410 passes no fmad flag)
@@ -90,6 +94,100 @@ extern "C" void ref_im2col(const float* im, int channels, int height, int width,
 '''
 
 
+# Second translation unit: small pieces of the per-frame host path and of the Caffe CPU layers the oracle restates, each a line
+# range of the reference spliced into a function body of ours whose locals carry the names the reference code uses.
+HOST2_PRELUDE = r"""
+// TEST INFRASTRUCTURE ONLY (oracle/_ref build): generated by oracle/build_ref.py, never committed.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+using std::min; using std::max; using std::vector;
+struct RefNullStream2 { template <typename T> RefNullStream2& operator<<(const T&) { return *this; } };
+#define REF_CHECK_OP(a, op, b) if (!((a)op(b))) { fprintf(stderr, "ref CHECK failed: %s %s %s\n", #a, #op, #b); abort(); } else RefNullStream2()
+#define CHECK_GE(a, b) REF_CHECK_OP(a, >=, b)
+#define CHECK_LE(a, b) REF_CHECK_OP(a, <=, b)
+#define CHECK_LT(a, b) REF_CHECK_OP(a, <, b)
+namespace cv { struct Mat { int cols, rows; unsigned char* data; }; }   // the three members process_and_pad_image reads
+struct RefBlob {                                                        // Blob::num / offset(n, c) for an N x C x H x W blob
+    int n_, c_, h_, w_;
+    int num() const { return n_; }
+    int offset(int n, int c) const { return (n * c_ + c) * h_ * w_; }
+};
+"""
+
+HOST2_BODY_A = r"""
+extern "C" void ref_process_and_pad_image(float* target, unsigned char* data, int ow, int oh, int tw, int th, int normalize) {
+    cv::Mat m{ow, oh, data};
+    process_and_pad_image(target, m, tw, th, normalize != 0);
+}
+extern "C" double ref_display_scale(int cols, int rows, int DISPLAY_RESOLUTION_WIDTH, int DISPLAY_RESOLUTION_HEIGHT) {
+    struct { int cols, rows; } image_uchar_orig = {cols, rows};
+"""
+HOST2_BODY_B = r"""
+    return scale;
+}
+extern "C" void ref_scale_target(int NET_RESOLUTION_WIDTH, int NET_RESOLUTION_HEIGHT, float START_SCALE, float SCALE_GAP, int i, int* tw, int* th) {
+    int target_width, target_height;
+"""
+HOST2_BODY_C = r"""
+    *tw = target_width; *th = target_height;
+}
+extern "C" void ref_write_json(const char* fname, const float* joints, int numPeople, int num_parts, double frame_scale) {
+    struct { const float* joints; int numPeople; double scale; } frame = {joints, numPeople, frame_scale};
+    double scale = 1.0/frame.scale;   // rtpose.cpp:1384
+    {
+"""
+HOST2_BODY_D = r"""
+    }
+}
+// PoolingLayer<float>::Reshape (pooled size) + Forward_cpu, MAX case
+extern "C" int ref_maxpool(const float* bottom_data, int num, int channels_, int height_, int width_, int kernel, int stride, int pad,
+                           float* top_data, int* pooled_hw) {
+    typedef float Dtype;
+    const int kernel_h_ = kernel, kernel_w_ = kernel, stride_h_ = stride, stride_w_ = stride, pad_h_ = pad, pad_w_ = pad;
+    int pooled_height_, pooled_width_;
+"""
+HOST2_BODY_E = r"""
+    pooled_hw[0] = pooled_height_; pooled_hw[1] = pooled_width_;
+    if (!top_data) return 0;
+    RefBlob b{num, channels_, height_, width_}, t{num, channels_, pooled_height_, pooled_width_};
+    vector<RefBlob*> bottom{&b}, top{&t};
+    const int top_count = num * channels_ * pooled_height_ * pooled_width_;
+    const bool use_top_mask = false;
+    float* top_mask = NULL;
+    vector<int> mask_store(top_count, -1);                       // caffe_set(top_count, -1, mask)            :147
+    int* mask = mask_store.data();
+    for (int i = 0; i < top_count; i++) top_data[i] = -FLT_MAX;  // caffe_set(top_count, Dtype(-FLT_MAX), ..) :149
+"""
+HOST2_BODY_F = r"""
+    return 0;
+}
+extern "C" void ref_relu(const float* bottom_data, float* top_data, int count, float negative_slope) {
+    typedef float Dtype;
+"""
+HOST2_BODY_G = r"""
+}
+"""
+
+
+def host2_tu():
+    return (HOST2_PRELUDE
+            + lines("examples/rtpose/rtpose.cpp", [(239, 269)])
+            + HOST2_BODY_A + lines("examples/rtpose/rtpose.cpp", [(474, 479)])
+            + HOST2_BODY_B + lines("examples/rtpose/rtpose.cpp", [(509, 511)])
+            + HOST2_BODY_C + lines("examples/rtpose/rtpose.cpp", [(1395, 1414)])
+            + HOST2_BODY_D + lines("src/caffe/layers/pooling_layer.cpp", [(90, 105)])
+            + HOST2_BODY_E + lines("src/caffe/layers/pooling_layer.cpp", [(151, 186)])
+            + HOST2_BODY_F + lines("src/caffe/layers/relu_layer.cpp", [(15, 18)])
+            + HOST2_BODY_G)
+
+
 def build_host(tmp):
     tu = ('#include "%s"\n' % os.path.join(HERE, "ref_host_prelude.h")
           + lines("examples/rtpose/rtpose.cpp", [(144, 152), (549, 751), (808, 1076)])
@@ -97,8 +195,10 @@ def build_host(tmp):
           + HOST_WRAPPER)
     src = os.path.join(tmp, "ref_host_tu.cpp")
     open(src, "w").write(tu)
+    src2 = os.path.join(tmp, "ref_host_tu2.cpp")
+    open(src2, "w").write(host2_tu())
     out = os.path.join(OUT, "libref_host.so")
-    cmd = ["g++", "-O3", "-std=c++11", "-fPIC", "-shared", "-w", "-I" + os.path.join(REF, "include"), src,
+    cmd = ["g++", "-O3", "-std=c++11", "-fPIC", "-shared", "-w", "-I" + os.path.join(REF, "include"), src, src2,
            os.path.join(REF, "src/rtpose/modelDescriptor.cpp"),
            os.path.join(REF, "src/rtpose/modelDescriptorFactory.cpp"), "-o", out]
     subprocess.check_call(cmd)

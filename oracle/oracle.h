@@ -17,10 +17,13 @@
  *                          by tests/golden fixtures generated with cv2 4.13)
  *   JSON                   rtpose.cpp:1383-1416
  *
- * Parity pinning: connectLimbs*, im2col and the model descriptors are checked bit-for-bit against the
- * reference's own code compiled from /root/reference (oracle/_ref/libref_host.so); ImResize and NMS are
- * checked bit-for-bit against the reference's own CUDA kernels (oracle/_ref/libref_cpm.so) on the GPU
- * box; conv/pool use the upstream Caffe known-answer vectors.
+ * Parity pinning: connectLimbs*, im2col, the model descriptors, process_and_pad_image + the scale
+ * arithmetic of the preprocessing (rtpose.cpp:239-269, 474-479, 509-511), the JSON block (:1395-1414),
+ * MAX pooling and ReLU (pooling_layer.cpp:90-105,151-186, relu_layer.cpp:15-18) are checked bit-for-bit
+ * against the reference's own code compiled from /root/reference (oracle/_ref/libref_host.so, recipe:
+ * oracle/build_ref.py); ImResize and NMS are checked bit-for-bit against the reference's own CUDA
+ * kernels (oracle/_ref/libref_cpm.so) on the GPU box; the sgemm of the convolutions is a third-party BLAS
+ * in the reference: upstream Caffe's naive-loop bar of 1e-4.
  */
 #ifndef RTPOSE_ORACLE_H
 #define RTPOSE_ORACLE_H

@@ -354,6 +354,14 @@ def ref_host():
         R.ref_im2col.argtypes = [_f32p] + [C.c_int] * 9 + [_f32p]
         R.ref_model_descriptor.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _i32p, _i32p, C.c_char_p,
                                            C.c_int]
+        if hasattr(R, "ref_maxpool"):   # second translation unit of build_ref.py (absent from libraries built before it existed)
+            R.ref_process_and_pad_image.argtypes = [_f32p, _u8p] + [C.c_int] * 5
+            R.ref_display_scale.restype = C.c_double
+            R.ref_display_scale.argtypes = [C.c_int] * 4
+            R.ref_scale_target.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+            R.ref_write_json.argtypes = [C.c_char_p, _f32p, C.c_int, C.c_int, C.c_double]
+            R.ref_maxpool.argtypes = [_f32p] + [C.c_int] * 7 + [C.c_void_p, _i32p]
+            R.ref_relu.argtypes = [_f32p, _f32p, C.c_int, C.c_float]
         _ref_host = R
     return _ref_host
 

@@ -124,6 +124,83 @@ def test_relu():
     assert np.array_equal(x, np.array([0, 0, 2, 0], np.float32))
 
 
+def _ref_host2():
+    R = orc.ref_host()
+    if R is None or not hasattr(R, "ref_maxpool"):
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    return R
+
+
+def test_pool_and_relu_vs_reference_code():
+    """PoolingLayer::Reshape + Forward_cpu MAX (pooling_layer.cpp:90-105, 151-186) and ReLULayer::Forward_cpu (relu_layer.cpp:15-18)
+    compiled from the reference: sizes (ceil mode, clipped last window), first-maximum semantics, -0.0 / NaN-free inputs."""
+    R = _ref_host2()
+    rng = np.random.default_rng(3)
+    for (n, c, h, w, k, s, pad) in [(2, 3, 8, 10, 2, 2, 0), (1, 4, 7, 9, 2, 2, 0), (1, 2, 46, 82, 2, 2, 0), (1, 2, 9, 9, 3, 2, 1), (2, 1, 5, 5, 3, 2, 0)]:
+        x = rng.standard_normal((n, c, h, w)).astype(np.float32)
+        x[0, 0, :2, :2] = 0.5          # ties inside one window
+        got = orc.maxpool(x, k, s, pad)
+        hw = np.zeros(2, np.int32)
+        R.ref_maxpool(x, n, c, h, w, k, s, pad, None, hw)
+        assert got.shape == (n, c, hw[0], hw[1])
+        ref = np.empty_like(got)
+        R.ref_maxpool(x, n, c, h, w, k, s, pad, ref.ctypes.data, hw)
+        assert np.array_equal(got, ref)
+    x = rng.standard_normal(4099).astype(np.float32)
+    x[:3] = (0.0, -0.0, -1e-38)
+    ref = np.empty_like(x)
+    R.ref_relu(x, ref, x.size, 0.0)
+    y = x.copy()
+    orc.lib().orc_relu(y, y.size)
+    assert np.array_equal(y, ref)
+
+
+def test_preprocess_vs_reference_code():
+    """process_and_pad_image (rtpose.cpp:239-269), the display scale (:474-479) and the per-scale target size (:509-511) compiled from
+    the reference; the INTER_AREA resize between them is OpenCV's (pinned to cv2 by the fixtures above)."""
+    R = _ref_host2()
+    import ctypes as C
+    for (nw, nh, start, gap, S) in [(656, 368, 1.0, 0.3, 3), (656, 368, 1.0, 0.15, 4), (496, 368, 1.0, 0.3, 2), (160, 96, 1.0, 0.3, 3), (992, 736, 1.0, 0.15, 4),
+                                    (656, 368, 0.9, 0.05, 6)]:
+        for i in range(S):
+            tw, th = C.c_int(), C.c_int()
+            R.ref_scale_target(nw, nh, start, gap, i, C.byref(tw), C.byref(th))
+            assert orc.scale_target(nw, nh, start, gap, i) == (tw.value, th.value)
+    for (cols, rows, dw, dh) in [(1280, 720, 1280, 720), (640, 480, 1280, 720), (1920, 1080, 1280, 720), (333, 777, 656, 368), (1000, 10, 64, 64)]:
+        assert orc.lib().orc_display_scale(cols, rows, dw, dh) == R.ref_display_scale(cols, rows, dw, dh)
+    img = synth.make_frame(2, 90, 160)
+    net_h, net_w, S, start, gap = 48, 96, 3, 1.0, 0.3
+    out = orc.preprocess(img, net_h, net_w, S, start, gap)
+    for i in range(S):
+        tw, th = orc.scale_target(net_w, net_h, start, gap, i)
+        small = orc.resize_area(img, th, tw)
+        ref = np.full((3, net_h, net_w), 7.0, np.float32)
+        R.ref_process_and_pad_image(ref, small, tw, th, net_w, net_h, 1)
+        assert np.array_equal(out[i], ref)
+    # normalize = 0: the float canvas of the renderers (rtpose.cpp:499)
+    ref = np.empty((3, 90, 160), np.float32)
+    R.ref_process_and_pad_image(ref, img, 160, 90, 160, 90, 0)
+    assert np.array_equal(orc.canvas_from_u8(img), ref)
+
+
+def test_json_writer_vs_reference_code(tmp_path):
+    """The JSON block of displayFrame (rtpose.cpp:1395-1414, `fs << double` formatting) compiled from the reference, byte for byte -
+    for the oracle AND for the product's pe_write_json."""
+    R = _ref_host2()
+    from caffe_rtpose_b200 import engine
+    rng = np.random.default_rng(5)
+    for people, parts, scale in [(0, 18, 1.0), (1, 18, 0.5), (3, 15, 1.0), (7, 18, 0.3333333), (2, 18, 2.25)]:
+        j = (rng.random((people, parts, 3)) * np.array([1280, 720, 1])).astype(np.float32)
+        if people:
+            j[0, 1] = 0.0                                    # a missing part
+            j[0, 2] = (1e-5, 123456.7, 1.0)                  # exponent and 6-digit rounding cases of operator<<(double/float)
+        path = str(tmp_path / "ref.json")
+        R.ref_write_json(path.encode(), j if j.size else np.zeros(1, np.float32), people, parts, scale)
+        want = open(path).read()
+        assert orc.json_text(j, parts, scale) == want
+        assert engine.write_json(j, parts, scale) == want
+
+
 def test_inter_area_vs_cv2_fixture(golden_dir):
     d = np.load(os.path.join(golden_dir, "area_cv2.npz"))
     n = len([k for k in d.files if k.startswith("src")])
