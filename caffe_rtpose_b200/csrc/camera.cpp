@@ -4,8 +4,9 @@
 // kernel interface (<linux/videodev2.h>, memory-mapped streaming I/O): /dev/video<index>, Motion-JPEG preferred (frames go
 // through pe_decode_jpeg, Annex K tables when the camera leaves DHT out), else packed YUYV 4:2:2 converted with the fixed-point
 // BT.601 arithmetic of cv::cvtColor(COLOR_YUV2BGR_YUYV) - what OpenCV's V4L2 back end applies (pinned to cv2 in tests/test_abi.py
-// through pe_yuyv_to_bgr).  The build container and the GPU boxes have no capture device: the conversion and the error paths are
-// tested, the streaming ioctl sequence is not exercised there.  Host code, no GPU.
+// through pe_yuyv_to_bgr).  The build container and the GPU boxes have no capture device: the streaming sequence below runs in
+// tests/test_camera_device.py against tests/stub/fake_v4l2.c, an LD_PRELOAD stand-in that enforces a driver's state machine; it has
+// not met real hardware.  Host code, no GPU.
 #include <errno.h>
 #include <fcntl.h>
 #include <poll.h>
@@ -159,11 +160,12 @@ extern "C" int pe_camera_grab(pe_camera* c, uint8_t* bgr, long long cap, int tim
         int rc = PE_ERR_IO;
         if (b.index < c->bufs.size() && !(b.flags & V4L2_BUF_FLAG_ERROR)) {
             const uint8_t* src = (const uint8_t*)c->bufs[b.index].p;
+            const long long used = b.bytesused <= c->bufs[b.index].len ? (long long)b.bytesused : (long long)c->bufs[b.index].len;   // never past the mapping
             if (c->pixfmt == V4L2_PIX_FMT_MJPEG) {
                 int jw = 0, jh = 0;
-                if (pe_decode_jpeg(src, (long long)b.bytesused, &jw, &jh, nullptr, 0) == 0 && jw == c->w && jh == c->h &&
-                    pe_decode_jpeg(src, (long long)b.bytesused, &jw, &jh, bgr, cap) == 0) rc = PE_OK;
-            } else if ((long long)b.bytesused >= c->stride * c->h) {
+                if (pe_decode_jpeg(src, used, &jw, &jh, nullptr, 0) == 0 && jw == c->w && jh == c->h &&
+                    pe_decode_jpeg(src, used, &jw, &jh, bgr, cap) == 0) rc = PE_OK;
+            } else if (used >= c->stride * c->h) {
                 rc = pe_yuyv_to_bgr(src, c->w, c->h, c->stride, bgr);
             }
         }
