@@ -130,7 +130,7 @@ def test_runtime_keys_reach_every_engine(exe, tmp_path):
     """handleKey (rtpose.cpp:1551-1671): '=' raises the NMS threshold by 0.005, ']' connect_inter_threshold, '}' the min-above count,
     \"'\" min_subset_cnt, '+' min_subset_score; the workers apply them before their next forward (:1145)."""
     log = tmp_path / "stub.log"
-    r = run(exe, ["--synthetic", "400", "--resolution", "32x24", "--net_resolution", "32x24", "--batch", "1", "--num_gpu", "2", "--engines_per_gpu", "1",
+    r = run(exe, ["--synthetic", "600", "--resolution", "32x24", "--net_resolution", "32x24", "--batch", "1", "--num_gpu", "2", "--engines_per_gpu", "1",
                   "--no_frame_drops", "--keys_from_stdin"], env={"STUB_LOG": str(log), "STUB_FORWARD_MS": "5"}, stdin="==]}'+\n")
     assert r.returncode == 0, r.stderr[-3000:]
     assert "nms_threshold: 0.06" in r.stderr
@@ -202,7 +202,7 @@ def test_video_loops_until_quit_and_quit_is_not_an_error(exe, tmp_path):
     base = ["--model", "COCO", "--caffeproto", "/nonexistent.prototxt", "--random_init", "he", "--video", path, "--resolution", "64x48",
             "--net_resolution", "32x24"]
     p = subprocess.Popen([exe] + base + ["--keys_from_stdin"], stdin=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
-    time.sleep(1.0)                       # 8 frames at 100 fps: several loops
+    time.sleep(1.5)                       # 8 frames at 100 fps: several loops
     _, err = p.communicate("Q", timeout=60)
     assert p.returncode == 0, err[-3000:]
     assert "ThreadSanitizer" not in err, err[-6000:]
