@@ -9,7 +9,8 @@ the resulting shared objects are kept under oracle/_ref/ (git-ignored, travels t
                         examples/rtpose/rtpose.cpp:144-152, 549-751, 808-1076 (ColumnCompare,
                         connectLimbs, connectLimbsCOCO)  src/caffe/util/im2col.cpp:8-56 (im2col_cpu)
                         second translation unit: rtpose.cpp:239-269 (process_and_pad_image), :474-479 (display scale),
-                        :509-511 (per-scale target size), :1395-1414 (JSON writer);
+                        :509-511 (per-scale target size), :1395-1414 (JSON writer), :271-300 (render() dispatch,
+                        launchers replaced by recording stand-ins);
                         src/caffe/layers/pooling_layer.cpp:90-105, 151-186 (pooled size, MAX loop),
                         src/caffe/layers/relu_layer.cpp:15-18
   libref_cpm.so   nvcc  src/caffe/cpm/layers/imresize_layer.cu:8-18,97-155
@@ -173,6 +174,35 @@ extern "C" void ref_relu(const float* bottom_data, float* top_data, int count, f
 """
 HOST2_BODY_G = r"""
 }
+// render() (rtpose.cpp:271-300): which of the three launchers runs for a --part_to_show value, and with which arguments.  The launchers
+// are recording stand-ins with the signatures of include/rtpose/renderFunctions.h; the dispatch itself is the reference's text.
+struct RefMD2 { int parts; int get_number_parts() const { return parts; } };
+struct RefNetCopy2 { float* canvas; float* joints; std::vector<int> num_people; RefMD2* up_model_descriptor; };
+static RefMD2 g_md2;
+static std::vector<RefNetCopy2> net_copies(1);
+static struct { int part_to_show; struct { bool is_googly_eyes; } uistate; } global;
+static int DISPLAY_RESOLUTION_WIDTH = 1280, DISPLAY_RESOLUTION_HEIGHT = 720, NET_RESOLUTION_WIDTH = 656, NET_RESOLUTION_HEIGHT = 368;
+const int BOX_SIZE = 368;
+static double get_wall_time() { return 0; }
+#define VLOG(x) RefNullStream2()
+static int g_rec[4];
+static void render_mpi_parts(float*, int, int, int, int, float*, int, float*, float*, std::vector<int>, int part) {
+    g_rec[0] = 0; g_rec[1] = part; g_rec[2] = 0; g_rec[3]++; }
+static void render_coco_parts(float*, int, int, int, int, float*, int, float*, float*, std::vector<int>, int part, bool googly_eyes) {
+    g_rec[0] = 1; g_rec[1] = part; g_rec[2] = googly_eyes; g_rec[3]++; }
+static void render_coco_aff(float*, int, int, int, int, float*, int, float*, float*, std::vector<int>, int part, int num_parts_accum) {
+    g_rec[0] = 2; g_rec[1] = part; g_rec[2] = num_parts_accum; g_rec[3]++; }
+"""
+HOST2_BODY_H = r"""
+extern "C" int ref_render_dispatch(int num_parts, int part_to_show, int googly_eyes, int* out3) {
+    g_md2.parts = num_parts;
+    net_copies[0].up_model_descriptor = &g_md2;
+    global.part_to_show = part_to_show; global.uistate.is_googly_eyes = googly_eyes != 0;
+    g_rec[3] = 0;
+    render(0, NULL);
+    for (int i = 0; i < 3; i++) out3[i] = g_rec[i];
+    return g_rec[3];   // launches made (0 for a model that is neither 15 nor 18 parts)
+}
 """
 
 
@@ -185,7 +215,8 @@ def host2_tu():
             + HOST2_BODY_D + lines("src/caffe/layers/pooling_layer.cpp", [(90, 105)])
             + HOST2_BODY_E + lines("src/caffe/layers/pooling_layer.cpp", [(151, 186)])
             + HOST2_BODY_F + lines("src/caffe/layers/relu_layer.cpp", [(15, 18)])
-            + HOST2_BODY_G)
+            + HOST2_BODY_G + lines("examples/rtpose/rtpose.cpp", [(271, 300)])
+            + HOST2_BODY_H)
 
 
 def build_host(tmp):

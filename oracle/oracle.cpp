@@ -1248,29 +1248,40 @@ extern "C" void orc_canvas_to_u8(const float* canvas, int h, int w, uint8_t* bgr
             bgr[(size_t)i * 3 + c] = (unsigned char)value;
         }
 }
-// render() (rtpose.cpp:271-300) + launchers (renderFunctions.cu:331-389, 978-1080).  heatmaps: the full-resolution
+// render() (rtpose.cpp:271-300): the launcher a --part_to_show value selects and the two arguments that depend on it.
+// out3 = {launcher (0 render_mpi_parts, 1 render_coco_parts, 2 render_coco_aff), its `part` argument, googly_eyes / num_parts_accum}.
+// Pinned against the reference's own text compiled with recording launchers (oracle/_ref, tests/test_oracle.py).
+extern "C" int orc_render_dispatch(int model, int part_to_show, int googly_eyes, int* out3) {
+    const int NP = model_desc(model).num_parts;
+    if (NP == 15) { out3[0] = 0; out3[1] = part_to_show; out3[2] = 0; return 0; }
+    if (part_to_show - 1 <= NP) { out3[0] = 1; out3[1] = part_to_show; out3[2] = googly_eyes != 0; return 0; }
+    int aff_part = ((part_to_show - 1) - NP - 1) * 2, accum = 1;
+    if (aff_part == 0) accum = 19; else aff_part -= 2;
+    aff_part += 1 + NP;
+    out3[0] = 2; out3[1] = aff_part; out3[2] = accum;
+    return 0;
+}
+// render() + the launchers (renderFunctions.cu:331-389, 978-1080).  heatmaps: the full-resolution
 // resized_map (num_maps x h_net x w_net), only read when part_to_show > 0.  Returns 0, or -1 for a bad part_to_show.
 extern "C" int orc_render(int model, float* canvas, int w_canvas, int h_canvas, int w_net, int h_net, const float* heatmaps,
                           const float* poses, int num_people, int part_to_show, int googly_eyes) {
     const ModelDesc& md = model_desc(model);
-    const int NP = md.num_parts;
+    const int NP = md.num_parts, num_maps = NP + 1 + 2 * md.num_limbs;
     if (part_to_show < 0) return -1;
-    if (NP == 15) {
-        if (part_to_show == 0) { if (num_people != 0) skeleton_mpi(canvas, w_canvas, h_canvas, poses, num_people); }
-        else { if (part_to_show - 1 >= NP + 1 + 2 * md.num_limbs) return -1; heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 0, part_to_show - 1, 0); }
-        return 0;
+    int d[3];
+    orc_render_dispatch(model, part_to_show, googly_eyes, d);
+    const int part = d[1];
+    if (d[0] == 0) {          // render_mpi_parts (renderFunctions.cu:331-389)
+        if (part == 0) { if (num_people != 0) skeleton_mpi(canvas, w_canvas, h_canvas, poses, num_people); }
+        else { if (part - 1 >= num_maps) return -1; heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 0, part - 1, 0); }
+    } else if (d[0] == 1) {   // render_coco_parts (:978-1036)
+        if (part == 0) { if (num_people != 0) skeleton_coco(canvas, w_canvas, h_canvas, poses, num_people, d[2] != 0); }
+        else if (part - 1 == NP) heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 2, 0, 0);
+        else heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 1, part - 1, 0);
+    } else {                  // render_coco_aff (:1038-1080)
+        if (part + 2 * d[2] > num_maps) return -1;
+        heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 3, part, d[2]);
     }
-    if (part_to_show - 1 <= NP) {
-        if (part_to_show == 0) { if (num_people != 0) skeleton_coco(canvas, w_canvas, h_canvas, poses, num_people, googly_eyes != 0); }
-        else if (part_to_show - 1 == NP) heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 2, 0, 0);
-        else heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 1, part_to_show - 1, 0);
-        return 0;
-    }
-    int aff_part = ((part_to_show - 1) - NP - 1) * 2, accum = 1;
-    if (aff_part == 0) accum = 19; else aff_part -= 2;
-    aff_part += 1 + NP;
-    if (aff_part + 2 * accum > NP + 1 + 2 * md.num_limbs) return -1;
-    heat_view(canvas, w_canvas, h_canvas, w_net, h_net, heatmaps, 3, aff_part, accum);
     return 0;
 }
 

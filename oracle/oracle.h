@@ -121,6 +121,7 @@ int orc_preprocess(const uint8_t* disp, int disp_h, int disp_w, int net_h, int n
  * planar BGR in/out; heatmaps: full-resolution resized_map (num_maps x h_net x w_net), read when part_to_show > 0. */
 void orc_canvas_from_u8(const uint8_t* bgr, int h, int w, float* canvas);
 void orc_canvas_to_u8(const float* canvas, int h, int w, uint8_t* bgr);
+int orc_render_dispatch(int model, int part_to_show, int googly_eyes, int* out3); /* {launcher, part, googly / num_parts_accum} */
 int orc_render(int model, float* canvas, int w_canvas, int h_canvas, int w_net, int h_net, const float* heatmaps,
                const float* poses, int num_people, int part_to_show, int googly_eyes);
 

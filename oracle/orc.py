@@ -111,6 +111,7 @@ def lib():
     L.orc_canvas_from_u8.argtypes = [_u8p, C.c_int, C.c_int, _f32p]
     L.orc_canvas_to_u8.argtypes = [_f32p, C.c_int, C.c_int, _u8p]
     L.orc_render.argtypes = [C.c_int, _f32p] + [C.c_int] * 4 + [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int]
+    L.orc_render_dispatch.argtypes = [C.c_int, C.c_int, C.c_int, _i32p]
     L.orc_process_frame.argtypes = [C.c_void_p, C.c_int, _u8p] + [C.c_int] * 5 + [C.c_double, C.c_double, C.c_float,
                                                                                 C.POINTER(ConnectParams), _f32p,
                                                                                 C.c_void_p, C.c_void_p]
@@ -362,6 +363,8 @@ def ref_host():
             R.ref_write_json.argtypes = [C.c_char_p, _f32p, C.c_int, C.c_int, C.c_double]
             R.ref_maxpool.argtypes = [_f32p] + [C.c_int] * 7 + [C.c_void_p, _i32p]
             R.ref_relu.argtypes = [_f32p, _f32p, C.c_int, C.c_float]
+        if hasattr(R, "ref_render_dispatch"):
+            R.ref_render_dispatch.argtypes = [C.c_int, C.c_int, C.c_int, _i32p]
         _ref_host = R
     return _ref_host
 

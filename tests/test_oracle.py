@@ -201,6 +201,21 @@ def test_json_writer_vs_reference_code(tmp_path):
         assert engine.write_json(j, parts, scale) == want
 
 
+def test_render_dispatch_vs_reference_code():
+    """render() (rtpose.cpp:271-300) compiled from the reference with recording launchers: for every --part_to_show value of both
+    models (and past the last view) the oracle picks the same launcher with the same `part`, googly / num_parts_accum arguments."""
+    R = _ref_host2()
+    if not hasattr(R, "ref_render_dispatch"):
+        pytest.skip("oracle/_ref predates the render() splice")
+    for model, parts in ((orc.MPI_15, 15), (orc.COCO_18, 18)):
+        for p2s in range(0, 48):
+            for googly in (0, 1):
+                ref, got = np.zeros(3, np.int32), np.zeros(3, np.int32)
+                assert R.ref_render_dispatch(parts, p2s, googly, ref) == 1
+                orc.lib().orc_render_dispatch(model, p2s, googly, got)
+                assert list(got) == list(ref), (model, p2s, googly)
+
+
 def test_inter_area_vs_cv2_fixture(golden_dir):
     d = np.load(os.path.join(golden_dir, "area_cv2.npz"))
     n = len([k for k in d.files if k.startswith("src")])
