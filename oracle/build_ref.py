@@ -8,6 +8,8 @@ the resulting shared objects are kept under oracle/_ref/ (git-ignored, travels t
   libref_host.so  g++   src/rtpose/modelDescriptor{,Factory}.cpp (unmodified)
                         examples/rtpose/rtpose.cpp:144-152, 549-751, 808-1076 (ColumnCompare,
                         connectLimbs, connectLimbsCOCO)  src/caffe/util/im2col.cpp:8-56 (im2col_cpu)
+                        conv_layer.cpp:27-39, base_conv_layer.cpp:259-271, 277-279, base_conv_layer.hpp:100-105,
+                        math_functions.cpp:12-21 (ConvolutionLayer::Forward_cpu down to the cblas_sgemm call, BLAS loaded at run time)
                         second translation unit: rtpose.cpp:239-269 (process_and_pad_image), :474-479 (display scale),
                         :509-511 (per-scale target size), :1395-1414 (JSON writer), :271-300 (render() dispatch,
                         launchers replaced by recording stand-ins);
@@ -218,12 +220,109 @@ def host2_tu():
             + HOST2_BODY_G + lines("examples/rtpose/rtpose.cpp", [(271, 300)])
             + HOST2_BODY_H)
 
+# Convolution forward of the reference (ConvolutionLayer::Forward_cpu -> forward_cpu_gemm / forward_cpu_bias -> caffe_cpu_gemm ->
+# cblas_sgemm) as members of a stand-in class that carries the members those bodies read.  The BLAS is third-party in the reference
+# (Makefile:369-386); cblas_sgemm is forwarded to whatever library ref_load_blas() opens - the tests hand it the same OpenBLAS the
+# oracle uses, so the two must then agree bit for bit.
+CONV_A = r"""
+enum CBLAS_ORDER { CblasRowMajor = 101, CblasColMajor = 102 };
+enum CBLAS_TRANSPOSE { CblasNoTrans = 111, CblasTrans = 112, CblasConjTrans = 113 };
+typedef void (*ref_sgemm_t)(int, int, int, int, int, int, float, const float*, int, const float*, int, float, float*, int);
+static ref_sgemm_t g_ref_sgemm = 0;
+static inline void cblas_sgemm(CBLAS_ORDER o, CBLAS_TRANSPOSE ta, CBLAS_TRANSPOSE tb, int M, int N, int K, float alpha, const float* A, int lda,
+                               const float* B, int ldb, float beta, float* C, int ldc) {
+    g_ref_sgemm(o, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+template <typename Dtype>
+void caffe_cpu_gemm(const CBLAS_TRANSPOSE TransA, const CBLAS_TRANSPOSE TransB, const int M, const int N, const int K, const Dtype alpha,
+                    const Dtype* A, const Dtype* B, const Dtype beta, Dtype* C);
+"""
+CONV_B = r"""
+template <typename T> struct RefBuf {   // the cpu_data() / mutable_cpu_data() face of Blob / SyncedMemory
+    std::vector<T> v;
+    T* mutable_cpu_data() { return v.data(); }
+    const T* cpu_data() const { return v.data(); }
+};
+template <typename T> struct RefPtr {
+    T* p;
+    const T* cpu_data() const { return p; }
+    T* mutable_cpu_data() { return p; }
+};
+template <typename Dtype>
+struct BaseConvolutionLayer {
+    bool is_1x1_, bias_term_, force_nd_im2col_;
+    int num_spatial_axes_, group_, conv_out_channels_, conv_in_channels_, conv_out_spatial_dim_, kernel_dim_, weight_offset_, col_offset_,
+        output_offset_, num_output_, out_spatial_dim_, num_, bottom_dim_, top_dim_;
+    RefBuf<Dtype> col_buffer_, bias_multiplier_;
+    RefBuf<int> conv_input_shape_, kernel_shape_, pad_, stride_, dilation_;
+    std::vector<RefPtr<Dtype>*> blobs_;
+    inline void conv_im2col_cpu(const Dtype* data, Dtype* col_buff) {   // base_conv_layer.hpp:98-105, the 2-D branch
+"""
+CONV_C = r"""
+    }
+    void forward_cpu_gemm(const Dtype* input, const Dtype* weights, Dtype* output, bool skip_im2col = false) {
+"""
+CONV_D = r"""
+    }
+    void forward_cpu_bias(Dtype* output, const Dtype* bias) {
+"""
+CONV_E = r"""
+    }
+};
+template <typename Dtype>
+struct ConvolutionLayer : public BaseConvolutionLayer<Dtype> {
+    void Forward_cpu(const std::vector<RefPtr<Dtype>*>& bottom, const std::vector<RefPtr<Dtype>*>& top) {
+"""
+CONV_F = r"""
+    }
+};
+"""
+CONV_WRAPPER = r"""
+#include <dlfcn.h>
+extern "C" int ref_load_blas(const char* path) {
+    void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) return -1;
+    void* f = dlsym(h, "cblas_sgemm");
+    if (!f) f = dlsym(h, "scipy_cblas_sgemm");
+    if (!f) return -2;
+    caffe::g_ref_sgemm = (caffe::ref_sgemm_t)f;
+    return 0;
+}
+// stride 1, dilation 1, group 1 (every convolution of the pose nets); members set as LayerSetUp / Reshape set them
+// (base_conv_layer.cpp:95-254: kernel_dim_ = blobs_[0]->count(1), weight_offset_ = conv_out_channels_ * kernel_dim_ / group_, ...)
+extern "C" int ref_conv_forward(const float* in, int n, int cin, int h, int w, const float* weight, const float* bias, int cout, int k, int pad,
+                                float* out) {
+    if (!caffe::g_ref_sgemm) return -1;
+    caffe::ConvolutionLayer<float> L;
+    const int oh = h + 2 * pad - k + 1, ow = w + 2 * pad - k + 1;
+    L.is_1x1_ = k == 1 && pad == 0; L.bias_term_ = bias != 0; L.force_nd_im2col_ = false; L.num_spatial_axes_ = 2; L.group_ = 1;
+    L.conv_out_channels_ = L.num_output_ = cout; L.conv_in_channels_ = cin;
+    L.conv_out_spatial_dim_ = L.out_spatial_dim_ = oh * ow; L.kernel_dim_ = cin * k * k;
+    L.weight_offset_ = cout * L.kernel_dim_; L.col_offset_ = L.kernel_dim_ * oh * ow; L.output_offset_ = cout * oh * ow;
+    L.num_ = n; L.bottom_dim_ = cin * h * w; L.top_dim_ = cout * oh * ow;
+    L.col_buffer_.v.resize((size_t)L.kernel_dim_ * oh * ow);
+    L.bias_multiplier_.v.assign((size_t)oh * ow, 1.0f);                                  // caffe_set(..., Dtype(1), ...) :251-252
+    L.conv_input_shape_.v = {cin, h, w}; L.kernel_shape_.v = {k, k}; L.pad_.v = {pad, pad}; L.stride_.v = {1, 1}; L.dilation_.v = {1, 1};
+    caffe::RefPtr<float> wb{const_cast<float*>(weight)}, bb{const_cast<float*>(bias)}, ib{const_cast<float*>(in)}, ob{out};
+    L.blobs_ = {&wb, &bb};
+    std::vector<caffe::RefPtr<float>*> bottom{&ib}, top{&ob};
+    L.Forward_cpu(bottom, top);
+    return 0;
+}
+"""
+
 
 def build_host(tmp):
     tu = ('#include "%s"\n' % os.path.join(HERE, "ref_host_prelude.h")
           + lines("examples/rtpose/rtpose.cpp", [(144, 152), (549, 751), (808, 1076)])
-          + "namespace caffe {\n" + lines("src/caffe/util/im2col.cpp", [(8, 56)]) + "}\n"
-          + HOST_WRAPPER)
+          + "namespace caffe {\n" + lines("src/caffe/util/im2col.cpp", [(8, 56)])
+          + CONV_A + lines("src/caffe/util/math_functions.cpp", [(12, 21)])
+          + CONV_B + lines("include/caffe/layers/base_conv_layer.hpp", [(100, 105)])
+          + CONV_C + lines("src/caffe/layers/base_conv_layer.cpp", [(259, 271)])
+          + CONV_D + lines("src/caffe/layers/base_conv_layer.cpp", [(277, 279)])
+          + CONV_E + lines("src/caffe/layers/conv_layer.cpp", [(27, 39)])
+          + CONV_F + "}\n"
+          + HOST_WRAPPER + CONV_WRAPPER)
     src = os.path.join(tmp, "ref_host_tu.cpp")
     open(src, "w").write(tu)
     src2 = os.path.join(tmp, "ref_host_tu2.cpp")
@@ -231,7 +330,7 @@ def build_host(tmp):
     out = os.path.join(OUT, "libref_host.so")
     cmd = ["g++", "-O3", "-std=c++11", "-fPIC", "-shared", "-w", "-I" + os.path.join(REF, "include"), src, src2,
            os.path.join(REF, "src/rtpose/modelDescriptor.cpp"),
-           os.path.join(REF, "src/rtpose/modelDescriptorFactory.cpp"), "-o", out]
+           os.path.join(REF, "src/rtpose/modelDescriptorFactory.cpp"), "-o", out, "-ldl"]
     subprocess.check_call(cmd)
     return out
 

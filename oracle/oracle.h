@@ -22,8 +22,10 @@
  * MAX pooling and ReLU (pooling_layer.cpp:90-105,151-186, relu_layer.cpp:15-18) are checked bit-for-bit
  * against the reference's own code compiled from /root/reference (oracle/_ref/libref_host.so, recipe:
  * oracle/build_ref.py); ImResize and NMS are checked bit-for-bit against the reference's own CUDA
- * kernels (oracle/_ref/libref_cpm.so) on the GPU box; the sgemm of the convolutions is a third-party BLAS
- * in the reference: upstream Caffe's naive-loop bar of 1e-4.
+ * kernels (oracle/_ref/libref_cpm.so) on the GPU box.  The convolution is checked bit-for-bit against
+ * ConvolutionLayer::Forward_cpu compiled from the reference with its cblas_sgemm bound to the same OpenBLAS
+ * this file loads; the BLAS binary itself is third-party and unpinned in the reference (Makefile:369-386),
+ * so against another BLAS the bar is upstream Caffe's naive-loop 1e-4.
  */
 #ifndef RTPOSE_ORACLE_H
 #define RTPOSE_ORACLE_H

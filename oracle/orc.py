@@ -363,6 +363,9 @@ def ref_host():
             R.ref_write_json.argtypes = [C.c_char_p, _f32p, C.c_int, C.c_int, C.c_double]
             R.ref_maxpool.argtypes = [_f32p] + [C.c_int] * 7 + [C.c_void_p, _i32p]
             R.ref_relu.argtypes = [_f32p, _f32p, C.c_int, C.c_float]
+        if hasattr(R, "ref_conv_forward"):
+            R.ref_load_blas.argtypes = [C.c_char_p]
+            R.ref_conv_forward.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p]
         if hasattr(R, "ref_render_dispatch"):
             R.ref_render_dispatch.argtypes = [C.c_int, C.c_int, C.c_int, _i32p]
         _ref_host = R

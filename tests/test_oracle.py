@@ -118,6 +118,29 @@ def test_conv_vs_naive_loop(k, pad):
     assert np.abs(orc.conv2d(x, w, b, pad) - _naive_conv(x, w, b, pad)).max() < 1e-4
 
 
+def test_conv_vs_reference_code_same_blas():
+    """ConvolutionLayer::Forward_cpu -> forward_cpu_gemm / forward_cpu_bias -> caffe_cpu_gemm (conv_layer.cpp:27-39,
+    base_conv_layer.cpp:259-271, 277-279, math_functions.cpp:12-21) compiled from the reference, its cblas_sgemm bound to the SAME
+    OpenBLAS the oracle loads: identical calls into an identical library, so the outputs must be bit-identical - including the
+    is_1x1_ shortcut, the bias-as-gemm form and batches.  (The BLAS binary itself is third-party and unpinned in the reference.)"""
+    R = orc.ref_host()
+    blas = orc.find_blas()
+    if R is None or not hasattr(R, "ref_conv_forward") or blas is None or not orc.lib().orc_have_blas():
+        pytest.skip("needs oracle/_ref (built from /root/reference) and an OpenBLAS")
+    assert R.ref_load_blas(blas.encode()) == 0
+    rng = np.random.default_rng(9)
+    for (n, cin, h, w, cout, k, pad, with_bias) in [(2, 3, 6, 4, 4, 3, 1, True), (1, 64, 23, 41, 64, 3, 1, True), (2, 128, 12, 21, 128, 7, 3, True),
+                                                      (1, 128, 12, 21, 512, 1, 0, True), (1, 185, 12, 21, 128, 7, 3, True)]:
+        x = rng.standard_normal((n, cin, h, w)).astype(np.float32)
+        wt = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float32)
+        b = rng.standard_normal(cout).astype(np.float32)
+        oh, ow = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+        ref = np.full((n, cout, oh, ow), 3.0, np.float32)
+        assert R.ref_conv_forward(x, n, cin, h, w, wt, b.ctypes.data, cout, k, pad, ref) == 0
+        got = orc.conv2d(x, wt, b, pad)
+        assert np.array_equal(got, ref), (n, cin, h, w, cout, k, pad, float(np.abs(got - ref).max()))
+
+
 def test_relu():
     x = np.array([-1.5, 0.0, 2.0, -0.0], np.float32)
     orc.lib().orc_relu(x, x.size)
