@@ -312,6 +312,25 @@ extern "C" int ref_conv_forward(const float* in, int n, int cin, int h, int w, c
 """
 
 
+# warmup()'s model selection (rtpose.cpp:212-229): the thresholds each model starts with
+DEFAULTS_A = r"""
+#ifndef CHECK
+#define CHECK(c) if (!(c)) { fprintf(stderr, "ref CHECK failed: %s\n", #c); abort(); } else RefNullStream()
+#endif
+extern "C" void ref_model_defaults(int num_parts, float* nms_threshold, int* min_subset_cnt, float* min_subset_score, float* inter_threshold,
+                                   int* inter_min_above_threshold) {
+    struct RefNetCopy { int nms_num_parts; std::unique_ptr<ModelDescriptor> up_model_descriptor; };
+    std::vector<RefNetCopy> net_copies(1);
+    const int device_id = 0;
+    net_copies[device_id].nms_num_parts = num_parts;
+"""
+DEFAULTS_B = r"""
+    *nms_threshold = global.nms_threshold; *min_subset_cnt = global.connect_min_subset_cnt; *min_subset_score = global.connect_min_subset_score;
+    *inter_threshold = global.connect_inter_threshold; *inter_min_above_threshold = global.connect_inter_min_above_threshold;
+}
+"""
+
+
 def build_host(tmp):
     tu = ('#include "%s"\n' % os.path.join(HERE, "ref_host_prelude.h")
           + lines("examples/rtpose/rtpose.cpp", [(144, 152), (549, 751), (808, 1076)])
@@ -322,7 +341,8 @@ def build_host(tmp):
           + CONV_D + lines("src/caffe/layers/base_conv_layer.cpp", [(277, 279)])
           + CONV_E + lines("src/caffe/layers/conv_layer.cpp", [(27, 39)])
           + CONV_F + "}\n"
-          + HOST_WRAPPER + CONV_WRAPPER)
+          + HOST_WRAPPER + CONV_WRAPPER
+          + DEFAULTS_A + lines("examples/rtpose/rtpose.cpp", [(212, 229)]) + DEFAULTS_B)
     src = os.path.join(tmp, "ref_host_tu.cpp")
     open(src, "w").write(tu)
     src2 = os.path.join(tmp, "ref_host_tu2.cpp")

@@ -31,11 +31,11 @@ def exe(tmp_path_factory):
     return out
 
 
-def run(exe, args, env=None, stdin=None, timeout=120):
+def run(exe, args, env=None, stdin=None, timeout=120, model="COCO"):
     e = dict(os.environ)
     e["TSAN_OPTIONS"] = "halt_on_error=0 exitcode=66"
     e.update(env or {})
-    base = ["--model", "COCO", "--caffeproto", "/nonexistent.prototxt", "--random_init", "he"]
+    base = ["--model", model, "--caffeproto", "/nonexistent.prototxt", "--random_init", "he"]
     r = subprocess.run([exe] + base + args, capture_output=True, text=True, env=e, input=stdin, timeout=timeout)
     assert "ThreadSanitizer" not in r.stderr, r.stderr[-6000:]
     assert "STUB: concurrent calls" not in r.stderr, r.stderr[-3000:]
@@ -141,6 +141,17 @@ def test_runtime_keys_reach_every_engine(exe, tmp_path):
     assert len(last) == 2
     for l in last.values():
         assert "nms=0.0600" in l and "connect=4,0.4050,0.0550,10" in l, l
+
+
+def test_model_defaults_reach_the_engines(exe, tmp_path):
+    """warmup()'s per-model thresholds (rtpose.cpp:212-226; pinned to the reference's text in tests/test_oracle.py) are what the
+    workers hand to their engines before the first forward."""
+    for model, want in (("COCO", "nms=0.0500 connect=3,0.4000,0.0500,9"), ("MPI", "nms=0.2000 connect=3,0.4000,0.0100,8")):
+        log = tmp_path / ("%s.log" % model)
+        r = run(exe, ["--synthetic", "6", "--resolution", "32x24", "--net_resolution", "32x24", "--no_frame_drops"], env={"STUB_LOG": str(log)}, model=model)
+        assert r.returncode == 0, r.stderr[-2000:]
+        fw = [l for l in log.read_text().splitlines() if l.startswith("forward") and "calibrate" not in l]
+        assert fw and all(want in l for l in fw), fw[:2]
 
 
 def test_device_failure_ends_the_run(exe, tmp_path):

@@ -224,6 +224,20 @@ def test_json_writer_vs_reference_code(tmp_path):
         assert engine.write_json(j, parts, scale) == want
 
 
+def test_model_default_thresholds_vs_reference_code():
+    """warmup()'s model selection (rtpose.cpp:212-229) compiled from the reference: the NMS / connect thresholds each model starts with."""
+    R = orc.ref_host()
+    if R is None or not hasattr(R, "ref_model_defaults"):
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    import ctypes as C
+    R.ref_model_defaults.argtypes = [C.c_int] + [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    for model, parts in ((orc.MPI_15, 15), (orc.COCO_18, 18)):
+        thr, cnt, score, inter, above = C.c_float(), C.c_int(), C.c_float(), C.c_float(), C.c_int()
+        R.ref_model_defaults(parts, C.byref(thr), C.byref(cnt), C.byref(score), C.byref(inter), C.byref(above))
+        othr, p = orc.default_params(model)
+        assert (othr, p.min_subset_cnt, p.min_subset_score, p.inter_threshold, p.inter_min_above) == (thr.value, cnt.value, score.value, inter.value, above.value)
+
+
 def test_render_dispatch_vs_reference_code():
     """render() (rtpose.cpp:271-300) compiled from the reference with recording launchers: for every --part_to_show value of both
     models (and past the last view) the oracle picks the same launcher with the same `part`, googly / num_parts_accum arguments."""
