@@ -706,7 +706,8 @@ static void worker(int tid, pe_engine* e) {
 
 // handleKey (rtpose.cpp:1551-1671) without a window: the same key characters, read from stdin with --keys_from_stdin
 static void handle_key(int c) {
-    auto bump = [](std::atomic<float>& v, float d, const char* name) { v = v + d; LOG_INFO("%s: %g", name, (double)v.load()); };
+    // `global.nms_threshold -= 0.005;` on a float member: the sum is formed in double and rounded to float once (rtpose.cpp:1617-1635)
+    auto bump = [](std::atomic<float>& v, double d, const char* name) { v = (float)((double)v.load() + d); LOG_INFO("%s: %g", name, (double)v.load()); };
     auto bumpi = [](std::atomic<int>& v, int d, const char* name) { v = v + d; LOG_INFO("%s: %d", name, v.load()); };
     const int max_show = global.model == PE_MODEL_MPI_15 ? 43 : 39;
     if (c == 27 || c == 'Q') { global.quit = true; return; }   // ESC as in the reference; 'Q' for terminals that cannot send it
@@ -719,9 +720,9 @@ static void handle_key(int c) {
         if (c == ' ') { global.video_paused = !global.video_paused; LOG_INFO("paused: %d", (int)global.video_paused.load()); }
         return;
     }
-    if (c == '-' || c == '=') bump(global.nms_threshold, c == '-' ? -0.005f : 0.005f, "nms_threshold");
-    else if (c == '_' || c == '+') bump(global.connect_min_subset_score, c == '_' ? -0.005f : 0.005f, "connect_min_subset_score");
-    else if (c == '[' || c == ']') bump(global.connect_inter_threshold, c == '[' ? -0.005f : 0.005f, "connect_inter_threshold");
+    if (c == '-' || c == '=') bump(global.nms_threshold, c == '-' ? -0.005 : 0.005, "nms_threshold");
+    else if (c == '_' || c == '+') bump(global.connect_min_subset_score, c == '_' ? -0.005 : 0.005, "connect_min_subset_score");
+    else if (c == '[' || c == ']') bump(global.connect_inter_threshold, c == '[' ? -0.005 : 0.005, "connect_inter_threshold");
     else if (c == '{' || c == '}') bumpi(global.connect_inter_min_above_threshold, c == '{' ? -1 : 1, "connect_inter_min_above_threshold");
     else if (c == ';' || c == '\'') bumpi(global.connect_min_subset_cnt, c == ';' ? -1 : 1, "connect_min_subset_cnt");
     else if (c == ',' || c == '.') {

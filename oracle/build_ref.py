@@ -12,7 +12,7 @@ the resulting shared objects are kept under oracle/_ref/ (git-ignored, travels t
                         math_functions.cpp:12-21 (ConvolutionLayer::Forward_cpu down to the cblas_sgemm call, BLAS loaded at run time)
                         second translation unit: rtpose.cpp:239-269 (process_and_pad_image), :474-479 (display scale),
                         :509-511 (per-scale target size), :1395-1414 (JSON writer), :271-300 (render() dispatch,
-                        launchers replaced by recording stand-ins);
+                        launchers replaced by recording stand-ins), :103-129 + :1551-1592, 1606-1671 (handleKey without its window calls);
                         src/caffe/layers/pooling_layer.cpp:90-105, 151-186 (pooled size, MAX loop),
                         src/caffe/layers/relu_layer.cpp:15-18
   libref_cpm.so   nvcc  src/caffe/cpm/layers/imresize_layer.cu:8-18,97-155
@@ -182,7 +182,11 @@ struct RefMD2 { int parts; int get_number_parts() const { return parts; } };
 struct RefNetCopy2 { float* canvas; float* joints; std::vector<int> num_people; RefMD2* up_model_descriptor; };
 static RefMD2 g_md2;
 static std::vector<RefNetCopy2> net_copies(1);
-static struct { int part_to_show; struct { bool is_googly_eyes; } uistate; } global;
+#define LOG(x) RefNullStream2()
+static struct RefGlobal2 {   // the members of `struct Global` that are not queues: rtpose.cpp:103-129, spliced
+"""
+HOST2_BODY_G2 = r"""
+} global;
 static int DISPLAY_RESOLUTION_WIDTH = 1280, DISPLAY_RESOLUTION_HEIGHT = 720, NET_RESOLUTION_WIDTH = 656, NET_RESOLUTION_HEIGHT = 368;
 const int BOX_SIZE = 368;
 static double get_wall_time() { return 0; }
@@ -207,6 +211,22 @@ extern "C" int ref_render_dispatch(int num_parts, int part_to_show, int googly_e
 }
 """
 
+HOST2_BODY_I = r"""
+// state: f[3] = nms_threshold, connect_min_subset_score, connect_inter_threshold; i[7] = connect_inter_min_above_threshold,
+// connect_min_subset_cnt, part_to_show, is_googly_eyes, is_video_paused, current_frame, quit_threads - in and out
+extern "C" void ref_handle_keys(const int* keys, int n, int has_video, float* f, int* i) {
+    FLAGS_video = has_video ? "clip.avi" : "";
+    global.nms_threshold = f[0]; global.connect_min_subset_score = f[1]; global.connect_inter_threshold = f[2];
+    global.connect_inter_min_above_threshold = i[0]; global.connect_min_subset_cnt = i[1]; global.part_to_show = i[2];
+    global.uistate.is_googly_eyes = i[3] != 0; global.uistate.is_video_paused = i[4] != 0; global.uistate.current_frame = i[5];
+    global.quit_threads = false;
+    for (int k = 0; k < n; k++) handleKey(keys[k]);
+    f[0] = global.nms_threshold; f[1] = global.connect_min_subset_score; f[2] = global.connect_inter_threshold;
+    i[0] = global.connect_inter_min_above_threshold; i[1] = global.connect_min_subset_cnt; i[2] = global.part_to_show;
+    i[3] = global.uistate.is_googly_eyes; i[4] = global.uistate.is_video_paused; i[5] = global.uistate.current_frame; i[6] = global.quit_threads;
+}
+"""
+
 
 def host2_tu():
     return (HOST2_PRELUDE
@@ -217,8 +237,12 @@ def host2_tu():
             + HOST2_BODY_D + lines("src/caffe/layers/pooling_layer.cpp", [(90, 105)])
             + HOST2_BODY_E + lines("src/caffe/layers/pooling_layer.cpp", [(151, 186)])
             + HOST2_BODY_F + lines("src/caffe/layers/relu_layer.cpp", [(15, 18)])
-            + HOST2_BODY_G + lines("examples/rtpose/rtpose.cpp", [(271, 300)])
-            + HOST2_BODY_H)
+            + HOST2_BODY_G + lines("examples/rtpose/rtpose.cpp", [(103, 129)])
+            + HOST2_BODY_G2 + lines("examples/rtpose/rtpose.cpp", [(271, 300)])
+            + HOST2_BODY_H
+            + "static std::string FLAGS_video;\n"
+            + lines("examples/rtpose/rtpose.cpp", [(1551, 1592), (1606, 1671)])     # handleKey without the cv:: window block of the 'f' key
+            + HOST2_BODY_I)
 
 # Convolution forward of the reference (ConvolutionLayer::Forward_cpu -> forward_cpu_gemm / forward_cpu_bias -> caffe_cpu_gemm ->
 # cblas_sgemm) as members of a stand-in class that carries the members those bodies read.  The BLAS is third-party in the reference

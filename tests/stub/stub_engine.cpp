@@ -94,8 +94,8 @@ int forward(pe_engine* e, const uint8_t* const* frames, int n, int w, int h, con
         if (getenv("STUB_KEEP_FRAMES")) r.frame.assign(p, p + (size_t)w * h * 3);
         e->results.push_back(std::move(r));
     }
-    logf("forward engine=%d call=%d n=%d %s size=%dx%d nms=%.4f connect=%d,%.4f,%.4f,%d", e->id, k, n, how, w, h, e->nms_threshold,
-         e->min_subset_cnt, e->min_subset_score, e->inter_threshold, e->inter_min_above);
+    logf("forward engine=%d call=%d n=%d %s size=%dx%d nms=%.4f connect=%d,%.4f,%.4f,%d exact=%.9g,%.9g,%.9g", e->id, k, n, how, w, h, e->nms_threshold,
+         e->min_subset_cnt, e->min_subset_score, e->inter_threshold, e->inter_min_above, e->nms_threshold, e->min_subset_score, e->inter_threshold);
     return PE_OK;
 }
 }  // namespace

@@ -224,3 +224,45 @@ def test_video_loops_until_quit_and_quit_is_not_an_error(exe, tmp_path):
     r = run(exe, base[6:] + ["--write_json", str(out), "--no_frame_drops"])
     assert r.returncode == 0 and sorted(os.listdir(out)) == ["frame%06d.json" % i for i in range(8)]
     assert "Looping" not in r.stderr
+
+
+def test_handle_key_vs_reference_code(exe, tmp_path):
+    """handleKey (rtpose.cpp:1551-1671) compiled from the reference (minus its cv:: window calls) against rtpose.bin's handle_key on
+    random key sequences: the thresholds the engines end up with are bit-identical (float members stepped by the double 0.005), the
+    integer parameters, the shown part and the googly-eyes switch equal."""
+    import ctypes as C
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from oracle import orc
+    R = orc.ref_host()
+    if R is None or not hasattr(R, "ref_handle_keys"):
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    R.ref_handle_keys.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    rng = np.random.default_rng(21)
+    alphabet = "-=_+[]{};'" * 3 + ",." + "0123456789qwertyuiopas" + "g"
+    for trial in range(3):
+        while True:
+            keys = "".join(alphabet[i] for i in rng.integers(0, len(alphabet), 60))
+            f = (C.c_float * 3)(0.05, 0.4, 0.05)              # COCO defaults (pinned in tests/test_oracle.py)
+            i = (C.c_int * 7)(9, 3, 0, 0, 0, 0, 0)
+            ok = True
+            for ch in keys:                                   # stay inside the views this build renders (0..39; the reference lets the counter run to 55)
+                k = (C.c_int * 1)(ord(ch))
+                R.ref_handle_keys(k, 1, 0, f, i)
+                ok = ok and 0 <= i[2] <= 39
+            if ok:
+                break
+        log = tmp_path / ("keys%d.log" % trial)
+        r = run(exe, ["--synthetic", "600", "--resolution", "32x24", "--net_resolution", "32x24", "--batch", "1", "--engines_per_gpu", "1", "--no_frame_drops",
+                      "--keys_from_stdin"], env={"STUB_LOG": str(log), "STUB_FORWARD_MS": "3"}, stdin=keys + "\n")
+        assert r.returncode == 0, r.stderr[-2000:]
+        last = [l for l in log.read_text().splitlines() if l.startswith("forward")][-1]
+        exact = [np.float32(v) for v in last.split("exact=")[1].split(",")]
+        assert [e.tobytes() for e in exact] == [np.float32(f[j]).tobytes() for j in range(3)], (keys, last, list(f))
+        cnt, above = int(last.split("connect=")[1].split(",")[0]), int(last.split("connect=")[1].split(",")[3].split()[0])
+        assert (above, cnt) == (i[0], i[1])
+        p2s = [int(l.split("p2s: ")[1]) for l in r.stderr.splitlines() if "p2s: " in l]
+        assert (p2s[-1] if p2s else 0) == i[2]
+        googly = [int(l.split("googly eyes: ")[1]) for l in r.stderr.splitlines() if "googly eyes: " in l]
+        assert (googly[-1] if googly else 0) == i[3]
