@@ -89,6 +89,8 @@ static void define_flags() {
            "--batch is automatic: the copies and the kernel tails of one batch overlap the other; weights are shared, not duplicated)");
     define("calibrate_range", "true", "[extension] parity mode: derive per-layer power-of-two activation scales from one synthetic frame at start-up "
            "(pe_calibrate), so that a model of any magnitude keeps fp32-level results", true);
+    define("num_writers", "0", "[extension] threads that encode and write the --write_frames images (a quality-98 720p JPEG takes ~20 ms to encode): "
+           "1 = on the display thread like the reference, 0 = automatic (a quarter of the host's cores, at most 16)");
     define("keys_from_stdin", "false", "[extension] read the reference's runtime keys (- = _ + [ ] { } ; ' , . 0-9 q-p a s, ESC or Q to quit) from stdin", true);
 }
 
@@ -746,6 +748,69 @@ static void key_reader() {
         if (c != '\n' && c != '\r') handle_key(c);
 }
 
+// [extension] --write_frames images leave the display thread: the reference encodes them there (cv::imwrite inside displayFrame,
+// rtpose.cpp:1363-1380), which bounds the whole pipeline by one thread's JPEG encoder (~50 frames/s at 720p, quality 98) while one GPU
+// renders hundreds.  The files are independent (the frame number is in the name), so N threads encode and write them; the queue is
+// bounded, the display thread waits when the writers fall behind.
+struct WriteJob { std::string fname; std::vector<uint8_t> bgr; int w = 0, h = 0; bool bmp = false; };
+static void write_image(const WriteJob& j) {
+    bool ok;
+    if (j.bmp) {
+        ok = write_bmp(j.fname, j.w, j.h, j.bgr.data());
+    } else {
+        // one encoding pass: a baseline JPEG never exceeds the raw size by more than its tables and headers
+        std::vector<uint8_t> jb((size_t)j.w * j.h * 3 + (1u << 16));
+        const long long need = pe_encode_jpeg(j.bgr.data(), j.w, j.h, 98, jb.data(), (long long)jb.size());
+        ok = need > 0 && need <= (long long)jb.size();
+        FILE* f = ok ? fopen(j.fname.c_str(), "wb") : nullptr;
+        ok = f != nullptr;
+        if (f) { ok = fwrite(jb.data(), 1, (size_t)need, f) == (size_t)need; fclose(f); }
+    }
+    if (!ok) LOG_ERROR("cannot write %s", j.fname.c_str());
+}
+class WriterPool {
+public:
+    void start(int n) {
+        limit_ = (size_t)std::max(2, 4 * n);
+        for (int i = 0; i < n; i++) threads_.emplace_back([this] { loop(); });
+    }
+    void submit(WriteJob&& j) {
+        if (threads_.empty()) { write_image(j); return; }   // --num_writers 1: on the caller's thread, as the reference
+        std::unique_lock<std::mutex> l(m_);
+        space_.wait(l, [&] { return q_.size() < limit_; });
+        q_.push(std::move(j));
+        l.unlock();
+        work_.notify_one();
+    }
+    void finish() {
+        { std::lock_guard<std::mutex> l(m_); done_ = true; }
+        work_.notify_all();
+        for (auto& t : threads_) t.join();
+        threads_.clear();
+    }
+private:
+    void loop() {
+        for (;;) {
+            WriteJob j;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                work_.wait(l, [&] { return done_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = std::move(q_.front());
+                q_.pop();
+            }
+            space_.notify_one();
+            write_image(j);
+        }
+    }
+    std::mutex m_;
+    std::condition_variable work_, space_;
+    std::queue<WriteJob> q_;
+    std::vector<std::thread> threads_;
+    size_t limit_ = 8;
+    bool done_ = false;
+};
+
 // re-order by frame index (buffer_and_order, rtpose.cpp:1214-1273) and write JSON (displayFrame, :1383-1416)
 static void orderer_and_writer(int num_workers) {
     auto cmp = [](const Frame& a, const Frame& b) { return a.index > b.index; };
@@ -754,7 +819,12 @@ static void orderer_and_writer(int num_workers) {
     const double t0 = now_s();
     double last = t0, fps_now = 0;   // FPS of the last 30 frames, as displayFrame keeps it
     const std::string out = F("write_json");
-    auto emit = [&](const Frame& fr) {
+    WriterPool writers;
+    if (!F("write_frames").empty()) {
+        const int nw = Fi("num_writers") > 0 ? Fi("num_writers") : std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / 4));
+        if (nw > 1) writers.start(nw);
+    }
+    auto emit = [&](Frame& fr) {
         if (!out.empty()) {
             char fname[1024];
             if (F("image_dir").empty()) snprintf(fname, sizeof fname, "%s/frame%06d.json", out.c_str(), fr.video_frame_number);
@@ -766,7 +836,7 @@ static void orderer_and_writer(int num_workers) {
             if (f) { fwrite(buf.data(), 1, (size_t)need, f); fclose(f); }
         }
         if (!F("write_frames").empty() && !fr.rendered.empty() && !Fb("no_text")) {   // displayFrame :1317-1353
-            Frame& mfr = const_cast<Frame&>(fr);
+            Frame& mfr = fr;
             char tmp[256];
             const int c_fps[3] = {255, 150, 150}, c_black[3] = {0, 0, 0}, c_cnt[3] = {150, 150, 255}, c_white[3] = {255, 255, 255};
             snprintf(tmp, sizeof tmp, "%4.2f s/gpu", fps_now > 0 ? std::max(1, Fi("num_gpu")) * 1.0 / fps_now : 0.0);
@@ -790,24 +860,14 @@ static void orderer_and_writer(int num_workers) {
             }
         }
         if (!F("write_frames").empty() && !fr.rendered.empty()) {   // displayFrame :1363-1380 (cv::imwrite, JPEG quality 98)
-            const bool bmp = F("frame_format") == "bmp";
+            WriteJob job;
+            job.bmp = F("frame_format") == "bmp";
             char fname[1024];
-            if (F("image_dir").empty()) snprintf(fname, sizeof fname, "%s/frame%06d.%s", F("write_frames").c_str(), fr.video_frame_number, bmp ? "bmp" : "jpg");
-            else snprintf(fname, sizeof fname, "%s/%s.%s", F("write_frames").c_str(), fr.stem.c_str(), bmp ? "bmp" : "jpg");
-            bool ok;
-            if (bmp) {
-                ok = write_bmp(fname, global.disp_w, global.disp_h, fr.rendered.data());
-            } else {
-                // one encoding pass: a baseline JPEG never exceeds the raw size by more than its tables and headers
-                std::vector<uint8_t> jb((size_t)global.disp_w * global.disp_h * 3 + (1u << 16));
-                const long long need = pe_encode_jpeg(fr.rendered.data(), global.disp_w, global.disp_h, 98, jb.data(), (long long)jb.size());
-                ok = need > 0 && need <= (long long)jb.size();
-                if (ok) jb.resize((size_t)need);
-                FILE* f = ok ? fopen(fname, "wb") : nullptr;
-                ok = f != nullptr;
-                if (f) { fwrite(jb.data(), 1, jb.size(), f); fclose(f); }
-            }
-            if (!ok) LOG_ERROR("cannot write %s", fname);
+            if (F("image_dir").empty()) snprintf(fname, sizeof fname, "%s/frame%06d.%s", F("write_frames").c_str(), fr.video_frame_number, job.bmp ? "bmp" : "jpg");
+            else snprintf(fname, sizeof fname, "%s/%s.%s", F("write_frames").c_str(), fr.stem.c_str(), job.bmp ? "bmp" : "jpg");
+            job.fname = fname; job.w = global.disp_w; job.h = global.disp_h;
+            job.bgr = std::move(fr.rendered);
+            writers.submit(std::move(job));
         }
         written++;
         if (written % 30 == 0) {   // the reference's line, every 30 frames (rtpose.cpp:1421-1441); stages that run on the GPU here read 0
@@ -834,12 +894,13 @@ static void orderer_and_writer(int num_workers) {
         }
         if (!got) {
             if (global.finished == num_workers && global.output_queue.size() == 0) {
-                while (!heap.empty()) { emit(heap.top()); heap.pop(); }   // flush (frames lost to an error leave gaps)
+                while (!heap.empty()) { Frame top = heap.top(); heap.pop(); emit(top); }   // flush (frames lost to an error leave gaps)
                 break;
             }
             std::this_thread::sleep_for(std::chrono::microseconds(200));
         }
     }
+    writers.finish();   // every image is on disk before the run reports its end
     const double dt = now_s() - t0;
     LOG_INFO("Done, exiting. # frames: %d  (%.1f frames/s overall, %d dropped)", written, written / std::max(dt, 1e-9), global.dropped.load());
 }

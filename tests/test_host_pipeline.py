@@ -192,6 +192,17 @@ def test_write_frames_with_overlays(exe, tmp_path):
         assert sorted(os.listdir(out)) == ["frame%06d.bmp" % i for i in range(35)]
         outs[name] = out
         assert all("part=3" in l for l in (tmp_path / (name + ".log")).read_text().splitlines() if l.startswith("render"))
+    # [extension] --num_writers: the images are encoded off the display thread; the files do not depend on how many threads write them
+    jpg = {}
+    for nw in (1, 4):
+        out = tmp_path / ("jpg%d" % nw)
+        r = run(exe, ["--synthetic", "40", "--resolution", "320x96", "--net_resolution", "32x24", "--write_frames", str(out), "--no_frame_drops", "--no_text",
+                      "--num_writers", str(nw)], env={"STUB_KEEP_FRAMES": "1"})
+        assert r.returncode == 0, r.stderr[-3000:]
+        assert sorted(os.listdir(out)) == ["frame%06d.jpg" % i for i in range(40)]
+        jpg[nw] = [(out / f).read_bytes() for f in sorted(os.listdir(out))]
+        assert all(b[:2] == b"\xff\xd8" and b[-2:] == b"\xff\xd9" for b in jpg[nw])   # complete files: the run ends after the writers
+    assert jpg[1] == jpg[4] and len(set(jpg[1])) > 30                                    # and every frame's own picture
     a = np.frombuffer((outs["text"] / "frame000034.bmp").read_bytes()[54:], dtype=np.uint8)
     b = np.frombuffer((outs["notext"] / "frame000034.bmp").read_bytes()[54:], dtype=np.uint8)
     assert (b == 40).mean() > 0.99            # the stub's flat canvas
