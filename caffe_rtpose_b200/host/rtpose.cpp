@@ -13,6 +13,7 @@
 // Frames older than 0.1 s are dropped unless --no_frame_drops, as in processFrame (rtpose.cpp:1107-1124).
 #include <dirent.h>
 #include <math.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -89,7 +90,7 @@ static void define_flags() {
            "--batch is automatic: the copies and the kernel tails of one batch overlap the other; weights are shared, not duplicated)");
     define("calibrate_range", "true", "[extension] parity mode: derive per-layer power-of-two activation scales from one synthetic frame at start-up "
            "(pe_calibrate), so that a model of any magnitude keeps fp32-level results", true);
-    define("num_writers", "0", "[extension] threads that encode and write the --write_frames images (a quality-98 720p JPEG takes ~20 ms to encode): "
+    define("num_writers", "0", "[extension] threads that format / encode and write the --write_json and --write_frames files (a quality-98 720p JPEG takes ~20 ms to encode): "
            "1 = on the display thread like the reference, 0 = automatic (a quarter of the host's cores, at most 16)");
     define("keys_from_stdin", "false", "[extension] read the reference's runtime keys (- = _ + [ ] { } ; ' , . 0-9 q-p a s, ESC or Q to quit) from stdin", true);
 }
@@ -124,8 +125,21 @@ static int parse_flags(int argc, char** argv) {
     return 0;
 }
 
-#define LOG_INFO(...) do { fprintf(stderr, "I rtpose] " __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
-#define LOG_ERROR(...) do { fprintf(stderr, "E rtpose] " __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
+// one write per line: producers, workers, the key reader and the display thread all log, and a line must not be cut by another one
+static void log_line(char level, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+static void log_line(char level, const char* fmt, ...) {
+    char buf[2048];
+    int n = snprintf(buf, sizeof buf, "%c rtpose] ", level);
+    va_list ap;
+    va_start(ap, fmt);
+    const int m = vsnprintf(buf + n, sizeof buf - (size_t)n - 1, fmt, ap);
+    va_end(ap);
+    n += m < 0 ? 0 : std::min(m, (int)sizeof buf - n - 2);
+    buf[n++] = '\n';
+    fwrite(buf, 1, (size_t)n, stderr);
+}
+#define LOG_INFO(...) log_line('I', __VA_ARGS__)
+#define LOG_ERROR(...) log_line('E', __VA_ARGS__)
 
 // ---------------------------------------------------------------------------------------------- frames
 struct Frame {
@@ -748,14 +762,25 @@ static void key_reader() {
         if (c != '\n' && c != '\r') handle_key(c);
 }
 
-// [extension] --write_frames images leave the display thread: the reference encodes them there (cv::imwrite inside displayFrame,
+// [extension] --write_frames images and --write_json files leave the display thread: the reference encodes them there (cv::imwrite inside displayFrame,
 // rtpose.cpp:1363-1380), which bounds the whole pipeline by one thread's JPEG encoder (~50 frames/s at 720p, quality 98) while one GPU
 // renders hundreds.  The files are independent (the frame number is in the name), so N threads encode and write them; the queue is
 // bounded, the display thread waits when the writers fall behind.
-struct WriteJob { std::string fname; std::vector<uint8_t> bgr; int w = 0, h = 0; bool bmp = false; };
+struct WriteJob {
+    std::string fname;
+    std::vector<uint8_t> bgr; int w = 0, h = 0; bool bmp = false;        // an image of --write_frames, or
+    std::vector<float> joints; int num_people = -1, num_parts = 0; double scale = 1.0;   // (num_people >= 0) the JSON block of --write_json
+};
 static void write_image(const WriteJob& j) {
     bool ok;
-    if (j.bmp) {
+    if (j.num_people >= 0) {   // displayFrame :1383-1416; one formatting pass into a buffer that holds any frame of this size
+        std::vector<char> buf(64 + (size_t)j.num_people * ((size_t)j.num_parts * 48 + 32));
+        int need = pe_write_json(j.joints.data(), j.num_people, j.num_parts, j.scale, buf.data(), (int)buf.size());
+        if (need >= (int)buf.size()) { buf.resize((size_t)need + 1); need = pe_write_json(j.joints.data(), j.num_people, j.num_parts, j.scale, buf.data(), need + 1); }
+        FILE* f = fopen(j.fname.c_str(), "wb");
+        ok = f != nullptr;
+        if (f) { ok = fwrite(buf.data(), 1, (size_t)need, f) == (size_t)need; fclose(f); }
+    } else if (j.bmp) {
         ok = write_bmp(j.fname, j.w, j.h, j.bgr.data());
     } else {
         // one encoding pass: a baseline JPEG never exceeds the raw size by more than its tables and headers
@@ -820,7 +845,7 @@ static void orderer_and_writer(int num_workers) {
     double last = t0, fps_now = 0;   // FPS of the last 30 frames, as displayFrame keeps it
     const std::string out = F("write_json");
     WriterPool writers;
-    if (!F("write_frames").empty()) {
+    if (!F("write_frames").empty() || !out.empty()) {
         const int nw = Fi("num_writers") > 0 ? Fi("num_writers") : std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / 4));
         if (nw > 1) writers.start(nw);
     }
@@ -829,11 +854,10 @@ static void orderer_and_writer(int num_workers) {
             char fname[1024];
             if (F("image_dir").empty()) snprintf(fname, sizeof fname, "%s/frame%06d.json", out.c_str(), fr.video_frame_number);
             else snprintf(fname, sizeof fname, "%s/%s.json", out.c_str(), fr.stem.c_str());
-            const int need = pe_write_json(fr.joints.data(), fr.num_people, global.num_parts, fr.scale, nullptr, 0);
-            std::vector<char> buf((size_t)need + 1);
-            pe_write_json(fr.joints.data(), fr.num_people, global.num_parts, fr.scale, buf.data(), need + 1);
-            FILE* f = fopen(fname, "wb");
-            if (f) { fwrite(buf.data(), 1, (size_t)need, f); fclose(f); }
+            WriteJob job;
+            job.fname = fname; job.num_people = fr.num_people; job.num_parts = global.num_parts; job.scale = fr.scale;
+            job.joints = fr.joints;   // (the frame keeps its copy: nothing after this reads it, but the status line prints fr.num_people)
+            writers.submit(std::move(job));
         }
         if (!F("write_frames").empty() && !fr.rendered.empty() && !Fb("no_text")) {   // displayFrame :1317-1353
             Frame& mfr = fr;
