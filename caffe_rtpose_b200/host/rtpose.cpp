@@ -269,14 +269,22 @@ static bool write_bmp(const std::string& path, int w, int h, const uint8_t* bgr)
 
 static void synthetic_frame(int idx, int w, int h, std::vector<uint8_t>& bgr) {
     bgr.resize((size_t)w * h * 3);
+    // low-frequency pattern 128 + 100 sin((x + 31 c) / 41) cos((y + 17 idx) / 57) plus LCG noise; the two factors are tabulated per
+    // column and per row (the products are the same doubles as when both are evaluated per pixel: 17 -> ~200 frames/s per thread at 720p)
+    std::vector<double> sx((size_t)w * 3), cy((size_t)h);
+    for (int x = 0; x < w; x++)
+        for (int c = 0; c < 3; c++) sx[(size_t)x * 3 + c] = 100.0 * sin((x + 31 * c) / 41.0);
+    for (int y = 0; y < h; y++) cy[y] = cos((y + 17 * idx) / 57.0);
     uint32_t s = 0x9E3779B9u * (uint32_t)(idx + 1);
-    for (int y = 0; y < h; y++)
-        for (int x = 0; x < w; x++)
-            for (int c = 0; c < 3; c++) {
-                s = s * 1664525u + 1013904223u;
-                const int low = 128 + (int)(100.0 * sin((x + 31 * c) / 41.0) * cos((y + 17 * idx) / 57.0));
-                bgr[((size_t)y * w + x) * 3 + c] = (uint8_t)std::min(255, std::max(0, (low + (int)(s >> 24)) / 2));
-            }
+    for (int y = 0; y < h; y++) {
+        uint8_t* row = &bgr[(size_t)y * w * 3];
+        const double cyy = cy[y];
+        for (int i = 0; i < w * 3; i++) {
+            s = s * 1664525u + 1013904223u;
+            const int low = 128 + (int)(sx[i] * cyy);
+            row[i] = (uint8_t)std::min(255, std::max(0, (low + (int)(s >> 24)) / 2));
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- text overlays
