@@ -34,73 +34,99 @@ void build_huff(const uint8_t* bits, const uint8_t* vals, Huff& h) {   // T.81 A
     }
 }
 
+// Entropy-coded bytes go into a buffer that is grown once per MCU (six blocks x 64 coefficients x at most 26 bits, doubled by byte
+// stuffing, stay below 4 KB), so put() never allocates; a Huffman code and the value bits that follow it leave in one call.
 struct BitWriter {
     std::vector<uint8_t>& out;
-    uint32_t acc = 0;
+    uint8_t* p = nullptr;
+    uint64_t acc = 0;
     int n = 0;
     explicit BitWriter(std::vector<uint8_t>& o) : out(o) {}
-    void put(uint32_t bits, int len) {
-        acc = (acc << len) | (bits & ((1u << len) - 1u));
+    void begin_mcu() {
+        const size_t used = out.size();
+        if (out.capacity() - used < 4096) out.reserve(out.capacity() * 2 + 65536);
+        out.resize(used + 4096);
+        p = out.data() + used;
+    }
+    void end_mcu() { out.resize((size_t)(p - out.data())); }
+    inline void put(uint32_t bits, int len) {   // len <= 32; at most 7 bits wait in acc
+        acc = (acc << len) | (bits & (uint32_t)((1ull << len) - 1ull));
         n += len;
         while (n >= 8) {
             const uint8_t b = (uint8_t)(acc >> (n - 8));
-            out.push_back(b);
-            if (b == 0xFF) out.push_back(0);   // byte stuffing
+            *p++ = b;
+            if (b == 0xFF) *p++ = 0;   // byte stuffing
             n -= 8;
         }
     }
     void flush() { if (n) put(0x7F, 8 - n); }   // pad with ones
 };
 
-void fdct8x8(const float* in, double* out) {   // separable DCT-II, orthonormal JPEG scaling
-    struct Basis { double c[8][8]; };
+struct Basis { double t[8][8]; };   // t[x][u] = c(u) cos((2x + 1) u pi / 16): separable DCT-II, orthonormal JPEG scaling
+const Basis& dct_basis() {
     static const Basis basis = [] {   // thread-safe one-time initialisation
         Basis b;
         for (int u = 0; u < 8; u++)
-            for (int x = 0; x < 8; x++) b.c[u][x] = (u == 0 ? sqrt(0.125) : 0.5) * cos((2 * x + 1) * u * M_PI / 16.0);
+            for (int x = 0; x < 8; x++) b.t[x][u] = (u == 0 ? sqrt(0.125) : 0.5) * cos((2 * x + 1) * u * M_PI / 16.0);
         return b;
     }();
-    const double (*c)[8] = basis.c;
-    double tmp[64];
-    for (int y = 0; y < 8; y++)
-        for (int u = 0; u < 8; u++) {
-            double s = 0;
-            for (int x = 0; x < 8; x++) s += c[u][x] * in[y * 8 + x];
-            tmp[y * 8 + u] = s;
-        }
-    for (int v = 0; v < 8; v++)
-        for (int u = 0; u < 8; u++) {
-            double s = 0;
-            for (int y = 0; y < 8; y++) s += c[v][y] * tmp[y * 8 + u];
-            out[v * 8 + u] = s;
-        }
+    return basis;
 }
+// Forward DCT + quantisation of one block: nat[i] = lrint(F[i] / q[i]), natural order.  Every DCT output is the sum over x (then y)
+// ascending of basis * sample, started from zero - the order a scalar loop per output uses - but written with the output index
+// innermost, so that the compiler keeps eight independent sums in vector registers; no fused multiply-add (the x86-64 baseline and
+// target("avx2") have none), so the generic and the AVX2 instance produce the same bits.
+static inline __attribute__((always_inline)) void fdct_quant_impl(const float* in, const uint8_t* q, int* nat, const double (*t)[8]) {
+    double tmp[64], f[64];
+    for (int y = 0; y < 8; y++) {
+        double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int x = 0; x < 8; x++) {
+            const double v = in[y * 8 + x];
+            for (int u = 0; u < 8; u++) s[u] += t[x][u] * v;
+        }
+        for (int u = 0; u < 8; u++) tmp[y * 8 + u] = s[u];
+    }
+    for (int v = 0; v < 8; v++) {
+        double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int y = 0; y < 8; y++) {
+            const double c = t[y][v];
+            for (int u = 0; u < 8; u++) s[u] += c * tmp[y * 8 + u];
+        }
+        for (int u = 0; u < 8; u++) f[v * 8 + u] = s[u];
+    }
+    for (int i = 0; i < 64; i++) f[i] = f[i] / q[i];
+    for (int i = 0; i < 64; i++) nat[i] = (int)lrint(f[i]);
+}
+static void fdct_quant_generic(const float* in, const uint8_t* q, int* nat, const double (*t)[8]) { fdct_quant_impl(in, q, nat, t); }
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(PE_JPEG_NO_AVX2)   // (tests build the generic instance with this macro)
+__attribute__((target("avx2"))) static void fdct_quant_avx2(const float* in, const uint8_t* q, int* nat, const double (*t)[8]) { fdct_quant_impl(in, q, nat, t); }
+static const bool g_enc_avx2 = __builtin_cpu_supports("avx2");
+#else
+static void fdct_quant_avx2(const float* in, const uint8_t* q, int* nat, const double (*t)[8]) { fdct_quant_impl(in, q, nat, t); }
+static const bool g_enc_avx2 = false;
+#endif
 
-inline int bit_size(int v) { int a = v < 0 ? -v : v, n = 0; while (a) { n++; a >>= 1; } return n; }
+inline int bit_size(int v) { const unsigned a = (unsigned)(v < 0 ? -v : v); return a ? 32 - __builtin_clz(a) : 0; }
 
 void encode_block(const float* px, const uint8_t* q, int& dc_pred, const Huff& dc, const Huff& ac, BitWriter& bw) {
-    double f[64];
-    fdct8x8(px, f);
-    int z[64];
+    int nat[64], z[64];
+    (g_enc_avx2 ? fdct_quant_avx2 : fdct_quant_generic)(px, q, nat, dct_basis().t);
     for (int i = 0; i < 64; i++) {
-        const int nat = kZigzag[i];
-        int v = (int)lrint(f[nat] / q[nat]);
+        const int v = nat[kZigzag[i]];
         const int lo = i == 0 ? -1024 : -1023;   // 8-bit baseline coefficient range (T.81 F.1.2): DC diff fits 11 bits, AC 10
         z[i] = v < lo ? lo : (v > 1023 ? 1023 : v);
     }
     const int diff = z[0] - dc_pred;
     dc_pred = z[0];
     int s = bit_size(diff);
-    bw.put(dc.code[s], dc.len[s]);
-    if (s) bw.put((uint32_t)(diff < 0 ? diff - 1 : diff), s);
+    bw.put(((uint32_t)dc.code[s] << s) | ((uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << s) - 1u)), dc.len[s] + s);
     int run = 0;
     for (int i = 1; i < 64; i++) {
         if (z[i] == 0) { run++; continue; }
         while (run > 15) { bw.put(ac.code[0xF0], ac.len[0xF0]); run -= 16; }
         s = bit_size(z[i]);
         const int sym = (run << 4) | s;
-        bw.put(ac.code[sym], ac.len[sym]);
-        bw.put((uint32_t)(z[i] < 0 ? z[i] - 1 : z[i]), s);
+        bw.put(((uint32_t)ac.code[sym] << s) | ((uint32_t)(z[i] < 0 ? z[i] - 1 : z[i]) & ((1u << s) - 1u)), ac.len[sym] + s);
         run = 0;
     }
     if (run) bw.put(ac.code[0], ac.len[0]);   // EOB
@@ -170,11 +196,15 @@ extern "C" long long pe_encode_jpeg(const uint8_t* bgr, int w, int h, int qualit
                     Cb[y * 8 + x] = 0.25f * (cb[2 * y][2 * x] + cb[2 * y][2 * x + 1] + cb[2 * y + 1][2 * x] + cb[2 * y + 1][2 * x + 1]);
                     Cr[y * 8 + x] = 0.25f * (cr[2 * y][2 * x] + cr[2 * y][2 * x + 1] + cr[2 * y + 1][2 * x] + cr[2 * y + 1][2 * x + 1]);
                 }
+            bw.begin_mcu();
             for (int b = 0; b < 4; b++) encode_block(Y[b], ql, pred[0], hdl, hal, bw);
             encode_block(Cb, qc, pred[1], hdc, hac, bw);
             encode_block(Cr, qc, pred[2], hdc, hac, bw);
+            bw.end_mcu();
         }
+    bw.begin_mcu();
     bw.flush();
+    bw.end_mcu();
     o.push_back(0xFF); o.push_back(0xD9);                                           // EOI
     if (buf && (long long)o.size() <= cap) memcpy(buf, o.data(), o.size());
     return (long long)o.size();

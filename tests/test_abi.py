@@ -351,6 +351,35 @@ def test_jpeg_idct_scalar_fallback_equals_avx2_form(tmp_path):
         assert np.array_equal(out, engine.decode_jpeg(data))
 
 
+def test_jpeg_encoder_stream_is_pinned_and_generic_equals_avx2_form(tmp_path):
+    """pe_encode_jpeg's byte stream on fixed images (the hashes are those of the round's first, scalar encoder: the faster DCT /
+    bit writer changed no byte), and the generic instance of the DCT + quantiser (a build without the AVX2 one) writes the same bytes
+    as the library on random images of every small size and quality."""
+    import ctypes as C
+    import hashlib
+
+    from caffe_rtpose_b200 import synth
+    pinned = {(96, 160, 98): "99d5b9ec7fc4373bd00a45c6cc10501666c0286699dcb912873c27424ffe6012",
+              (33, 70, 50): "bae0e1ac675574e862c7ad234608388c1c7c073f683351e5ece63a6a64429a13"}
+    for (h, w, q), want in pinned.items():
+        assert hashlib.sha256(engine.encode_jpeg(synth.make_frame(3, h, w), q)).hexdigest() == want
+    so = str(tmp_path / "libjpegenc_generic.so")
+    src = os.path.join(ROOT, "caffe_rtpose_b200", "csrc", "jpeg.cpp")
+    r = subprocess.run(["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-DPE_JPEG_NO_AVX2", "-I", os.path.join(ROOT, "include"), src, "-o", so],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    alt = C.CDLL(so)
+    alt.pe_encode_jpeg.restype = C.c_longlong
+    alt.pe_encode_jpeg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
+    rng = np.random.default_rng(17)
+    for i in range(120):
+        h, w, q = int(rng.integers(1, 60)), int(rng.integers(1, 80)), int(rng.integers(1, 101))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if i % 3 else np.full((h, w, 3), int(rng.integers(0, 256)), np.uint8)
+        buf = np.zeros(h * w * 3 + 70000, np.uint8)
+        n = alt.pe_encode_jpeg(img.ctypes.data, w, h, q, buf.ctypes.data, buf.size)
+        assert n > 0 and buf[:n].tobytes() == engine.encode_jpeg(img, q), (h, w, q)
+
+
 def _png_chunk(tag, body):
     import struct
     import zlib
